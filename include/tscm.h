@@ -1,0 +1,197 @@
+/*
+ * tscm.h — C-ABI of the B200-native TSCM-Calib calibration solve.
+ *
+ * This is the drop-in boundary for the ONE path this repo replaces: the two
+ * `ceres::Solve` call sites of the reference,
+ *
+ *   TripleSphereCamera::refinement   /root/reference/TS.cpp:247-282   (mono)
+ *   MultiCalib::calibrate            /root/reference/multi_calib.cpp:155-218 (rig)
+ *
+ * together with the residual functors Ceres differentiates for them
+ * (TS.h:100-131, multi_calib.h:146-195).  Everything crosses the boundary as
+ * plain pointers and sizes; no C++/torch/OpenCV types, no exceptions.
+ *
+ * Data conventions (all taken from the reference, units mm / pixels):
+ *   intrinsics  C x 9 doubles  {fx, fy, cx, cy, xi, lambda, alpha, b, c}
+ *               packing of TS.cpp:53-61 / multi_calib.h:22.  b, c are carried but
+ *               never read by the functors (TS.h:122-125, multi_calib.h:175-178).
+ *   cam_rt      C x 6 doubles  {angle-axis(3), t(3)}  reference->camera
+ *               (MultiCalib_camera::rt_, multi_calib.h:18,70)
+ *   board_rt    F x 6 doubles  {angle-axis(3), t(3)}  board->reference
+ *               (MultiCalib_chessboard::rt_, multi_calib.h:96,111;
+ *                TripleSphereCamera::rt_[i], TS.cpp:72)
+ *   A "view" is one (camera m, frame i) pair in which camera m detected the
+ *   board.  Views are ordered camera-major, frame-minor — the loop order of
+ *   multi_calib.cpp:162-169 — and every view carries exactly K corners
+ *   (all-or-nothing detection, main.cpp:33-37).
+ *   obs_xy is the concatenation of cameras_[m].pixels()[i] (cv::Point2d =
+ *   {double x, y}) over views in that order: num_views x K x 2 doubles.
+ *
+ * The mono problem (TS.cpp) is the rig problem with C = 1, fixed_camera = 0 and
+ * cam_rt = 0: AngleAxisRotatePoint with a zero vector takes its Taylor branch
+ * and returns the point bit-exactly, so both functors produce identical
+ * residuals.
+ */
+#ifndef TSCM_H_
+#define TSCM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSCM_INTRINSIC_SIZE 9  /* AutoDiffCostFunction<...,9> block, TS.cpp:264 */
+#define TSCM_POSE_SIZE 6       /* AutoDiffCostFunction<...,6,6,...>, multi_calib.cpp:180 */
+
+/* ceres::TerminationType values the reference tests against (TS.cpp:281). */
+enum {
+  TSCM_CONVERGENCE = 0,
+  TSCM_NO_CONVERGENCE = 1,
+  TSCM_FAILURE = 2
+};
+
+/* loss_type: the reference passes NULL (TS.cpp:265, multi_calib.cpp:181,198). */
+enum {
+  TSCM_LOSS_NONE = 0,
+  TSCM_LOSS_HUBER = 1,   /* ceres::HuberLoss(a)  */
+  TSCM_LOSS_CAUCHY = 2   /* ceres::CauchyLoss(a) */
+};
+
+/* Return codes of every entry point (0 = ok). */
+enum {
+  TSCM_OK = 0,
+  TSCM_ERR_INVALID_ARGUMENT = 1,
+  TSCM_ERR_CUDA = 2,          /* CUDA runtime error; tscm_last_error() has the text */
+  TSCM_ERR_NO_DEVICE = 3,     /* no sm_100 device: there is NO CPU fallback */
+  TSCM_ERR_COMM = 4,          /* NCCL failure */
+  TSCM_ERR_UNSUPPORTED = 5
+};
+
+typedef struct tscm_problem {
+  int32_t num_cameras;        /* C  (cameras_.size(), multi_calib.cpp:157) */
+  int32_t num_frames;         /* F  (chessboards_.size(), multi_calib.cpp:158); every frame
+                                 must be seen by >= 1 camera (multi_calib.cpp:102,167) */
+  int32_t corners_per_board;  /* K  (worlds_.size()) */
+  int32_t num_views;          /* number of (camera, frame) pairs with a detection */
+  const double* board_xy;     /* K x 2: worlds_[j].x, worlds_[j].y; z is ignored
+                                 exactly as in TS.h:107-109 / multi_calib.h:154-156 */
+  const int32_t* view_camera; /* num_views: camera index m, non-decreasing */
+  const int32_t* view_frame;  /* num_views: frame index i, increasing within a camera */
+  const double* obs_xy;       /* num_views x K x 2 observed pixels */
+  int32_t fixed_camera;       /* camera whose cam_rt is held constant
+                                 (SetParameterBlockConstant, multi_calib.cpp:186): 0 for
+                                 the rig and for mono; -1 = none */
+} tscm_problem;
+
+/* Solver options.  tscm_options_init() fills the ceres::Solver::Options
+ * defaults that are in effect at TS.cpp:271-274 / multi_calib.cpp:209-212. */
+typedef struct tscm_options {
+  int32_t max_num_iterations;               /* 50 (rig, Ceres default) / 100 (mono, TS.cpp:274) */
+  double function_tolerance;                /* 1e-6  */
+  double gradient_tolerance;                /* 1e-10 */
+  double parameter_tolerance;               /* 1e-8  */
+  double initial_trust_region_radius;       /* 1e4   */
+  double max_trust_region_radius;           /* 1e16  */
+  double min_trust_region_radius;           /* 1e-32 */
+  double min_relative_decrease;             /* 1e-3  */
+  double min_lm_diagonal;                   /* 1e-6  */
+  double max_lm_diagonal;                   /* 1e32  */
+  int32_t max_num_consecutive_invalid_steps;/* 5     */
+  int32_t jacobi_scaling;                   /* 1     */
+  int32_t loss_type;                        /* TSCM_LOSS_NONE */
+  double loss_scale;                        /* `a` of HuberLoss(a)/CauchyLoss(a) */
+  int32_t parameter_tolerance_needs_successful_step;
+                                            /* 0: Ceres <= 2.0 (test on every valid step);
+                                               1: Ceres >= 2.1 */
+  int32_t disable_tolerances;               /* 1: fixed-iteration timing mode — run exactly
+                                               max_num_iterations LM iterations */
+  int32_t verbose;                          /* 1: print BriefReport() line (TS.cpp:280) */
+} tscm_options;
+
+typedef struct tscm_summary {
+  int32_t termination_type;        /* TSCM_CONVERGENCE / NO_CONVERGENCE / FAILURE */
+  int32_t num_iterations;          /* summary.iterations.size(): iteration 0 included */
+  int32_t num_successful_steps;    /* iteration 0 counts, as in Ceres */
+  int32_t num_unsuccessful_steps;
+  double initial_cost;             /* 1/2 sum r^2 (after loss) at the start */
+  double final_cost;               /* min over recorded iterations */
+  double final_radius;
+  /* Optional per-iteration trace, caller-owned, `trace_capacity` entries each
+   * (may be NULL).  Entry k describes recorded iteration k. */
+  int32_t trace_capacity;
+  double* trace_cost;              /* IterationSummary::cost */
+  double* trace_radius;            /* IterationSummary::trust_region_radius */
+  double* trace_gradient_max_norm; /* IterationSummary::gradient_max_norm */
+  double* trace_step_norm;         /* IterationSummary::step_norm */
+  int32_t* trace_step_flags;       /* bit0 step_is_valid, bit1 step_is_successful */
+} tscm_summary;
+
+void tscm_options_init(tscm_options* options);
+
+/* One-shot solve: the call a reference adapter makes instead of ceres::Solve.
+ * Host pointers in, parameters updated in place (as Ceres does through the raw
+ * double* it was handed: TS.cpp:266-267, multi_calib.cpp:182-184).  Uses CUDA
+ * device `device` (-1 = current device). */
+int tscm_solve(const tscm_problem* problem, const tscm_options* options,
+               double* intrinsics, double* cam_rt, double* board_rt,
+               tscm_summary* summary, int device);
+
+/* Resident solver: observations stay in HBM between solves. */
+typedef struct tscm_solver tscm_solver;
+
+int tscm_solver_create(const tscm_problem* problem, const tscm_options* options,
+                       int device, tscm_solver** out);
+void tscm_solver_destroy(tscm_solver* solver);
+int tscm_solver_set_options(tscm_solver* solver, const tscm_options* options);
+/* Host -> device parameter upload / device -> host download. */
+int tscm_solver_set_parameters(tscm_solver* solver, const double* intrinsics,
+                               const double* cam_rt, const double* board_rt);
+int tscm_solver_get_parameters(tscm_solver* solver, double* intrinsics,
+                               double* cam_rt, double* board_rt);
+/* Replace the observations (host pointer, num_views x K x 2). */
+int tscm_solver_set_observations(tscm_solver* solver, const double* obs_xy);
+/* Run the LM loop on the parameters currently on the device. */
+int tscm_solver_run(tscm_solver* solver, tscm_summary* summary);
+
+/* Multi-GPU: frames are sharded across ranks (each rank's tscm_problem holds
+ * only its own frames/views; cameras are replicated).  `unique_id` is the
+ * 128-byte ncclUniqueId produced by tscm_comm_unique_id() on rank 0 and
+ * broadcast by the host (torch.distributed / MPI / a file). */
+int tscm_comm_unique_id(void* unique_id_128);
+int tscm_solver_attach_comm(tscm_solver* solver, int rank, int num_ranks,
+                            const void* unique_id_128);
+
+/* ---- inspection entry points (used by the parity tests and the bench) ---- */
+
+/* One residual + analytic-Jacobian pass at the current device parameters.
+ * residuals: N x 2 (N = num_views*K), jacobian: N x 2 x 21 with the column
+ * order of AutoDiffCostFunction<...,2,6,6,9> (multi_calib.cpp:177-180):
+ * camera_rt(6), chessboard_rt(6), intrinsic(9).  Either may be NULL. Host
+ * pointers.  The fixed camera's rt columns are reported as zeros. */
+int tscm_solver_eval_jacobian(tscm_solver* solver, double* residuals, double* jacobian,
+                              double* cost);
+/* Reduced camera system of the next LM step at the current point and radius:
+ * lhs n x n (row-major, symmetric, both triangles), rhs n, n = tscm_solver_reduced_size();
+ * per camera: [rt(6) unless fixed][fx fy cx cy xi lambda alpha]. */
+int tscm_solver_reduced_size(const tscm_solver* solver);
+int tscm_solver_reduced_system(tscm_solver* solver, double radius, double* lhs, double* rhs);
+/* Mean Euclidean reprojection error per camera and overall, the reference's
+ * accuracy read-out (multi_calib.cpp:235-283): per_camera has C entries. */
+int tscm_solver_reprojection_error(tscm_solver* solver, double* per_camera, double* overall,
+                                   double* rms);
+/* Time `repeats` back-to-back launches of one stage on the solver's stream with
+ * CUDA events; returns the average milliseconds per launch.
+ * stage: 0 = residual+Jacobian+normal-equation pass, 1 = Schur elimination,
+ *        2 = reduced solve, 3 = back-substitution, 4 = whole LM iteration. */
+int tscm_solver_time_stage(tscm_solver* solver, int stage, int repeats, double* ms_per_launch);
+/* Number of kernels launched by this solver since creation. */
+int64_t tscm_solver_launch_count(const tscm_solver* solver);
+
+const char* tscm_last_error(void);
+const char* tscm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSCM_H_ */

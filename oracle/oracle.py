@@ -1,0 +1,148 @@
+"""ctypes binding of the CPU oracle (oracle/libtscm_oracle.so).
+
+TEST INFRASTRUCTURE ONLY — see oracle/tscm_oracle.h.  Importable from tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs,
+never from the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from tscm_calib_b200.capi import (ProblemArrays, SummaryBuffers, TscmOptions, TscmProblem,
+                                  TscmSummary, _dp, c_double_p, default_options)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtscm_oracle.so")
+_lib = None
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("tscm_oracle.cpp", "tscm_oracle.h")]
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in src)):
+        return LIB_PATH
+    subprocess.run(["make", "-C", _HERE, "-B", "libtscm_oracle.so"], check=True,
+                   stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        build()
+    lib = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    lib.tscm_oracle_solve.argtypes = [P(TscmProblem), P(TscmOptions), c_double_p, c_double_p,
+                                      c_double_p, P(TscmSummary), C.c_int]
+    lib.tscm_oracle_solve.restype = C.c_int
+    lib.tscm_oracle_eval_jacobian.argtypes = [P(TscmProblem), c_double_p, c_double_p, c_double_p,
+                                              c_double_p, c_double_p, c_double_p]
+    lib.tscm_oracle_eval_jacobian.restype = C.c_int
+    lib.tscm_oracle_eval_jacobian_mono.argtypes = [P(TscmProblem), c_double_p, c_double_p,
+                                                   c_double_p, c_double_p, c_double_p]
+    lib.tscm_oracle_eval_jacobian_mono.restype = C.c_int
+    lib.tscm_oracle_reduced_size.argtypes = [P(TscmProblem)]
+    lib.tscm_oracle_reduced_size.restype = C.c_int
+    lib.tscm_oracle_reduced_system.argtypes = [P(TscmProblem), P(TscmOptions), c_double_p,
+                                               c_double_p, c_double_p, C.c_double, c_double_p,
+                                               c_double_p]
+    lib.tscm_oracle_reduced_system.restype = C.c_int
+    lib.tscm_oracle_reprojection_error.argtypes = [P(TscmProblem), c_double_p, c_double_p,
+                                                   c_double_p, c_double_p, c_double_p, c_double_p]
+    lib.tscm_oracle_reprojection_error.restype = C.c_int
+    lib.tscm_oracle_project.argtypes = [c_double_p, c_double_p, C.c_int, c_double_p]
+    lib.tscm_oracle_project.restype = None
+    _lib = lib
+    return lib
+
+
+def _params(problem, intrinsics, cam_rt, board_rt):
+    a = np.array(intrinsics, dtype=np.float64, order="C").reshape(problem.num_cameras, 9)
+    b = np.array(cam_rt, dtype=np.float64, order="C").reshape(problem.num_cameras, 6)
+    c = np.array(board_rt, dtype=np.float64, order="C").reshape(problem.num_frames, 6)
+    return a, b, c
+
+
+def solve(problem: ProblemArrays, intrinsics, cam_rt, board_rt, options=None, num_threads=1):
+    lib = load()
+    options = options or default_options()
+    a, b, c = _params(problem, intrinsics, cam_rt, board_rt)
+    buf = SummaryBuffers(options.max_num_iterations + 2)
+    rc = lib.tscm_oracle_solve(C.byref(problem.c), C.byref(options), _dp(a), _dp(b), _dp(c),
+                               C.byref(buf.c), num_threads)
+    if rc != 0:
+        raise RuntimeError(f"oracle solve failed rc={rc}")
+    return a, b, c, buf.result()
+
+
+def eval_jacobian(problem: ProblemArrays, intrinsics, cam_rt, board_rt):
+    lib = load()
+    a, b, c = _params(problem, intrinsics, cam_rt, board_rt)
+    N = problem.num_observations
+    r, J, cost = np.zeros((N, 2)), np.zeros((N, 2, 21)), C.c_double()
+    rc = lib.tscm_oracle_eval_jacobian(C.byref(problem.c), _dp(a), _dp(b), _dp(c), _dp(r), _dp(J),
+                                       C.byref(cost))
+    assert rc == 0
+    return r, J, cost.value
+
+
+def eval_jacobian_mono(problem: ProblemArrays, intrinsics, board_rt):
+    lib = load()
+    a = np.array(intrinsics, dtype=np.float64, order="C").reshape(9)
+    c = np.array(board_rt, dtype=np.float64, order="C").reshape(problem.num_frames, 6)
+    N = problem.num_observations
+    r, J, cost = np.zeros((N, 2)), np.zeros((N, 2, 15)), C.c_double()
+    rc = lib.tscm_oracle_eval_jacobian_mono(C.byref(problem.c), _dp(a), _dp(c), _dp(r), _dp(J),
+                                            C.byref(cost))
+    assert rc == 0
+    return r, J, cost.value
+
+
+def reduced_system(problem: ProblemArrays, intrinsics, cam_rt, board_rt, radius, options=None):
+    lib = load()
+    options = options or default_options()
+    a, b, c = _params(problem, intrinsics, cam_rt, board_rt)
+    n = lib.tscm_oracle_reduced_size(C.byref(problem.c))
+    lhs, rhs = np.zeros((n, n)), np.zeros(n)
+    rc = lib.tscm_oracle_reduced_system(C.byref(problem.c), C.byref(options), _dp(a), _dp(b),
+                                        _dp(c), radius, _dp(lhs), _dp(rhs))
+    assert rc == 0
+    return lhs, rhs
+
+
+def live_reduced_index(problem: ProblemArrays):
+    """Indices of the oracle's reduced system (9 intrinsics per camera, Ceres
+    layout) that the CUDA library keeps (it drops the structurally-zero b, c
+    columns: 7 intrinsics per camera)."""
+    idx, off = [], 0
+    for m in range(problem.num_cameras):
+        rts = 0 if m == problem.fixed_camera else 6
+        idx += list(range(off, off + rts + 7))
+        off += rts + 9
+    return np.array(idx)
+
+
+def reprojection_error(problem: ProblemArrays, intrinsics, cam_rt, board_rt):
+    lib = load()
+    a, b, c = _params(problem, intrinsics, cam_rt, board_rt)
+    per = np.zeros(problem.num_cameras)
+    overall, rms = C.c_double(), C.c_double()
+    rc = lib.tscm_oracle_reprojection_error(C.byref(problem.c), _dp(a), _dp(b), _dp(c), _dp(per),
+                                            C.byref(overall), C.byref(rms))
+    assert rc == 0
+    return per, overall.value, rms.value
+
+
+def project(intrinsic9, pts):
+    lib = load()
+    a = np.array(intrinsic9, dtype=np.float64, order="C").reshape(9)
+    p = np.array(pts, dtype=np.float64, order="C").reshape(-1, 3)
+    uv = np.zeros((p.shape[0], 2))
+    lib.tscm_oracle_project(_dp(a), _dp(p), p.shape[0], _dp(uv))
+    return uv

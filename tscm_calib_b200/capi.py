@@ -1,0 +1,393 @@
+"""ctypes mirror of include/tscm.h (the C-ABI of libtscm_b200.so).
+
+Plumbing only: struct layouts, library loading, and a thin `Solver` handle.
+The product is the shared library; nothing here computes.
+There is NO CPU fallback: if the CUDA library is missing `load_library()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtscm_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+
+TERMINATION = {0: "CONVERGENCE", 1: "NO_CONVERGENCE", 2: "FAILURE"}
+LOSS = {"none": 0, "huber": 1, "cauchy": 2}
+
+
+class TscmProblem(C.Structure):
+    _fields_ = [
+        ("num_cameras", C.c_int32),
+        ("num_frames", C.c_int32),
+        ("corners_per_board", C.c_int32),
+        ("num_views", C.c_int32),
+        ("board_xy", c_double_p),
+        ("view_camera", c_int32_p),
+        ("view_frame", c_int32_p),
+        ("obs_xy", c_double_p),
+        ("fixed_camera", C.c_int32),
+    ]
+
+
+class TscmOptions(C.Structure):
+    _fields_ = [
+        ("max_num_iterations", C.c_int32),
+        ("function_tolerance", C.c_double),
+        ("gradient_tolerance", C.c_double),
+        ("parameter_tolerance", C.c_double),
+        ("initial_trust_region_radius", C.c_double),
+        ("max_trust_region_radius", C.c_double),
+        ("min_trust_region_radius", C.c_double),
+        ("min_relative_decrease", C.c_double),
+        ("min_lm_diagonal", C.c_double),
+        ("max_lm_diagonal", C.c_double),
+        ("max_num_consecutive_invalid_steps", C.c_int32),
+        ("jacobi_scaling", C.c_int32),
+        ("loss_type", C.c_int32),
+        ("loss_scale", C.c_double),
+        ("parameter_tolerance_needs_successful_step", C.c_int32),
+        ("disable_tolerances", C.c_int32),
+        ("verbose", C.c_int32),
+    ]
+
+
+class TscmSummary(C.Structure):
+    _fields_ = [
+        ("termination_type", C.c_int32),
+        ("num_iterations", C.c_int32),
+        ("num_successful_steps", C.c_int32),
+        ("num_unsuccessful_steps", C.c_int32),
+        ("initial_cost", C.c_double),
+        ("final_cost", C.c_double),
+        ("final_radius", C.c_double),
+        ("trace_capacity", C.c_int32),
+        ("trace_cost", c_double_p),
+        ("trace_radius", c_double_p),
+        ("trace_gradient_max_norm", c_double_p),
+        ("trace_step_norm", c_double_p),
+        ("trace_step_flags", c_int32_p),
+    ]
+
+
+def default_options(**overrides) -> TscmOptions:
+    """ceres::Solver::Options defaults in force at TS.cpp:271-274 /
+    multi_calib.cpp:209-212 (same values tscm_options_init() writes)."""
+    o = TscmOptions()
+    o.max_num_iterations = 50
+    o.function_tolerance = 1e-6
+    o.gradient_tolerance = 1e-10
+    o.parameter_tolerance = 1e-8
+    o.initial_trust_region_radius = 1e4
+    o.max_trust_region_radius = 1e16
+    o.min_trust_region_radius = 1e-32
+    o.min_relative_decrease = 1e-3
+    o.min_lm_diagonal = 1e-6
+    o.max_lm_diagonal = 1e32
+    o.max_num_consecutive_invalid_steps = 5
+    o.jacobi_scaling = 1
+    o.loss_type = 0
+    o.loss_scale = 1.0
+    o.parameter_tolerance_needs_successful_step = 0
+    o.disable_tolerances = 0
+    o.verbose = 0
+    for k, v in overrides.items():
+        if k == "loss_type" and isinstance(v, str):
+            v = LOSS[v]
+        if not hasattr(o, k):
+            raise AttributeError(k)
+        setattr(o, k, v)
+    return o
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _ip(a: np.ndarray):
+    return a.ctypes.data_as(c_int32_p)
+
+
+@dataclass
+class SummaryResult:
+    termination: str
+    num_iterations: int
+    num_successful_steps: int
+    num_unsuccessful_steps: int
+    initial_cost: float
+    final_cost: float
+    final_radius: float
+    cost: np.ndarray = field(repr=False, default=None)
+    radius: np.ndarray = field(repr=False, default=None)
+    gradient_max_norm: np.ndarray = field(repr=False, default=None)
+    step_norm: np.ndarray = field(repr=False, default=None)
+    step_flags: np.ndarray = field(repr=False, default=None)
+
+
+class SummaryBuffers:
+    """Owns the caller-side trace arrays of a tscm_summary."""
+
+    def __init__(self, capacity: int):
+        self.capacity = int(capacity)
+        self.cost = np.zeros(capacity)
+        self.radius = np.zeros(capacity)
+        self.gmax = np.zeros(capacity)
+        self.step_norm = np.zeros(capacity)
+        self.flags = np.zeros(capacity, dtype=np.int32)
+        s = TscmSummary()
+        s.trace_capacity = capacity
+        s.trace_cost = _dp(self.cost)
+        s.trace_radius = _dp(self.radius)
+        s.trace_gradient_max_norm = _dp(self.gmax)
+        s.trace_step_norm = _dp(self.step_norm)
+        s.trace_step_flags = _ip(self.flags)
+        self.c = s
+
+    def result(self) -> SummaryResult:
+        n = min(self.c.num_iterations, self.capacity)
+        return SummaryResult(
+            TERMINATION.get(self.c.termination_type, str(self.c.termination_type)),
+            self.c.num_iterations, self.c.num_successful_steps, self.c.num_unsuccessful_steps,
+            self.c.initial_cost, self.c.final_cost, self.c.final_radius,
+            self.cost[:n].copy(), self.radius[:n].copy(), self.gmax[:n].copy(),
+            self.step_norm[:n].copy(), self.flags[:n].copy())
+
+
+class ProblemArrays:
+    """Keeps the numpy arrays behind a tscm_problem alive and C-contiguous."""
+
+    def __init__(self, board_xy, view_camera, view_frame, obs_xy, num_cameras, num_frames,
+                 fixed_camera=0):
+        self.board_xy = np.ascontiguousarray(board_xy, dtype=np.float64).reshape(-1, 2)
+        self.view_camera = np.ascontiguousarray(view_camera, dtype=np.int32).reshape(-1)
+        self.view_frame = np.ascontiguousarray(view_frame, dtype=np.int32).reshape(-1)
+        K = self.board_xy.shape[0]
+        V = self.view_camera.shape[0]
+        self.obs_xy = np.ascontiguousarray(obs_xy, dtype=np.float64).reshape(V, K, 2)
+        self.num_cameras = int(num_cameras)
+        self.num_frames = int(num_frames)
+        self.fixed_camera = int(fixed_camera)
+        p = TscmProblem()
+        p.num_cameras = self.num_cameras
+        p.num_frames = self.num_frames
+        p.corners_per_board = K
+        p.num_views = V
+        p.board_xy = _dp(self.board_xy)
+        p.view_camera = _ip(self.view_camera)
+        p.view_frame = _ip(self.view_frame)
+        p.obs_xy = _dp(self.obs_xy)
+        p.fixed_camera = self.fixed_camera
+        self.c = p
+
+    @property
+    def num_views(self):
+        return self.view_camera.shape[0]
+
+    @property
+    def corners_per_board(self):
+        return self.board_xy.shape[0]
+
+    @property
+    def num_observations(self):
+        return self.num_views * self.corners_per_board
+
+
+_lib = None
+
+
+def load_library(path: str | None = None):
+    """Load libtscm_b200.so and declare every entry point of include/tscm.h.
+    Raises (never falls back) when the library is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`."
+            " There is no CPU fallback for the calibration solve.")
+    lib = C.CDLL(p, mode=C.RTLD_GLOBAL)
+    P = C.POINTER
+    lib.tscm_options_init.argtypes = [P(TscmOptions)]
+    lib.tscm_options_init.restype = None
+    lib.tscm_solve.argtypes = [P(TscmProblem), P(TscmOptions), c_double_p, c_double_p,
+                               c_double_p, P(TscmSummary), C.c_int]
+    lib.tscm_solve.restype = C.c_int
+    lib.tscm_solver_create.argtypes = [P(TscmProblem), P(TscmOptions), C.c_int, P(C.c_void_p)]
+    lib.tscm_solver_create.restype = C.c_int
+    lib.tscm_solver_destroy.argtypes = [C.c_void_p]
+    lib.tscm_solver_destroy.restype = None
+    lib.tscm_solver_set_options.argtypes = [C.c_void_p, P(TscmOptions)]
+    lib.tscm_solver_set_options.restype = C.c_int
+    lib.tscm_solver_set_parameters.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
+    lib.tscm_solver_set_parameters.restype = C.c_int
+    lib.tscm_solver_get_parameters.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
+    lib.tscm_solver_get_parameters.restype = C.c_int
+    lib.tscm_solver_set_observations.argtypes = [C.c_void_p, c_double_p]
+    lib.tscm_solver_set_observations.restype = C.c_int
+    lib.tscm_solver_run.argtypes = [C.c_void_p, P(TscmSummary)]
+    lib.tscm_solver_run.restype = C.c_int
+    lib.tscm_comm_unique_id.argtypes = [C.c_void_p]
+    lib.tscm_comm_unique_id.restype = C.c_int
+    lib.tscm_solver_attach_comm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.tscm_solver_attach_comm.restype = C.c_int
+    lib.tscm_solver_eval_jacobian.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
+    lib.tscm_solver_eval_jacobian.restype = C.c_int
+    lib.tscm_solver_reduced_size.argtypes = [C.c_void_p]
+    lib.tscm_solver_reduced_size.restype = C.c_int
+    lib.tscm_solver_reduced_system.argtypes = [C.c_void_p, C.c_double, c_double_p, c_double_p]
+    lib.tscm_solver_reduced_system.restype = C.c_int
+    lib.tscm_solver_reprojection_error.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
+    lib.tscm_solver_reprojection_error.restype = C.c_int
+    lib.tscm_solver_time_stage.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p]
+    lib.tscm_solver_time_stage.restype = C.c_int
+    lib.tscm_solver_launch_count.argtypes = [C.c_void_p]
+    lib.tscm_solver_launch_count.restype = C.c_int64
+    lib.tscm_last_error.argtypes = []
+    lib.tscm_last_error.restype = C.c_char_p
+    lib.tscm_version.argtypes = []
+    lib.tscm_version.restype = C.c_char_p
+    if path is None:
+        _lib = lib
+    return lib
+
+
+# Every symbol include/tscm.h declares (checked by tests/test_abi.py).
+EXPORTED_SYMBOLS = [
+    "tscm_options_init", "tscm_solve", "tscm_solver_create", "tscm_solver_destroy",
+    "tscm_solver_set_options", "tscm_solver_set_parameters", "tscm_solver_get_parameters",
+    "tscm_solver_set_observations", "tscm_solver_run", "tscm_comm_unique_id",
+    "tscm_solver_attach_comm", "tscm_solver_eval_jacobian", "tscm_solver_reduced_size",
+    "tscm_solver_reduced_system", "tscm_solver_reprojection_error", "tscm_solver_time_stage",
+    "tscm_solver_launch_count", "tscm_last_error", "tscm_version",
+]
+
+
+class TscmError(RuntimeError):
+    pass
+
+
+def check(rc: int, lib=None):
+    if rc != 0:
+        lib = lib or load_library()
+        msg = lib.tscm_last_error()
+        raise TscmError(f"tscm error {rc}: {msg.decode() if msg else ''}")
+
+
+class Solver:
+    """Resident solver handle (observations stay in HBM)."""
+
+    def __init__(self, problem: ProblemArrays, options: TscmOptions | None = None, device: int = -1):
+        self.lib = load_library()
+        self.problem = problem
+        self.options = options or default_options()
+        h = C.c_void_p()
+        check(self.lib.tscm_solver_create(C.byref(problem.c), C.byref(self.options), device,
+                                          C.byref(h)), self.lib)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tscm_solver_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_options(self, options: TscmOptions):
+        self.options = options
+        check(self.lib.tscm_solver_set_options(self.h, C.byref(options)), self.lib)
+
+    def set_parameters(self, intrinsics, cam_rt, board_rt):
+        a = np.ascontiguousarray(intrinsics, dtype=np.float64)
+        b = np.ascontiguousarray(cam_rt, dtype=np.float64)
+        c = np.ascontiguousarray(board_rt, dtype=np.float64)
+        assert a.size == 9 * self.problem.num_cameras and b.size == 6 * self.problem.num_cameras
+        assert c.size == 6 * self.problem.num_frames
+        check(self.lib.tscm_solver_set_parameters(self.h, _dp(a), _dp(b), _dp(c)), self.lib)
+
+    def get_parameters(self):
+        Cn, F = self.problem.num_cameras, self.problem.num_frames
+        a, b, c = np.zeros((Cn, 9)), np.zeros((Cn, 6)), np.zeros((F, 6))
+        check(self.lib.tscm_solver_get_parameters(self.h, _dp(a), _dp(b), _dp(c)), self.lib)
+        return a, b, c
+
+    def set_observations(self, obs_xy):
+        o = np.ascontiguousarray(obs_xy, dtype=np.float64)
+        assert o.size == self.problem.num_observations * 2
+        check(self.lib.tscm_solver_set_observations(self.h, _dp(o)), self.lib)
+
+    def run(self, trace_capacity: int | None = None) -> SummaryResult:
+        cap = trace_capacity if trace_capacity is not None else self.options.max_num_iterations + 2
+        buf = SummaryBuffers(cap)
+        check(self.lib.tscm_solver_run(self.h, C.byref(buf.c)), self.lib)
+        return buf.result()
+
+    def attach_comm(self, rank: int, num_ranks: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        b = C.create_string_buffer(unique_id, 128)
+        check(self.lib.tscm_solver_attach_comm(self.h, rank, num_ranks, b), self.lib)
+
+    def eval_jacobian(self, want_jacobian=True):
+        N = self.problem.num_observations
+        r = np.zeros((N, 2))
+        J = np.zeros((N, 2, 21)) if want_jacobian else None
+        cost = C.c_double()
+        check(self.lib.tscm_solver_eval_jacobian(self.h, _dp(r), _dp(J) if want_jacobian else None,
+                                                 C.byref(cost)), self.lib)
+        return r, J, cost.value
+
+    def reduced_size(self) -> int:
+        return self.lib.tscm_solver_reduced_size(self.h)
+
+    def reduced_system(self, radius: float):
+        n = self.reduced_size()
+        lhs, rhs = np.zeros((n, n)), np.zeros(n)
+        check(self.lib.tscm_solver_reduced_system(self.h, radius, _dp(lhs), _dp(rhs)), self.lib)
+        return lhs, rhs
+
+    def reprojection_error(self):
+        per = np.zeros(self.problem.num_cameras)
+        overall, rms = C.c_double(), C.c_double()
+        check(self.lib.tscm_solver_reprojection_error(self.h, _dp(per), C.byref(overall),
+                                                      C.byref(rms)), self.lib)
+        return per, overall.value, rms.value
+
+    def time_stage(self, stage: int, repeats: int) -> float:
+        ms = C.c_double()
+        check(self.lib.tscm_solver_time_stage(self.h, stage, repeats, C.byref(ms)), self.lib)
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.tscm_solver_launch_count(self.h))
+
+
+def comm_unique_id() -> bytes:
+    lib = load_library()
+    b = C.create_string_buffer(128)
+    check(lib.tscm_comm_unique_id(b), lib)
+    return b.raw
+
+
+def solve(problem: ProblemArrays, intrinsics, cam_rt, board_rt, options: TscmOptions | None = None,
+          device: int = -1):
+    """One-shot host-buffer solve through tscm_solve() — what a reference
+    adapter calls in place of ceres::Solve.  Returns (intr, cam_rt, board_rt, summary)."""
+    lib = load_library()
+    options = options or default_options()
+    a = np.array(intrinsics, dtype=np.float64, order="C").reshape(problem.num_cameras, 9)
+    b = np.array(cam_rt, dtype=np.float64, order="C").reshape(problem.num_cameras, 6)
+    c = np.array(board_rt, dtype=np.float64, order="C").reshape(problem.num_frames, 6)
+    buf = SummaryBuffers(options.max_num_iterations + 2)
+    check(lib.tscm_solve(C.byref(problem.c), C.byref(options), _dp(a), _dp(b), _dp(c),
+                         C.byref(buf.c), device), lib)
+    return a, b, c, buf.result()
