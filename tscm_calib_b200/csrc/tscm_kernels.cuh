@@ -1,0 +1,1019 @@
+// tscm_kernels.cuh — sm_100a FP64 kernels of the calibration solve.
+//
+// Stage map (reference stage each replaces):
+//   k_prep_cams, k_eval        K1+K2  Jet evaluation of multi_calib.h:146-195 for every
+//                                     residual block + SchurEliminator's E^T E / E^T F /
+//                                     F^T F / E^T b / F^T b products (multi_calib.cpp:162-207)
+//   k_reduce_cam_{a,b}         K2     per-camera F^T F, F^T b, cost
+//   k_schur, k_reduce_s        K3     SchurEliminator::Eliminate chunk loop
+//   k_solve                    K4     DenseSchurComplementSolver (Eigen LLT) on the reduced
+//                                     camera system
+//   k_backsub                  K4     SchurEliminator::BackSubstitute + candidate point
+//   k_frame_grad, k_pack,
+//   k_decide                   K5     TrustRegionMinimizer / LevenbergMarquardtStrategy
+//                                     control flow (accept/reject, radius, termination)
+#pragma once
+
+#include <cstdint>
+
+#include "tscm_math.cuh"
+
+namespace tscm {
+
+// ---------------------------------------------------------------------------
+// Device-resident LM state (one per solver).  Every kernel of the iteration
+// graph reads it; only k_solve / k_pack / k_decide / k_init write it.
+// ---------------------------------------------------------------------------
+struct LmOptions {
+  int max_num_iterations;
+  double function_tolerance, gradient_tolerance, parameter_tolerance;
+  double initial_radius, max_radius, min_radius;
+  double min_relative_decrease, min_lm_diagonal, max_lm_diagonal;
+  int max_num_consecutive_invalid_steps;
+  int jacobi_scaling;
+  int loss_type;
+  double loss_scale;
+  int ptol_needs_success;
+  int disable_tolerances;
+};
+
+struct LmState {
+  int done;
+  int termination;
+  int iteration;            // index of the last finalized iteration
+  int recorded;             // entries written to the trace
+  int cur;                  // which of the two parameter/Gram buffers holds x
+  int num_successful, num_unsuccessful, num_consecutive_invalid;
+  int atleast_one_successful_step;
+  int solve_ok;             // reduced-system Cholesky succeeded (k_solve)
+  int pad0, pad1;
+  double radius, decrease_factor;
+  double x_cost, x_norm, gmax;
+  double initial_cost, final_cost, minimum_cost;
+  double model_cost_change, candidate_cost, step_norm;  // last step (diagnostics)
+  // camera-side partial sums of the current step (k_solve)
+  double cam_lin, cam_quad, cam_dn2, cam_xn2;
+};
+
+// Comm record: what must be globally summed after an evaluation
+//   [0, C*kCamRec)            per-camera U / g_c / cost / err sums
+//   +0 frame lin, +1 frame quad, +2 frame |delta|^2, +3 frame |x+|^2
+constexpr int kCommExtra = 4;
+
+struct Trace {
+  double* cost; double* radius; double* gmax; double* step_norm; int* flags;
+  int capacity;
+};
+
+// Static problem description on the device.
+struct DeviceProblem {
+  int C, F, K, V, Vpad, fixed_camera;
+  int NL;                    // live reduced-system size: sum_c (free_rt ? 13 : 7)
+  int Q;                     // NL (NL + 1) / 2
+  const double2* obsT;       // [K][Vpad] observed pixels, corner-major
+  const double* board_xy;    // [K][2]
+  const int* view_camera;    // [V]
+  const int* view_frame;     // [V]
+  const int* frame_ptr;      // [F+1] CSR over frames
+  const int* frame_views;    // [V] view ids grouped by frame (camera order)
+  const int* cam_view_begin; // [C+1] views of camera c are [begin[c], begin[c+1])
+  const int* live_off;       // [C+1] offset of camera c in the live reduced system
+  const short* live_cam;     // [NL]
+  const short* live_kk;      // [NL] index inside the camera's [rt 6 | intr 7] block
+  const short* q_i;          // [Q] row of packed upper entry q
+  const short* q_j;          // [Q] col
+  const int* chunk_cam;      // [nchunk] camera of reduce chunk
+  const int* chunk_begin;    // [nchunk+1] view range of reduce chunk
+  const int* cam_chunk_begin;// [C+1]
+  int nchunk;
+};
+
+// One parameter set (there are two: current / candidate).
+struct ParamSet {
+  double* intr;      // [C][9]
+  double* cam_rt;    // [C][6]
+  double* board_rt;  // [F][6]
+  CamConst* cam;     // [C] derived constants (k_prep_cams)
+  double* G;         // [V][kViewStride] per-view Gram records
+  double* comm;      // [C*kCamRec + kCommExtra] (+ gmax stored separately)
+  double* gmax;      // [1]
+};
+
+// ---------------------------------------------------------------------------
+// K1: per-camera constants
+// ---------------------------------------------------------------------------
+__global__ void k_prep_cams(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st,
+                            int which /*0 = current, 1 = candidate, 2/3 = absolute*/) {
+  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
+  if (which < 2 && st->done) return;
+  const ParamSet& ps = sel ? ps1 : ps0;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= P.C) return;
+  CamConst cc;
+  make_cam_const(ps.cam_rt + 6 * c, ps.intr + 9 * c, c != P.fixed_camera, cc);
+  ps.cam[c] = cc;
+}
+
+// ---------------------------------------------------------------------------
+// K1+K2: residual + analytic Jacobian + normal-equation blocks.
+// One lane per (view, slice); the lane streams through the K corners of its
+// view and keeps its slice of the 20x20 Gram matrix of [J | r] in registers, so
+// there is no cross-thread reduction at all.  Observations are read through the
+// corner-major transposed copy (coalesced across lanes = consecutive views).
+//   slice 0: BB + BC   slice 1: BI   slice 2: CC + II + cost + err   slice 3: CI
+// ---------------------------------------------------------------------------
+constexpr int kEvalThreads = 128;
+
+template <int SLICE>
+__device__ __forceinline__ void eval_view_slice(const DeviceProblem& P, const CamConst& cc,
+                                                const FrameConst& fc, const double* s_board,
+                                                int v, int loss_type, double loss_scale,
+                                                double* __restrict__ Gv) {
+  constexpr int NACC = (SLICE == 0) ? 57 : (SLICE == 1) ? 48 : (SLICE == 2) ? 59 : 48;
+  double acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
+
+  const double2* obs = P.obsT + v;
+  for (int j = 0; j < P.K; ++j) {
+    const double2 uv = obs[(size_t)j * P.Vpad];
+    const double X = s_board[2 * j], Y = s_board[2 * j + 1];
+    ObsRow o;
+    double err;
+    if (SLICE == 0) {
+      obs_jacobian<true, true, false>(cc, fc, X, Y, uv.x, uv.y, o);
+      if (loss_type) obs_apply_loss<0, 12>(loss_type, loss_scale, o, &err);
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int b = a; b < 6; ++b)
+          acc[tri6(a, b)] += o.Ju[a] * o.Ju[b] + o.Jv[a] * o.Jv[b];
+#pragma unroll
+        for (int b = 0; b < 6; ++b)
+          acc[21 + a * 6 + b] += o.Ju[a] * o.Ju[6 + b] + o.Jv[a] * o.Jv[6 + b];
+      }
+    } else if (SLICE == 1) {
+      obs_jacobian<true, false, true>(cc, fc, X, Y, uv.x, uv.y, o);
+      if (loss_type) {
+        // columns 0..5 and 12..18 are live here
+        obs_apply_loss<0, 19>(loss_type, loss_scale, o, &err);
+      }
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+          acc[a * 8 + b] += o.Ju[a] * o.Ju[12 + b] + o.Jv[a] * o.Jv[12 + b];
+    } else if (SLICE == 2) {
+      obs_jacobian<false, true, true>(cc, fc, X, Y, uv.x, uv.y, o);
+      const double half_rho = obs_apply_loss<6, 19>(loss_type, loss_scale, o, &err);
+      acc[57] += half_rho;
+      acc[58] += err;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = a; b < 6; ++b)
+          acc[tri6(a, b)] += o.Ju[6 + a] * o.Ju[6 + b] + o.Jv[6 + a] * o.Jv[6 + b];
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = a; b < 8; ++b)
+          acc[21 + tri8(a, b)] += o.Ju[12 + a] * o.Ju[12 + b] + o.Jv[12 + a] * o.Jv[12 + b];
+    } else {
+      obs_jacobian<false, true, true>(cc, fc, X, Y, uv.x, uv.y, o);
+      if (loss_type) obs_apply_loss<6, 19>(loss_type, loss_scale, o, &err);
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+          acc[a * 8 + b] += o.Ju[6 + a] * o.Ju[12 + b] + o.Jv[6 + a] * o.Jv[12 + b];
+    }
+  }
+  if (SLICE == 0) {
+#pragma unroll
+    for (int i = 0; i < 57; ++i) Gv[kOffBB + i] = acc[i];
+  } else if (SLICE == 1) {
+#pragma unroll
+    for (int i = 0; i < 48; ++i) Gv[kOffBI + i] = acc[i];
+  } else if (SLICE == 2) {
+#pragma unroll
+    for (int i = 0; i < 21; ++i) Gv[kOffCC + i] = acc[i];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) Gv[kOffII + i] = acc[21 + i];
+    Gv[kOffCost] = acc[57];
+    Gv[kOffErr] = acc[58];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 48; ++i) Gv[kOffCI + i] = acc[i];
+  }
+}
+
+__global__ void __launch_bounds__(kEvalThreads)
+k_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which,
+       LmOptions opt) {
+  if (which < 2 && st->done) return;
+  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
+  const ParamSet& ps = sel ? ps1 : ps0;
+  extern __shared__ double s_mem[];
+  double* s_board = s_mem;                                          // [K][2]
+  CamConst* s_cam = reinterpret_cast<CamConst*>(s_mem + 2 * P.K);   // [C]
+  for (int i = threadIdx.x; i < 2 * P.K; i += blockDim.x) s_board[i] = P.board_xy[i];
+  {
+    const int n = P.C * (int)(sizeof(CamConst) / sizeof(double));
+    const double* src = reinterpret_cast<const double*>(ps.cam);
+    double* dst = reinterpret_cast<double*>(s_cam);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= P.V) return;
+  const int m = P.view_camera[v];
+  const CamConst& cc = s_cam[m];
+  FrameConst fc;
+  make_frame_const(ps.board_rt + 6 * P.view_frame[v], fc);
+  double* Gv = ps.G + (size_t)v * kViewStride;
+  const int slice = blockIdx.y;
+  if (slice == 0) eval_view_slice<0>(P, cc, fc, s_board, v, opt.loss_type, opt.loss_scale, Gv);
+  else if (slice == 1) eval_view_slice<1>(P, cc, fc, s_board, v, opt.loss_type, opt.loss_scale, Gv);
+  else if (slice == 2) eval_view_slice<2>(P, cc, fc, s_board, v, opt.loss_type, opt.loss_scale, Gv);
+  else {
+    if (cc.free_rt) {
+      eval_view_slice<3>(P, cc, fc, s_board, v, opt.loss_type, opt.loss_scale, Gv);
+    } else {
+      for (int i = 0; i < 48; ++i) Gv[kOffCI + i] = 0.0;
+    }
+  }
+}
+
+// Inspection kernel: one thread per observation, full residual + Jacobian rows
+// in the reference's column order (camera_rt 6, chessboard_rt 6, intrinsic 9).
+__global__ void k_eval_rows(DeviceProblem P, ParamSet ps, LmOptions opt, double* residuals,
+                            double* jacobian) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)P.V * P.K) return;
+  const int v = (int)(idx / P.K), j = (int)(idx % P.K);
+  const CamConst cc = ps.cam[P.view_camera[v]];
+  FrameConst fc;
+  make_frame_const(ps.board_rt + 6 * P.view_frame[v], fc);
+  const double2 uv = P.obsT[(size_t)j * P.Vpad + v];
+  ObsRow o;
+  obs_jacobian<true, true, true>(cc, fc, P.board_xy[2 * j], P.board_xy[2 * j + 1], uv.x, uv.y, o);
+  double err;
+  obs_apply_loss<0, 19>(opt.loss_type, opt.loss_scale, o, &err);
+  if (residuals) { residuals[2 * idx] = o.Ju[19]; residuals[2 * idx + 1] = o.Jv[19]; }
+  if (jacobian) {
+    double* Ju = jacobian + idx * 42;
+    double* Jv = Ju + 21;
+    for (int k = 0; k < 6; ++k) { Ju[k] = o.Ju[6 + k]; Jv[k] = o.Jv[6 + k]; }
+    for (int k = 0; k < 6; ++k) { Ju[6 + k] = o.Ju[k]; Jv[6 + k] = o.Jv[k]; }
+    for (int k = 0; k < 7; ++k) { Ju[12 + k] = o.Ju[12 + k]; Jv[12 + k] = o.Jv[12 + k]; }
+    Ju[19] = Ju[20] = Jv[19] = Jv[20] = 0.0;
+  }
+}
+
+// Observation transpose [V][K] (reference layout, cv::Point2d) -> [K][Vpad].
+__global__ void k_transpose_obs(const double2* __restrict__ in, double2* __restrict__ out, int V,
+                                int K, int Vpad) {
+  __shared__ double2 tile[32][33];
+  const int v0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int v = v0 + r, j = j0 + threadIdx.x;
+    if (v < V && j < K) tile[r][threadIdx.x] = in[(size_t)v * K + j];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int j = j0 + r, v = v0 + threadIdx.x;
+    if (v < V && j < K) out[(size_t)j * Vpad + v] = tile[threadIdx.x][r];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2: per-camera sums of the camera part of the view records (deterministic
+// two-level tree: chunk partials, then chunks in order).
+// ---------------------------------------------------------------------------
+__global__ void k_reduce_cam_a(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st,
+                               int which, double* __restrict__ part /*[nchunk][kCamRec]*/) {
+  if (which < 2 && st->done) return;
+  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
+  const ParamSet& ps = sel ? ps1 : ps0;
+  const int ch = blockIdx.x, e = threadIdx.x;
+  if (e >= kCamRec) return;
+  const int v0 = P.chunk_begin[ch], v1 = P.chunk_begin[ch + 1];
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const double* g = ps.G + kOffCC + e;
+  int v = v0;
+  for (; v + 3 < v1; v += 4) {
+    s0 += g[(size_t)v * kViewStride];
+    s1 += g[(size_t)(v + 1) * kViewStride];
+    s2 += g[(size_t)(v + 2) * kViewStride];
+    s3 += g[(size_t)(v + 3) * kViewStride];
+  }
+  for (; v < v1; ++v) s0 += g[(size_t)v * kViewStride];
+  part[(size_t)ch * kCamRec + e] = (s0 + s1) + (s2 + s3);
+}
+
+__global__ void k_reduce_cam_b(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st,
+                               int which, const double* __restrict__ part) {
+  if (which < 2 && st->done) return;
+  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
+  const ParamSet& ps = sel ? ps1 : ps0;
+  const int c = blockIdx.x, e = threadIdx.x;
+  if (e >= kCamRec) return;
+  double s = 0.0;
+  for (int ch = P.cam_chunk_begin[c]; ch < P.cam_chunk_begin[c + 1]; ++ch)
+    s += part[(size_t)ch * kCamRec + e];
+  ps.comm[c * kCamRec + e] = s;
+}
+
+// Block-wide deterministic sum / max helpers (blockDim.x <= 1024, power of 2).
+__device__ __forceinline__ double block_sum(double v, double* s_red) {
+  const int t = threadIdx.x;
+  s_red[t] = v;
+  __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (t < s) s_red[t] += s_red[t + s];
+    __syncthreads();
+  }
+  const double r = s_red[0];
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ double block_max(double v, double* s_red) {
+  const int t = threadIdx.x;
+  s_red[t] = v;
+  __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (t < s) s_red[t] = fmax(s_red[t], s_red[t + s]);
+    __syncthreads();
+  }
+  const double r = s_red[0];
+  __syncthreads();
+  return r;
+}
+
+// Frame gradient max-norm |x - (x - g)|_inf (EvaluateGradientAndJacobian) and
+// |x_f|^2 of a parameter set: one thread per (frame, pose component).
+__global__ void k_frame_grad(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st,
+                             int which, double* __restrict__ gmax_part,
+                             double* __restrict__ xn2_part) {
+  __shared__ double s_red[256];
+  if (which < 2 && st->done) return;
+  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
+  const ParamSet& ps = sel ? ps1 : ps0;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  double gm = 0.0, xn2 = 0.0;
+  if (idx < P.F * 6) {
+    const int f = idx / 6, b = idx % 6;
+    double g = 0.0;
+    for (int p = P.frame_ptr[f]; p < P.frame_ptr[f + 1]; ++p)
+      g += ps.G[(size_t)P.frame_views[p] * kViewStride + kOffBI + b * 8 + 7];
+    const double x = ps.board_rt[idx];
+    const double projected = x + (-g);
+    gm = fabs(x - projected);
+    xn2 = x * x;
+  }
+  const double m = block_max(gm, s_red);
+  const double s = block_sum(xn2, s_red);
+  if (threadIdx.x == 0) { gmax_part[blockIdx.x] = m; xn2_part[blockIdx.x] = s; }
+}
+
+// ---------------------------------------------------------------------------
+// Jacobi scaling (iteration 0): scale = 1 / (1 + sqrt(sum J_col^2)).
+// ---------------------------------------------------------------------------
+__global__ void k_jacobi_scale(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st,
+                               LmOptions opt, double* __restrict__ scale_e /*[F][6]*/,
+                               double* __restrict__ scale_c /*[C][13]*/) {
+  const ParamSet& ps = st->cur ? ps1 : ps0;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < P.F * 6) {
+    const int f = idx / 6, b = idx % 6;
+    double d = 0.0;
+    for (int p = P.frame_ptr[f]; p < P.frame_ptr[f + 1]; ++p)
+      d += ps.G[(size_t)P.frame_views[p] * kViewStride + kOffBB + tri6(b, b)];
+    scale_e[idx] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(d)) : 1.0;
+  } else if (idx < P.F * 6 + P.C * 13) {
+    const int k = idx - P.F * 6;
+    const int c = k / 13, kk = k % 13;
+    const double* U = ps.comm + c * kCamRec;   // globally summed camera record
+    const double d = kk < 6 ? U[tri6(kk, kk)] : U[(kOffII - kOffCC) + tri8(kk - 6, kk - 6)];
+    scale_c[k] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(d)) : 1.0;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3: Schur elimination of the frame poses onto the reduced camera system.
+// A CTA walks a contiguous range of frames in batches of kSchurFB (one warp per
+// frame): V_f + D_e^2 -> Cholesky -> Y = V^-1 W_s, z = V^-1 g_s staged in shared
+// memory; then every thread updates the packed upper-triangular S entries it
+// owns (registers) with  S_ij -= sum_r W_s[r][i] Y[r][j].
+// Per-frame record saved for the back-substitution (SoA over frames):
+//   [0,21) L (row-major lower), [21,27) z, [27,48) V_s upper, [48,54) g_s
+// ---------------------------------------------------------------------------
+constexpr int kSchurFB = 8;
+constexpr int kFrameRec = 54;
+
+struct SchurArgs {
+  const double* scale_e;   // [F][6]
+  const double* scale_c;   // [C][13]
+  double* frame_rec;       // [kFrameRec][Fpad]
+  int Fpad;
+  double* Spart;           // [nblk][Q]
+  double* rpart;           // [nblk][NL]
+  int frames_per_block;
+  double radius_override;  // > 0: use instead of st->radius (inspection)
+};
+
+template <int EPT, int NT>
+__global__ void __launch_bounds__(NT)
+k_schur(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
+        SchurArgs A) {
+  if (st->done) return;
+  const ParamSet& ps = st->cur ? ps1 : ps0;
+  const double radius = A.radius_override > 0.0 ? A.radius_override : st->radius;
+  extern __shared__ double s_mem[];
+  const int NL = P.NL;
+  double* Ws = s_mem;                               // [FB][6][NL]
+  double* Ys = Ws + kSchurFB * 6 * NL;              // [FB][6][NL]
+  double* zs = Ys + kSchurFB * 6 * NL;              // [FB][6]
+  double* scr = zs + kSchurFB * 6;                  // [FB][64] per-warp scratch
+  int* colbase = reinterpret_cast<int*>(scr + kSchurFB * 64);  // [FB][32]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int qi[EPT], qj[EPT];
+  double acc[EPT];
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int q = tid + k * NT;
+    acc[k] = 0.0;
+    qi[k] = q < P.Q ? P.q_i[q] : 0;
+    qj[k] = q < P.Q ? P.q_j[q] : 0;
+  }
+  double racc = 0.0;
+
+  const int f_begin = blockIdx.x * A.frames_per_block;
+  const int f_end = min(P.F, f_begin + A.frames_per_block);
+  for (int fb = f_begin; fb < f_end; fb += kSchurFB) {
+    // zero the staging area
+    for (int i = tid; i < 2 * kSchurFB * 6 * NL + kSchurFB * 6; i += NT) s_mem[i] = 0.0;
+    __syncthreads();
+    const int f = fb + warp;
+    if (warp < kSchurFB && f < f_end) {
+      double* my = scr + warp * 64;
+      int* cb = colbase + warp * 32;
+      const int p0 = P.frame_ptr[f], nv = P.frame_ptr[f + 1] - p0;
+      if (lane < 27) {
+        const int e = lane < 21 ? kOffBB + lane : kOffBI + (lane - 21) * 8 + 7;
+        double s = 0.0;
+        for (int p = 0; p < nv; ++p) s += ps.G[(size_t)P.frame_views[p0 + p] * kViewStride + e];
+        my[lane] = s;
+      }
+      if (lane == 0) {
+        int c0 = 0;
+        for (int p = 0; p < nv; ++p) {
+          cb[p] = c0;
+          const int m = P.view_camera[P.frame_views[p0 + p]];
+          c0 += P.live_off[m + 1] - P.live_off[m];
+        }
+        cb[nv] = c0;
+      }
+      __syncwarp();
+      // every lane builds the damped, scaled 6x6 system redundantly
+      double se[6], M[36], gs[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) se[i] = A.scale_e[f * 6 + i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = i; j < 6; ++j) {
+          const double v = se[i] * se[j] * my[tri6(i, j)];
+          M[i * 6 + j] = v;
+          M[j * 6 + i] = v;
+        }
+        gs[i] = se[i] * my[21 + i];
+      }
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+          for (int j = i; j < 6; ++j) my[27 + tri6(i, j)] = M[i * 6 + j];
+          my[48 + i] = gs[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const double d = fmin(fmax(M[i * 6 + i], opt.min_lm_diagonal), opt.max_lm_diagonal);
+        const double D = sqrt(d / radius);
+        M[i * 6 + i] += D * D;
+      }
+      chol6(M);   // a failed pivot yields NaNs that k_decide turns into an invalid step
+      double z[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) z[i] = gs[i];
+      chol6_solve(M, z);
+      if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+          for (int j = 0; j <= i; ++j) my[(i * (i + 1)) / 2 + j] = M[i * 6 + j];
+          my[21 + i] = z[i];
+          zs[warp * 6 + i] = z[i];
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < kFrameRec; i += 32) A.frame_rec[(size_t)i * A.Fpad + f] = my[i];
+      // columns of W_s and Y = (V + D^2)^-1 W_s
+      const int ncols = cb[nv];
+      for (int col = lane; col < ncols; col += 32) {
+        int vi = 0;
+        while (col >= cb[vi + 1]) ++vi;
+        const int v = P.frame_views[p0 + vi];
+        const int m = P.view_camera[v];
+        const int k = col - cb[vi];
+        const int kk = (P.live_off[m + 1] - P.live_off[m] == 13) ? k : k + 6;
+        const double sc = A.scale_c[m * 13 + kk];
+        const double* Gv = ps.G + (size_t)v * kViewStride;
+        double w[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const double raw = kk < 6 ? Gv[kOffBC + r * 6 + kk] : Gv[kOffBI + r * 8 + (kk - 6)];
+          w[r] = se[r] * raw * sc;
+        }
+        const int gcol = P.live_off[m] + k;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) Ws[(warp * 6 + r) * NL + gcol] = w[r];
+        chol6_solve(M, w);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) Ys[(warp * 6 + r) * NL + gcol] = w[r];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      double a = acc[k];
+      const double* wp = Ws + qi[k];
+      const double* yp = Ys + qj[k];
+#pragma unroll 4
+      for (int r = 0; r < kSchurFB * 6; ++r) a -= wp[r * NL] * yp[r * NL];
+      acc[k] = a;
+    }
+    if (tid < NL) {
+      double a = racc;
+      for (int r = 0; r < kSchurFB * 6; ++r) a -= Ws[r * NL + tid] * zs[r];
+      racc = a;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int q = tid + k * NT;
+    if (q < P.Q) A.Spart[(size_t)blockIdx.x * P.Q + q] = acc[k];
+  }
+  if (tid < NL) A.rpart[(size_t)blockIdx.x * NL + tid] = racc;
+}
+
+// Sum the per-CTA partials: out = [S packed upper (Q) | rhs (NL)].
+__global__ void k_reduce_s(DeviceProblem P, const LmState* st, const double* __restrict__ Spart,
+                           const double* __restrict__ rpart, int nblk, double* __restrict__ out) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.Q + P.NL) return;
+  const double* src = i < P.Q ? Spart + i : rpart + (i - P.Q);
+  const size_t stride = i < P.Q ? P.Q : P.NL;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int b = 0;
+  for (; b + 3 < nblk; b += 4) {
+    s0 += src[(size_t)b * stride];
+    s1 += src[(size_t)(b + 1) * stride];
+    s2 += src[(size_t)(b + 2) * stride];
+    s3 += src[(size_t)(b + 3) * stride];
+  }
+  for (; b < nblk; ++b) s0 += src[(size_t)b * stride];
+  out[i] = (s0 + s1) + (s2 + s3);
+}
+
+// ---------------------------------------------------------------------------
+// K4: reduced camera system — assemble, dense Cholesky, solve (single CTA).
+// lhs = sum_f(-W^T V^-1 W) [allreduced] + U_s + D_c^2, packed lower in smem.
+// ---------------------------------------------------------------------------
+constexpr int kSolveThreads = 512;
+
+__device__ __forceinline__ int idxL(int r, int c) { return (r * (r + 1)) / 2 + c; }  // r >= c
+
+// U(i, j) of camera record `U` for in-camera indices a <= b (0..12 over [rt 6 | intr 7]).
+__device__ __forceinline__ double cam_block(const double* U, int a, int b) {
+  if (b < 6) return U[tri6(a, b)];
+  if (a < 6) return U[(kOffCI - kOffCC) + a * 8 + (b - 6)];
+  return U[(kOffII - kOffCC) + tri8(a - 6, b - 6)];
+}
+__device__ __forceinline__ double cam_grad(const double* U, int a) {
+  return a < 6 ? U[(kOffCI - kOffCC) + a * 8 + 7] : U[(kOffII - kOffCC) + tri8(a - 6, 7)];
+}
+
+__global__ void __launch_bounds__(kSolveThreads)
+k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
+        const double* __restrict__ Sr /*[Q + NL]*/, const double* __restrict__ scale_c,
+        double* __restrict__ y_c /*[NL]*/, double radius_override,
+        double* __restrict__ dbg_lhs, double* __restrict__ dbg_rhs) {
+  if (st->done) return;
+  const int sel = st->cur;
+  const ParamSet& ps = sel ? ps1 : ps0;     // current x
+  const ParamSet& pc = sel ? ps0 : ps1;     // candidate
+  const double radius = radius_override > 0.0 ? radius_override : st->radius;
+  extern __shared__ double s_mem[];
+  const int NL = P.NL, tid = threadIdx.x;
+  double* L = s_mem;                 // packed lower, Q entries
+  double* b = L + P.Q;               // [NL] rhs -> y
+  double* gsv = b + NL;              // [NL] scaled gradient
+  double* sc = gsv + NL;             // [NL] scale
+  double* s_red = sc + NL;           // [kSolveThreads]
+  __shared__ int s_ok;
+  if (tid == 0) s_ok = 1;
+  for (int i = tid; i < NL; i += kSolveThreads) sc[i] = scale_c[P.live_cam[i] * 13 + P.live_kk[i]];
+  __syncthreads();
+  for (int q = tid; q < P.Q; q += kSolveThreads) {
+    const int i = P.q_i[q], j = P.q_j[q];   // i <= j
+    double v = Sr[q];
+    const int ci = P.live_cam[i], cj = P.live_cam[j];
+    if (ci == cj) {
+      const double* U = ps.comm + ci * kCamRec;
+      const double us = sc[i] * sc[j] * cam_block(U, P.live_kk[i], P.live_kk[j]);
+      v += us;
+      if (i == j) {
+        const double d = fmin(fmax(us, opt.min_lm_diagonal), opt.max_lm_diagonal);
+        const double D = sqrt(d / radius);
+        v += D * D;
+      }
+    }
+    L[idxL(j, i)] = v;
+  }
+  for (int i = tid; i < NL; i += kSolveThreads) {
+    const double* U = ps.comm + P.live_cam[i] * kCamRec;
+    const double g = sc[i] * cam_grad(U, P.live_kk[i]);
+    gsv[i] = g;
+    b[i] = Sr[P.Q + i] + g;
+  }
+  __syncthreads();
+  if (dbg_lhs) {
+    for (int idx = tid; idx < NL * NL; idx += kSolveThreads) {
+      const int r = idx / NL, c = idx % NL;
+      dbg_lhs[idx] = r >= c ? L[idxL(r, c)] : L[idxL(c, r)];
+    }
+    for (int i = tid; i < NL; i += kSolveThreads) dbg_rhs[i] = b[i];
+    __syncthreads();
+  }
+  // Right-looking Cholesky on the packed lower triangle.
+  for (int j = 0; j < NL; ++j) {
+    if (tid == 0) {
+      const double d = L[idxL(j, j)];
+      if (!(d > 0.0)) s_ok = 0;
+      L[idxL(j, j)] = sqrt(d);
+    }
+    __syncthreads();
+    const double inv = 1.0 / L[idxL(j, j)];
+    for (int i = j + 1 + tid; i < NL; i += kSolveThreads) L[idxL(i, j)] *= inv;
+    __syncthreads();
+    // trailing update: rows i > j, cols j < k <= i
+    const int m = NL - j - 1;
+    const int cnt = (m * (m + 1)) / 2;
+    for (int t = tid; t < cnt; t += kSolveThreads) {
+      // t -> (ri, rk) with 0 <= rk <= ri < m  (row-major lower)
+      int ri = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+      while ((ri * (ri + 1)) / 2 > t) --ri;
+      while (((ri + 1) * (ri + 2)) / 2 <= t) ++ri;
+      const int rk = t - (ri * (ri + 1)) / 2;
+      const int i = j + 1 + ri, k = j + 1 + rk;
+      L[idxL(i, k)] -= L[idxL(i, j)] * L[idxL(k, j)];
+    }
+    __syncthreads();
+  }
+  // Triangular solves by warp 0 (lanes own rows i = lane mod 32).
+  if (tid < 32) {
+    const int lane = tid;
+    for (int j = 0; j < NL; ++j) {
+      double xj = 0.0;
+      if ((j & 31) == lane) { xj = b[j] / L[idxL(j, j)]; b[j] = xj; }
+      xj = __shfl_sync(0xffffffffu, xj, j & 31);
+      for (int i = j + 1 + ((lane - (j + 1)) & 31); i < NL; i += 32) b[i] -= L[idxL(i, j)] * xj;
+      __syncwarp();
+    }
+    for (int j = NL - 1; j >= 0; --j) {
+      double xj = 0.0;
+      if ((j & 31) == lane) { xj = b[j] / L[idxL(j, j)]; b[j] = xj; }
+      xj = __shfl_sync(0xffffffffu, xj, j & 31);
+      for (int i = lane; i < j; i += 32) b[i] -= L[idxL(j, i)] * xj;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // y_c, candidate camera parameters, camera-side partial sums.
+  double lin = 0.0, dn2 = 0.0, quad = 0.0;
+  for (int i = tid; i < NL; i += kSolveThreads) {
+    const double y = b[i];
+    y_c[i] = y;
+    lin += y * gsv[i];
+    const double delta = -y * sc[i];
+    dn2 += delta * delta;
+    // quad: y^T U_s y restricted to this row (both triangles)
+    const int ci = P.live_cam[i];
+    const double* U = ps.comm + ci * kCamRec;
+    const int o0 = P.live_off[ci], n = P.live_off[ci + 1] - o0;
+    const int ki = P.live_kk[i];
+    double row = 0.0;
+    for (int t = 0; t < n; ++t) {
+      const int jj = o0 + t, kj = P.live_kk[jj];
+      const double u = ki <= kj ? cam_block(U, ki, kj) : cam_block(U, kj, ki);
+      row += sc[i] * sc[jj] * u * b[jj];
+    }
+    quad += y * row;
+  }
+  // candidate camera parameters (b, c intrinsics are carried unchanged)
+  double xn2 = 0.0;
+  for (int idx = tid; idx < P.C * 15; idx += kSolveThreads) {
+    const int c = idx / 15, k = idx % 15;   // k < 6: rt, else intrinsic k - 6
+    const bool free_rt = (c != P.fixed_camera);
+    double x = k < 6 ? ps.cam_rt[c * 6 + k] : ps.intr[c * 9 + (k - 6)];
+    double xn = x;
+    if (k < 6) {
+      if (free_rt) xn = x + (-b[P.live_off[c] + k] * sc[P.live_off[c] + k]);
+    } else if (k - 6 < 7) {
+      const int li = P.live_off[c] + (free_rt ? 6 : 0) + (k - 6);
+      xn = x + (-b[li] * sc[li]);
+    }
+    if (k < 6) pc.cam_rt[c * 6 + k] = xn; else pc.intr[c * 9 + (k - 6)] = xn;
+    if (k >= 6 || free_rt) xn2 += xn * xn;
+  }
+  const double t_lin = block_sum(lin, s_red);
+  const double t_quad = block_sum(quad, s_red);
+  const double t_dn2 = block_sum(dn2, s_red);
+  const double t_xn2 = block_sum(xn2, s_red);
+  if (tid == 0) {
+    st->cam_lin = t_lin; st->cam_quad = t_quad; st->cam_dn2 = t_dn2; st->cam_xn2 = t_xn2;
+    st->solve_ok = s_ok;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K4: back-substitution y_e = z - (V + D^2)^-1 W_s y_c, candidate board poses
+// and the frame-side sums of the model cost change.  One warp per frame.
+// ---------------------------------------------------------------------------
+constexpr int kBacksubThreads = 256;
+
+__global__ void __launch_bounds__(kBacksubThreads)
+k_backsub(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, SchurArgs A,
+          const double* __restrict__ y_c, double* __restrict__ part /*[4][nblk]*/, int nblk) {
+  __shared__ double s_red[kBacksubThreads];
+  if (st->done) return;
+  const int sel = st->cur;
+  const ParamSet& ps = sel ? ps1 : ps0;
+  const ParamSet& pc = sel ? ps0 : ps1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * (kBacksubThreads / 32) + warp;
+  double lin = 0.0, quad = 0.0, dn2 = 0.0, xn2 = 0.0;
+  if (f < P.F) {
+    double se[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) se[i] = A.scale_e[f * 6 + i];
+    // w = W_s y_c : lanes stride over the frame's live columns
+    double w[6] = {0, 0, 0, 0, 0, 0};
+    const int p0 = P.frame_ptr[f], nv = P.frame_ptr[f + 1] - p0;
+    for (int p = 0; p < nv; ++p) {
+      const int v = P.frame_views[p0 + p];
+      const int m = P.view_camera[v];
+      const int o0 = P.live_off[m], n = P.live_off[m + 1] - o0;
+      const double* Gv = ps.G + (size_t)v * kViewStride;
+      for (int k = lane; k < n; k += 32) {
+        const int kk = n == 13 ? k : k + 6;
+        const double f_sc = A.scale_c[m * 13 + kk] * y_c[o0 + k];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          const double raw = kk < 6 ? Gv[kOffBC + r * 6 + kk] : Gv[kOffBI + r * 8 + (kk - 6)];
+          w[r] += raw * f_sc;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) w[r] += __shfl_xor_sync(0xffffffffu, w[r], s);
+      w[r] *= se[r];
+    }
+    if (lane == 0) {
+      double Lm[36], z[6], Vs[21], gs[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) Lm[i * 6 + j] = A.frame_rec[(size_t)((i * (i + 1)) / 2 + j) * A.Fpad + f];
+        z[i] = A.frame_rec[(size_t)(21 + i) * A.Fpad + f];
+        gs[i] = A.frame_rec[(size_t)(48 + i) * A.Fpad + f];
+      }
+#pragma unroll
+      for (int i = 0; i < 21; ++i) Vs[i] = A.frame_rec[(size_t)(27 + i) * A.Fpad + f];
+      double t[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) t[i] = w[i];
+      chol6_solve(Lm, t);
+      double y[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) y[i] = z[i] - t[i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        lin += y[i] * gs[i];
+        double row = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) row += (i <= j ? Vs[tri6(i, j)] : Vs[tri6(j, i)]) * y[j];
+        quad += y[i] * (row + 2.0 * w[i]);
+        const double delta = -y[i] * se[i];
+        const double xn = ps.board_rt[f * 6 + i] + delta;
+        pc.board_rt[f * 6 + i] = xn;
+        dn2 += delta * delta;
+        xn2 += xn * xn;
+      }
+    }
+  }
+  const double t0 = block_sum(lin, s_red);
+  const double t1 = block_sum(quad, s_red);
+  const double t2 = block_sum(dn2, s_red);
+  const double t3 = block_sum(xn2, s_red);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = t0; part[nblk + blockIdx.x] = t1;
+    part[2 * nblk + blockIdx.x] = t2; part[3 * nblk + blockIdx.x] = t3;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K5: pack the scalars that need a global sum next to the camera records, then
+// decide.  k_pack(which): comm[C*kCamRec + 0..3] = frame lin / quad / |delta|^2 /
+// |x+|^2 and gmax[0] = frame gradient max-norm of the evaluated set.
+// ---------------------------------------------------------------------------
+__global__ void k_pack(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which,
+                       const double* __restrict__ bs_part, int bs_nblk,
+                       const double* __restrict__ gmax_part, const double* __restrict__ xn2_part,
+                       int fg_nblk, int initial) {
+  __shared__ double s_red[256];
+  if (which < 2 && st->done) return;
+  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
+  const ParamSet& ps = sel ? ps1 : ps0;
+  double* extra = ps.comm + P.C * kCamRec;
+  for (int k = 0; k < 4; ++k) {
+    double s = 0.0;
+    if (!initial) {
+      for (int i = threadIdx.x; i < bs_nblk; i += blockDim.x) s += bs_part[k * bs_nblk + i];
+    } else if (k == 3) {
+      for (int i = threadIdx.x; i < fg_nblk; i += blockDim.x) s += xn2_part[i];
+    }
+    const double t = block_sum(s, s_red);
+    if (threadIdx.x == 0) extra[k] = t;
+  }
+  double m = 0.0;
+  for (int i = threadIdx.x; i < fg_nblk; i += blockDim.x) m = fmax(m, gmax_part[i]);
+  const double t = block_max(m, s_red);
+  if (threadIdx.x == 0) ps.gmax[0] = t;
+}
+
+// Camera part of |x - (x - g)|_inf and |x_c|^2 for a parameter set whose comm
+// record is globally summed.
+__device__ inline void camera_grad_norms(const DeviceProblem& P, const ParamSet& ps, double* gmax,
+                                         double* xn2) {
+  double gm = 0.0, s = 0.0;
+  for (int c = 0; c < P.C; ++c) {
+    const double* U = ps.comm + c * kCamRec;
+    const bool free_rt = c != P.fixed_camera;
+    for (int k = 0; k < 15; ++k) {
+      if (k < 6 && !free_rt) continue;
+      const double x = k < 6 ? ps.cam_rt[c * 6 + k] : ps.intr[c * 9 + (k - 6)];
+      double g = 0.0;
+      if (k < 6) g = cam_grad(U, k); else if (k - 6 < 7) g = cam_grad(U, k);
+      const double projected = x + (-g);
+      gm = fmax(gm, fabs(x - projected));
+      s += x * x;
+    }
+  }
+  *gmax = gm; *xn2 = s;
+}
+
+__device__ inline double total_cost(const DeviceProblem& P, const ParamSet& ps) {
+  double c = 0.0;
+  for (int m = 0; m < P.C; ++m) c += ps.comm[m * kCamRec + (kOffCost - kOffCC)];
+  return c;
+}
+
+__device__ inline void trace_push(Trace tr, LmState* st, double cost, double gmax,
+                                  double step_norm, int flags) {
+  const int k = st->recorded;
+  if (k < tr.capacity) {
+    tr.cost[k] = cost; tr.radius[k] = st->radius; tr.gmax[k] = gmax;
+    tr.step_norm[k] = step_norm; tr.flags[k] = flags;
+  }
+  st->final_cost = k == 0 ? cost : fmin(st->final_cost, cost);
+  st->recorded = k + 1;
+}
+
+// FinalizeIterationAndCheckIfMinimizerCanContinue
+__device__ inline void finalize_iteration(LmState* st, const LmOptions& opt, Trace tr,
+                                          int iteration, bool valid, bool successful,
+                                          double cost, double step_norm) {
+  if (successful) {
+    st->num_successful++;
+    if (st->x_cost < st->minimum_cost) st->minimum_cost = st->x_cost;
+  } else {
+    st->num_unsuccessful++;
+  }
+  trace_push(tr, st, cost, st->gmax, step_norm, (valid ? 1 : 0) | (successful ? 2 : 0));
+  st->iteration = iteration;
+  if (iteration >= opt.max_num_iterations) { st->termination = 1; st->done = 1; return; }
+  if (!opt.disable_tolerances) {
+    if (successful && st->gmax <= opt.gradient_tolerance) { st->termination = 0; st->done = 1; return; }
+    if (!(st->radius > opt.min_radius)) { st->termination = 0; st->done = 1; return; }
+  }
+}
+
+// IterationZero: consumes the evaluation of the initial point (set `cur`).
+__global__ void k_init(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
+                       Trace tr) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const ParamSet& ps = st->cur ? ps1 : ps0;
+  double cgm, cxn2;
+  camera_grad_norms(P, ps, &cgm, &cxn2);
+  st->x_cost = total_cost(P, ps);
+  st->initial_cost = st->x_cost;
+  st->x_norm = sqrt(cxn2 + ps.comm[P.C * kCamRec + 3]);
+  st->gmax = fmax(cgm, ps.gmax[0]);
+  st->radius = opt.initial_radius;
+  st->decrease_factor = 2.0;
+  st->minimum_cost = DBL_MAX;
+  st->num_successful = st->num_unsuccessful = st->num_consecutive_invalid = 0;
+  st->atleast_one_successful_step = 0;
+  st->recorded = 0;
+  st->done = 0;
+  st->termination = 1;
+  st->solve_ok = 1;
+  finalize_iteration(st, opt, tr, 0, true, true, st->x_cost, 0.0);
+}
+
+__global__ void k_decide(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
+                         Trace tr) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (st->done) return;
+  const ParamSet& pc = st->cur ? ps0 : ps1;   // candidate
+  const double* extra = pc.comm + P.C * kCamRec;
+  const double lin = st->cam_lin + extra[0];
+  const double quad = st->cam_quad + extra[1];
+  const double dn2 = st->cam_dn2 + extra[2];
+  const double xn2c = st->cam_xn2 + extra[3];
+  const double model_cost_change = lin - 0.5 * quad;
+  st->model_cost_change = model_cost_change;
+  const int iteration = st->iteration + 1;
+  const bool solver_ok = st->solve_ok && isfinite(dn2) && isfinite(model_cost_change);
+  const bool valid = solver_ok && model_cost_change > 0.0;
+  if (!valid) {
+    // HandleInvalidStep
+    if (++st->num_consecutive_invalid >= opt.max_num_consecutive_invalid_steps) {
+      st->termination = 2; st->done = 1; return;
+    }
+    st->radius = st->radius / st->decrease_factor;
+    st->decrease_factor *= 2.0;
+    finalize_iteration(st, opt, tr, iteration, false, false, st->x_cost, 0.0);
+    return;
+  }
+  st->num_consecutive_invalid = 0;
+  double candidate_cost = total_cost(P, pc);
+  if (!isfinite(candidate_cost)) candidate_cost = DBL_MAX;
+  st->candidate_cost = candidate_cost;
+  const double step_norm = sqrt(dn2);
+  st->step_norm = step_norm;
+  if (!opt.disable_tolerances) {
+    // ParameterToleranceReached
+    const bool armed = !opt.ptol_needs_success || st->atleast_one_successful_step;
+    if (armed && step_norm <= opt.parameter_tolerance * (st->x_norm + opt.parameter_tolerance)) {
+      st->termination = 0; st->done = 1; return;
+    }
+    // FunctionToleranceReached
+    if (fabs(st->x_cost - candidate_cost) <= opt.function_tolerance * st->x_cost) {
+      st->termination = 0; st->done = 1; return;
+    }
+  }
+  // IsStepSuccessful (monotonic TrustRegionStepEvaluator)
+  const double relative_decrease =
+      candidate_cost >= DBL_MAX ? -DBL_MAX : (st->x_cost - candidate_cost) / model_cost_change;
+  if (relative_decrease > opt.min_relative_decrease) {
+    // HandleSuccessfulStep: x = candidate, gradient/Jacobian are already there
+    st->cur ^= 1;
+    st->x_cost = candidate_cost;
+    st->x_norm = sqrt(xn2c);
+    double cgm, cxn2;
+    camera_grad_norms(P, pc, &cgm, &cxn2);
+    st->gmax = fmax(cgm, pc.gmax[0]);
+    const double t = 2.0 * relative_decrease - 1.0;
+    st->radius = st->radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
+    st->radius = fmin(opt.max_radius, st->radius);
+    st->decrease_factor = 2.0;
+    st->atleast_one_successful_step = 1;
+    finalize_iteration(st, opt, tr, iteration, true, true, st->x_cost, step_norm);
+  } else {
+    st->radius = st->radius / st->decrease_factor;
+    st->decrease_factor *= 2.0;
+    finalize_iteration(st, opt, tr, iteration, true, false, candidate_cost, step_norm);
+  }
+}
+
+}  // namespace tscm

@@ -1,0 +1,382 @@
+// tscm_math.cuh — per-observation TS projection, residual and hand-derived
+// analytic Jacobian, plus the small dense helpers of the Schur step.
+//
+// Everything here is __host__ __device__ so that tests/ can compile the very
+// same arithmetic with g++ and compare it to the CPU oracle without a GPU.
+// The shipped library only ever calls it from kernels (tscm_kernels.cu).
+//
+// Replaces the Jet<double,21> evaluation Ceres performs on
+//   MultiCalib::ReprojectionError::operator()   /root/reference/multi_calib.h:146-195
+//   TripleSphereCamera::ReprojectionError       /root/reference/TS.h:100-131
+// (formula sheet: SURVEY.md Appendix B).
+#pragma once
+
+#include <cfloat>
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define TSCM_HD __host__ __device__ __forceinline__
+#define TSCM_UNROLL _Pragma("unroll")
+#else
+#define TSCM_HD inline
+#define TSCM_UNROLL
+#endif
+
+namespace tscm {
+
+// Column order of the per-observation Jacobian row used on the device:
+//   B 0..5   chessboard_rt  {w_f(3), t_f(3)}     (Schur e-block)
+//   C 6..11  camera_rt      {w_c(3), t_c(3)}
+//   I 12..18 intrinsic      {fx fy cx cy xi lambda alpha}  (b, c columns are
+//            identically zero: TS.h:122-125 / multi_calib.h:175-178, dropped)
+//   r 19     the residual itself (Gram of [J | r] gives J^T J, J^T r and r^T r)
+constexpr int kNB = 6, kNC = 6, kNI = 7;
+constexpr int kCols = kNB + kNC + kNI + 1;  // 20
+
+// Per-view Gram record written by the evaluation kernel (doubles):
+//   BB  0..20    6x6 upper triangle, row-major         -> V
+//   BC  21..56   6x6  [b][c]                           -> W (camera_rt part)
+//   BI  57..104  6x8  [b][i], i = 7 intrinsics then r  -> W (intrinsic part), g_e
+//   CC  105..125 6x6 upper triangle                    -> U
+//   CI  126..173 6x8  [c][i]                           -> U, g_c
+//   II  174..209 8x8 upper triangle                    -> U, g_c, r^T r
+//   210          cost  sum 1/2 rho(s)
+//   211          sum sqrt(s)  (mean Euclidean reprojection error read-out,
+//                multi_calib.cpp:273; s taken BEFORE the loss correction)
+constexpr int kOffBB = 0, kOffBC = 21, kOffBI = 57, kOffCC = 105, kOffCI = 126, kOffII = 174;
+constexpr int kOffCost = 210, kOffErr = 211;
+constexpr int kViewStride = 212;
+// Camera record (sum over a camera's views of entries 105..211).
+constexpr int kCamRec = kViewStride - kOffCC;  // 107
+
+TSCM_HD constexpr int tri6(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }   // i <= j
+TSCM_HD constexpr int tri8(int i, int j) { return i * 8 - (i * (i - 1)) / 2 + (j - i); }
+
+// Rotation matrix of an angle-axis vector and its partial derivatives,
+// matching ceres::AngleAxisRotatePoint: Rodrigues' formula for theta^2 > eps,
+// R = I + hat(w) (so dR/dw_b = hat(e_b)) otherwise.
+// R is row-major; dR[b] = dR/dw_b row-major.
+TSCM_HD void rotation_with_derivative(const double w[3], double R[9], double dR[3][9]) {
+  const double theta2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  if (theta2 > DBL_EPSILON) {
+    const double theta = sqrt(theta2);
+    const double c = cos(theta), s = sin(theta);
+    const double it = 1.0 / theta;
+    const double sh = sin(0.5 * theta);
+    const double c1 = 2.0 * sh * sh;  // 1 - cos(theta) without cancellation
+    const double k[3] = {w[0] * it, w[1] * it, w[2] * it};
+    // R = c I + s [k]x + c1 k k^T
+    R[0] = c + c1 * k[0] * k[0];        R[1] = c1 * k[0] * k[1] - s * k[2]; R[2] = c1 * k[0] * k[2] + s * k[1];
+    R[3] = c1 * k[0] * k[1] + s * k[2]; R[4] = c + c1 * k[1] * k[1];        R[5] = c1 * k[1] * k[2] - s * k[0];
+    R[6] = c1 * k[0] * k[2] - s * k[1]; R[7] = c1 * k[1] * k[2] + s * k[0]; R[8] = c + c1 * k[2] * k[2];
+    // d theta / d w_b = k_b ;  d k_i / d w_b = (delta_ib - k_i k_b) / theta
+    TSCM_UNROLL
+    for (int b = 0; b < 3; ++b) {
+      double dk[3];
+      TSCM_UNROLL
+      for (int i = 0; i < 3; ++i) dk[i] = ((i == b ? 1.0 : 0.0) - k[i] * k[b]) * it;
+      const double dc = -s * k[b];   // d cos
+      const double ds = c * k[b];    // d sin
+      const double dc1 = s * k[b];   // d (1 - cos)
+      double* D = dR[b];
+      // d(c I)
+      D[0] = dc; D[4] = dc; D[8] = dc;
+      D[1] = D[2] = D[3] = D[5] = D[6] = D[7] = 0.0;
+      // d(s [k]x) = ds [k]x + s [dk]x
+      D[1] += -(ds * k[2] + s * dk[2]); D[2] += (ds * k[1] + s * dk[1]);
+      D[3] += (ds * k[2] + s * dk[2]);  D[5] += -(ds * k[0] + s * dk[0]);
+      D[6] += -(ds * k[1] + s * dk[1]); D[7] += (ds * k[0] + s * dk[0]);
+      // d(c1 k k^T) = dc1 k k^T + c1 (dk k^T + k dk^T)
+      TSCM_UNROLL
+      for (int i = 0; i < 3; ++i) {
+        TSCM_UNROLL
+        for (int j = 0; j < 3; ++j)
+          D[3 * i + j] += dc1 * k[i] * k[j] + c1 * (dk[i] * k[j] + k[i] * dk[j]);
+      }
+    }
+  } else {
+    R[0] = 1.0;   R[1] = -w[2]; R[2] = w[1];
+    R[3] = w[2];  R[4] = 1.0;   R[5] = -w[0];
+    R[6] = -w[1]; R[7] = w[0];  R[8] = 1.0;
+    TSCM_UNROLL
+    for (int b = 0; b < 3; ++b) {
+      TSCM_UNROLL
+      for (int i = 0; i < 9; ++i) dR[b][i] = 0.0;
+    }
+    dR[0][5] = -1.0; dR[0][7] = 1.0;   // hat(e_x)
+    dR[1][2] = 1.0;  dR[1][6] = -1.0;  // hat(e_y)
+    dR[2][1] = -1.0; dR[2][3] = 1.0;   // hat(e_z)
+  }
+}
+
+// Per-camera constants of one evaluation point (built once per evaluation).
+struct CamConst {
+  double R[9];       // reference -> camera rotation
+  double t[3];
+  double dR[3][9];   // dR/dw_b
+  double fx, fy, cx, cy, xi, lam, k, dk;  // k = alpha/(1-alpha), dk = 1/(1-alpha)^2
+  int free_rt;       // 0 for the constant block (multi_calib.cpp:186)
+  int pad_;
+};
+
+TSCM_HD void make_cam_const(const double rt[6], const double intr[9], int free_rt, CamConst& c) {
+  rotation_with_derivative(rt, c.R, c.dR);
+  c.t[0] = rt[3]; c.t[1] = rt[4]; c.t[2] = rt[5];
+  c.fx = intr[0]; c.fy = intr[1]; c.cx = intr[2]; c.cy = intr[3];
+  c.xi = intr[4]; c.lam = intr[5];
+  const double om = 1.0 - intr[6];
+  c.k = intr[6] / om;
+  c.dk = 1.0 / (om * om);
+  c.free_rt = free_rt;
+  c.pad_ = 0;
+}
+
+// Per-view constants (board pose of the view's frame).  The board point is
+// (X, Y, 0), so only the first two columns of R_f and dR_f/dw_b are needed.
+struct FrameConst {
+  double r1[3], r2[3], t[3];   // R_f e_x, R_f e_y, t_f
+  double d1[3][3], d2[3][3];   // d1[b] = dR_f/dw_b e_x, d2[b] = dR_f/dw_b e_y
+};
+
+TSCM_HD void make_frame_const(const double rt[6], FrameConst& f) {
+  double R[9], dR[3][9];
+  rotation_with_derivative(rt, R, dR);
+  TSCM_UNROLL
+  for (int i = 0; i < 3; ++i) {
+    f.r1[i] = R[3 * i]; f.r2[i] = R[3 * i + 1]; f.t[i] = rt[3 + i];
+    TSCM_UNROLL
+    for (int b = 0; b < 3; ++b) { f.d1[b][i] = dR[b][3 * i]; f.d2[b][i] = dR[b][3 * i + 1]; }
+  }
+}
+
+// One observation: residual rows and Jacobian rows in the column order above.
+struct ObsRow {
+  double Ju[kCols], Jv[kCols];   // [19] holds the residual
+};
+
+// Loss (ceres::HuberLoss / CauchyLoss + Corrector); type 0 = none.
+TSCM_HD void loss_rho(int type, double a, double s, double rho[3]) {
+  const double b = a * a;
+  if (type == 1) {
+    if (s > b) {
+      const double r = sqrt(s);
+      rho[0] = 2.0 * a * r - b;
+      rho[1] = fmax(DBL_MIN, a / r);
+      rho[2] = -rho[1] / (2.0 * s);
+    } else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
+  } else if (type == 2) {
+    const double c = 1.0 / b;
+    const double sum = 1.0 + s * c;
+    const double inv = 1.0 / sum;
+    rho[0] = b * log(sum);
+    rho[1] = fmax(DBL_MIN, inv);
+    rho[2] = -c * (inv * inv);
+  } else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
+}
+
+// Forward TS projection of a camera-frame point.  Returns the intermediate
+// quantities the Jacobian needs.
+struct TsForward {
+  double x, y, z, d1, d2, d3, z1, z2, D, iD, mx, my;
+};
+
+TSCM_HD void ts_forward(const CamConst& c, const double P[3], TsForward& f) {
+  f.x = P[0]; f.y = P[1]; f.z = P[2];
+  const double rho2 = f.x * f.x + f.y * f.y;
+  f.d1 = sqrt(rho2 + f.z * f.z);
+  f.z1 = f.z + c.xi * f.d1;
+  f.d2 = sqrt(rho2 + f.z1 * f.z1);
+  f.z2 = f.z1 + c.lam * f.d2;
+  f.d3 = sqrt(rho2 + f.z2 * f.z2);
+  f.D = f.z2 + c.k * f.d3;
+  f.iD = 1.0 / f.D;
+  f.mx = f.x * f.iD;
+  f.my = f.y * f.iD;
+}
+
+// Camera-frame point of board corner (X, Y, 0) and the world point.
+TSCM_HD void view_point(const CamConst& c, const FrameConst& f, double X, double Y,
+                        double Pw[3], double P[3]) {
+  TSCM_UNROLL
+  for (int i = 0; i < 3; ++i) Pw[i] = X * f.r1[i] + Y * f.r2[i] + f.t[i];
+  TSCM_UNROLL
+  for (int i = 0; i < 3; ++i)
+    P[i] = c.R[3 * i] * Pw[0] + c.R[3 * i + 1] * Pw[1] + c.R[3 * i + 2] * Pw[2] + c.t[i];
+}
+
+// Residual only (cost-only evaluation).
+TSCM_HD void obs_residual(const CamConst& c, const FrameConst& f, double X, double Y,
+                          double uo, double vo, double& ru, double& rv) {
+  double Pw[3], P[3];
+  view_point(c, f, X, Y, Pw, P);
+  TsForward t;
+  ts_forward(c, P, t);
+  ru = uo - (c.fx * t.mx + c.cx);
+  rv = vo - (c.fy * t.my + c.cy);
+}
+
+// Residual + analytic Jacobian.  NEED_* let a caller that only consumes some
+// column groups drop the others at compile time.
+template <bool NEED_B, bool NEED_C, bool NEED_I>
+TSCM_HD void obs_jacobian(const CamConst& c, const FrameConst& f, double X, double Y,
+                          double uo, double vo, ObsRow& o) {
+  double Pw[3], P[3];
+  view_point(c, f, X, Y, Pw, P);
+  TsForward t;
+  ts_forward(c, P, t);
+  o.Ju[19] = uo - (c.fx * t.mx + c.cx);
+  o.Jv[19] = vo - (c.fy * t.my + c.cy);
+
+  // grad D = (e x, e y, h)  (radial symmetry of the three-sphere chain)
+  const double id1 = 1.0 / t.d1, id2 = 1.0 / t.d2, id3 = 1.0 / t.d3;
+  const double a1 = c.xi * id1;                       // grad z1 = (a1 x, a1 y, 1 + a1 z)
+  const double g1 = 1.0 + a1 * t.z;
+  const double b1 = (1.0 + t.z1 * a1) * id2;          // grad d2 = (b1 x, b1 y, c1)
+  const double c1 = t.z1 * g1 * id2;
+  const double a2 = a1 + c.lam * b1;                  // grad z2 = (a2 x, a2 y, g2)
+  const double g2 = g1 + c.lam * c1;
+  const double b2 = (1.0 + t.z2 * a2) * id3;          // grad d3 = (b2 x, b2 y, c2)
+  const double c2 = t.z2 * g2 * id3;
+  const double e = a2 + c.k * b2;
+  const double h = g2 + c.k * c2;
+  // A = d(u,v)/dP
+  const double fu = c.fx * t.iD, fv = c.fy * t.iD;
+  const double Au[3] = {fu * (1.0 - t.mx * e * t.x), -fu * t.mx * e * t.y, -fu * t.mx * h};
+  const double Av[3] = {-fv * t.my * e * t.x, fv * (1.0 - t.my * e * t.y), -fv * t.my * h};
+
+  if (NEED_C) {
+    if (c.free_rt) {
+      TSCM_UNROLL
+      for (int b = 0; b < 3; ++b) {
+        const double* D = c.dR[b];
+        const double v0 = D[0] * Pw[0] + D[1] * Pw[1] + D[2] * Pw[2];
+        const double v1 = D[3] * Pw[0] + D[4] * Pw[1] + D[5] * Pw[2];
+        const double v2 = D[6] * Pw[0] + D[7] * Pw[1] + D[8] * Pw[2];
+        o.Ju[6 + b] = -(Au[0] * v0 + Au[1] * v1 + Au[2] * v2);
+        o.Jv[6 + b] = -(Av[0] * v0 + Av[1] * v1 + Av[2] * v2);
+      }
+      TSCM_UNROLL
+      for (int i = 0; i < 3; ++i) { o.Ju[9 + i] = -Au[i]; o.Jv[9 + i] = -Av[i]; }
+    } else {
+      TSCM_UNROLL
+      for (int i = 0; i < 6; ++i) { o.Ju[6 + i] = 0.0; o.Jv[6 + i] = 0.0; }
+    }
+  }
+  if (NEED_B) {
+    double ARu[3], ARv[3];   // A R_c
+    TSCM_UNROLL
+    for (int j = 0; j < 3; ++j) {
+      ARu[j] = Au[0] * c.R[j] + Au[1] * c.R[3 + j] + Au[2] * c.R[6 + j];
+      ARv[j] = Av[0] * c.R[j] + Av[1] * c.R[3 + j] + Av[2] * c.R[6 + j];
+    }
+    TSCM_UNROLL
+    for (int b = 0; b < 3; ++b) {
+      const double v0 = X * f.d1[b][0] + Y * f.d2[b][0];
+      const double v1 = X * f.d1[b][1] + Y * f.d2[b][1];
+      const double v2 = X * f.d1[b][2] + Y * f.d2[b][2];
+      o.Ju[b] = -(ARu[0] * v0 + ARu[1] * v1 + ARu[2] * v2);
+      o.Jv[b] = -(ARv[0] * v0 + ARv[1] * v1 + ARv[2] * v2);
+    }
+    TSCM_UNROLL
+    for (int i = 0; i < 3; ++i) { o.Ju[3 + i] = -ARu[i]; o.Jv[3 + i] = -ARv[i]; }
+  }
+  if (NEED_I) {
+    // dD/dxi, dD/dlambda, dD/dalpha
+    const double d2xi = t.z1 * t.d1 * id2;
+    const double z2xi = t.d1 + c.lam * d2xi;
+    const double Dxi = z2xi + c.k * (t.z2 * z2xi * id3);
+    const double Dlam = t.d2 + c.k * (t.z2 * t.d2 * id3);
+    const double Dal = t.d3 * c.dk;
+    const double ex = fu * t.mx, ey = fv * t.my;   // fx x / D^2, fy y / D^2
+    o.Ju[12] = -t.mx; o.Jv[12] = 0.0;
+    o.Ju[13] = 0.0;   o.Jv[13] = -t.my;
+    o.Ju[14] = -1.0;  o.Jv[14] = 0.0;
+    o.Ju[15] = 0.0;   o.Jv[15] = -1.0;
+    o.Ju[16] = ex * Dxi;  o.Jv[16] = ey * Dxi;
+    o.Ju[17] = ex * Dlam; o.Jv[17] = ey * Dlam;
+    o.Ju[18] = ex * Dal;  o.Jv[18] = ey * Dal;
+  }
+}
+
+// Loss correction of one observation's rows (ResidualBlock::Evaluate order:
+// Jacobian first with the uncorrected residual, then the residual).  Returns
+// 1/2 rho(s); *err receives sqrt(s) of the raw residual.
+template <int LO, int HI>
+TSCM_HD double obs_apply_loss(int loss_type, double loss_scale, ObsRow& o, double* err) {
+  const double ru = o.Ju[19], rv = o.Jv[19];
+  const double s = ru * ru + rv * rv;
+  *err = sqrt(s);
+  if (loss_type == 0) return 0.5 * s;
+  double rho[3];
+  loss_rho(loss_type, loss_scale, s, rho);
+  const double sqrt_rho1 = sqrt(rho[1]);
+  double residual_scaling, alpha_sq_norm;
+  if (s == 0.0 || rho[2] <= 0.0) {
+    residual_scaling = sqrt_rho1; alpha_sq_norm = 0.0;
+  } else {
+    const double D = 1.0 + 2.0 * s * rho[2] / rho[1];
+    const double alpha = 1.0 - sqrt(D);
+    residual_scaling = sqrt_rho1 / (1.0 - alpha);
+    alpha_sq_norm = alpha / s;
+  }
+  if (alpha_sq_norm == 0.0) {
+    TSCM_UNROLL
+    for (int k = LO; k < HI; ++k) { o.Ju[k] *= sqrt_rho1; o.Jv[k] *= sqrt_rho1; }
+  } else {
+    TSCM_UNROLL
+    for (int k = LO; k < HI; ++k) {
+      const double rtj = ru * o.Ju[k] + rv * o.Jv[k];
+      o.Ju[k] = sqrt_rho1 * (o.Ju[k] - alpha_sq_norm * ru * rtj);
+      o.Jv[k] = sqrt_rho1 * (o.Jv[k] - alpha_sq_norm * rv * rtj);
+    }
+  }
+  o.Ju[19] = ru * residual_scaling;
+  o.Jv[19] = rv * residual_scaling;
+  return 0.5 * rho[0];
+}
+
+// ---------------------------------------------------------------------------
+// 6x6 SPD helpers for the Schur step (InvertPSDMatrix<6> of Ceres'
+// SchurEliminator).  M is a full row-major 6x6; L overwrites its lower part.
+// Returns false if a pivot is not positive.
+// ---------------------------------------------------------------------------
+TSCM_HD bool chol6(double M[36]) {
+  bool ok = true;
+  TSCM_UNROLL
+  for (int j = 0; j < 6; ++j) {
+    double d = M[j * 6 + j];
+    TSCM_UNROLL
+    for (int k = 0; k < j; ++k) d -= M[j * 6 + k] * M[j * 6 + k];
+    if (!(d > 0.0)) ok = false;
+    d = sqrt(d);
+    M[j * 6 + j] = d;
+    const double inv = 1.0 / d;
+    TSCM_UNROLL
+    for (int i = j + 1; i < 6; ++i) {
+      double s = M[i * 6 + j];
+      TSCM_UNROLL
+      for (int k = 0; k < j; ++k) s -= M[i * 6 + k] * M[j * 6 + k];
+      M[i * 6 + j] = s * inv;
+    }
+  }
+  return ok;
+}
+// Solve L L^T x = b in place.
+TSCM_HD void chol6_solve(const double L[36], double b[6]) {
+  TSCM_UNROLL
+  for (int i = 0; i < 6; ++i) {
+    double s = b[i];
+    TSCM_UNROLL
+    for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * b[k];
+    b[i] = s / L[i * 6 + i];
+  }
+  TSCM_UNROLL
+  for (int i = 5; i >= 0; --i) {
+    double s = b[i];
+    TSCM_UNROLL
+    for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * b[k];
+    b[i] = s / L[i * 6 + i];
+  }
+}
+
+}  // namespace tscm
