@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — LM iterations/s and residual+Jacobian Gobs/s of the calibration solve.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--scaling weak|strong]
+
+A "step" is ONE Levenberg-Marquardt iteration (Schur elimination, reduced solve,
+back-substitution, residual+Jacobian+normal-equation pass at the candidate point,
+accept/reject) over BASELINE.json config 3: 8 cameras x 5,000 frames x 88 corners =
+3.52 M observations per GPU, synthetic, generated through the TS model.
+
+Default scaling is "weak": every rank owns 5,000 frames (its own frames, one common
+rig), the reduced camera system is all-reduced over NCCL each iteration; `value` is
+the whole-job residual+Jacobian throughput in Gobs/s = observations on all ranks x
+LM iterations / s.  `--scaling strong` shards the 5,000 frames of ONE config-3
+problem over the ranks instead.
+
+The JSON line also carries:
+  lm_iterations_per_sec   the other half of BASELINE.json's metric
+  roofline                the dominant kernel (k_eval) against measured HBM peak, plus
+                          roofline_fp64 against the measured DFMA peak (the kernel is
+                          FP64-pipe bound)
+  cpu_baseline            the CPU oracle (Ceres-semantics port) timed on this box
+  e2e                     the same metric through tscm_solve() with host buffers
+
+`--impl reference` times the CPU restatement of the reference's Ceres path (the
+reference itself cannot be built: Ceres/Eigen/OpenCV are absent) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = "config3: 8 cameras x 5000 frames x 88 corners (3.52M observations), dense visibility"
+METRIC = "LM residual+Jacobian throughput at 3.52M corner observations per GPU"
+UNIT = "Gobs/s"
+ALG_BYTES_PER_OBS_EVAL = 24.0   # J-pass with per-view blocks materialised
+ALG_FLOPS_PER_OBS_EVAL = 1060.0  # forward 130 + Jacobian 250 + outer products 680
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, val in zip(names, r[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(rank: int, world: int, scaling: str, frames: int):
+    from tscm_calib_b200 import synth
+    if scaling == "strong" and world > 1:
+        sp = synth.config(3, num_frames=frames)
+        local, fr = synth.shard_frames(sp, rank, world)
+        return (local, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt[fr],
+                sp.num_observations)
+    sp = synth.config(3, num_frames=frames, frame_seed=rank)
+    return (sp.problem, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt,
+            sp.num_observations * world)
+
+
+def fixed_iteration_options(n):
+    from tscm_calib_b200 import capi
+    return capi.default_options(max_num_iterations=int(n), disable_tolerances=1)
+
+
+def time_oracle(problem, intr, cam_rt, board_rt, iterations, threads):
+    from oracle import oracle
+    opt = fixed_iteration_options(iterations)
+    t0 = time.perf_counter()
+    _, _, _, s = oracle.solve(problem, intr, cam_rt, board_rt, opt, num_threads=threads)
+    dt = time.perf_counter() - t0
+    assert s.num_iterations == iterations + 1, s
+    return dt
+
+
+def run_reference(args):
+    """The reference arm: CPU restatement of the reference's Ceres path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tscm_calib_b200 import synth
+    threads = os.cpu_count() or 1
+    frames = args.reference_frames
+    sp = synth.config(3, num_frames=frames)
+    if args.warmup > 0:
+        time_oracle(sp.problem, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt,
+                    min(args.warmup, 1), threads)
+    dt = time_oracle(sp.problem, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt, args.steps,
+                     threads)
+    gobs = sp.num_observations * args.steps / dt / 1e9
+    sample = (f"{frames} of 5000 frames of config 3 ({sp.num_observations} observations), "
+              f"{args.steps} LM iterations incl. iteration-0 evaluation, {threads} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gobs, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "lm_iterations_per_sec_at_sample": args.steps / dt,
+        "lm_iterations_per_sec_at_3.52M": gobs * 1e9 / 3.52e6,
+        "cpu_baseline": {"value": gobs, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": gobs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from tscm_calib_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the calibration solve has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    capi.load_library()
+
+    problem, intr, cam_rt, board_rt, total_obs = make_workload(rank, world, args.scaling, args.frames)
+    total_iters = args.warmup + args.steps
+    opt = fixed_iteration_options(total_iters + 8)
+    solver = capi.Solver(problem, opt, device=local_rank)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        solver.attach_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
+    solver.set_parameters(intr, cam_rt, board_rt)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up, then EXACTLY `steps` LM iterations, device-timed ------------------
+    if args.warmup > 0:
+        solver.time_stage(4, args.warmup)
+        solver.set_parameters(intr, cam_rt, board_rt)     # restart from the same initial point
+    barrier()
+    launches0 = solver.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_iter = solver.time_stage(4, args.steps)      # CUDA events on the solver's stream
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = solver.launch_count() - launches0
+    t = torch.tensor([ms_iter], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_iter = float(t.item())
+    it_per_s = 1e3 / ms_iter
+    value = total_obs * it_per_s / 1e9
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_iter, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "observations_total": int(total_obs),
+                   "observations_per_gpu": int(problem.num_observations),
+                   "step": "one LM iteration (Schur + reduced solve + back-substitution + "
+                           "residual/Jacobian/normal-equation pass + accept/reject)",
+                   "l2": "per-step working set (observations 56 MB + two 68 MB Gram-record "
+                         "buffers) exceeds the 126 MB L2; no explicit flush",
+                   "parallelism": f"frames sharded over {world} GPU(s), NCCL all-reduce of the "
+                                  "reduced camera system" if world > 1 else "single GPU"},
+        "lm_iterations_per_sec": it_per_s,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (k_eval), timed alone with CUDA events ---
+        solver.time_stage(0, 3)
+        ms_eval = solver.time_stage(0, 20)
+        n_obs = problem.num_observations
+        hbm_peak, how = measured_peaks()
+        achieved = n_obs * ALG_BYTES_PER_OBS_EVAL / (ms_eval * 1e-3) / 1e9
+        line["roofline"] = {
+            "kernel": "k_eval", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "peak_source": how, "ms_per_launch": ms_eval,
+            "algorithmic_bytes_per_observation": ALG_BYTES_PER_OBS_EVAL,
+            "note": "k_eval is FP64-pipe bound (arithmetic intensity ~44 flop/B vs machine "
+                    "balance ~5.7 flop/B); see roofline_fp64",
+        }
+        fp64_peak = capi.device_fp64_peak(local_rank)
+        tf = n_obs * ALG_FLOPS_PER_OBS_EVAL / (ms_eval * 1e-3) / 1e12
+        line["roofline_fp64"] = {
+            "kernel": "k_eval", "bound": "fp64", "achieved": tf, "peak": fp64_peak,
+            "unit": "TFLOP/s", "frac": tf / fp64_peak,
+            "peak_source": "measured in this run (DFMA microbenchmark, tscm_device_fp64_peak)",
+            "algorithmic_flops_per_observation": ALG_FLOPS_PER_OBS_EVAL,
+        }
+        stages = {}
+        for sid, name in ((5, "evaluation_pass"), (1, "schur"), (2, "reduced_solve"), (3, "backsub")):
+            solver.time_stage(sid, 2)
+            stages[name] = solver.time_stage(sid, 10)
+        line["stage_ms"] = stages
+
+    # ---- end to end through the public one-shot C-ABI call with HOST buffers ----------
+    solver.close()
+    e2e_iters = args.steps
+    pinned = torch.empty(problem.obs_xy.shape, dtype=torch.float64).pin_memory()
+    pinned.copy_(torch.from_numpy(problem.obs_xy))
+    host_problem = capi.ProblemArrays(problem.board_xy, problem.view_camera, problem.view_frame,
+                                      pinned.numpy(), problem.num_cameras, problem.num_frames,
+                                      problem.fixed_camera)
+    if world == 1:
+        e_opt = fixed_iteration_options(e2e_iters)
+        capi.solve(host_problem, intr, cam_rt, board_rt, e_opt, device=local_rank)   # warm-up call
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        a, b, c, s = capi.solve(host_problem, intr, cam_rt, board_rt, e_opt, device=local_rank)
+        dt = time.perf_counter() - t0
+        assert s.num_iterations == e2e_iters + 1
+        h2d = problem.obs_xy.nbytes + intr.nbytes + cam_rt.nbytes + board_rt.nbytes + \
+            problem.view_camera.nbytes + problem.view_frame.nbytes + problem.board_xy.nbytes
+        d2h = a.nbytes + b.nbytes + c.nbytes + 5 * 8 * (e2e_iters + 1)
+        line["e2e"] = {
+            "value": total_obs * e2e_iters / dt / 1e9, "unit": UNIT,
+            "h2d_bytes_per_step": h2d / e2e_iters, "d2h_bytes_per_step": d2h / e2e_iters,
+            "lm_iterations_per_sec": e2e_iters / dt, "seconds_per_call": dt,
+            "what": f"one tscm_solve() call = {e2e_iters} LM iterations from pinned host buffers: "
+                    "solver creation, H2D of observations and parameters, transposition, "
+                    "iteration zero, the iterations, D2H of parameters and the trace, teardown; "
+                    "inputs are uploaded once per call, bytes are per call / steps",
+        }
+    else:
+        # each rank times its own resident-create + run from host buffers
+        t0 = time.perf_counter()
+        s2 = capi.Solver(host_problem, fixed_iteration_options(e2e_iters), device=local_rank)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        s2.attach_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        s2.set_parameters(intr, cam_rt, board_rt)
+        res = s2.run()
+        s2.get_parameters()
+        dt = time.perf_counter() - t0
+        s2.close()
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        assert res.num_iterations == e2e_iters + 1
+        line["e2e"] = {
+            "value": total_obs * e2e_iters / dt / 1e9, "unit": UNIT,
+            "h2d_bytes_per_step": problem.obs_xy.nbytes / e2e_iters,
+            "d2h_bytes_per_step": (intr.nbytes + cam_rt.nbytes + board_rt.nbytes) / e2e_iters,
+            "lm_iterations_per_sec": e2e_iters / dt, "seconds_per_call": dt,
+            "what": "per rank: solver creation from host buffers, NCCL communicator, H2D, "
+                    f"{e2e_iters} LM iterations, D2H; max over ranks",
+        }
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from tscm_calib_b200 import synth
+        threads = os.cpu_count() or 1
+        frames = args.cpu_frames
+        sp = synth.config(3, num_frames=frames)
+        iters = 3
+        dt = time_oracle(sp.problem, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt, iters,
+                         threads)
+        line["cpu_baseline"] = {
+            "value": sp.num_observations * iters / dt / 1e9, "unit": UNIT, "cores": threads,
+            "kind": "port",
+            "sample": f"{frames} of 5000 frames of config 3 ({sp.num_observations} observations), "
+                      f"{iters} LM iterations incl. iteration-0 evaluation, Ceres-semantics oracle "
+                      f"(dual-number autodiff, dense Schur), {threads} threads, {dt:.1f} s",
+            "lm_iterations_per_sec_at_3.52M": sp.num_observations * iters / dt / 3.52e6,
+        }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--frames", type=int, default=5000, help="frames of config 3 (per GPU if weak)")
+    ap.add_argument("--cpu-frames", type=int, default=1000, help="cpu_baseline sample size")
+    ap.add_argument("--reference-frames", type=int, default=500, help="--impl reference sample size")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -182,11 +182,16 @@ int tscm_solver_reprojection_error(tscm_solver* solver, double* per_camera, doub
                                    double* rms);
 /* Time `repeats` back-to-back launches of one stage on the solver's stream with
  * CUDA events; returns the average milliseconds per launch.
- * stage: 0 = residual+Jacobian+normal-equation pass, 1 = Schur elimination,
- *        2 = reduced solve, 3 = back-substitution, 4 = whole LM iteration. */
+ * stage: 0 = residual+Jacobian+normal-equation kernel, 1 = Schur elimination,
+ *        2 = reduced solve, 3 = back-substitution, 4 = whole LM iterations (iteration
+ *        zero, then `repeats` replays of the iteration graph; fails if the loop
+ *        terminates early), 5 = whole evaluation pass (kernel + reductions). */
 int tscm_solver_time_stage(tscm_solver* solver, int stage, int repeats, double* ms_per_launch);
 /* Number of kernels launched by this solver since creation. */
 int64_t tscm_solver_launch_count(const tscm_solver* solver);
+/* Measured FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops): the
+ * denominator of the FP64 roofline this FP64-bound path is judged against. */
+int tscm_device_fp64_peak(int device, double* tflops);
 
 const char* tscm_last_error(void);
 const char* tscm_version(void);

@@ -1,0 +1,57 @@
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_golden(name):
+    """A golden fixture as (ProblemArrays, dict of arrays)."""
+    from tscm_calib_b200.capi import ProblemArrays
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    p = ProblemArrays(z["board_xy"], z["view_camera"], z["view_frame"], z["obs_xy"],
+                      int(z["num_cameras"]), int(z["num_frames"]), int(z["fixed_camera"]))
+    return p, z
+
+
+def golden_options(z, **kw):
+    from tscm_calib_b200 import capi
+    o = z["options"]
+    return capi.default_options(max_num_iterations=int(o[0]), loss_type=int(o[1]),
+                                loss_scale=float(o[2]), **kw)
+
+
+@pytest.fixture(scope="session")
+def hostmath():
+    """Host build of csrc/tscm_math.cuh (the kernels' per-observation arithmetic)."""
+    src = os.path.join(ROOT, "tests", "hostmath", "hostmath.cpp")
+    out = os.path.join(ROOT, "tests", "hostmath", "libhostmath.so")
+    deps = [src, os.path.join(ROOT, "tscm_calib_b200", "csrc", "tscm_math.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, src], check=True)
+    return ctypes.CDLL(out)
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as o
+    o.build()
+    o.load()
+    return o
+
+
+def rel_err(a, b, floor=1e-12):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / (np.abs(b) + floor))) if a.size else 0.0

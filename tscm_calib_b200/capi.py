@@ -249,6 +249,8 @@ def load_library(path: str | None = None):
     lib.tscm_solver_time_stage.restype = C.c_int
     lib.tscm_solver_launch_count.argtypes = [C.c_void_p]
     lib.tscm_solver_launch_count.restype = C.c_int64
+    lib.tscm_device_fp64_peak.argtypes = [C.c_int, c_double_p]
+    lib.tscm_device_fp64_peak.restype = C.c_int
     lib.tscm_last_error.argtypes = []
     lib.tscm_last_error.restype = C.c_char_p
     lib.tscm_version.argtypes = []
@@ -265,7 +267,7 @@ EXPORTED_SYMBOLS = [
     "tscm_solver_set_observations", "tscm_solver_run", "tscm_comm_unique_id",
     "tscm_solver_attach_comm", "tscm_solver_eval_jacobian", "tscm_solver_reduced_size",
     "tscm_solver_reduced_system", "tscm_solver_reprojection_error", "tscm_solver_time_stage",
-    "tscm_solver_launch_count", "tscm_last_error", "tscm_version",
+    "tscm_solver_launch_count", "tscm_device_fp64_peak", "tscm_last_error", "tscm_version",
 ]
 
 
@@ -369,6 +371,13 @@ class Solver:
 
     def launch_count(self) -> int:
         return int(self.lib.tscm_solver_launch_count(self.h))
+
+
+def device_fp64_peak(device: int = -1) -> float:
+    lib = load_library()
+    v = C.c_double()
+    check(lib.tscm_device_fp64_peak(device, C.byref(v)), lib)
+    return v.value
 
 
 def comm_unique_id() -> bytes:

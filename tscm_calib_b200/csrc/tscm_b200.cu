@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -123,7 +124,8 @@ struct tscm_solver {
   double* d_dbg_rhs = nullptr;
   SchurArgs schur{};
   int schur_nblk = 0, schur_nt = 256, schur_ept = 20;
-  size_t schur_smem = 0, solve_smem = 0, eval_smem = 0;
+  size_t schur_smem = 0, solve_smem = 0, eval_smem = 0, eval2_smem = 0;
+  int eval_variant = 2;
   int bs_nblk = 0, fg_nblk = 0;
   // graph of one LM iteration
   cudaGraph_t graph = nullptr;
@@ -214,13 +216,24 @@ int validate_problem(const tscm_problem* p) {
   return TSCM_OK;
 }
 
+// The residual + Jacobian + normal-equation kernel (variant 2 = shared rows, default;
+// variant 1 = independent slices, kept for A/B timing: TSCM_EVAL_VARIANT=1).
+void launch_eval_kernel(tscm_solver* s, int which) {
+  const DeviceProblem& P = s->P;
+  if (s->eval_variant == 1) {
+    dim3 grid((P.V + kEvalThreads - 1) / kEvalThreads, 4);
+    k_eval<<<grid, kEvalThreads, s->eval_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->lm);
+  } else {
+    k_eval2<<<(P.V + 31) / 32, 128, s->eval2_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->lm);
+  }
+}
+
 // which: 0 = current, 1 = candidate (relative to st->cur); 2/3 = absolute set 0/1.
 void launch_evaluation(tscm_solver* s, int which, int initial) {
   const DeviceProblem& P = s->P;
   cudaStream_t st = s->stream;
   k_prep_cams<<<(P.C + 31) / 32, 32, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which);
-  dim3 grid((P.V + kEvalThreads - 1) / kEvalThreads, 4);
-  k_eval<<<grid, kEvalThreads, s->eval_smem, st>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->lm);
+  launch_eval_kernel(s, which);
   k_reduce_cam_a<<<P.nchunk, 128, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->d_cam_part);
   k_reduce_cam_b<<<P.C, 128, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->d_cam_part);
   k_frame_grad<<<s->fg_nblk, 256, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which,
@@ -253,12 +266,12 @@ int launch_eval_allreduce(tscm_solver* s, int which) {
 void launch_schur(tscm_solver* s, double radius_override) {
   SchurArgs a = s->schur;
   a.radius_override = radius_override;
-  if (s->schur_nt == 256)
-    k_schur<20, 256><<<s->schur_nblk, 256, s->schur_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
-                                                                      s->d_state, s->lm, a);
+  if (s->schur_ept == 1)
+    k_schur<1, 512><<<s->schur_nblk, s->schur_nt, s->schur_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
+                                                                             s->d_state, s->lm, a);
   else
-    k_schur<21, 1024><<<s->schur_nblk, 1024, s->schur_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
-                                                                        s->d_state, s->lm, a);
+    k_schur<2, 768><<<s->schur_nblk, s->schur_nt, s->schur_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
+                                                                             s->d_state, s->lm, a);
   const int n = s->P.Q + s->P.NL;
   k_reduce_s<<<(n + 255) / 256, 256, 0, s->stream>>>(s->P, s->d_state, s->d_Spart, s->d_rpart,
                                                     s->schur_nblk, s->d_Sr);
@@ -274,9 +287,16 @@ int launch_schur_allreduce(tscm_solver* s) {
 }
 
 void launch_solve(tscm_solver* s, double radius_override, bool debug) {
-  k_solve<<<1, kSolveThreads, s->solve_smem, s->stream>>>(
-      s->P, s->ps[0], s->ps[1], s->d_state, s->lm, s->d_Sr, s->d_scale_c, s->d_yc, radius_override,
-      debug ? s->d_dbg_lhs : nullptr, debug ? s->d_dbg_rhs : nullptr);
+  double* dl = debug ? s->d_dbg_lhs : nullptr;
+  double* dr = debug ? s->d_dbg_rhs : nullptr;
+  const int bmax = (s->P.NL + 1 + 31) / 32;
+#define TSCM_SOLVE(B)                                                                          \
+  k_solve<B><<<1, kSolveThreads, s->solve_smem, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, \
+      s->lm, s->d_Sr, s->d_scale_c, s->d_yc, radius_override, dl, dr)
+  if (bmax <= 2) TSCM_SOLVE(2);
+  else if (bmax <= 4) TSCM_SOLVE(4);
+  else TSCM_SOLVE(7);
+#undef TSCM_SOLVE
   s->launches += 1;
 }
 
@@ -476,10 +496,15 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     if (chunk_end[ch] != chunk_begin[ch + 1]) { set_error("internal: chunk table"); delete s; return TSCM_ERR_INVALID_ARGUMENT; }
   P.nchunk = (int)chunk_cam.size();
 
-  if (NL > 221) {
-    set_error("reduced system of %d live parameters exceeds this build's limit (221, i.e. 17 cameras)", NL);
+  if (NL > 216) {
+    set_error("reduced system of %d live parameters exceeds this build's limit (216, i.e. 17 cameras)", NL);
     delete s; return TSCM_ERR_UNSUPPORTED;
   }
+  // 4x4 tiles of the upper block triangle, row-major
+  const int nb = (NL + 3) / 4;
+  std::vector<short> tile_bi, tile_bj;
+  for (int bi = 0; bi < nb; ++bi) for (int bj = bi; bj < nb; ++bj) { tile_bi.push_back((short)bi); tile_bj.push_back((short)bj); }
+  const int ntiles = (int)tile_bi.size();
 #define TRY_RC(x) do { rc = (x); if (rc) { tscm_solver_destroy(s); return rc; } } while (0)
   std::vector<double> board(p->board_xy, p->board_xy + 2 * (size_t)K);
   std::vector<int> vcam(p->view_camera, p->view_camera + V), vfrm(p->view_frame, p->view_frame + V);
@@ -518,19 +543,26 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   TRY_RC(s->alloc(&s->d_scale_e, (size_t)F * 6));
   TRY_RC(s->alloc(&s->d_scale_c, (size_t)C * 13));
   TRY_RC(s->alloc(&s->d_cam_part, (size_t)P.nchunk * kCamRec));
-  // Schur configuration
-  if (P.Q <= 20 * 256) { s->schur_nt = 256; s->schur_ept = 20; }
-  else { s->schur_nt = 1024; s->schur_ept = 21; }
+  // Schur configuration: one 4x4 tile per thread up to 512 tiles, two beyond
+  s->schur_ept = ntiles <= 512 ? 1 : 2;
+  s->schur_nt = std::max(256, ((ntiles + s->schur_ept - 1) / s->schur_ept + 31) / 32 * 32);
+  s->schur.ntiles = ntiles;
+  s->schur.NLp = nb * 4;
+  TRY_RC(s->put(&s->schur.tile_bi, tile_bi));
+  TRY_RC(s->put(&s->schur.tile_bj, tile_bj));
   s->schur_nblk = std::max(1, std::min(s->sm_count, (F + kSchurFB - 1) / kSchurFB));
   int fpb = (F + s->schur_nblk - 1) / s->schur_nblk;
   fpb = (fpb + kSchurFB - 1) / kSchurFB * kSchurFB;
   s->schur_nblk = (F + fpb - 1) / fpb;
   s->schur.frames_per_block = fpb;
   s->schur.Fpad = (F + 31) / 32 * 32;
-  s->schur_smem = (size_t)(2 * kSchurFB * 6 * NL + kSchurFB * 6 + kSchurFB * 64) * sizeof(double) +
+  s->schur_smem = (size_t)(2 * kSchurFB * 6 * s->schur.NLp + kSchurFB * 6 + kSchurFB * 64) * sizeof(double) +
                   kSchurFB * 32 * sizeof(int);
-  s->solve_smem = (size_t)(P.Q + 3 * NL + kSolveThreads + 2 * NL) * sizeof(double);
+  s->solve_smem = (size_t)((NL + 1) * (NL + 2) / 2 + 4 * NL + kSolveThreads + 8) * sizeof(double);
   s->eval_smem = (size_t)2 * K * sizeof(double) + (size_t)C * sizeof(CamConst);
+  s->eval2_smem = (size_t)(2 * kE2Group * kE2Elems * 32 + kFcElems * 32 + 2 * K) * sizeof(double) +
+                  (size_t)C * sizeof(CamConst);
+  if (const char* ev = getenv("TSCM_EVAL_VARIANT")) s->eval_variant = atoi(ev) == 1 ? 1 : 2;
   TRY_RC(s->alloc(&s->schur.frame_rec, (size_t)kFrameRec * s->schur.Fpad));
   TRY_RC(s->alloc(&s->d_Spart, (size_t)s->schur_nblk * P.Q));
   TRY_RC(s->alloc(&s->d_rpart, (size_t)s->schur_nblk * NL));
@@ -557,10 +589,13 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
               s->solve_smem, (size_t)prop.sharedMemPerBlockOptin);
     tscm_solver_destroy(s); return TSCM_ERR_UNSUPPORTED;
   }
-  TRY_RC(set_smem((const void*)k_schur<20, 256>, s->schur_smem));
-  TRY_RC(set_smem((const void*)k_schur<21, 1024>, s->schur_smem));
-  TRY_RC(set_smem((const void*)k_solve, s->solve_smem));
+  TRY_RC(set_smem((const void*)k_schur<1, 512>, s->schur_smem));
+  TRY_RC(set_smem((const void*)k_schur<2, 768>, s->schur_smem));
+  TRY_RC(set_smem((const void*)k_solve<2>, s->solve_smem));
+  TRY_RC(set_smem((const void*)k_solve<4>, s->solve_smem));
+  TRY_RC(set_smem((const void*)k_solve<7>, s->solve_smem));
   TRY_RC(set_smem((const void*)k_eval, s->eval_smem));
+  TRY_RC(set_smem((const void*)k_eval2, s->eval2_smem));
 
   TRY_RC(tscm_solver_set_observations(s, p->obs_xy));
 #undef TRY_RC
@@ -833,12 +868,7 @@ int tscm_solver_time_stage(tscm_solver* s, int stage, int repeats, double* ms_pe
     const DeviceProblem& P = s->P;
     for (int r = 0; r < repeats; ++r) {
       switch (stage) {
-        case 0: {
-          dim3 grid((P.V + kEvalThreads - 1) / kEvalThreads, 4);
-          k_eval<<<grid, kEvalThreads, s->eval_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, 3, s->lm);
-          s->launches += 1;
-          break;
-        }
+        case 0: launch_eval_kernel(s, 3); s->launches += 1; break;
         case 1: launch_schur(s, 0.0); break;
         case 2: launch_solve(s, 0.0, false); break;
         case 3: launch_backsub(s); break;
@@ -865,9 +895,49 @@ int tscm_solver_time_stage(tscm_solver* s, int stage, int repeats, double* ms_pe
   CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   *ms_per_launch = (double)ms / repeats;
+  if (stage == 4) {
+    // a solve that terminated early turns the remaining launches into no-ops:
+    // such a measurement is not a measurement
+    if ((rc = fetch_state(s))) return rc;
+    if (s->h_state->done || s->h_state->iteration != repeats) {
+      set_error("LM loop stopped after %d of %d timed iterations (termination %d)",
+                s->h_state->iteration, repeats, s->h_state->termination);
+      return TSCM_ERR_UNSUPPORTED;
+    }
+  }
   return TSCM_OK;
 }
 
 int64_t tscm_solver_launch_count(const tscm_solver* s) { return s ? s->launches : 0; }
+
+int tscm_device_fp64_peak(int device, double* tflops) {
+  if (!tflops) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
+  if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  double* d_out = nullptr;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  CUDA_TRY(cudaMalloc((void**)&d_out, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0));
+    k_dfma_peak<<<blocks, threads>>>(d_out, iters, 1.0000001);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_out);
+  CUDA_TRY(cudaGetLastError());
+  *tflops = best;
+  return TSCM_OK;
+}
 
 }  // extern "C"

@@ -244,6 +244,170 @@ k_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which
   }
 }
 
+// ---------------------------------------------------------------------------
+// K1+K2, second form (default): the four slice-warps of a CTA work on the SAME
+// 32 views (lane = view) and share the per-observation rows through shared
+// memory, so the projection and the Jacobian are computed once per observation
+// instead of once per slice.  Per group of 4 corners, warp w evaluates corner
+// j0 + w of every lane's view and publishes the row [J_u | r_u | J_v | r_v | 1/2 rho |
+// sqrt(s)] (42 doubles) to a double-buffered staging area laid out
+// [corner-in-group][element][lane] (bank-conflict free); after one barrier each
+// warp folds the 4 rows into its slice of the Gram matrix with plain FMAs.
+// ---------------------------------------------------------------------------
+constexpr int kE2Elems = 42;
+constexpr int kE2Group = 4;
+constexpr int kFcElems = 27;
+
+__device__ __forceinline__ double e2_ld(const double* rows, int e, int lane) { return rows[e * 32 + lane]; }
+
+template <int ROLE>
+__device__ __forceinline__ void eval2_consume(const double* __restrict__ rows, int lane,
+                                              double* __restrict__ acc) {
+  // element map: Ju[k] at k, Jv[k] at 20 + k (k = 0..19, 19 = residual), 40 cost, 41 err
+  if (ROLE == 0) {
+    double u[12], v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { u[k] = e2_ld(rows, k, lane); v[k] = e2_ld(rows, 20 + k, lane); }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int b = a; b < 6; ++b) acc[tri6(a, b)] = fma(v[a], v[b], fma(u[a], u[b], acc[tri6(a, b)]));
+#pragma unroll
+      for (int b = 0; b < 6; ++b)
+        acc[21 + a * 6 + b] = fma(v[a], v[6 + b], fma(u[a], u[6 + b], acc[21 + a * 6 + b]));
+    }
+  } else if (ROLE == 1 || ROLE == 3) {
+    constexpr int base = ROLE == 1 ? 0 : 6;
+    double u[6], v[6], ui[8], vi[8];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { u[k] = e2_ld(rows, base + k, lane); v[k] = e2_ld(rows, 20 + base + k, lane); }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ui[k] = e2_ld(rows, 12 + k, lane); vi[k] = e2_ld(rows, 32 + k, lane); }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a * 8 + b] = fma(v[a], vi[b], fma(u[a], ui[b], acc[a * 8 + b]));
+  } else {
+    double u[6], v[6], ui[8], vi[8];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { u[k] = e2_ld(rows, 6 + k, lane); v[k] = e2_ld(rows, 26 + k, lane); }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { ui[k] = e2_ld(rows, 12 + k, lane); vi[k] = e2_ld(rows, 32 + k, lane); }
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = a; b < 6; ++b) acc[tri6(a, b)] = fma(v[a], v[b], fma(u[a], u[b], acc[tri6(a, b)]));
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = a; b < 8; ++b)
+        acc[21 + tri8(a, b)] = fma(vi[a], vi[b], fma(ui[a], ui[b], acc[21 + tri8(a, b)]));
+    acc[57] += e2_ld(rows, 40, lane);
+    acc[58] += e2_ld(rows, 41, lane);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k_eval2(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which, LmOptions opt) {
+  if (which < 2 && st->done) return;
+  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
+  const ParamSet& ps = sel ? ps1 : ps0;
+  extern __shared__ __align__(16) double s_mem[];
+  double* s_rows = s_mem;                                             // [2][4][42][32]
+  double* s_fc = s_rows + 2 * kE2Group * kE2Elems * 32;               // [27][32]
+  double* s_board = s_fc + kFcElems * 32;                             // [K][2]
+  CamConst* s_cam = reinterpret_cast<CamConst*>(s_board + 2 * P.K);   // [C]
+  for (int i = threadIdx.x; i < 2 * P.K; i += blockDim.x) s_board[i] = P.board_xy[i];
+  {
+    const int n = P.C * (int)(sizeof(CamConst) / sizeof(double));
+    const double* src = reinterpret_cast<const double*>(ps.cam);
+    double* dst = reinterpret_cast<double*>(s_cam);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v0 = blockIdx.x * 32 + lane;
+  const bool valid = v0 < P.V;
+  const int v = valid ? v0 : P.V - 1;
+  if (warp == 0) {
+    FrameConst fc;
+    make_frame_const(ps.board_rt + 6 * P.view_frame[v], fc);
+    const double* fp = reinterpret_cast<const double*>(&fc);
+#pragma unroll
+    for (int e = 0; e < kFcElems; ++e) s_fc[e * 32 + lane] = fp[e];
+  }
+  __syncthreads();
+  const CamConst& cc = s_cam[P.view_camera[v]];
+  const double2* obs = P.obsT + v;
+
+  // One accumulator array for every role (a role uses a prefix of it); the role
+  // switch sits INSIDE the corner loop and the per-corner fold is not unrolled, so
+  // the whole kernel stays within the instruction cache: the producer code is
+  // shared by the four warps, each consumer variant is ~150 instructions.
+  double acc[59];
+#pragma unroll
+  for (int i = 0; i < 59; ++i) acc[i] = 0.0;
+
+  int parity = 0;
+  for (int j0 = 0; j0 < P.K; j0 += kE2Group, parity ^= 1) {
+    double* buf = s_rows + parity * (kE2Group * kE2Elems * 32);
+    {
+      const int j = j0 + warp;
+      double* mine = buf + warp * (kE2Elems * 32);
+      if (j < P.K && valid) {
+        FrameConst fc;
+        double* fp = reinterpret_cast<double*>(&fc);
+#pragma unroll
+        for (int e = 0; e < kFcElems; ++e) fp[e] = s_fc[e * 32 + lane];
+        const double2 uv = obs[(size_t)j * P.Vpad];
+        ObsRow o;
+        obs_jacobian<true, true, true>(cc, fc, s_board[2 * j], s_board[2 * j + 1], uv.x, uv.y, o);
+        double err;
+        const double half_rho = obs_apply_loss<0, 19>(opt.loss_type, opt.loss_scale, o, &err);
+#pragma unroll
+        for (int k = 0; k < 20; ++k) { mine[k * 32 + lane] = o.Ju[k]; mine[(20 + k) * 32 + lane] = o.Jv[k]; }
+        mine[40 * 32 + lane] = half_rho;
+        mine[41 * 32 + lane] = err;
+      } else {
+#pragma unroll
+        for (int k = 0; k < kE2Elems; ++k) mine[k * 32 + lane] = 0.0;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll 1
+      for (int o = 0; o < kE2Group; ++o) eval2_consume<0>(buf + o * (kE2Elems * 32), lane, acc);
+    } else if (warp == 1) {
+#pragma unroll 1
+      for (int o = 0; o < kE2Group; ++o) eval2_consume<1>(buf + o * (kE2Elems * 32), lane, acc);
+    } else if (warp == 2) {
+#pragma unroll 1
+      for (int o = 0; o < kE2Group; ++o) eval2_consume<2>(buf + o * (kE2Elems * 32), lane, acc);
+    } else {
+#pragma unroll 1
+      for (int o = 0; o < kE2Group; ++o) eval2_consume<3>(buf + o * (kE2Elems * 32), lane, acc);
+    }
+  }
+  if (!valid) return;
+  double* Gv = ps.G + (size_t)v * kViewStride;
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < 57; ++i) Gv[kOffBB + i] = acc[i];
+  } else if (warp == 1) {
+#pragma unroll
+    for (int i = 0; i < 48; ++i) Gv[kOffBI + i] = acc[i];
+  } else if (warp == 2) {
+#pragma unroll
+    for (int i = 0; i < 21; ++i) Gv[kOffCC + i] = acc[i];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) Gv[kOffII + i] = acc[21 + i];
+    Gv[kOffCost] = acc[57];
+    Gv[kOffErr] = acc[58];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 48; ++i) Gv[kOffCI + i] = acc[i];
+  }
+}
+
 // Inspection kernel: one thread per observation, full residual + Jacobian rows
 // in the reference's column order (camera_rt 6, chessboard_rt 6, intrinsic 9).
 __global__ void k_eval_rows(DeviceProblem P, ParamSet ps, LmOptions opt, double* residuals,
@@ -318,10 +482,17 @@ __global__ void k_reduce_cam_b(DeviceProblem P, ParamSet ps0, ParamSet ps1, cons
   const ParamSet& ps = sel ? ps1 : ps0;
   const int c = blockIdx.x, e = threadIdx.x;
   if (e >= kCamRec) return;
-  double s = 0.0;
-  for (int ch = P.cam_chunk_begin[c]; ch < P.cam_chunk_begin[c + 1]; ++ch)
-    s += part[(size_t)ch * kCamRec + e];
-  ps.comm[c * kCamRec + e] = s;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int ch = P.cam_chunk_begin[c];
+  const int ce = P.cam_chunk_begin[c + 1];
+  for (; ch + 3 < ce; ch += 4) {
+    s0 += part[(size_t)ch * kCamRec + e];
+    s1 += part[(size_t)(ch + 1) * kCamRec + e];
+    s2 += part[(size_t)(ch + 2) * kCamRec + e];
+    s3 += part[(size_t)(ch + 3) * kCamRec + e];
+  }
+  for (; ch < ce; ++ch) s0 += part[(size_t)ch * kCamRec + e];
+  ps.comm[c * kCamRec + e] = (s0 + s1) + (s2 + s3);
 }
 
 // Block-wide deterministic sum / max helpers (blockDim.x <= 1024, power of 2).
@@ -403,10 +574,13 @@ __global__ void k_jacobi_scale(DeviceProblem P, ParamSet ps0, ParamSet ps1, cons
 // K3: Schur elimination of the frame poses onto the reduced camera system.
 // A CTA walks a contiguous range of frames in batches of kSchurFB (one warp per
 // frame): V_f + D_e^2 -> Cholesky -> Y = V^-1 W_s, z = V^-1 g_s staged in shared
-// memory; then every thread updates the packed upper-triangular S entries it
-// owns (registers) with  S_ij -= sum_r W_s[r][i] Y[r][j].
+// memory; then every thread updates the 4x4 register tile(s) of S it owns with
+//   S_ij -= sum_r W_s[r][i] Y[r][j]      (r over the 6 rows of the batch's frames)
+// Tiles are enumerated row-major over the upper block triangle, so the lanes of
+// a warp share the W operand (broadcast) and read consecutive Y operands.
 // Per-frame record saved for the back-substitution (SoA over frames):
-//   [0,21) L (row-major lower), [21,27) z, [27,48) V_s upper, [48,54) g_s
+//   [0,21) L (row-major lower, reciprocal diagonal), [21,27) z, [27,48) V_s upper,
+//   [48,54) g_s
 // ---------------------------------------------------------------------------
 constexpr int kSchurFB = 8;
 constexpr int kFrameRec = 54;
@@ -420,40 +594,44 @@ struct SchurArgs {
   double* rpart;           // [nblk][NL]
   int frames_per_block;
   double radius_override;  // > 0: use instead of st->radius (inspection)
+  const short* tile_bi;    // [ntiles] block row of tile t
+  const short* tile_bj;    // [ntiles] block col (bj >= bi)
+  int ntiles;
+  int NLp;                 // NL rounded up to a multiple of 4
 };
 
-template <int EPT, int NT>
-__global__ void __launch_bounds__(NT)
+template <int T, int MAXNT>
+__global__ void __launch_bounds__(MAXNT)
 k_schur(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
         SchurArgs A) {
   if (st->done) return;
   const ParamSet& ps = st->cur ? ps1 : ps0;
   const double radius = A.radius_override > 0.0 ? A.radius_override : st->radius;
-  extern __shared__ double s_mem[];
-  const int NL = P.NL;
-  double* Ws = s_mem;                               // [FB][6][NL]
-  double* Ys = Ws + kSchurFB * 6 * NL;              // [FB][6][NL]
-  double* zs = Ys + kSchurFB * 6 * NL;              // [FB][6]
+  extern __shared__ __align__(32) double s_mem[];
+  const int NL = P.NL, NLp = A.NLp, NT = blockDim.x;
+  double* Ws = s_mem;                               // [FB*6][NLp]
+  double* Ys = Ws + kSchurFB * 6 * NLp;             // [FB*6][NLp]
+  double* zs = Ys + kSchurFB * 6 * NLp;             // [FB*6]
   double* scr = zs + kSchurFB * 6;                  // [FB][64] per-warp scratch
   int* colbase = reinterpret_cast<int*>(scr + kSchurFB * 64);  // [FB][32]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int qi[EPT], qj[EPT];
-  double acc[EPT];
+  int tbi[T], tbj[T];
+  double acc[T][16];
 #pragma unroll
-  for (int k = 0; k < EPT; ++k) {
-    const int q = tid + k * NT;
-    acc[k] = 0.0;
-    qi[k] = q < P.Q ? P.q_i[q] : 0;
-    qj[k] = q < P.Q ? P.q_j[q] : 0;
+  for (int k = 0; k < T; ++k) {
+    const int t = tid + k * NT;
+    tbi[k] = t < A.ntiles ? A.tile_bi[t] : -1;
+    tbj[k] = t < A.ntiles ? A.tile_bj[t] : 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[k][e] = 0.0;
   }
   double racc = 0.0;
 
   const int f_begin = blockIdx.x * A.frames_per_block;
   const int f_end = min(P.F, f_begin + A.frames_per_block);
   for (int fb = f_begin; fb < f_end; fb += kSchurFB) {
-    // zero the staging area
-    for (int i = tid; i < 2 * kSchurFB * 6 * NL + kSchurFB * 6; i += NT) s_mem[i] = 0.0;
+    for (int i = tid; i < 2 * kSchurFB * 6 * NLp + kSchurFB * 6; i += NT) s_mem[i] = 0.0;
     __syncthreads();
     const int f = fb + warp;
     if (warp < kSchurFB && f < f_end) {
@@ -540,33 +718,50 @@ k_schur(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOption
         }
         const int gcol = P.live_off[m] + k;
 #pragma unroll
-        for (int r = 0; r < 6; ++r) Ws[(warp * 6 + r) * NL + gcol] = w[r];
+        for (int r = 0; r < 6; ++r) Ws[(warp * 6 + r) * NLp + gcol] = w[r];
         chol6_solve(M, w);
 #pragma unroll
-        for (int r = 0; r < 6; ++r) Ys[(warp * 6 + r) * NL + gcol] = w[r];
+        for (int r = 0; r < 6; ++r) Ys[(warp * 6 + r) * NLp + gcol] = w[r];
       }
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < EPT; ++k) {
-      double a = acc[k];
-      const double* wp = Ws + qi[k];
-      const double* yp = Ys + qj[k];
+    for (int k = 0; k < T; ++k) {
+      if (tbi[k] >= 0) {
+        const double* wp = Ws + 4 * tbi[k];
+        const double* yp = Ys + 4 * tbj[k];
 #pragma unroll 4
-      for (int r = 0; r < kSchurFB * 6; ++r) a -= wp[r * NL] * yp[r * NL];
-      acc[k] = a;
+        for (int r = 0; r < kSchurFB * 6; ++r) {
+          const double4 w4 = *reinterpret_cast<const double4*>(wp + r * NLp);
+          const double4 y4 = *reinterpret_cast<const double4*>(yp + r * NLp);
+          const double w[4] = {w4.x, w4.y, w4.z, w4.w};
+          const double y[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[k][a * 4 + b] = fma(-w[a], y[b], acc[k][a * 4 + b]);
+        }
+      }
     }
     if (tid < NL) {
       double a = racc;
-      for (int r = 0; r < kSchurFB * 6; ++r) a -= Ws[r * NL + tid] * zs[r];
+      for (int r = 0; r < kSchurFB * 6; ++r) a = fma(-Ws[r * NLp + tid], zs[r], a);
       racc = a;
     }
     __syncthreads();
   }
+  double* Sp = A.Spart + (size_t)blockIdx.x * P.Q;
 #pragma unroll
-  for (int k = 0; k < EPT; ++k) {
-    const int q = tid + k * NT;
-    if (q < P.Q) A.Spart[(size_t)blockIdx.x * P.Q + q] = acc[k];
+  for (int k = 0; k < T; ++k) {
+    if (tbi[k] < 0) continue;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = 4 * tbi[k] + a, j = 4 * tbj[k] + b;
+        if (i <= j && j < NL) Sp[i * NL - (i * (i - 1)) / 2 + (j - i)] = acc[k][a * 4 + b];
+      }
+    }
   }
   if (tid < NL) A.rpart[(size_t)blockIdx.x * NL + tid] = racc;
 }
@@ -592,10 +787,17 @@ __global__ void k_reduce_s(DeviceProblem P, const LmState* st, const double* __r
 }
 
 // ---------------------------------------------------------------------------
-// K4: reduced camera system — assemble, dense Cholesky, solve (single CTA).
-// lhs = sum_f(-W^T V^-1 W) [allreduced] + U_s + D_c^2, packed lower in smem.
+// K4: reduced camera system — assemble, factor, solve (single CTA).
+//   lhs = sum_f(-W^T V^-1 W) [all-reduced] + U_s + D_c^2
+// Square-root-free Cholesky (L D L^T) on the packed lower triangle of the
+// AUGMENTED matrix [[lhs, rhs], [rhs^T, .]]: the extra row carries the forward
+// substitution through the factorisation for free, the column scaling is folded
+// into the rank-1 update (A_ik -= A_ij A_kj / d_j), so there is exactly one
+// __syncthreads per column and no square root or column-scaling pass; a warp
+// then back-substitutes.  Same pivots and the same positive-definiteness test
+// (d_j > 0) as the Eigen LLT Ceres uses here.
 // ---------------------------------------------------------------------------
-constexpr int kSolveThreads = 512;
+constexpr int kSolveThreads = 1024;
 
 __device__ __forceinline__ int idxL(int r, int c) { return (r * (r + 1)) / 2 + c; }  // r >= c
 
@@ -609,6 +811,7 @@ __device__ __forceinline__ double cam_grad(const double* U, int a) {
   return a < 6 ? U[(kOffCI - kOffCC) + a * 8 + 7] : U[(kOffII - kOffCC) + tri8(a - 6, 7)];
 }
 
+template <int BMAX>   // ceil((NL + 1) / 32): lanes cover a row in BMAX strides
 __global__ void __launch_bounds__(kSolveThreads)
 k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
         const double* __restrict__ Sr /*[Q + NL]*/, const double* __restrict__ scale_c,
@@ -620,12 +823,14 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
   const ParamSet& pc = sel ? ps0 : ps1;     // candidate
   const double radius = radius_override > 0.0 ? radius_override : st->radius;
   extern __shared__ double s_mem[];
-  const int NL = P.NL, tid = threadIdx.x;
-  double* L = s_mem;                 // packed lower, Q entries
-  double* b = L + P.Q;               // [NL] rhs -> y
-  double* gsv = b + NL;              // [NL] scaled gradient
-  double* sc = gsv + NL;             // [NL] scale
-  double* s_red = sc + NL;           // [kSolveThreads]
+  const int NL = P.NL, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kWarps = kSolveThreads / 32;
+  double* L = s_mem;                       // packed lower of the (NL+1)x(NL+1) augmented matrix
+  double* x = L + idxL(NL + 1, 0);         // [NL] solution y
+  double* gsv = x + NL;                    // [NL] scaled gradient
+  double* sc = gsv + NL;                   // [NL] scale
+  double* dinv = sc + NL;                  // [NL] 1 / d_j
+  double* s_red = dinv + NL;               // [kSolveThreads]
   __shared__ int s_ok;
   if (tid == 0) s_ok = 1;
   for (int i = tid; i < NL; i += kSolveThreads) sc[i] = scale_c[P.live_cam[i] * 13 + P.live_kk[i]];
@@ -650,7 +855,7 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
     const double* U = ps.comm + P.live_cam[i] * kCamRec;
     const double g = sc[i] * cam_grad(U, P.live_kk[i]);
     gsv[i] = g;
-    b[i] = Sr[P.Q + i] + g;
+    L[idxL(NL, i)] = Sr[P.Q + i] + g;       // augmented row = rhs
   }
   __syncthreads();
   if (dbg_lhs) {
@@ -658,57 +863,90 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
       const int r = idx / NL, c = idx % NL;
       dbg_lhs[idx] = r >= c ? L[idxL(r, c)] : L[idxL(c, r)];
     }
-    for (int i = tid; i < NL; i += kSolveThreads) dbg_rhs[i] = b[i];
+    for (int i = tid; i < NL; i += kSolveThreads) dbg_rhs[i] = L[idxL(NL, i)];
     __syncthreads();
   }
-  // Right-looking Cholesky on the packed lower triangle.
+  // L D L^T, right-looking, one barrier per column.  Rows j+1..NL (NL = rhs row)
+  // are dealt to the warps round-robin, two rows per pass; lanes run along the row
+  // with every load of a pass issued before the first store (the compiler cannot
+  // reorder them itself: they alias).  The lane that produces the next pivot also
+  // publishes its reciprocal, taking the division off the next column's critical path.
+  if (tid == 0) {
+    const double d0 = L[0];
+    dinv[0] = 1.0 / d0;
+    if (!(d0 > 0.0)) s_ok = 0;
+  }
+  __syncthreads();
   for (int j = 0; j < NL; ++j) {
-    if (tid == 0) {
-      const double d = L[idxL(j, j)];
-      if (!(d > 0.0)) s_ok = 0;
-      L[idxL(j, j)] = sqrt(d);
+    const double inv = dinv[j];
+    const int k0 = j + 1 + lane;
+    double cj[BMAX];
+#pragma unroll
+    for (int bb = 0; bb < BMAX; ++bb) {
+      const int k = k0 + 32 * bb;
+      cj[bb] = k < NL ? L[(k * (k + 1)) / 2 + j] : 0.0;
     }
-    __syncthreads();
-    const double inv = 1.0 / L[idxL(j, j)];
-    for (int i = j + 1 + tid; i < NL; i += kSolveThreads) L[idxL(i, j)] *= inv;
-    __syncthreads();
-    // trailing update: rows i > j, cols j < k <= i
-    const int m = NL - j - 1;
-    const int cnt = (m * (m + 1)) / 2;
-    for (int t = tid; t < cnt; t += kSolveThreads) {
-      // t -> (ri, rk) with 0 <= rk <= ri < m  (row-major lower)
-      int ri = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-      while ((ri * (ri + 1)) / 2 > t) --ri;
-      while (((ri + 1) * (ri + 2)) / 2 <= t) ++ri;
-      const int rk = t - (ri * (ri + 1)) / 2;
-      const int i = j + 1 + ri, k = j + 1 + rk;
-      L[idxL(i, k)] -= L[idxL(i, j)] * L[idxL(k, j)];
+    for (int i = j + 1 + warp; i <= NL; i += 2 * kWarps) {
+      const int i2 = i + kWarps;
+      const bool has2 = i2 <= NL;
+      const int r1 = (i * (i + 1)) / 2, r2 = has2 ? (i2 * (i2 + 1)) / 2 : r1;
+      const double f1 = L[r1 + j] * inv;
+      const double f2 = has2 ? L[r2 + j] * inv : 0.0;
+      const int e1 = i < NL ? i : NL - 1;
+      const int e2 = has2 ? (i2 < NL ? i2 : NL - 1) : -1;
+      double v1[BMAX], v2[BMAX];
+#pragma unroll
+      for (int bb = 0; bb < BMAX; ++bb) {
+        const int k = k0 + 32 * bb;
+        v1[bb] = k <= e1 ? L[r1 + k] : 0.0;
+        v2[bb] = k <= e2 ? L[r2 + k] : 0.0;
+      }
+#pragma unroll
+      for (int bb = 0; bb < BMAX; ++bb) {
+        const int k = k0 + 32 * bb;
+        if (k <= e1) {
+          const double nv = fma(-f1, cj[bb], v1[bb]);
+          L[r1 + k] = nv;
+          if (k == i && i == j + 1 && i < NL) {      // the next pivot
+            dinv[j + 1] = 1.0 / nv;
+            if (!(nv > 0.0)) s_ok = 0;
+          }
+        }
+        if (k <= e2) L[r2 + k] = fma(-f2, cj[bb], v2[bb]);
+      }
     }
     __syncthreads();
   }
-  // Triangular solves by warp 0 (lanes own rows i = lane mod 32).
-  if (tid < 32) {
-    const int lane = tid;
-    for (int j = 0; j < NL; ++j) {
-      double xj = 0.0;
-      if ((j & 31) == lane) { xj = b[j] / L[idxL(j, j)]; b[j] = xj; }
-      xj = __shfl_sync(0xffffffffu, xj, j & 31);
-      for (int i = j + 1 + ((lane - (j + 1)) & 31); i < NL; i += 32) b[i] -= L[idxL(i, j)] * xj;
-      __syncwarp();
-    }
+  // Back-substitution by warp 0, column-oriented:  x_j = (rhs'_j - acc_j) / d_j, then
+  // acc_i += A[j][i] x_j for the rows i < j this lane owns (i = lane mod 32).
+  if (warp == 0) {
+    const int rN = (NL * (NL + 1)) / 2;
+    double accr[BMAX];
+#pragma unroll
+    for (int bb = 0; bb < BMAX; ++bb) accr[bb] = 0.0;
     for (int j = NL - 1; j >= 0; --j) {
-      double xj = 0.0;
-      if ((j & 31) == lane) { xj = b[j] / L[idxL(j, j)]; b[j] = xj; }
+      const int rj = (j * (j + 1)) / 2;
+      double rowv[BMAX];
+#pragma unroll
+      for (int bb = 0; bb < BMAX; ++bb) {
+        const int i = lane + 32 * bb;
+        rowv[bb] = i < j ? L[rj + i] : 0.0;
+      }
+      double a = 0.0;
+#pragma unroll
+      for (int bb = 0; bb < BMAX; ++bb) if (bb == (j >> 5)) a = accr[bb];
+      double xj = (L[rN + j] - a) * dinv[j];
       xj = __shfl_sync(0xffffffffu, xj, j & 31);
-      for (int i = lane; i < j; i += 32) b[i] -= L[idxL(j, i)] * xj;
-      __syncwarp();
+      if (lane == (j & 31)) x[j] = xj;
+#pragma unroll
+      for (int bb = 0; bb < BMAX; ++bb) accr[bb] = fma(rowv[bb], xj, accr[bb]);
     }
   }
   __syncthreads();
   // y_c, candidate camera parameters, camera-side partial sums.
   double lin = 0.0, dn2 = 0.0, quad = 0.0;
   for (int i = tid; i < NL; i += kSolveThreads) {
-    const double y = b[i];
+    const double y = x[i];
     y_c[i] = y;
     lin += y * gsv[i];
     const double delta = -y * sc[i];
@@ -722,7 +960,7 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
     for (int t = 0; t < n; ++t) {
       const int jj = o0 + t, kj = P.live_kk[jj];
       const double u = ki <= kj ? cam_block(U, ki, kj) : cam_block(U, kj, ki);
-      row += sc[i] * sc[jj] * u * b[jj];
+      row += sc[i] * sc[jj] * u * x[jj];
     }
     quad += y * row;
   }
@@ -731,13 +969,13 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
   for (int idx = tid; idx < P.C * 15; idx += kSolveThreads) {
     const int c = idx / 15, k = idx % 15;   // k < 6: rt, else intrinsic k - 6
     const bool free_rt = (c != P.fixed_camera);
-    double x = k < 6 ? ps.cam_rt[c * 6 + k] : ps.intr[c * 9 + (k - 6)];
-    double xn = x;
+    const double xv = k < 6 ? ps.cam_rt[c * 6 + k] : ps.intr[c * 9 + (k - 6)];
+    double xn = xv;
     if (k < 6) {
-      if (free_rt) xn = x + (-b[P.live_off[c] + k] * sc[P.live_off[c] + k]);
+      if (free_rt) xn = xv + (-x[P.live_off[c] + k] * sc[P.live_off[c] + k]);
     } else if (k - 6 < 7) {
       const int li = P.live_off[c] + (free_rt ? 6 : 0) + (k - 6);
-      xn = x + (-b[li] * sc[li]);
+      xn = xv + (-x[li] * sc[li]);
     }
     if (k < 6) pc.cam_rt[c * 6 + k] = xn; else pc.intr[c * 9 + (k - 6)] = xn;
     if (k >= 6 || free_rt) xn2 += xn * xn;
@@ -1014,6 +1252,17 @@ __global__ void k_decide(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* s
     st->decrease_factor *= 2.0;
     finalize_iteration(st, opt, tr, iteration, true, false, candidate_cost, step_norm);
   }
+}
+
+// DFMA throughput probe (the FP64 roofline denominator is measured, not assumed).
+__global__ void k_dfma_peak(double* out, int iters, double m) {
+  double a0 = threadIdx.x, a1 = 1.0, a2 = 2.0, a3 = 3.0, a4 = 4.0, a5 = 5.0, a6 = 6.0, a7 = 7.0;
+  const double c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
 }  // namespace tscm

@@ -337,20 +337,20 @@ TSCM_HD double obs_apply_loss(int loss_type, double loss_scale, ObsRow& o, doubl
 
 // ---------------------------------------------------------------------------
 // 6x6 SPD helpers for the Schur step (InvertPSDMatrix<6> of Ceres'
-// SchurEliminator).  M is a full row-major 6x6; L overwrites its lower part.
-// Returns false if a pivot is not positive.
+// SchurEliminator).  M is a full row-major 6x6; on return its lower triangle
+// holds the Cholesky factor L with the RECIPROCAL of the diagonal stored on the
+// diagonal (every later use multiplies instead of dividing).  A non-positive
+// pivot produces NaN/Inf that propagate into the step, which the LM loop then
+// rejects as an invalid step, as Ceres does for a failed linear solve.
 // ---------------------------------------------------------------------------
-TSCM_HD bool chol6(double M[36]) {
-  bool ok = true;
+TSCM_HD void chol6(double M[36]) {
   TSCM_UNROLL
   for (int j = 0; j < 6; ++j) {
     double d = M[j * 6 + j];
     TSCM_UNROLL
     for (int k = 0; k < j; ++k) d -= M[j * 6 + k] * M[j * 6 + k];
-    if (!(d > 0.0)) ok = false;
-    d = sqrt(d);
-    M[j * 6 + j] = d;
-    const double inv = 1.0 / d;
+    const double inv = 1.0 / sqrt(d);
+    M[j * 6 + j] = inv;
     TSCM_UNROLL
     for (int i = j + 1; i < 6; ++i) {
       double s = M[i * 6 + j];
@@ -359,23 +359,22 @@ TSCM_HD bool chol6(double M[36]) {
       M[i * 6 + j] = s * inv;
     }
   }
-  return ok;
 }
-// Solve L L^T x = b in place.
+// Solve L L^T x = b in place (L as produced by chol6).
 TSCM_HD void chol6_solve(const double L[36], double b[6]) {
   TSCM_UNROLL
   for (int i = 0; i < 6; ++i) {
     double s = b[i];
     TSCM_UNROLL
     for (int k = 0; k < i; ++k) s -= L[i * 6 + k] * b[k];
-    b[i] = s / L[i * 6 + i];
+    b[i] = s * L[i * 6 + i];
   }
   TSCM_UNROLL
   for (int i = 5; i >= 0; --i) {
     double s = b[i];
     TSCM_UNROLL
     for (int k = i + 1; k < 6; ++k) s -= L[k * 6 + i] * b[k];
-    b[i] = s / L[i * 6 + i];
+    b[i] = s * L[i * 6 + i];
   }
 }
 

@@ -223,23 +223,26 @@ def _compose_views(intr, cam_rt, board_rt, board_xy):
 
 def generate(num_cameras: int, num_frames: int, board=(11, 8), rig="calib", dense=False,
              seed=0, noise_px=0.1, outlier_fraction=0.0, perturb=1.0, max_incidence_deg=110.0,
-             margin_px=2.0, name="") -> SyntheticProblem:
+             margin_px=2.0, name="", frame_seed=0) -> SyntheticProblem:
     """Build one synthetic calibration problem.
 
     rig: 'calib' (calib.yaml cameras, <=4), 'ring' (outward ring, masks), 'array'
     (forward array, use with dense=True).  dense=True keeps only frames seen by
     every camera.  perturb scales the initial-value perturbation of §8d
-    (0 = start at ground truth).
+    (0 = start at ground truth).  `seed` fixes the rig (cameras, their initial
+    values); `frame_seed` varies the frames only, so ranks of a weak-scaling run
+    can each draw their own frames for one common rig.
     """
-    rng = np.random.default_rng(np.random.PCG64(0x7C5C0000 + seed))
+    rig_rng = np.random.default_rng(np.random.PCG64(0x7C5C0000 + seed))
+    rng = np.random.default_rng(np.random.PCG64([0x7C5C0000 + seed, 1 + frame_seed]))
     board_xy = make_board(*board)
     K = board_xy.shape[0]
     if rig == "calib":
         intr, cam_rt = rig_from_calib_yaml(num_cameras)
     elif rig == "ring":
-        intr, cam_rt = rig_ring(num_cameras, rng)
+        intr, cam_rt = rig_ring(num_cameras, rig_rng)
     elif rig == "array":
-        intr, cam_rt = rig_forward_array(num_cameras, rng)
+        intr, cam_rt = rig_forward_array(num_cameras, rig_rng)
     else:
         raise ValueError(rig)
     C = num_cameras
@@ -302,7 +305,7 @@ def generate(num_cameras: int, num_frames: int, board=(11, 8), rig="calib", dens
     view_frame = frames.astype(np.int32)
     obs_xy = obs[cams, frames]                                          # V,K,2
 
-    e = rng.standard_normal
+    e = rig_rng.standard_normal
     init_intr = intr.copy()
     init_intr[:, 0:2] *= 1 + perturb * 0.02 * e((C, 2))
     init_intr[:, 2:4] += perturb * 3.0 * e((C, 2))
@@ -313,6 +316,7 @@ def generate(num_cameras: int, num_frames: int, board=(11, 8), rig="calib", dens
     init_cam_rt[:, :3] += perturb * 0.02 * e((C, 3))
     init_cam_rt[:, 3:] += perturb * 5.0 * e((C, 3))
     init_cam_rt[0] = cam_rt[0]                 # camera 0 is the (constant) reference
+    e = rng.standard_normal
     init_board_rt = gt_board_rt.copy()
     init_board_rt[:, :3] += perturb * 0.02 * e((F, 3))
     init_board_rt[:, 3:] += perturb * 5.0 * e((F, 3))
