@@ -126,6 +126,7 @@ struct tscm_solver {
   int schur_nblk = 0, schur_nt = 256, schur_ept = 20;
   size_t schur_smem = 0, solve_smem = 0, eval_smem = 0, eval2_smem = 0;
   int eval_variant = 2;
+  int prof = 0;
   int bs_nblk = 0, fg_nblk = 0;
   // graph of one LM iteration
   cudaGraph_t graph = nullptr;
@@ -292,7 +293,7 @@ void launch_solve(tscm_solver* s, double radius_override, bool debug) {
   const int bmax = (s->P.NL + 1 + 31) / 32;
 #define TSCM_SOLVE(B)                                                                          \
   k_solve<B><<<1, kSolveThreads, s->solve_smem, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, \
-      s->lm, s->d_Sr, s->d_scale_c, s->d_yc, radius_override, dl, dr)
+      s->lm, s->d_Sr, s->d_scale_c, s->d_yc, radius_override, dl, dr, s->prof)
   if (bmax <= 2) TSCM_SOLVE(2);
   else if (bmax <= 4) TSCM_SOLVE(4);
   else TSCM_SOLVE(7);
@@ -558,10 +559,12 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   s->schur.Fpad = (F + 31) / 32 * 32;
   s->schur_smem = (size_t)(2 * kSchurFB * 6 * s->schur.NLp + kSchurFB * 6 + kSchurFB * 64) * sizeof(double) +
                   kSchurFB * 32 * sizeof(int);
-  s->solve_smem = (size_t)((NL + 1) * (NL + 2) / 2 + 4 * NL + kSolveThreads + 8) * sizeof(double);
+  s->solve_smem = (size_t)((NL + 1) * (NL + 2) / 2 + 4 * NL + 4 + 4 * (NL + 1) + 2 * kSolveThreads + 8) * sizeof(double) +
+                  (size_t)2 * NL * sizeof(short) + 16;
   s->eval_smem = (size_t)2 * K * sizeof(double) + (size_t)C * sizeof(CamConst);
   s->eval2_smem = (size_t)(2 * kE2Group * kE2Elems * 32 + kFcElems * 32 + 2 * K) * sizeof(double) +
                   (size_t)C * sizeof(CamConst);
+  if (const char* pv = getenv("TSCM_PROF")) s->prof = atoi(pv);
   if (const char* ev = getenv("TSCM_EVAL_VARIANT")) s->eval_variant = atoi(ev) == 1 ? 1 : 2;
   TRY_RC(s->alloc(&s->schur.frame_rec, (size_t)kFrameRec * s->schur.Fpad));
   TRY_RC(s->alloc(&s->d_Spart, (size_t)s->schur_nblk * P.Q));

@@ -787,17 +787,21 @@ __global__ void k_reduce_s(DeviceProblem P, const LmState* st, const double* __r
 }
 
 // ---------------------------------------------------------------------------
-// K4: reduced camera system — assemble, factor, solve (single CTA).
+// K4: reduced camera system — assemble, factor, solve (single CTA, 512 threads).
 //   lhs = sum_f(-W^T V^-1 W) [all-reduced] + U_s + D_c^2
-// Square-root-free Cholesky (L D L^T) on the packed lower triangle of the
-// AUGMENTED matrix [[lhs, rhs], [rhs^T, .]]: the extra row carries the forward
-// substitution through the factorisation for free, the column scaling is folded
-// into the rank-1 update (A_ik -= A_ij A_kj / d_j), so there is exactly one
-// __syncthreads per column and no square root or column-scaling pass; a warp
-// then back-substitutes.  Same pivots and the same positive-definiteness test
-// (d_j > 0) as the Eigen LLT Ceres uses here.
+// Square-root-free blocked Cholesky (L D L^T, 4 columns per step) of the
+// AUGMENTED matrix [[lhs, rhs], [rhs^T, .]] held column-major packed in shared
+// memory: the extra row carries the forward substitution through the
+// factorisation for free.  Per step: (1) every thread factors the 4x4 pivot
+// block redundantly (Newton reciprocals, no divisions), one thread per row
+// eliminates the 4 panel columns of its row; (2) rank-4 update of the trailing
+// triangle, lanes along rows (contiguous, conflict-free) and warps along
+// columns, 4 FMAs per shared-memory load/store pair.  Two barriers per 4
+// columns.  A warp then back-substitutes.  Same pivots and the same
+// positive-definiteness test (d_j > 0) as the Eigen LLT Ceres uses here.
 // ---------------------------------------------------------------------------
-constexpr int kSolveThreads = 1024;
+constexpr int kSolveThreads = 512;
+constexpr int kSolveNB = 4;
 
 __device__ __forceinline__ int idxL(int r, int c) { return (r * (r + 1)) / 2 + c; }  // r >= c
 
@@ -811,138 +815,209 @@ __device__ __forceinline__ double cam_grad(const double* U, int a) {
   return a < 6 ? U[(kOffCI - kOffCC) + a * 8 + 7] : U[(kOffII - kOffCC) + tri8(a - 6, 7)];
 }
 
-template <int BMAX>   // ceil((NL + 1) / 32): lanes cover a row in BMAX strides
+// 1/d to ~1 ulp: hardware seed + two Newton steps (no IEEE division sequence on
+// the factorisation's critical path).
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  x = fma(x, fma(-d, x, 1.0), x);
+  x = fma(x, fma(-d, x, 1.0), x);
+  return x;
+}
+
+template <int AMAX>   // ceil((NL + 1) / 32): 32-row blocks a lane may own
 __global__ void __launch_bounds__(kSolveThreads)
 k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
         const double* __restrict__ Sr /*[Q + NL]*/, const double* __restrict__ scale_c,
         double* __restrict__ y_c /*[NL]*/, double radius_override,
-        double* __restrict__ dbg_lhs, double* __restrict__ dbg_rhs) {
+        double* __restrict__ dbg_lhs, double* __restrict__ dbg_rhs, int prof) {
   if (st->done) return;
+  long long tk0 = clock64(), tk1 = 0, tk2 = 0, tk3 = 0;
   const int sel = st->cur;
   const ParamSet& ps = sel ? ps1 : ps0;     // current x
   const ParamSet& pc = sel ? ps0 : ps1;     // candidate
   const double radius = radius_override > 0.0 ? radius_override : st->radius;
   extern __shared__ double s_mem[];
-  const int NL = P.NL, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NL = P.NL, n1 = NL + 1, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int kWarps = kSolveThreads / 32;
-  double* L = s_mem;                       // packed lower of the (NL+1)x(NL+1) augmented matrix
-  double* x = L + idxL(NL + 1, 0);         // [NL] solution y
+  // column-major packed lower triangle of the n1 x n1 augmented matrix:
+  // element (i, k), i >= k, at colptr(k) + i - k, colptr(k) = k n1 - k (k - 1) / 2
+  double* L = s_mem;
+  double* x = L + (n1 * (n1 + 1)) / 2;     // [NL] solution y
   double* gsv = x + NL;                    // [NL] scaled gradient
   double* sc = gsv + NL;                   // [NL] scale
-  double* dinv = sc + NL;                  // [NL] 1 / d_j
-  double* s_red = dinv + NL;               // [kSolveThreads]
+  double* dinv = sc + NL;                  // [NL + 4] 1 / d_j
+  double* Pb = dinv + NL + 4;              // [4][n1] panel P[c][i]
+  double* dummy = Pb + 4 * n1;             // [kSolveThreads] sink for masked lanes
+  double* s_red = dummy + kSolveThreads;   // [kSolveThreads]
+  short* s_cam = reinterpret_cast<short*>(s_red + kSolveThreads);   // [NL]
+  short* s_kk = s_cam + NL;                                         // [NL]
   __shared__ int s_ok;
+#define COLPTR(k) ((k) * n1 - ((k) * ((k) - 1)) / 2)
   if (tid == 0) s_ok = 1;
-  for (int i = tid; i < NL; i += kSolveThreads) sc[i] = scale_c[P.live_cam[i] * 13 + P.live_kk[i]];
-  __syncthreads();
-  for (int q = tid; q < P.Q; q += kSolveThreads) {
-    const int i = P.q_i[q], j = P.q_j[q];   // i <= j
-    double v = Sr[q];
-    const int ci = P.live_cam[i], cj = P.live_cam[j];
-    if (ci == cj) {
-      const double* U = ps.comm + ci * kCamRec;
-      const double us = sc[i] * sc[j] * cam_block(U, P.live_kk[i], P.live_kk[j]);
-      v += us;
-      if (i == j) {
-        const double d = fmin(fmax(us, opt.min_lm_diagonal), opt.max_lm_diagonal);
-        const double D = sqrt(d / radius);
-        v += D * D;
-      }
-    }
-    L[idxL(j, i)] = v;
-  }
   for (int i = tid; i < NL; i += kSolveThreads) {
-    const double* U = ps.comm + P.live_cam[i] * kCamRec;
-    const double g = sc[i] * cam_grad(U, P.live_kk[i]);
-    gsv[i] = g;
-    L[idxL(NL, i)] = Sr[P.Q + i] + g;       // augmented row = rhs
+    const int c = P.live_cam[i], kk = P.live_kk[i];
+    s_cam[i] = (short)c; s_kk[i] = (short)kk;
+    sc[i] = scale_c[c * 13 + kk];
+  }
+  __syncthreads();
+  // assemble: column k by warp, rows along lanes (Sr is packed upper row-major: row k, col i)
+  for (int k = warp; k < NL; k += kWarps) {
+    const int qb = k * NL - (k * (k - 1)) / 2 - k;   // q(k, i) = qb + i
+    const int cp = COLPTR(k) - k;
+    const int ck = s_cam[k], kkk = s_kk[k];
+    const double* U = ps.comm + ck * kCamRec;
+    const double sk = sc[k];
+    for (int i = k + lane; i < NL; i += 32) {
+      double v = Sr[qb + i];
+      if (s_cam[i] == ck) {
+        const double us = sk * sc[i] * cam_block(U, kkk, s_kk[i]);
+        v += us;
+        if (i == k) {
+          const double d = fmin(fmax(us, opt.min_lm_diagonal), opt.max_lm_diagonal);
+          const double D = sqrt(d / radius);
+          v += D * D;
+        }
+      }
+      L[cp + i] = v;
+    }
+    if (lane == 0) {
+      const double g = sk * cam_grad(U, kkk);
+      gsv[k] = g;
+      L[cp + NL] = Sr[P.Q + k] + g;          // augmented row = rhs
+    }
   }
   __syncthreads();
   if (dbg_lhs) {
     for (int idx = tid; idx < NL * NL; idx += kSolveThreads) {
       const int r = idx / NL, c = idx % NL;
-      dbg_lhs[idx] = r >= c ? L[idxL(r, c)] : L[idxL(c, r)];
+      dbg_lhs[idx] = r >= c ? L[COLPTR(c) + r - c] : L[COLPTR(r) + c - r];
     }
-    for (int i = tid; i < NL; i += kSolveThreads) dbg_rhs[i] = L[idxL(NL, i)];
+    for (int i = tid; i < NL; i += kSolveThreads) dbg_rhs[i] = L[COLPTR(i) + NL - i];
     __syncthreads();
   }
-  // L D L^T, right-looking, one barrier per column.  Rows j+1..NL (NL = rhs row)
-  // are dealt to the warps round-robin, two rows per pass; lanes run along the row
-  // with every load of a pass issued before the first store (the compiler cannot
-  // reorder them itself: they alias).  The lane that produces the next pivot also
-  // publishes its reciprocal, taking the division off the next column's critical path.
-  if (tid == 0) {
-    const double d0 = L[0];
-    dinv[0] = 1.0 / d0;
-    if (!(d0 > 0.0)) s_ok = 0;
-  }
-  __syncthreads();
-  for (int j = 0; j < NL; ++j) {
-    const double inv = dinv[j];
-    const int k0 = j + 1 + lane;
-    double cj[BMAX];
-#pragma unroll
-    for (int bb = 0; bb < BMAX; ++bb) {
-      const int k = k0 + 32 * bb;
-      cj[bb] = k < NL ? L[(k * (k + 1)) / 2 + j] : 0.0;
+  tk1 = clock64();
+  for (int j = 0; j < NL; j += kSolveNB) {
+    const int nb = min(kSolveNB, NL - j);
+    // ---- pivot block (every thread, redundantly) -------------------------------
+    const int c0 = COLPTR(j), c1 = COLPTR(j + 1), c2 = COLPTR(j + 2), c3 = COLPTR(j + 3);
+    const double t00 = L[c0];
+    const double t10 = nb > 1 ? L[c0 + 1] : 0.0, t11 = nb > 1 ? L[c1] : 1.0;
+    const double t20 = nb > 2 ? L[c0 + 2] : 0.0, t21 = nb > 2 ? L[c1 + 1] : 0.0, t22 = nb > 2 ? L[c2] : 1.0;
+    const double t30 = nb > 3 ? L[c0 + 3] : 0.0, t31 = nb > 3 ? L[c1 + 2] : 0.0,
+                 t32 = nb > 3 ? L[c2 + 1] : 0.0, t33 = nb > 3 ? L[c3] : 1.0;
+    const double d0 = t00, i0 = fast_rcp(d0);
+    const double l10 = t10 * i0;
+    const double d1 = fma(-t10, l10, t11), i1 = fast_rcp(d1);
+    const double l20 = t20 * i0;
+    const double w21 = fma(-t20, l10, t21), l21 = w21 * i1;
+    const double d2 = fma(-w21, l21, fma(-t20, l20, t22)), i2 = fast_rcp(d2);
+    const double l30 = t30 * i0;
+    const double w31 = fma(-t30, l10, t31), l31 = w31 * i1;
+    const double w32 = fma(-w31, l21, fma(-t30, l20, t32)), l32 = w32 * i2;
+    const double d3 = fma(-w32, l32, fma(-w31, l31, fma(-t30, l30, t33))), i3 = fast_rcp(d3);
+    const double g0 = i0, g1 = nb > 1 ? i1 : 0.0, g2 = nb > 2 ? i2 : 0.0, g3 = nb > 3 ? i3 : 0.0;
+    __syncthreads();   // everyone has read the pivot block before it is rewritten
+    if (tid == 0) {
+      dinv[j] = i0;
+      bool ok = d0 > 0.0;
+      if (nb > 1) { dinv[j + 1] = i1; ok = ok && d1 > 0.0; }
+      if (nb > 2) { dinv[j + 2] = i2; L[c1 + 1] = w21; ok = ok && d2 > 0.0; }
+      if (nb > 3) { dinv[j + 3] = i3; L[c1 + 2] = w31; L[c2 + 1] = w32; ok = ok && d3 > 0.0; }
+      if (!ok) s_ok = 0;
     }
-    for (int i = j + 1 + warp; i <= NL; i += 2 * kWarps) {
-      const int i2 = i + kWarps;
-      const bool has2 = i2 <= NL;
-      const int r1 = (i * (i + 1)) / 2, r2 = has2 ? (i2 * (i2 + 1)) / 2 : r1;
-      const double f1 = L[r1 + j] * inv;
-      const double f2 = has2 ? L[r2 + j] * inv : 0.0;
-      const int e1 = i < NL ? i : NL - 1;
-      const int e2 = has2 ? (i2 < NL ? i2 : NL - 1) : -1;
-      double v1[BMAX], v2[BMAX];
+    // ---- panel: one thread per row below the pivot block ------------------------
+    for (int i = j + nb + tid; i <= NL; i += kSolveThreads) {
+      const double p0 = L[c0 + i - j];
+      double p1 = 0.0, p2 = 0.0, p3 = 0.0;
+      if (nb > 1) { p1 = fma(-p0, l10, L[c1 + i - j - 1]); L[c1 + i - j - 1] = p1; }
+      if (nb > 2) { p2 = fma(-p1, l21, fma(-p0, l20, L[c2 + i - j - 2])); L[c2 + i - j - 2] = p2; }
+      if (nb > 3) { p3 = fma(-p2, l32, fma(-p1, l31, fma(-p0, l30, L[c3 + i - j - 3]))); L[c3 + i - j - 3] = p3; }
+      Pb[i] = p0; Pb[n1 + i] = p1; Pb[2 * n1 + i] = p2; Pb[3 * n1 + i] = p3;
+    }
+    __syncthreads();
+    // ---- rank-4 update of the trailing triangle ---------------------------------
+    const int base = j + nb;
+    if (base < NL) {
+      double f[AMAX][4];
 #pragma unroll
-      for (int bb = 0; bb < BMAX; ++bb) {
-        const int k = k0 + 32 * bb;
-        v1[bb] = k <= e1 ? L[r1 + k] : 0.0;
-        v2[bb] = k <= e2 ? L[r2 + k] : 0.0;
+      for (int a = 0; a < AMAX; ++a) {
+        const int i = base + lane + 32 * a;
+        const bool ok = i <= NL;
+        f[a][0] = ok ? Pb[i] : 0.0;
+        f[a][1] = ok ? Pb[n1 + i] : 0.0;
+        f[a][2] = ok ? Pb[2 * n1 + i] : 0.0;
+        f[a][3] = ok ? Pb[3 * n1 + i] : 0.0;
       }
+      // two columns per pass; all loads of a pass are issued before the first
+      // store so the 2 * AMAX FMA chains overlap (the compiler cannot hoist them
+      // itself: the stores alias).
+      for (int k = base + warp; k < NL; k += 2 * kWarps) {
+        const int k2 = k + kWarps;
+        const bool has2 = k2 < NL;
+        const int kk2 = has2 ? k2 : k;
+        const double q0 = Pb[k] * g0, q1 = Pb[n1 + k] * g1, q2 = Pb[2 * n1 + k] * g2,
+                     q3 = Pb[3 * n1 + k] * g3;
+        const double r0 = Pb[kk2] * g0, r1 = Pb[n1 + kk2] * g1, r2 = Pb[2 * n1 + kk2] * g2,
+                     r3 = Pb[3 * n1 + kk2] * g3;
+        const int cp = COLPTR(k) - k, cp2 = COLPTR(kk2) - kk2;
+        double* pa[AMAX];
+        double* pb[AMAX];
+        double va[AMAX], vb[AMAX];
 #pragma unroll
-      for (int bb = 0; bb < BMAX; ++bb) {
-        const int k = k0 + 32 * bb;
-        if (k <= e1) {
-          const double nv = fma(-f1, cj[bb], v1[bb]);
-          L[r1 + k] = nv;
-          if (k == i && i == j + 1 && i < NL) {      // the next pivot
-            dinv[j + 1] = 1.0 / nv;
-            if (!(nv > 0.0)) s_ok = 0;
-          }
+        for (int a = 0; a < AMAX; ++a) {
+          const int i = base + lane + 32 * a;
+          pa[a] = (i >= k && i <= NL) ? &L[cp + i] : &dummy[tid];
+          pb[a] = (has2 && i >= k2 && i <= NL) ? &L[cp2 + i] : &dummy[tid];
+          va[a] = *pa[a];
+          vb[a] = *pb[a];
         }
-        if (k <= e2) L[r2 + k] = fma(-f2, cj[bb], v2[bb]);
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a) {
+          va[a] = fma(-f[a][0], q0, va[a]); vb[a] = fma(-f[a][0], r0, vb[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a) {
+          va[a] = fma(-f[a][1], q1, va[a]); vb[a] = fma(-f[a][1], r1, vb[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a) {
+          va[a] = fma(-f[a][2], q2, va[a]); vb[a] = fma(-f[a][2], r2, vb[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a) {
+          va[a] = fma(-f[a][3], q3, va[a]); vb[a] = fma(-f[a][3], r3, vb[a]);
+        }
+#pragma unroll
+        for (int a = 0; a < AMAX; ++a) {
+          *pa[a] = va[a];
+          *pb[a] = vb[a];
+        }
       }
     }
     __syncthreads();
   }
-  // Back-substitution by warp 0, column-oriented:  x_j = (rhs'_j - acc_j) / d_j, then
-  // acc_i += A[j][i] x_j for the rows i < j this lane owns (i = lane mod 32).
+  tk2 = clock64();
+  // Back-substitution by warp 0: x_j = (rhs'_j - sum_{i>j} A[i][j] x_i) / d_j; column j is
+  // contiguous, the sum is a warp dot product.
   if (warp == 0) {
-    const int rN = (NL * (NL + 1)) / 2;
-    double accr[BMAX];
-#pragma unroll
-    for (int bb = 0; bb < BMAX; ++bb) accr[bb] = 0.0;
     for (int j = NL - 1; j >= 0; --j) {
-      const int rj = (j * (j + 1)) / 2;
-      double rowv[BMAX];
+      const int cp = COLPTR(j) - j;
+      double s0 = 0.0;
 #pragma unroll
-      for (int bb = 0; bb < BMAX; ++bb) {
-        const int i = lane + 32 * bb;
-        rowv[bb] = i < j ? L[rj + i] : 0.0;
+      for (int bb = 0; bb < AMAX; ++bb) {
+        const int i = j + 1 + lane + 32 * bb;
+        if (i < NL) s0 = fma(L[cp + i], x[i], s0);
       }
-      double a = 0.0;
 #pragma unroll
-      for (int bb = 0; bb < BMAX; ++bb) if (bb == (j >> 5)) a = accr[bb];
-      double xj = (L[rN + j] - a) * dinv[j];
-      xj = __shfl_sync(0xffffffffu, xj, j & 31);
-      if (lane == (j & 31)) x[j] = xj;
-#pragma unroll
-      for (int bb = 0; bb < BMAX; ++bb) accr[bb] = fma(rowv[bb], xj, accr[bb]);
+      for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      if (lane == 0) x[j] = (L[cp + NL] - s0) * dinv[j];
+      __syncwarp();
     }
   }
   __syncthreads();
+#undef COLPTR
+  tk3 = clock64();
   // y_c, candidate camera parameters, camera-side partial sums.
   double lin = 0.0, dn2 = 0.0, quad = 0.0;
   for (int i = tid; i < NL; i += kSolveThreads) {
@@ -952,13 +1027,13 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
     const double delta = -y * sc[i];
     dn2 += delta * delta;
     // quad: y^T U_s y restricted to this row (both triangles)
-    const int ci = P.live_cam[i];
+    const int ci = s_cam[i];
     const double* U = ps.comm + ci * kCamRec;
     const int o0 = P.live_off[ci], n = P.live_off[ci + 1] - o0;
-    const int ki = P.live_kk[i];
+    const int ki = s_kk[i];
     double row = 0.0;
     for (int t = 0; t < n; ++t) {
-      const int jj = o0 + t, kj = P.live_kk[jj];
+      const int jj = o0 + t, kj = s_kk[jj];
       const double u = ki <= kj ? cam_block(U, ki, kj) : cam_block(U, kj, ki);
       row += sc[i] * sc[jj] * u * x[jj];
     }
@@ -987,6 +1062,9 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
   if (tid == 0) {
     st->cam_lin = t_lin; st->cam_quad = t_quad; st->cam_dn2 = t_dn2; st->cam_xn2 = t_xn2;
     st->solve_ok = s_ok;
+    if (prof)
+      printf("k_solve cycles: assemble %lld  ldlt %lld  backsub %lld  tail %lld\n", tk1 - tk0,
+             tk2 - tk1, tk3 - tk2, clock64() - tk3);
   }
 }
 
