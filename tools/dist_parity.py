@@ -1,0 +1,44 @@
+"""Multi-GPU parity: frames sharded over the ranks must reproduce the single-GPU solve
+(and therefore the oracle) — same iteration count, per-iteration cost to 1e-9 relative."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+from tscm_calib_b200 import capi, synth
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+local = int(os.environ.get("LOCAL_RANK", rank))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+ok = True
+for cfg, frames in ((2, 200), (3, 600)):
+    sp = synth.config(cfg, num_frames=frames)
+    opt = capi.default_options()
+    prob, fr = synth.shard_frames(sp, rank, world)
+    s = capi.Solver(prob, opt, device=local)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    s.attach_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
+    s.set_parameters(sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt[fr])
+    res = s.run()
+    intr, cam_rt, board_rt = s.get_parameters()
+    s.close()
+    if rank == 0:
+        a, b, c, ref = capi.solve(sp.problem, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt, opt, device=local)
+        same_iters = res.num_iterations == ref.num_iterations and res.termination == ref.termination
+        n = min(len(res.cost), len(ref.cost))
+        cost_rel = float(np.max(np.abs(res.cost[:n] - ref.cost[:n]) / ref.cost[:n]))
+        p_rel = max(float(np.max(np.abs(intr - a) / (np.abs(a) + 1e-9))),
+                    float(np.max(np.abs(cam_rt - b) / (np.abs(b) + 1e-9))),
+                    float(np.max(np.abs(board_rt - c[fr]) / (np.abs(c[fr]) + 1e-9))))
+        good = same_iters and cost_rel < 1e-9 and p_rel < 1e-7
+        ok = ok and good
+        print(f"cfg{cfg} world={world}: iters {res.num_iterations}/{ref.num_iterations} {res.termination} "
+              f"cost_rel {cost_rel:.2e} param_rel {p_rel:.2e} -> {'OK' if good else 'MISMATCH'}", flush=True)
+dist.barrier()
+dist.destroy_process_group()
+if rank == 0:
+    print("DIST PARITY", "PASS" if ok else "FAIL")

@@ -1,0 +1,19 @@
+#!/bin/bash
+# Multi-GPU visit: N ranks over NCCL (weak and strong), plus N=1 for reference.
+N=${N:-2}
+mkdir -p gpurun_out
+nvidia-smi -L > gpurun_out/smi_L.txt 2>&1
+python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/bench_n${N}_weak.json 2> gpurun_out/bench_n${N}_weak.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 30 --warmup 5 --scaling strong > gpurun_out/bench_n${N}_strong.json 2> gpurun_out/bench_n${N}_strong.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tools/dist_parity.py > gpurun_out/dist_parity_n${N}.log 2>&1
+for f in gpurun_out/bench_n1.json gpurun_out/bench_n${N}_weak.json gpurun_out/bench_n${N}_strong.json; do python - "$f" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1], {k: d.get(k) for k in ('n_gpus','scaling','value','ms_per_step','lm_iterations_per_sec')}, 'e2e', d.get('e2e',{}).get('lm_iterations_per_sec'))
+except Exception as e:
+    print(sys.argv[1], 'FAILED', e)
+PY
+done
+tail -5 gpurun_out/bench_n${N}_weak.err; tail -12 gpurun_out/dist_parity_n${N}.log

@@ -48,3 +48,28 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(res.stderr)
     return LIB
+
+
+HOST = os.path.join(_HERE, "host")
+HOST_DEMO = os.path.join(HOST, "host_demo")
+HOST_SOURCES = ["host_demo.cpp", "multi_calib_b200.cpp", "ts_camera.cpp"]
+HOST_HEADERS = ["multi_calib_b200.h", "ts_camera.h", "cv_compat.h"]
+
+
+def build_host(force: bool = False) -> str:
+    """Compile the C++ drop-in adapters (TripleSphereCamera / MultiCalib shaped) and their
+    demo driver against libtscm_b200.so."""
+    build_cuda()
+    deps = [os.path.join(HOST, f) for f in HOST_SOURCES + HOST_HEADERS] + [LIB]
+    if not force and os.path.exists(HOST_DEMO) and \
+            all(os.path.getmtime(d) <= os.path.getmtime(HOST_DEMO) for d in deps):
+        return HOST_DEMO
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", HOST_DEMO] + \
+          [os.path.join(HOST, f) for f in HOST_SOURCES] + \
+          ["-L" + _HERE, "-ltscm_b200", "-Wl,-rpath,$ORIGIN/.."]
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise RuntimeError("host adapter build failed:\n" + res.stdout + res.stderr)
+    return HOST_DEMO

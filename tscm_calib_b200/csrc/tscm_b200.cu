@@ -124,8 +124,8 @@ struct tscm_solver {
   double* d_dbg_rhs = nullptr;
   SchurArgs schur{};
   int schur_nblk = 0, schur_nt = 256, schur_ept = 20;
-  size_t schur_smem = 0, solve_smem = 0, eval_smem = 0, eval2_smem = 0;
-  int eval_variant = 2;
+  size_t schur_smem = 0, solve_smem = 0, eval_smem = 0, eval2_smem = 0, eval3_smem = 0;
+  int eval_variant = 3;
   int prof = 0;
   int bs_nblk = 0, fg_nblk = 0;
   // graph of one LM iteration
@@ -217,15 +217,18 @@ int validate_problem(const tscm_problem* p) {
   return TSCM_OK;
 }
 
-// The residual + Jacobian + normal-equation kernel (variant 2 = shared rows, default;
-// variant 1 = independent slices, kept for A/B timing: TSCM_EVAL_VARIANT=1).
+// The residual + Jacobian + normal-equation kernel.  Variant 3 (default) = warp-specialised
+// producers/consumers; 2 = shared rows, symmetric warps; 1 = independent slices.  The older
+// variants are kept for A/B timing (TSCM_EVAL_VARIANT=1|2).
 void launch_eval_kernel(tscm_solver* s, int which) {
   const DeviceProblem& P = s->P;
   if (s->eval_variant == 1) {
     dim3 grid((P.V + kEvalThreads - 1) / kEvalThreads, 4);
     k_eval<<<grid, kEvalThreads, s->eval_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->lm);
-  } else {
+  } else if (s->eval_variant == 2) {
     k_eval2<<<(P.V + 31) / 32, 128, s->eval2_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->lm);
+  } else {
+    k_eval3<<<(P.V + 31) / 32, kE3Threads, s->eval3_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->lm, s->prof);
   }
 }
 
@@ -565,7 +568,12 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   s->eval2_smem = (size_t)(2 * kE2Group * kE2Elems * 32 + kFcElems * 32 + 2 * K) * sizeof(double) +
                   (size_t)C * sizeof(CamConst);
   if (const char* pv = getenv("TSCM_PROF")) s->prof = atoi(pv);
-  if (const char* ev = getenv("TSCM_EVAL_VARIANT")) s->eval_variant = atoi(ev) == 1 ? 1 : 2;
+  s->eval3_smem = (size_t)(2 * kE3Group * kE2Elems * 32 + 2 * K) * sizeof(double) +
+                  (size_t)C * sizeof(CamConst);
+  if (const char* ev = getenv("TSCM_EVAL_VARIANT")) {
+    const int e = atoi(ev);
+    if (e >= 1 && e <= 3) s->eval_variant = e;
+  }
   TRY_RC(s->alloc(&s->schur.frame_rec, (size_t)kFrameRec * s->schur.Fpad));
   TRY_RC(s->alloc(&s->d_Spart, (size_t)s->schur_nblk * P.Q));
   TRY_RC(s->alloc(&s->d_rpart, (size_t)s->schur_nblk * NL));
@@ -599,6 +607,7 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   TRY_RC(set_smem((const void*)k_solve<7>, s->solve_smem));
   TRY_RC(set_smem((const void*)k_eval, s->eval_smem));
   TRY_RC(set_smem((const void*)k_eval2, s->eval2_smem));
+  TRY_RC(set_smem((const void*)k_eval3, s->eval3_smem));
 
   TRY_RC(tscm_solver_set_observations(s, p->obs_xy));
 #undef TRY_RC

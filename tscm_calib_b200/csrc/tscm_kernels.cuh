@@ -408,6 +408,202 @@ k_eval2(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
   }
 }
 
+// ---------------------------------------------------------------------------
+// K1+K2, third form (default): warp-specialised.  A CTA owns 32 views (lane =
+// view) and runs 4 CONSUMER warps (one Gram slice each, accumulators in
+// registers) plus 8 PRODUCER warps.  Per group of 8 corners, producer p
+// evaluates corner j0 + p of every lane's view (projection, residual, analytic
+// Jacobian, loss) and publishes the 42-double row to a double-buffered staging
+// area [buffer][corner][element][lane]; the consumers fold the previous group
+// at the same time.  One __syncthreads per group.  The producers' long
+// dependent FP64 chains (3 sqrt + reciprocals, ~25-cycle FP64 latency) are
+// hidden behind the consumers' independent FMAs on the same SM sub-partition
+// (warps 0-3 = consumers, one per sub-partition; two producers on each).
+// A consumer folds a corner as two rank-1 sweeps (u row, then v row) so that
+// consecutive FMAs on one accumulator are a full sweep apart, and loads the
+// operands of the next sweep-but-one while the current sweep runs.
+// ---------------------------------------------------------------------------
+constexpr int kE3Group = 8;
+constexpr int kE3Consumers = 4;
+constexpr int kE3Threads = 32 * (kE3Consumers + kE3Group);   // 384
+
+// operand vector of one residual row for a consumer role; `row` points at element 0
+// of that row (Ju: rows, Jv: rows + 20 * 32)
+template <int ROLE>
+__device__ __forceinline__ void e3_load(const double* __restrict__ row, int lane, double* x) {
+  if (ROLE == 0) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) x[k] = row[k * 32 + lane];
+  } else {
+    constexpr int base = ROLE == 1 ? 0 : 6;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x[k] = row[(base + k) * 32 + lane];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[6 + k] = row[(12 + k) * 32 + lane];
+  }
+}
+
+template <int ROLE>
+__device__ __forceinline__ void e3_sweep(const double* x, double* __restrict__ acc) {
+  if (ROLE == 0) {
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int b = a; b < 6; ++b) acc[tri6(a, b)] = fma(x[a], x[b], acc[tri6(a, b)]);
+#pragma unroll
+      for (int b = 0; b < 6; ++b) acc[21 + a * 6 + b] = fma(x[a], x[6 + b], acc[21 + a * 6 + b]);
+    }
+  } else if (ROLE == 2) {
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = a; b < 6; ++b) acc[tri6(a, b)] = fma(x[a], x[b], acc[tri6(a, b)]);
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = a; b < 8; ++b) acc[21 + tri8(a, b)] = fma(x[6 + a], x[6 + b], acc[21 + tri8(a, b)]);
+  } else {
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a * 8 + b] = fma(x[a], x[6 + b], acc[a * 8 + b]);
+  }
+}
+
+template <int ROLE>
+__device__ __forceinline__ void e3_consume_group(const double* __restrict__ buf, int lane,
+                                                 double* __restrict__ acc) {
+  constexpr int kRow = kE2Elems * 32;
+  double xu[14], xv[14];
+  e3_load<ROLE>(buf, lane, xu);
+  e3_load<ROLE>(buf + 20 * 32, lane, xv);
+#pragma unroll 1
+  for (int o = 0; o < kE3Group; ++o) {
+    const double* nxt = buf + (o + 1 < kE3Group ? o + 1 : o) * kRow;
+    e3_sweep<ROLE>(xu, acc);
+    if (ROLE == 2) { acc[57] += buf[o * kRow + 40 * 32 + lane]; acc[58] += buf[o * kRow + 41 * 32 + lane]; }
+    e3_load<ROLE>(nxt, lane, xu);              // next corner's u row, hidden behind the v sweep
+    e3_sweep<ROLE>(xv, acc);
+    e3_load<ROLE>(nxt + 20 * 32, lane, xv);    // next corner's v row, hidden behind the next u sweep
+  }
+}
+
+__global__ void __launch_bounds__(kE3Threads, 1)
+k_eval3(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which, LmOptions opt,
+        int prof) {
+  if (which < 2 && st->done) return;
+  const long long t_start = clock64();
+  long long t_work = 0;
+  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
+  const ParamSet& ps = sel ? ps1 : ps0;
+  extern __shared__ __align__(16) double s_mem[];
+  double* s_rows = s_mem;                                             // [2][8][42][32]
+  double* s_board = s_rows + 2 * kE3Group * kE2Elems * 32;            // [K][2]
+  CamConst* s_cam = reinterpret_cast<CamConst*>(s_board + 2 * P.K);   // [C]
+  for (int i = threadIdx.x; i < 2 * P.K; i += blockDim.x) s_board[i] = P.board_xy[i];
+  {
+    const int n = P.C * (int)(sizeof(CamConst) / sizeof(double));
+    const double* src = reinterpret_cast<const double*>(ps.cam);
+    double* dst = reinterpret_cast<double*>(s_cam);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v0 = blockIdx.x * 32 + lane;
+  const bool valid = v0 < P.V;
+  const int v = valid ? v0 : P.V - 1;
+  __syncthreads();
+  const int ngroups = (P.K + kE3Group - 1) / kE3Group;
+  constexpr int kBuf = kE3Group * kE2Elems * 32;
+
+  // Register re-partition between the warpgroups (sm_90a+/sm_100a setmaxnreg): the
+  // kernel launches with 168 registers per thread (384 threads); the two producer
+  // warpgroups release 24 each, the consumer warpgroup takes 48 more so that its 59
+  // FP64 accumulators and two operand sets live in registers without spilling.
+  if (warp >= kE3Consumers) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 144;");
+    // ------------------------------ producer ------------------------------------
+    const int p = warp - kE3Consumers;
+    const CamConst& cc = s_cam[P.view_camera[v]];
+    const double2* obs = P.obsT + v;
+    FrameConst fc;
+    make_frame_const(ps.board_rt + 6 * P.view_frame[v], fc);
+    for (int g = 0; g <= ngroups; ++g) {
+      const long long tw0 = clock64();
+      if (g < ngroups) {
+        const int j = g * kE3Group + p;
+        double* mine = s_rows + (g & 1) * kBuf + p * (kE2Elems * 32);
+        if (j < P.K && valid) {
+          const double2 uv = obs[(size_t)j * P.Vpad];
+          ObsRow o;
+          obs_jacobian<true, true, true>(cc, fc, s_board[2 * j], s_board[2 * j + 1], uv.x, uv.y, o);
+          double err;
+          const double half_rho = obs_apply_loss<0, 19>(opt.loss_type, opt.loss_scale, o, &err);
+#pragma unroll
+          for (int k = 0; k < 20; ++k) { mine[k * 32 + lane] = o.Ju[k]; mine[(20 + k) * 32 + lane] = o.Jv[k]; }
+          mine[40 * 32 + lane] = half_rho;
+          mine[41 * 32 + lane] = err;
+        } else {
+#pragma unroll
+          for (int k = 0; k < kE2Elems; ++k) mine[k * 32 + lane] = 0.0;
+        }
+      }
+      t_work += clock64() - tw0;
+      __syncthreads();
+    }
+    if (prof && blockIdx.x == 0 && lane == 0 && (p == 0 || p == 5))
+      printf("k_eval3 producer %d: work %lld cycles over %d groups, total %lld\n", p, t_work, ngroups,
+             clock64() - t_start);
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    // ------------------------------ consumer ------------------------------------
+    double acc[59];
+#pragma unroll
+    for (int i = 0; i < 59; ++i) acc[i] = 0.0;
+    for (int g = 0; g <= ngroups; ++g) {
+      const long long tw0 = clock64();
+      if (g > 0) {
+        const double* buf = s_rows + ((g - 1) & 1) * kBuf;
+        if (warp == 0) e3_consume_group<0>(buf, lane, acc);
+        else if (warp == 1) e3_consume_group<1>(buf, lane, acc);
+        else if (warp == 2) e3_consume_group<2>(buf, lane, acc);
+        else e3_consume_group<3>(buf, lane, acc);
+      }
+      t_work += clock64() - tw0;
+      __syncthreads();
+    }
+    if (prof && blockIdx.x == 0 && lane == 0)
+      printf("k_eval3 consumer %d: work %lld cycles over %d groups, total %lld\n", warp, t_work,
+             ngroups, clock64() - t_start);
+    // stage the per-view records [view][212] in shared memory (the row buffers are free now)
+    double* rec = s_rows + lane * kViewStride;
+    if (warp == 0) {
+#pragma unroll
+      for (int i = 0; i < 57; ++i) rec[kOffBB + i] = acc[i];
+    } else if (warp == 1) {
+#pragma unroll
+      for (int i = 0; i < 48; ++i) rec[kOffBI + i] = acc[i];
+    } else if (warp == 2) {
+#pragma unroll
+      for (int i = 0; i < 21; ++i) rec[kOffCC + i] = acc[i];
+#pragma unroll
+      for (int i = 0; i < 36; ++i) rec[kOffII + i] = acc[21 + i];
+      rec[kOffCost] = acc[57];
+      rec[kOffErr] = acc[58];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 48; ++i) rec[kOffCI + i] = acc[i];
+    }
+  }
+  __syncthreads();
+  // coalesced copy-out: the 32 records of this CTA are contiguous in G
+  {
+    const int nv = min(32, P.V - blockIdx.x * 32);
+    double* dst = ps.G + (size_t)blockIdx.x * 32 * kViewStride;
+    const int n = nv * kViewStride;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = s_rows[i];
+  }
+}
+
 // Inspection kernel: one thread per observation, full residual + Jacobian rows
 // in the reference's column order (camera_rt 6, chessboard_rt 6, intrinsic 9).
 __global__ void k_eval_rows(DeviceProblem P, ParamSet ps, LmOptions opt, double* residuals,
