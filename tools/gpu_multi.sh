@@ -3,10 +3,10 @@
 N=${N:-2}
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/smi_L.txt 2>&1
-python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/bench_n${N}_weak.json 2> gpurun_out/bench_n${N}_weak.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 30 --warmup 5 --scaling strong > gpurun_out/bench_n${N}_strong.json 2> gpurun_out/bench_n${N}_strong.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tools/dist_parity.py > gpurun_out/dist_parity_n${N}.log 2>&1
+timeout 150 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/bench_n${N}_weak.json 2> gpurun_out/bench_n${N}_weak.err
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 30 --warmup 5 --scaling strong > gpurun_out/bench_n${N}_strong.json 2> gpurun_out/bench_n${N}_strong.err
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 tools/dist_parity.py > gpurun_out/dist_parity_n${N}.log 2>&1
 for f in gpurun_out/bench_n1.json gpurun_out/bench_n${N}_weak.json gpurun_out/bench_n${N}_strong.json; do python - "$f" <<'PY'
 import json, sys
 try:

@@ -112,7 +112,6 @@ struct tscm_solver {
   double2* d_obsT = nullptr;
   double* d_scale_e = nullptr;
   double* d_scale_c = nullptr;
-  double* d_cam_part = nullptr;
   double* d_Spart = nullptr;
   double* d_rpart = nullptr;
   double* d_Sr = nullptr;
@@ -120,12 +119,16 @@ struct tscm_solver {
   double* d_bs_part = nullptr;
   double* d_gmax_part = nullptr;
   double* d_xn2_part = nullptr;
+  unsigned int* d_ticket = nullptr;
   double* d_dbg_lhs = nullptr;
   double* d_dbg_rhs = nullptr;
   SchurArgs schur{};
+  Schur2Args schur2{};
+  bool schur2_ok = false;
+  int schur2_nt = 0;
+  size_t schur2_smem = 0;
   int schur_nblk = 0, schur_nt = 256, schur_ept = 20;
-  size_t schur_smem = 0, solve_smem = 0, eval_smem = 0, eval2_smem = 0, eval3_smem = 0;
-  int eval_variant = 3;
+  size_t schur_smem = 0, solve_smem = 0, eval3_smem = 0;
   int prof = 0;
   int bs_nblk = 0, fg_nblk = 0;
   // graph of one LM iteration
@@ -217,34 +220,32 @@ int validate_problem(const tscm_problem* p) {
   return TSCM_OK;
 }
 
-// The residual + Jacobian + normal-equation kernel.  Variant 3 (default) = warp-specialised
-// producers/consumers; 2 = shared rows, symmetric warps; 1 = independent slices.  The older
-// variants are kept for A/B timing (TSCM_EVAL_VARIANT=1|2).
+// The residual + Jacobian + normal-equation kernel (warp-specialised k_eval3).
 void launch_eval_kernel(tscm_solver* s, int which) {
   const DeviceProblem& P = s->P;
-  if (s->eval_variant == 1) {
-    dim3 grid((P.V + kEvalThreads - 1) / kEvalThreads, 4);
-    k_eval<<<grid, kEvalThreads, s->eval_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->lm);
-  } else if (s->eval_variant == 2) {
-    k_eval2<<<(P.V + 31) / 32, 128, s->eval2_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->lm);
-  } else {
-    k_eval3<<<(P.V + 31) / 32, kE3Threads, s->eval3_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->lm, s->prof);
-  }
+  k_eval3<<<(P.V + 31) / 32, kE3Threads, s->eval3_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state,
+                                                                    which, s->lm, s->prof);
 }
 
 // which: 0 = current, 1 = candidate (relative to st->cur); 2/3 = absolute set 0/1.
-void launch_evaluation(tscm_solver* s, int which, int initial) {
+// prep: run k_prep_cams first (the iteration graph does not: k_solve already wrote the
+// candidate's constants).  decide: fold the accept/reject decision into the tail block
+// (single GPU; with several GPUs the records are all-reduced first and k_decide follows).
+void launch_evaluation(tscm_solver* s, int which, int initial, bool prep = true, bool decide = false) {
   const DeviceProblem& P = s->P;
   cudaStream_t st = s->stream;
-  k_prep_cams<<<(P.C + 31) / 32, 32, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which);
+  if (prep) {
+    k_prep_cams<<<(P.C + 31) / 32, 32, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which);
+    s->launches += 1;
+  }
   launch_eval_kernel(s, which);
-  k_reduce_cam_a<<<P.nchunk, 128, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->d_cam_part);
-  k_reduce_cam_b<<<P.C, 128, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->d_cam_part);
-  k_frame_grad<<<s->fg_nblk, 256, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which,
-                                           s->d_gmax_part, s->d_xn2_part);
-  k_pack<<<1, 256, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which, s->d_bs_part, s->bs_nblk,
-                            s->d_gmax_part, s->d_xn2_part, s->fg_nblk, initial);
-  s->launches += 6;
+  PostArgs a;
+  a.gmax_part = s->d_gmax_part; a.xn2_part = s->d_xn2_part;
+  a.bs_part = s->d_bs_part; a.bs_nblk = s->bs_nblk; a.fg_nblk = s->fg_nblk;
+  a.ticket = s->d_ticket; a.initial = initial; a.decide = decide ? 1 : 0;
+  k_post_eval<<<P.C + s->fg_nblk, kPostThreads, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which,
+                                                            s->lm, s->trace, a);
+  s->launches += 2;
 }
 
 // Global sums of the evaluation record.  The record lives in ps[sel].comm; the
@@ -270,7 +271,12 @@ int launch_eval_allreduce(tscm_solver* s, int which) {
 void launch_schur(tscm_solver* s, double radius_override) {
   SchurArgs a = s->schur;
   a.radius_override = radius_override;
-  if (s->schur_ept == 1)
+  if (s->schur2_ok) {
+    Schur2Args b = s->schur2;
+    b.a = a;
+    k_schur2<<<s->schur_nblk, s->schur2_nt, s->schur2_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
+                                                                        s->d_state, s->lm, b);
+  } else if (s->schur_ept == 1)
     k_schur<1, 512><<<s->schur_nblk, s->schur_nt, s->schur_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
                                                                              s->d_state, s->lm, a);
   else
@@ -316,15 +322,18 @@ int launch_iteration(tscm_solver* s) {
   if (rc) return rc;
   launch_solve(s, 0.0, false);
   launch_backsub(s);
-  launch_evaluation(s, 1, 0);
-  rc = launch_eval_allreduce(s, 1);
-  if (rc) return rc;
-  k_decide<<<1, 32, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, s->trace);
-  s->launches += 1;
+  const bool single = s->num_ranks <= 1;
+  launch_evaluation(s, 1, 0, /*prep=*/false, /*decide=*/single);
+  if (!single) {
+    rc = launch_eval_allreduce(s, 1);
+    if (rc) return rc;
+    k_decide<<<1, 32, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, s->trace);
+    s->launches += 1;
+  }
   return TSCM_OK;
 }
 
-constexpr int kLaunchesPerIteration = 11;
+int launches_per_iteration(const tscm_solver* s) { return s->num_ranks <= 1 ? 6 : 7; }
 
 int ensure_graph(tscm_solver* s) {
   if (!s->graph_dirty && s->graph_exec) return TSCM_OK;
@@ -479,26 +488,25 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     std::vector<int> fill(frame_ptr.begin(), frame_ptr.end() - 1);
     for (int v = 0; v < V; ++v) frame_views[fill[p->view_frame[v]]++] = v;   // camera order kept
   }
-  constexpr int kChunk = 64;
-  std::vector<int> chunk_cam, chunk_begin, cam_chunk_begin(C + 1, 0);
-  for (int c = 0; c < C; ++c) {
-    cam_chunk_begin[c] = (int)chunk_cam.size();
-    for (int v0 = cam_view_begin[c]; v0 < cam_view_begin[c + 1]; v0 += kChunk) {
-      chunk_cam.push_back(c);
-      chunk_begin.push_back(v0);
+  // camera-partial slots: one per (evaluation CTA of 32 views, distinct camera in it)
+  const int nblk_eval = (V + 31) / 32;
+  std::vector<int> blk_slot(nblk_eval + 1, 0), cam_slot_begin(C + 1, 0);
+  {
+    std::vector<int> slot_cam;
+    for (int b = 0; b < nblk_eval; ++b) {
+      blk_slot[b] = (int)slot_cam.size();
+      int last = -1;
+      for (int v = 32 * b; v < std::min(V, 32 * b + 32); ++v)
+        if (p->view_camera[v] != last) { last = p->view_camera[v]; slot_cam.push_back(last); }
     }
+    blk_slot[nblk_eval] = (int)slot_cam.size();
+    P.nslot = (int)slot_cam.size();
+    for (int c : slot_cam) cam_slot_begin[c + 1]++;
+    for (int c = 0; c < C; ++c) cam_slot_begin[c + 1] += cam_slot_begin[c];
+    // camera-major views => slots are camera-major too (checked, not assumed)
+    for (size_t i = 1; i < slot_cam.size(); ++i)
+      if (slot_cam[i] < slot_cam[i - 1]) { set_error("internal: slot table"); delete s; return TSCM_ERR_INVALID_ARGUMENT; }
   }
-  cam_chunk_begin[C] = (int)chunk_cam.size();
-  chunk_begin.push_back(V);
-  // chunk_begin[ch+1] must not cross a camera boundary: fix the last chunk of each camera
-  std::vector<int> chunk_end(chunk_cam.size());
-  for (size_t ch = 0; ch < chunk_cam.size(); ++ch)
-    chunk_end[ch] = std::min(chunk_begin[ch] + kChunk, cam_view_begin[chunk_cam[ch] + 1]);
-  // store as begin[ch], begin[ch+1] pairs by construction: consecutive chunks are contiguous
-  // because cameras with no views simply contribute no chunk.
-  for (size_t ch = 0; ch + 1 < chunk_cam.size(); ++ch)
-    if (chunk_end[ch] != chunk_begin[ch + 1]) { set_error("internal: chunk table"); delete s; return TSCM_ERR_INVALID_ARGUMENT; }
-  P.nchunk = (int)chunk_cam.size();
 
   if (NL > 216) {
     set_error("reduced system of %d live parameters exceeds this build's limit (216, i.e. 17 cameras)", NL);
@@ -523,9 +531,8 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   TRY_RC(s->put(&P.live_kk, live_kk));
   TRY_RC(s->put(&P.q_i, q_i));
   TRY_RC(s->put(&P.q_j, q_j));
-  TRY_RC(s->put(&P.chunk_cam, chunk_cam));
-  TRY_RC(s->put(&P.chunk_begin, chunk_begin));
-  TRY_RC(s->put(&P.cam_chunk_begin, cam_chunk_begin));
+  TRY_RC(s->put(&P.blk_slot, blk_slot));
+  TRY_RC(s->put(&P.cam_slot_begin, cam_slot_begin));
 
   // ---- buffers --------------------------------------------------------------
   TRY_RC(s->alloc(&s->d_obs_in, (size_t)V * K));
@@ -537,6 +544,7 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     TRY_RC(s->alloc(&s->ps[k].board_rt, (size_t)F * 6));
     TRY_RC(s->alloc(&s->ps[k].cam, (size_t)C));
     TRY_RC(s->alloc(&s->ps[k].G, (size_t)V * kViewStride));
+    TRY_RC(s->alloc(&s->ps[k].cam_part, (size_t)P.nslot * kCamRec));
     TRY_RC(s->alloc(&s->ps[k].comm, (size_t)C * kCamRec + kCommExtra));
     TRY_RC(s->alloc(&s->ps[k].gmax, 1));
   }
@@ -546,7 +554,6 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   }
   TRY_RC(s->alloc(&s->d_scale_e, (size_t)F * 6));
   TRY_RC(s->alloc(&s->d_scale_c, (size_t)C * 13));
-  TRY_RC(s->alloc(&s->d_cam_part, (size_t)P.nchunk * kCamRec));
   // Schur configuration: one 4x4 tile per thread up to 512 tiles, two beyond
   s->schur_ept = ntiles <= 512 ? 1 : 2;
   s->schur_nt = std::max(256, ((ntiles + s->schur_ept - 1) / s->schur_ept + 31) / 32 * 32);
@@ -564,25 +571,43 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
                   kSchurFB * 32 * sizeof(int);
   s->solve_smem = (size_t)((NL + 1) * (NL + 2) / 2 + 4 * NL + 4 + 4 * (NL + 1) + 2 * kSolveThreads + 8) * sizeof(double) +
                   (size_t)2 * NL * sizeof(short) + 16;
-  s->eval_smem = (size_t)2 * K * sizeof(double) + (size_t)C * sizeof(CamConst);
-  s->eval2_smem = (size_t)(2 * kE2Group * kE2Elems * 32 + kFcElems * 32 + 2 * K) * sizeof(double) +
-                  (size_t)C * sizeof(CamConst);
   if (const char* pv = getenv("TSCM_PROF")) s->prof = atoi(pv);
   s->eval3_smem = (size_t)(2 * kE3Group * kE2Elems * 32 + 2 * K) * sizeof(double) +
                   (size_t)C * sizeof(CamConst);
-  if (const char* ev = getenv("TSCM_EVAL_VARIANT")) {
-    const int e = atoi(ev);
-    if (e >= 1 && e <= 3) s->eval_variant = e;
-  }
   TRY_RC(s->alloc(&s->schur.frame_rec, (size_t)kFrameRec * s->schur.Fpad));
   TRY_RC(s->alloc(&s->d_Spart, (size_t)s->schur_nblk * P.Q));
   TRY_RC(s->alloc(&s->d_rpart, (size_t)s->schur_nblk * NL));
   s->schur.Spart = s->d_Spart; s->schur.rpart = s->d_rpart;
   s->schur.scale_e = s->d_scale_e; s->schur.scale_c = s->d_scale_c;
   TRY_RC(s->alloc(&s->d_Sr, (size_t)P.Q + NL));
+  {
+    // per-frame column descriptors for the pipelined Schur kernel
+    std::vector<int> col_ptr(F + 1, 0), col_src;
+    std::vector<short> col_g;
+    for (int f = 0; f < F; ++f) {
+      for (int q = frame_ptr[f]; q < frame_ptr[f + 1]; ++q) {
+        const int v = frame_views[q], m = p->view_camera[v];
+        const int n = live_off[m + 1] - live_off[m];
+        for (int k = 0; k < n; ++k) {
+          col_src.push_back(v * 16 + (n == 13 ? k : k + 6));
+          col_g.push_back((short)(live_off[m] + k));
+        }
+      }
+      col_ptr[f + 1] = (int)col_src.size();
+    }
+    TRY_RC(s->put(&s->schur2.col_ptr, col_ptr));
+    TRY_RC(s->put(&s->schur2.col_src, col_src));
+    TRY_RC(s->put(&s->schur2.col_g, col_g));
+    const int cons = (ntiles + 31) / 32 * 32;
+    s->schur2_nt = kSchurFB * 32 + cons;
+    s->schur2_smem = (size_t)(2 * (2 * kSchurFB * 6 * s->schur.NLp + kSchurFB * 6) + kSchurFB * 64) * sizeof(double);
+    s->schur2_ok = s->schur2_nt <= 640 && s->schur2_smem <= (size_t)prop.sharedMemPerBlockOptin &&
+                   V < (1 << 27) && !getenv("TSCM_SCHUR_V1");
+  }
   TRY_RC(s->alloc(&s->d_yc, (size_t)NL));
   s->bs_nblk = (F + kBacksubThreads / 32 - 1) / (kBacksubThreads / 32);
-  s->fg_nblk = (F * 6 + 255) / 256;
+  s->fg_nblk = (F * 6 + kPostThreads - 1) / kPostThreads;
+  TRY_RC(s->alloc(&s->d_ticket, 1));
   TRY_RC(s->alloc(&s->d_bs_part, (size_t)4 * s->bs_nblk));
   TRY_RC(s->alloc(&s->d_gmax_part, (size_t)s->fg_nblk));
   TRY_RC(s->alloc(&s->d_xn2_part, (size_t)s->fg_nblk));
@@ -600,13 +625,12 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
               s->solve_smem, (size_t)prop.sharedMemPerBlockOptin);
     tscm_solver_destroy(s); return TSCM_ERR_UNSUPPORTED;
   }
+  if (s->schur2_ok) TRY_RC(set_smem((const void*)k_schur2, s->schur2_smem));
   TRY_RC(set_smem((const void*)k_schur<1, 512>, s->schur_smem));
   TRY_RC(set_smem((const void*)k_schur<2, 768>, s->schur_smem));
   TRY_RC(set_smem((const void*)k_solve<2>, s->solve_smem));
   TRY_RC(set_smem((const void*)k_solve<4>, s->solve_smem));
   TRY_RC(set_smem((const void*)k_solve<7>, s->solve_smem));
-  TRY_RC(set_smem((const void*)k_eval, s->eval_smem));
-  TRY_RC(set_smem((const void*)k_eval2, s->eval2_smem));
   TRY_RC(set_smem((const void*)k_eval3, s->eval3_smem));
 
   TRY_RC(tscm_solver_set_observations(s, p->obs_xy));
@@ -691,7 +715,7 @@ int tscm_solver_run(tscm_solver* s, tscm_summary* summary) {
   while (launched < s->options.max_num_iterations) {
     const int n = std::min(batch, s->options.max_num_iterations - launched);
     for (int k = 0; k < n; ++k) CUDA_TRY(cudaGraphLaunch(s->graph_exec, s->stream));
-    s->launches += (int64_t)n * kLaunchesPerIteration;
+    s->launches += (int64_t)n * launches_per_iteration(s);
     launched += n;
     if ((rc = fetch_state(s))) return rc;
     if (s->h_state->done) break;
@@ -787,7 +811,7 @@ int tscm_solver_eval_jacobian(tscm_solver* s, double* residuals, double* jacobia
     std::vector<double> comm((size_t)s->C * kCamRec);
     CUDA_TRY(cudaMemcpy(comm.data(), s->ps[cur].comm, comm.size() * sizeof(double), cudaMemcpyDeviceToHost));
     double c = 0.0;
-    for (int m = 0; m < s->C; ++m) c += comm[(size_t)m * kCamRec + (kOffCost - kOffCC)];
+    for (int m = 0; m < s->C; ++m) c += comm[(size_t)m * kCamRec + kCamCost];
     *cost = c;
   }
   return TSCM_OK;
@@ -846,11 +870,11 @@ int tscm_solver_reprojection_error(tscm_solver* s, double* per_camera, double* o
   CUDA_TRY(cudaMemcpy(cvb.data(), s->P.cam_view_begin, cvb.size() * sizeof(int), cudaMemcpyDeviceToHost));
   double sum = 0.0, cost = 0.0, total = 0.0;
   for (int m = 0; m < s->C; ++m) {
-    const double e = comm[(size_t)m * kCamRec + (kOffErr - kOffCC)];
+    const double e = comm[(size_t)m * kCamRec + kCamErr];
     const double n = (double)(cvb[m + 1] - cvb[m]) * s->K;
     if (per_camera) per_camera[m] = n > 0 ? e / n : 0.0;
     sum += e; total += n;
-    cost += comm[(size_t)m * kCamRec + (kOffCost - kOffCC)];
+    cost += comm[(size_t)m * kCamRec + kCamCost];
   }
   if (overall) *overall = total > 0 ? sum / total : 0.0;
   if (rms) *rms = total > 0 ? std::sqrt(2.0 * cost / total) : 0.0;
@@ -898,7 +922,7 @@ int tscm_solver_time_stage(tscm_solver* s, int stage, int repeats, double* ms_pe
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     CUDA_TRY(cudaEventRecord(e0, s->stream));
     for (int r = 0; r < repeats; ++r) CUDA_TRY(cudaGraphLaunch(s->graph_exec, s->stream));
-    s->launches += (int64_t)repeats * kLaunchesPerIteration;
+    s->launches += (int64_t)repeats * launches_per_iteration(s);
     CUDA_TRY(cudaEventRecord(e1, s->stream));
   }
   CUDA_TRY(cudaEventSynchronize(e1));

@@ -1,16 +1,16 @@
 // tscm_kernels.cuh — sm_100a FP64 kernels of the calibration solve.
 //
 // Stage map (reference stage each replaces):
-//   k_prep_cams, k_eval        K1+K2  Jet evaluation of multi_calib.h:146-195 for every
+//   k_prep_cams, k_eval3       K1+K2  Jet evaluation of multi_calib.h:146-195 for every
 //                                     residual block + SchurEliminator's E^T E / E^T F /
 //                                     F^T F / E^T b / F^T b products (multi_calib.cpp:162-207)
-//   k_reduce_cam_{a,b}         K2     per-camera F^T F, F^T b, cost
-//   k_schur, k_reduce_s        K3     SchurEliminator::Eliminate chunk loop
+//   k_post_eval                K2     per-camera F^T F, F^T b, cost; gradient max-norm
+//   k_schur2 (k_schur), k_reduce_s  K3  SchurEliminator::Eliminate chunk loop
 //   k_solve                    K4     DenseSchurComplementSolver (Eigen LLT) on the reduced
 //                                     camera system
 //   k_backsub                  K4     SchurEliminator::BackSubstitute + candidate point
-//   k_frame_grad, k_pack,
-//   k_decide                   K5     TrustRegionMinimizer / LevenbergMarquardtStrategy
+//   k_init, k_decide (or the
+//   tail of k_post_eval)       K5     TrustRegionMinimizer / LevenbergMarquardtStrategy
 //                                     control flow (accept/reject, radius, termination)
 #pragma once
 
@@ -22,7 +22,7 @@ namespace tscm {
 
 // ---------------------------------------------------------------------------
 // Device-resident LM state (one per solver).  Every kernel of the iteration
-// graph reads it; only k_solve / k_pack / k_decide / k_init write it.
+// graph reads it; only k_solve / k_post_eval / k_decide / k_init write it.
 // ---------------------------------------------------------------------------
 struct LmOptions {
   int max_num_iterations;
@@ -82,10 +82,12 @@ struct DeviceProblem {
   const short* live_kk;      // [NL] index inside the camera's [rt 6 | intr 7] block
   const short* q_i;          // [Q] row of packed upper entry q
   const short* q_j;          // [Q] col
-  const int* chunk_cam;      // [nchunk] camera of reduce chunk
-  const int* chunk_begin;    // [nchunk+1] view range of reduce chunk
-  const int* cam_chunk_begin;// [C+1]
-  int nchunk;
+  // camera-partial slots written by the evaluation kernel: CTA b (views 32b..32b+31)
+  // owns slots [blk_slot[b], blk_slot[b+1]), one per distinct camera among its views;
+  // views are camera-major, so camera c's slots are [cam_slot_begin[c], cam_slot_begin[c+1])
+  const int* blk_slot;       // [nblk+1]
+  const int* cam_slot_begin; // [C+1]
+  int nslot;
 };
 
 // One parameter set (there are two: current / candidate).
@@ -94,7 +96,8 @@ struct ParamSet {
   double* cam_rt;    // [C][6]
   double* board_rt;  // [F][6]
   CamConst* cam;     // [C] derived constants (k_prep_cams)
-  double* G;         // [V][kViewStride] per-view Gram records
+  double* G;         // [V][kViewStride] per-view records (BB | BC | BI)
+  double* cam_part;  // [nslot][kCamRec] camera-block partial sums of the evaluation kernel
   double* comm;      // [C*kCamRec + kCommExtra] (+ gmax stored separately)
   double* gmax;      // [1]
 };
@@ -115,301 +118,7 @@ __global__ void k_prep_cams(DeviceProblem P, ParamSet ps0, ParamSet ps1, const L
 }
 
 // ---------------------------------------------------------------------------
-// K1+K2: residual + analytic Jacobian + normal-equation blocks.
-// One lane per (view, slice); the lane streams through the K corners of its
-// view and keeps its slice of the 20x20 Gram matrix of [J | r] in registers, so
-// there is no cross-thread reduction at all.  Observations are read through the
-// corner-major transposed copy (coalesced across lanes = consecutive views).
-//   slice 0: BB + BC   slice 1: BI   slice 2: CC + II + cost + err   slice 3: CI
-// ---------------------------------------------------------------------------
-constexpr int kEvalThreads = 128;
-
-template <int SLICE>
-__device__ __forceinline__ void eval_view_slice(const DeviceProblem& P, const CamConst& cc,
-                                                const FrameConst& fc, const double* s_board,
-                                                int v, int loss_type, double loss_scale,
-                                                double* __restrict__ Gv) {
-  constexpr int NACC = (SLICE == 0) ? 57 : (SLICE == 1) ? 48 : (SLICE == 2) ? 59 : 48;
-  double acc[NACC];
-#pragma unroll
-  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
-
-  const double2* obs = P.obsT + v;
-  for (int j = 0; j < P.K; ++j) {
-    const double2 uv = obs[(size_t)j * P.Vpad];
-    const double X = s_board[2 * j], Y = s_board[2 * j + 1];
-    ObsRow o;
-    double err;
-    if (SLICE == 0) {
-      obs_jacobian<true, true, false>(cc, fc, X, Y, uv.x, uv.y, o);
-      if (loss_type) obs_apply_loss<0, 12>(loss_type, loss_scale, o, &err);
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-#pragma unroll
-        for (int b = a; b < 6; ++b)
-          acc[tri6(a, b)] += o.Ju[a] * o.Ju[b] + o.Jv[a] * o.Jv[b];
-#pragma unroll
-        for (int b = 0; b < 6; ++b)
-          acc[21 + a * 6 + b] += o.Ju[a] * o.Ju[6 + b] + o.Jv[a] * o.Jv[6 + b];
-      }
-    } else if (SLICE == 1) {
-      obs_jacobian<true, false, true>(cc, fc, X, Y, uv.x, uv.y, o);
-      if (loss_type) {
-        // columns 0..5 and 12..18 are live here
-        obs_apply_loss<0, 19>(loss_type, loss_scale, o, &err);
-      }
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b)
-          acc[a * 8 + b] += o.Ju[a] * o.Ju[12 + b] + o.Jv[a] * o.Jv[12 + b];
-    } else if (SLICE == 2) {
-      obs_jacobian<false, true, true>(cc, fc, X, Y, uv.x, uv.y, o);
-      const double half_rho = obs_apply_loss<6, 19>(loss_type, loss_scale, o, &err);
-      acc[57] += half_rho;
-      acc[58] += err;
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll
-        for (int b = a; b < 6; ++b)
-          acc[tri6(a, b)] += o.Ju[6 + a] * o.Ju[6 + b] + o.Jv[6 + a] * o.Jv[6 + b];
-#pragma unroll
-      for (int a = 0; a < 8; ++a)
-#pragma unroll
-        for (int b = a; b < 8; ++b)
-          acc[21 + tri8(a, b)] += o.Ju[12 + a] * o.Ju[12 + b] + o.Jv[12 + a] * o.Jv[12 + b];
-    } else {
-      obs_jacobian<false, true, true>(cc, fc, X, Y, uv.x, uv.y, o);
-      if (loss_type) obs_apply_loss<6, 19>(loss_type, loss_scale, o, &err);
-#pragma unroll
-      for (int a = 0; a < 6; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b)
-          acc[a * 8 + b] += o.Ju[6 + a] * o.Ju[12 + b] + o.Jv[6 + a] * o.Jv[12 + b];
-    }
-  }
-  if (SLICE == 0) {
-#pragma unroll
-    for (int i = 0; i < 57; ++i) Gv[kOffBB + i] = acc[i];
-  } else if (SLICE == 1) {
-#pragma unroll
-    for (int i = 0; i < 48; ++i) Gv[kOffBI + i] = acc[i];
-  } else if (SLICE == 2) {
-#pragma unroll
-    for (int i = 0; i < 21; ++i) Gv[kOffCC + i] = acc[i];
-#pragma unroll
-    for (int i = 0; i < 36; ++i) Gv[kOffII + i] = acc[21 + i];
-    Gv[kOffCost] = acc[57];
-    Gv[kOffErr] = acc[58];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 48; ++i) Gv[kOffCI + i] = acc[i];
-  }
-}
-
-__global__ void __launch_bounds__(kEvalThreads)
-k_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which,
-       LmOptions opt) {
-  if (which < 2 && st->done) return;
-  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
-  const ParamSet& ps = sel ? ps1 : ps0;
-  extern __shared__ double s_mem[];
-  double* s_board = s_mem;                                          // [K][2]
-  CamConst* s_cam = reinterpret_cast<CamConst*>(s_mem + 2 * P.K);   // [C]
-  for (int i = threadIdx.x; i < 2 * P.K; i += blockDim.x) s_board[i] = P.board_xy[i];
-  {
-    const int n = P.C * (int)(sizeof(CamConst) / sizeof(double));
-    const double* src = reinterpret_cast<const double*>(ps.cam);
-    double* dst = reinterpret_cast<double*>(s_cam);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-  }
-  __syncthreads();
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= P.V) return;
-  const int m = P.view_camera[v];
-  const CamConst& cc = s_cam[m];
-  FrameConst fc;
-  make_frame_const(ps.board_rt + 6 * P.view_frame[v], fc);
-  double* Gv = ps.G + (size_t)v * kViewStride;
-  const int slice = blockIdx.y;
-  if (slice == 0) eval_view_slice<0>(P, cc, fc, s_board, v, opt.loss_type, opt.loss_scale, Gv);
-  else if (slice == 1) eval_view_slice<1>(P, cc, fc, s_board, v, opt.loss_type, opt.loss_scale, Gv);
-  else if (slice == 2) eval_view_slice<2>(P, cc, fc, s_board, v, opt.loss_type, opt.loss_scale, Gv);
-  else {
-    if (cc.free_rt) {
-      eval_view_slice<3>(P, cc, fc, s_board, v, opt.loss_type, opt.loss_scale, Gv);
-    } else {
-      for (int i = 0; i < 48; ++i) Gv[kOffCI + i] = 0.0;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
-// K1+K2, second form (default): the four slice-warps of a CTA work on the SAME
-// 32 views (lane = view) and share the per-observation rows through shared
-// memory, so the projection and the Jacobian are computed once per observation
-// instead of once per slice.  Per group of 4 corners, warp w evaluates corner
-// j0 + w of every lane's view and publishes the row [J_u | r_u | J_v | r_v | 1/2 rho |
-// sqrt(s)] (42 doubles) to a double-buffered staging area laid out
-// [corner-in-group][element][lane] (bank-conflict free); after one barrier each
-// warp folds the 4 rows into its slice of the Gram matrix with plain FMAs.
-// ---------------------------------------------------------------------------
-constexpr int kE2Elems = 42;
-constexpr int kE2Group = 4;
-constexpr int kFcElems = 27;
-
-__device__ __forceinline__ double e2_ld(const double* rows, int e, int lane) { return rows[e * 32 + lane]; }
-
-template <int ROLE>
-__device__ __forceinline__ void eval2_consume(const double* __restrict__ rows, int lane,
-                                              double* __restrict__ acc) {
-  // element map: Ju[k] at k, Jv[k] at 20 + k (k = 0..19, 19 = residual), 40 cost, 41 err
-  if (ROLE == 0) {
-    double u[12], v[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) { u[k] = e2_ld(rows, k, lane); v[k] = e2_ld(rows, 20 + k, lane); }
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-#pragma unroll
-      for (int b = a; b < 6; ++b) acc[tri6(a, b)] = fma(v[a], v[b], fma(u[a], u[b], acc[tri6(a, b)]));
-#pragma unroll
-      for (int b = 0; b < 6; ++b)
-        acc[21 + a * 6 + b] = fma(v[a], v[6 + b], fma(u[a], u[6 + b], acc[21 + a * 6 + b]));
-    }
-  } else if (ROLE == 1 || ROLE == 3) {
-    constexpr int base = ROLE == 1 ? 0 : 6;
-    double u[6], v[6], ui[8], vi[8];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { u[k] = e2_ld(rows, base + k, lane); v[k] = e2_ld(rows, 20 + base + k, lane); }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { ui[k] = e2_ld(rows, 12 + k, lane); vi[k] = e2_ld(rows, 32 + k, lane); }
-#pragma unroll
-    for (int a = 0; a < 6; ++a)
-#pragma unroll
-      for (int b = 0; b < 8; ++b) acc[a * 8 + b] = fma(v[a], vi[b], fma(u[a], ui[b], acc[a * 8 + b]));
-  } else {
-    double u[6], v[6], ui[8], vi[8];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) { u[k] = e2_ld(rows, 6 + k, lane); v[k] = e2_ld(rows, 26 + k, lane); }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { ui[k] = e2_ld(rows, 12 + k, lane); vi[k] = e2_ld(rows, 32 + k, lane); }
-#pragma unroll
-    for (int a = 0; a < 6; ++a)
-#pragma unroll
-      for (int b = a; b < 6; ++b) acc[tri6(a, b)] = fma(v[a], v[b], fma(u[a], u[b], acc[tri6(a, b)]));
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int b = a; b < 8; ++b)
-        acc[21 + tri8(a, b)] = fma(vi[a], vi[b], fma(ui[a], ui[b], acc[21 + tri8(a, b)]));
-    acc[57] += e2_ld(rows, 40, lane);
-    acc[58] += e2_ld(rows, 41, lane);
-  }
-}
-
-__global__ void __launch_bounds__(128)
-k_eval2(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which, LmOptions opt) {
-  if (which < 2 && st->done) return;
-  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
-  const ParamSet& ps = sel ? ps1 : ps0;
-  extern __shared__ __align__(16) double s_mem[];
-  double* s_rows = s_mem;                                             // [2][4][42][32]
-  double* s_fc = s_rows + 2 * kE2Group * kE2Elems * 32;               // [27][32]
-  double* s_board = s_fc + kFcElems * 32;                             // [K][2]
-  CamConst* s_cam = reinterpret_cast<CamConst*>(s_board + 2 * P.K);   // [C]
-  for (int i = threadIdx.x; i < 2 * P.K; i += blockDim.x) s_board[i] = P.board_xy[i];
-  {
-    const int n = P.C * (int)(sizeof(CamConst) / sizeof(double));
-    const double* src = reinterpret_cast<const double*>(ps.cam);
-    double* dst = reinterpret_cast<double*>(s_cam);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int v0 = blockIdx.x * 32 + lane;
-  const bool valid = v0 < P.V;
-  const int v = valid ? v0 : P.V - 1;
-  if (warp == 0) {
-    FrameConst fc;
-    make_frame_const(ps.board_rt + 6 * P.view_frame[v], fc);
-    const double* fp = reinterpret_cast<const double*>(&fc);
-#pragma unroll
-    for (int e = 0; e < kFcElems; ++e) s_fc[e * 32 + lane] = fp[e];
-  }
-  __syncthreads();
-  const CamConst& cc = s_cam[P.view_camera[v]];
-  const double2* obs = P.obsT + v;
-
-  // One accumulator array for every role (a role uses a prefix of it); the role
-  // switch sits INSIDE the corner loop and the per-corner fold is not unrolled, so
-  // the whole kernel stays within the instruction cache: the producer code is
-  // shared by the four warps, each consumer variant is ~150 instructions.
-  double acc[59];
-#pragma unroll
-  for (int i = 0; i < 59; ++i) acc[i] = 0.0;
-
-  int parity = 0;
-  for (int j0 = 0; j0 < P.K; j0 += kE2Group, parity ^= 1) {
-    double* buf = s_rows + parity * (kE2Group * kE2Elems * 32);
-    {
-      const int j = j0 + warp;
-      double* mine = buf + warp * (kE2Elems * 32);
-      if (j < P.K && valid) {
-        FrameConst fc;
-        double* fp = reinterpret_cast<double*>(&fc);
-#pragma unroll
-        for (int e = 0; e < kFcElems; ++e) fp[e] = s_fc[e * 32 + lane];
-        const double2 uv = obs[(size_t)j * P.Vpad];
-        ObsRow o;
-        obs_jacobian<true, true, true>(cc, fc, s_board[2 * j], s_board[2 * j + 1], uv.x, uv.y, o);
-        double err;
-        const double half_rho = obs_apply_loss<0, 19>(opt.loss_type, opt.loss_scale, o, &err);
-#pragma unroll
-        for (int k = 0; k < 20; ++k) { mine[k * 32 + lane] = o.Ju[k]; mine[(20 + k) * 32 + lane] = o.Jv[k]; }
-        mine[40 * 32 + lane] = half_rho;
-        mine[41 * 32 + lane] = err;
-      } else {
-#pragma unroll
-        for (int k = 0; k < kE2Elems; ++k) mine[k * 32 + lane] = 0.0;
-      }
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll 1
-      for (int o = 0; o < kE2Group; ++o) eval2_consume<0>(buf + o * (kE2Elems * 32), lane, acc);
-    } else if (warp == 1) {
-#pragma unroll 1
-      for (int o = 0; o < kE2Group; ++o) eval2_consume<1>(buf + o * (kE2Elems * 32), lane, acc);
-    } else if (warp == 2) {
-#pragma unroll 1
-      for (int o = 0; o < kE2Group; ++o) eval2_consume<2>(buf + o * (kE2Elems * 32), lane, acc);
-    } else {
-#pragma unroll 1
-      for (int o = 0; o < kE2Group; ++o) eval2_consume<3>(buf + o * (kE2Elems * 32), lane, acc);
-    }
-  }
-  if (!valid) return;
-  double* Gv = ps.G + (size_t)v * kViewStride;
-  if (warp == 0) {
-#pragma unroll
-    for (int i = 0; i < 57; ++i) Gv[kOffBB + i] = acc[i];
-  } else if (warp == 1) {
-#pragma unroll
-    for (int i = 0; i < 48; ++i) Gv[kOffBI + i] = acc[i];
-  } else if (warp == 2) {
-#pragma unroll
-    for (int i = 0; i < 21; ++i) Gv[kOffCC + i] = acc[i];
-#pragma unroll
-    for (int i = 0; i < 36; ++i) Gv[kOffII + i] = acc[21 + i];
-    Gv[kOffCost] = acc[57];
-    Gv[kOffErr] = acc[58];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 48; ++i) Gv[kOffCI + i] = acc[i];
-  }
-}
-
-// ---------------------------------------------------------------------------
-// K1+K2, third form (default): warp-specialised.  A CTA owns 32 views (lane =
+// K1+K2: residual + analytic Jacobian + normal-equation blocks, warp-specialised.  A CTA owns 32 views (lane =
 // view) and runs 4 CONSUMER warps (one Gram slice each, accumulators in
 // registers) plus 8 PRODUCER warps.  Per group of 8 corners, producer p
 // evaluates corner j0 + p of every lane's view (projection, residual, analytic
@@ -423,6 +132,7 @@ k_eval2(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
 // consecutive FMAs on one accumulator are a full sweep apart, and loads the
 // operands of the next sweep-but-one while the current sweep runs.
 // ---------------------------------------------------------------------------
+constexpr int kE2Elems = 42;     // doubles per published row: Ju[20] | Jv[20] | 1/2 rho | sqrt(s)
 constexpr int kE3Group = 8;
 constexpr int kE3Consumers = 4;
 constexpr int kE3Threads = 32 * (kE3Consumers + kE3Group);   // 384
@@ -443,7 +153,16 @@ __device__ __forceinline__ void e3_load(const double* __restrict__ row, int lane
   }
 }
 
-template <int ROLE>
+// One rank-1 sweep acc += x x^T restricted to the role's slice.  ROW selects the residual
+// row (0 = u, 1 = v): the intrinsic block of a row has structural zeros (u does not depend
+// on fy, cy; v not on fx, cx — TS.h:124-125), which also survive the loss scaling, so those
+// products are skipped; fma(x, 0, acc) == acc, the result is bit-identical.
+__device__ __forceinline__ constexpr bool e3_live(int row, int icol) {
+  // icol: 0 fx, 1 fy, 2 cx, 3 cy, 4 xi, 5 lambda, 6 alpha, 7 residual
+  return row == 0 ? !(icol == 1 || icol == 3) : !(icol == 0 || icol == 2);
+}
+
+template <int ROLE, int ROW>
 __device__ __forceinline__ void e3_sweep(const double* x, double* __restrict__ acc) {
   if (ROLE == 0) {
 #pragma unroll
@@ -461,12 +180,15 @@ __device__ __forceinline__ void e3_sweep(const double* x, double* __restrict__ a
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-      for (int b = a; b < 8; ++b) acc[21 + tri8(a, b)] = fma(x[6 + a], x[6 + b], acc[21 + tri8(a, b)]);
+      for (int b = a; b < 8; ++b)
+        if (e3_live(ROW, a) && e3_live(ROW, b))
+          acc[21 + tri8(a, b)] = fma(x[6 + a], x[6 + b], acc[21 + tri8(a, b)]);
   } else {
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
-      for (int b = 0; b < 8; ++b) acc[a * 8 + b] = fma(x[a], x[6 + b], acc[a * 8 + b]);
+      for (int b = 0; b < 8; ++b)
+        if (e3_live(ROW, b)) acc[a * 8 + b] = fma(x[a], x[6 + b], acc[a * 8 + b]);
   }
 }
 
@@ -480,10 +202,10 @@ __device__ __forceinline__ void e3_consume_group(const double* __restrict__ buf,
 #pragma unroll 1
   for (int o = 0; o < kE3Group; ++o) {
     const double* nxt = buf + (o + 1 < kE3Group ? o + 1 : o) * kRow;
-    e3_sweep<ROLE>(xu, acc);
+    e3_sweep<ROLE, 0>(xu, acc);
     if (ROLE == 2) { acc[57] += buf[o * kRow + 40 * 32 + lane]; acc[58] += buf[o * kRow + 41 * 32 + lane]; }
     e3_load<ROLE>(nxt, lane, xu);              // next corner's u row, hidden behind the v sweep
-    e3_sweep<ROLE>(xv, acc);
+    e3_sweep<ROLE, 1>(xv, acc);
     e3_load<ROLE>(nxt + 20 * 32, lane, xv);    // next corner's v row, hidden behind the next u sweep
   }
 }
@@ -574,28 +296,58 @@ k_eval3(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
     if (prof && blockIdx.x == 0 && lane == 0)
       printf("k_eval3 consumer %d: work %lld cycles over %d groups, total %lld\n", warp, t_work,
              ngroups, clock64() - t_start);
-    // stage the per-view records [view][212] in shared memory (the row buffers are free now)
-    double* rec = s_rows + lane * kViewStride;
-    if (warp == 0) {
+    // View part (BB | BC | BI) -> per-view record staged in shared memory (the row buffers
+    // are free now); camera part (CC | CI | II | cost | err) -> summed over the lanes that
+    // share a camera with a fixed-order butterfly and written as one partial per
+    // (CTA, camera).  Views are camera-major, so a CTA normally sees a single camera.
+    if (warp < 2) {
+      double* rec = s_rows + lane * kViewStride;
+      if (warp == 0) {
 #pragma unroll
-      for (int i = 0; i < 57; ++i) rec[kOffBB + i] = acc[i];
-    } else if (warp == 1) {
+        for (int i = 0; i < 57; ++i) rec[kOffBB + i] = acc[i];
+      } else {
 #pragma unroll
-      for (int i = 0; i < 48; ++i) rec[kOffBI + i] = acc[i];
-    } else if (warp == 2) {
-#pragma unroll
-      for (int i = 0; i < 21; ++i) rec[kOffCC + i] = acc[i];
-#pragma unroll
-      for (int i = 0; i < 36; ++i) rec[kOffII + i] = acc[21 + i];
-      rec[kOffCost] = acc[57];
-      rec[kOffErr] = acc[58];
+        for (int i = 0; i < 48; ++i) rec[kOffBI + i] = acc[i];
+        rec[kViewStride - 1] = 0.0;
+      }
     } else {
+      // camera part: staged [entry][33] (conflict free both ways); summed over lanes below
+      double* cs = s_rows + 32 * kViewStride;
+      if (warp == 2) {
 #pragma unroll
-      for (int i = 0; i < 48; ++i) rec[kOffCI + i] = acc[i];
+        for (int i = 0; i < 21; ++i) cs[(kCamCC + i) * 33 + lane] = acc[i];
+#pragma unroll
+        for (int i = 0; i < 36; ++i) cs[(kCamII + i) * 33 + lane] = acc[21 + i];
+        cs[kCamCost * 33 + lane] = acc[57];
+        cs[kCamErr * 33 + lane] = acc[58];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 48; ++i) cs[(kCamCI + i) * 33 + lane] = acc[i];
+      }
     }
   }
   __syncthreads();
-  // coalesced copy-out: the 32 records of this CTA are contiguous in G
+  // Camera partials: one record per (CTA, camera).  Views are camera-major, so the lanes of
+  // one camera are contiguous; thread e sums entry e over each camera's lane range in lane
+  // order (fixed order => deterministic).
+  if (threadIdx.x < kCamRec) {
+    const double* cs = s_rows + 32 * kViewStride + threadIdx.x * 33;
+    const int nv = min(32, P.V - blockIdx.x * 32);
+    const int* vc = P.view_camera + blockIdx.x * 32;
+    int slot = P.blk_slot[blockIdx.x];
+    int l = 0;
+    while (l < nv) {
+      const int c = vc[l];
+      double s0 = 0.0, s1 = 0.0;
+      int k = l;
+      for (; k + 1 < nv && vc[k + 1] == c; k += 2) { s0 += cs[k]; s1 += cs[k + 1]; }
+      if (k < nv && vc[k] == c) { s0 += cs[k]; ++k; }
+      ps.cam_part[(size_t)slot * kCamRec + threadIdx.x] = s0 + s1;
+      ++slot;
+      l = k;
+    }
+  }
+  // coalesced copy-out: the 32 view records of this CTA are contiguous in G
   {
     const int nv = min(32, P.V - blockIdx.x * 32);
     double* dst = ps.G + (size_t)blockIdx.x * 32 * kViewStride;
@@ -646,51 +398,6 @@ __global__ void k_transpose_obs(const double2* __restrict__ in, double2* __restr
   }
 }
 
-// ---------------------------------------------------------------------------
-// K2: per-camera sums of the camera part of the view records (deterministic
-// two-level tree: chunk partials, then chunks in order).
-// ---------------------------------------------------------------------------
-__global__ void k_reduce_cam_a(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st,
-                               int which, double* __restrict__ part /*[nchunk][kCamRec]*/) {
-  if (which < 2 && st->done) return;
-  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
-  const ParamSet& ps = sel ? ps1 : ps0;
-  const int ch = blockIdx.x, e = threadIdx.x;
-  if (e >= kCamRec) return;
-  const int v0 = P.chunk_begin[ch], v1 = P.chunk_begin[ch + 1];
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  const double* g = ps.G + kOffCC + e;
-  int v = v0;
-  for (; v + 3 < v1; v += 4) {
-    s0 += g[(size_t)v * kViewStride];
-    s1 += g[(size_t)(v + 1) * kViewStride];
-    s2 += g[(size_t)(v + 2) * kViewStride];
-    s3 += g[(size_t)(v + 3) * kViewStride];
-  }
-  for (; v < v1; ++v) s0 += g[(size_t)v * kViewStride];
-  part[(size_t)ch * kCamRec + e] = (s0 + s1) + (s2 + s3);
-}
-
-__global__ void k_reduce_cam_b(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st,
-                               int which, const double* __restrict__ part) {
-  if (which < 2 && st->done) return;
-  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
-  const ParamSet& ps = sel ? ps1 : ps0;
-  const int c = blockIdx.x, e = threadIdx.x;
-  if (e >= kCamRec) return;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int ch = P.cam_chunk_begin[c];
-  const int ce = P.cam_chunk_begin[c + 1];
-  for (; ch + 3 < ce; ch += 4) {
-    s0 += part[(size_t)ch * kCamRec + e];
-    s1 += part[(size_t)(ch + 1) * kCamRec + e];
-    s2 += part[(size_t)(ch + 2) * kCamRec + e];
-    s3 += part[(size_t)(ch + 3) * kCamRec + e];
-  }
-  for (; ch < ce; ++ch) s0 += part[(size_t)ch * kCamRec + e];
-  ps.comm[c * kCamRec + e] = (s0 + s1) + (s2 + s3);
-}
-
 // Block-wide deterministic sum / max helpers (blockDim.x <= 1024, power of 2).
 __device__ __forceinline__ double block_sum(double v, double* s_red) {
   const int t = threadIdx.x;
@@ -717,32 +424,6 @@ __device__ __forceinline__ double block_max(double v, double* s_red) {
   return r;
 }
 
-// Frame gradient max-norm |x - (x - g)|_inf (EvaluateGradientAndJacobian) and
-// |x_f|^2 of a parameter set: one thread per (frame, pose component).
-__global__ void k_frame_grad(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st,
-                             int which, double* __restrict__ gmax_part,
-                             double* __restrict__ xn2_part) {
-  __shared__ double s_red[256];
-  if (which < 2 && st->done) return;
-  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
-  const ParamSet& ps = sel ? ps1 : ps0;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  double gm = 0.0, xn2 = 0.0;
-  if (idx < P.F * 6) {
-    const int f = idx / 6, b = idx % 6;
-    double g = 0.0;
-    for (int p = P.frame_ptr[f]; p < P.frame_ptr[f + 1]; ++p)
-      g += ps.G[(size_t)P.frame_views[p] * kViewStride + kOffBI + b * 8 + 7];
-    const double x = ps.board_rt[idx];
-    const double projected = x + (-g);
-    gm = fabs(x - projected);
-    xn2 = x * x;
-  }
-  const double m = block_max(gm, s_red);
-  const double s = block_sum(xn2, s_red);
-  if (threadIdx.x == 0) { gmax_part[blockIdx.x] = m; xn2_part[blockIdx.x] = s; }
-}
-
 // ---------------------------------------------------------------------------
 // Jacobi scaling (iteration 0): scale = 1 / (1 + sqrt(sum J_col^2)).
 // ---------------------------------------------------------------------------
@@ -761,7 +442,7 @@ __global__ void k_jacobi_scale(DeviceProblem P, ParamSet ps0, ParamSet ps1, cons
     const int k = idx - P.F * 6;
     const int c = k / 13, kk = k % 13;
     const double* U = ps.comm + c * kCamRec;   // globally summed camera record
-    const double d = kk < 6 ? U[tri6(kk, kk)] : U[(kOffII - kOffCC) + tri8(kk - 6, kk - 6)];
+    const double d = kk < 6 ? U[kCamCC + tri6(kk, kk)] : U[kCamII + tri8(kk - 6, kk - 6)];
     scale_c[k] = opt.jacobi_scaling ? 1.0 / (1.0 + sqrt(d)) : 1.0;
   }
 }
@@ -962,6 +643,236 @@ k_schur(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOption
   if (tid < NL) A.rpart[(size_t)blockIdx.x * NL + tid] = racc;
 }
 
+// ---------------------------------------------------------------------------
+// K3, pipelined form (used when two staging buffers fit in shared memory):
+// kSchurFB PRODUCER warps (one frame each: gather V / g_e, damp, 6x6 Cholesky,
+// Y = V^-1 W_s, z) fill staging buffer (b+1)&1 while the CONSUMER warps fold
+// buffer b&1 into their 4x4 register tiles of S; one __syncthreads per batch.
+// The per-frame column list (view, in-camera index, reduced column) is
+// precomputed on the host, so a producer issues all its global loads — the 27
+// V/g entries over the frame's views and the raw W columns — back to back
+// instead of through chains of dependent index loads.
+// ---------------------------------------------------------------------------
+struct Schur2Args {
+  SchurArgs a;
+  const int* col_ptr;      // [F+1] first column descriptor of frame f
+  const int* col_src;      // [ncol] view * 16 + kk
+  const short* col_g;      // [ncol] reduced (live) column
+};
+
+constexpr int kS2ColsPerLane = 4;   // raw W columns a lane keeps in registers per round
+
+__global__ void __launch_bounds__(640)
+k_schur2(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
+         Schur2Args B) {
+  if (st->done) return;
+  const SchurArgs& A = B.a;
+  const ParamSet& ps = st->cur ? ps1 : ps0;
+  const double radius = A.radius_override > 0.0 ? A.radius_override : st->radius;
+  extern __shared__ __align__(32) double s_mem[];
+  const int NL = P.NL, NLp = A.NLp;
+  const int buf_doubles = 2 * kSchurFB * 6 * NLp + kSchurFB * 6;   // Ws | Ys | zs
+  double* scr = s_mem + 2 * buf_doubles;                            // [FB][64]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int f_begin = blockIdx.x * A.frames_per_block;
+  const int f_end = min(P.F, f_begin + A.frames_per_block);
+  const int nbatch = (f_end - f_begin + kSchurFB - 1) / kSchurFB;
+
+  if (warp < kSchurFB) {
+    // ------------------------------- producer -------------------------------------
+    double* my = scr + warp * 64;
+    for (int b = 0; b <= nbatch; ++b) {
+      if (b < nbatch) {
+        double* Ws = s_mem + (b & 1) * buf_doubles;
+        double* Ys = Ws + kSchurFB * 6 * NLp;
+        double* zs = Ys + kSchurFB * 6 * NLp;
+        // clear this warp's 12 staging rows (columns of cameras that do not see the frame)
+        for (int i = lane; i < 6 * NLp; i += 32) {
+          Ws[warp * 6 * NLp + i] = 0.0;
+          Ys[warp * 6 * NLp + i] = 0.0;
+        }
+        if (lane < 6) zs[warp * 6 + lane] = 0.0;
+        const int f = f_begin + b * kSchurFB + warp;
+        if (f < f_end) {
+          const int p0 = P.frame_ptr[f], nv = P.frame_ptr[f + 1] - p0;
+          const int c0 = B.col_ptr[f], ncols = B.col_ptr[f + 1] - c0;
+          // independent loads first: view ids, column descriptors
+          int vid = lane < nv ? P.frame_views[p0 + lane] : 0;
+          int csrc[kS2ColsPerLane], cg[kS2ColsPerLane];
+#pragma unroll
+          for (int r = 0; r < kS2ColsPerLane; ++r) {
+            const int col = lane + 32 * r;
+            csrc[r] = col < ncols ? B.col_src[c0 + col] : -1;
+            cg[r] = col < ncols ? B.col_g[c0 + col] : 0;
+          }
+          double se[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) se[i] = A.scale_e[f * 6 + i];
+          // second level: V / g_e entries and raw W columns
+          double raw[kS2ColsPerLane][6];
+#pragma unroll
+          for (int r = 0; r < kS2ColsPerLane; ++r) {
+            if (csrc[r] >= 0) {
+              const int kk = csrc[r] & 15;
+              const double* Gv = ps.G + (size_t)(csrc[r] >> 4) * kViewStride;
+#pragma unroll
+              for (int q = 0; q < 6; ++q)
+                raw[r][q] = kk < 6 ? Gv[kOffBC + q * 6 + kk] : Gv[kOffBI + q * 8 + (kk - 6)];
+            } else {
+#pragma unroll
+              for (int q = 0; q < 6; ++q) raw[r][q] = 0.0;
+            }
+          }
+          {
+            const int e = lane < 21 ? kOffBB + lane : kOffBI + (min(lane, 26) - 21) * 8 + 7;
+            double s0 = 0.0, s1 = 0.0;
+            int p = 0;
+            for (; p + 1 < nv; p += 2) {
+              const int va = __shfl_sync(0xffffffffu, vid, p), vb = __shfl_sync(0xffffffffu, vid, p + 1);
+              s0 += ps.G[(size_t)va * kViewStride + e];
+              s1 += ps.G[(size_t)vb * kViewStride + e];
+            }
+            if (p < nv) {
+              const int va = __shfl_sync(0xffffffffu, vid, p);
+              s0 += ps.G[(size_t)va * kViewStride + e];
+            }
+            if (lane < 27) my[lane] = s0 + s1;
+          }
+          __syncwarp();
+          double M[36], gs[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int j = i; j < 6; ++j) {
+              const double v = se[i] * se[j] * my[tri6(i, j)];
+              M[i * 6 + j] = v;
+              M[j * 6 + i] = v;
+            }
+            gs[i] = se[i] * my[21 + i];
+          }
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+              for (int j = i; j < 6; ++j) my[27 + tri6(i, j)] = M[i * 6 + j];
+              my[48 + i] = gs[i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const double d = fmin(fmax(M[i * 6 + i], opt.min_lm_diagonal), opt.max_lm_diagonal);
+            const double D = sqrt(d / radius);
+            M[i * 6 + i] += D * D;
+          }
+          chol6(M);
+          double z[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) z[i] = gs[i];
+          chol6_solve(M, z);
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+              for (int j = 0; j <= i; ++j) my[(i * (i + 1)) / 2 + j] = M[i * 6 + j];
+              my[21 + i] = z[i];
+              zs[warp * 6 + i] = z[i];
+            }
+          }
+          __syncwarp();
+          for (int i = lane; i < kFrameRec; i += 32) A.frame_rec[(size_t)i * A.Fpad + f] = my[i];
+          // scaled W columns and Y = (V + D^2)^-1 W_s
+#pragma unroll
+          for (int r = 0; r < kS2ColsPerLane; ++r) {
+            if (csrc[r] >= 0) {
+              const int kk = csrc[r] & 15;
+              const int m = P.view_camera[csrc[r] >> 4];
+              const double sc = A.scale_c[m * 13 + kk];
+              double w[6];
+#pragma unroll
+              for (int q = 0; q < 6; ++q) w[q] = se[q] * raw[r][q] * sc;
+#pragma unroll
+              for (int q = 0; q < 6; ++q) Ws[(warp * 6 + q) * NLp + cg[r]] = w[q];
+              chol6_solve(M, w);
+#pragma unroll
+              for (int q = 0; q < 6; ++q) Ys[(warp * 6 + q) * NLp + cg[r]] = w[q];
+            }
+          }
+          // frames with more live columns than a lane holds in registers (C > 9)
+          for (int col = lane + 32 * kS2ColsPerLane; col < ncols; col += 32) {
+            const int src = B.col_src[c0 + col], g = B.col_g[c0 + col];
+            const int kk = src & 15;
+            const int m = P.view_camera[src >> 4];
+            const double sc = A.scale_c[m * 13 + kk];
+            const double* Gv = ps.G + (size_t)(src >> 4) * kViewStride;
+            double w[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+              const double rv = kk < 6 ? Gv[kOffBC + q * 6 + kk] : Gv[kOffBI + q * 8 + (kk - 6)];
+              w[q] = se[q] * rv * sc;
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) Ws[(warp * 6 + q) * NLp + g] = w[q];
+            chol6_solve(M, w);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) Ys[(warp * 6 + q) * NLp + g] = w[q];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    return;
+  }
+  // --------------------------------- consumer ---------------------------------------
+  const int ct = tid - kSchurFB * 32;            // consumer thread index
+  const int tbi = ct < A.ntiles ? A.tile_bi[ct] : -1;
+  const int tbj = ct < A.ntiles ? A.tile_bj[ct] : 0;
+  double acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+  double racc = 0.0;
+  for (int b = 0; b <= nbatch; ++b) {
+    if (b > 0) {
+      const double* Ws = s_mem + ((b - 1) & 1) * buf_doubles;
+      const double* Ys = Ws + kSchurFB * 6 * NLp;
+      const double* zs = Ys + kSchurFB * 6 * NLp;
+      if (tbi >= 0) {
+        const double* wp = Ws + 4 * tbi;
+        const double* yp = Ys + 4 * tbj;
+#pragma unroll 4
+        for (int r = 0; r < kSchurFB * 6; ++r) {
+          const double4 w4 = *reinterpret_cast<const double4*>(wp + r * NLp);
+          const double4 y4 = *reinterpret_cast<const double4*>(yp + r * NLp);
+          const double w[4] = {w4.x, w4.y, w4.z, w4.w};
+          const double y[4] = {y4.x, y4.y, y4.z, y4.w};
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a * 4 + c] = fma(-w[a], y[c], acc[a * 4 + c]);
+        }
+      }
+      if (ct < NL) {
+        double a = racc;
+        for (int r = 0; r < kSchurFB * 6; ++r) a = fma(-Ws[r * NLp + ct], zs[r], a);
+        racc = a;
+      }
+    }
+    __syncthreads();
+  }
+  double* Sp = A.Spart + (size_t)blockIdx.x * P.Q;
+  if (tbi >= 0) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = 4 * tbi + a, j = 4 * tbj + c;
+        if (i <= j && j < NL) Sp[i * NL - (i * (i - 1)) / 2 + (j - i)] = acc[a * 4 + c];
+      }
+    }
+  }
+  if (ct < NL) A.rpart[(size_t)blockIdx.x * NL + ct] = racc;
+}
+
 // Sum the per-CTA partials: out = [S packed upper (Q) | rhs (NL)].
 __global__ void k_reduce_s(DeviceProblem P, const LmState* st, const double* __restrict__ Spart,
                            const double* __restrict__ rpart, int nblk, double* __restrict__ out) {
@@ -1003,12 +914,12 @@ __device__ __forceinline__ int idxL(int r, int c) { return (r * (r + 1)) / 2 + c
 
 // U(i, j) of camera record `U` for in-camera indices a <= b (0..12 over [rt 6 | intr 7]).
 __device__ __forceinline__ double cam_block(const double* U, int a, int b) {
-  if (b < 6) return U[tri6(a, b)];
-  if (a < 6) return U[(kOffCI - kOffCC) + a * 8 + (b - 6)];
-  return U[(kOffII - kOffCC) + tri8(a - 6, b - 6)];
+  if (b < 6) return U[kCamCC + tri6(a, b)];
+  if (a < 6) return U[kCamCI + a * 8 + (b - 6)];
+  return U[kCamII + tri8(a - 6, b - 6)];
 }
 __device__ __forceinline__ double cam_grad(const double* U, int a) {
-  return a < 6 ? U[(kOffCI - kOffCC) + a * 8 + 7] : U[(kOffII - kOffCC) + tri8(a - 6, 7)];
+  return a < 6 ? U[kCamCI + a * 8 + 7] : U[kCamII + tri8(a - 6, 7)];
 }
 
 // 1/d to ~1 ulp: hardware seed + two Newton steps (no IEEE division sequence on
@@ -1251,6 +1162,13 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
     if (k < 6) pc.cam_rt[c * 6 + k] = xn; else pc.intr[c * 9 + (k - 6)] = xn;
     if (k >= 6 || free_rt) xn2 += xn * xn;
   }
+  __syncthreads();   // candidate parameters are complete
+  if (tid < P.C) {
+    // per-camera constants of the candidate (what k_prep_cams would do)
+    CamConst cc;
+    make_cam_const(pc.cam_rt + 6 * tid, pc.intr + 9 * tid, tid != P.fixed_camera, cc);
+    pc.cam[tid] = cc;
+  }
   const double t_lin = block_sum(lin, s_red);
   const double t_quad = block_sum(quad, s_red);
   const double t_dn2 = block_sum(dn2, s_red);
@@ -1353,35 +1271,10 @@ k_backsub(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, SchurA
 }
 
 // ---------------------------------------------------------------------------
-// K5: pack the scalars that need a global sum next to the camera records, then
-// decide.  k_pack(which): comm[C*kCamRec + 0..3] = frame lin / quad / |delta|^2 /
-// |x+|^2 and gmax[0] = frame gradient max-norm of the evaluated set.
+// K5: trust-region bookkeeping.  The comm record of an evaluated parameter set holds the
+// per-camera sums and, at [C*kCamRec + 0..3], frame lin / quad / |delta|^2 / |x+|^2;
+// gmax[0] is the frame gradient max-norm (all written by k_post_eval).
 // ---------------------------------------------------------------------------
-__global__ void k_pack(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which,
-                       const double* __restrict__ bs_part, int bs_nblk,
-                       const double* __restrict__ gmax_part, const double* __restrict__ xn2_part,
-                       int fg_nblk, int initial) {
-  __shared__ double s_red[256];
-  if (which < 2 && st->done) return;
-  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
-  const ParamSet& ps = sel ? ps1 : ps0;
-  double* extra = ps.comm + P.C * kCamRec;
-  for (int k = 0; k < 4; ++k) {
-    double s = 0.0;
-    if (!initial) {
-      for (int i = threadIdx.x; i < bs_nblk; i += blockDim.x) s += bs_part[k * bs_nblk + i];
-    } else if (k == 3) {
-      for (int i = threadIdx.x; i < fg_nblk; i += blockDim.x) s += xn2_part[i];
-    }
-    const double t = block_sum(s, s_red);
-    if (threadIdx.x == 0) extra[k] = t;
-  }
-  double m = 0.0;
-  for (int i = threadIdx.x; i < fg_nblk; i += blockDim.x) m = fmax(m, gmax_part[i]);
-  const double t = block_max(m, s_red);
-  if (threadIdx.x == 0) ps.gmax[0] = t;
-}
-
 // Camera part of |x - (x - g)|_inf and |x_c|^2 for a parameter set whose comm
 // record is globally summed.
 __device__ inline void camera_grad_norms(const DeviceProblem& P, const ParamSet& ps, double* gmax,
@@ -1405,7 +1298,7 @@ __device__ inline void camera_grad_norms(const DeviceProblem& P, const ParamSet&
 
 __device__ inline double total_cost(const DeviceProblem& P, const ParamSet& ps) {
   double c = 0.0;
-  for (int m = 0; m < P.C; ++m) c += ps.comm[m * kCamRec + (kOffCost - kOffCC)];
+  for (int m = 0; m < P.C; ++m) c += ps.comm[m * kCamRec + kCamCost];
   return c;
 }
 
@@ -1462,9 +1355,9 @@ __global__ void k_init(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st,
   finalize_iteration(st, opt, tr, 0, true, true, st->x_cost, 0.0);
 }
 
-__global__ void k_decide(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
-                         Trace tr) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// TrustRegionMinimizer step bookkeeping for the candidate just evaluated (one thread).
+__device__ inline void decide_step(const DeviceProblem& P, const ParamSet& ps0, const ParamSet& ps1,
+                                   LmState* st, const LmOptions& opt, Trace tr) {
   if (st->done) return;
   const ParamSet& pc = st->cur ? ps0 : ps1;   // candidate
   const double* extra = pc.comm + P.C * kCamRec;
@@ -1525,6 +1418,115 @@ __global__ void k_decide(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* s
     st->radius = st->radius / st->decrease_factor;
     st->decrease_factor *= 2.0;
     finalize_iteration(st, opt, tr, iteration, true, false, candidate_cost, step_norm);
+  }
+}
+
+__global__ void k_decide(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
+                         Trace tr) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  decide_step(P, ps0, ps1, st, opt, tr);
+}
+
+// ---------------------------------------------------------------------------
+// Post-evaluation kernel.  Blocks [0, C): camera c sums its partial slots (written by
+// k_eval3, one per (CTA, camera)) in a fixed order into the comm record.  Blocks
+// [C, C + fg_nblk): frame gradient max-norm |x - (x - g)|_inf and |x_f|^2 partials.  The LAST
+// block to finish (threadfence + ticket) folds the frame partials and the step scalars into
+// the record and — on a single GPU — runs the accept/reject decision itself.  Which block
+// runs the tail varies; the arithmetic it performs does not, so results stay deterministic.
+// ---------------------------------------------------------------------------
+struct PostArgs {
+  double* gmax_part;       // [fg_nblk]
+  double* xn2_part;        // [fg_nblk]
+  const double* bs_part;   // [4][bs_nblk]
+  int bs_nblk, fg_nblk;
+  unsigned int* ticket;
+  int initial;             // evaluation of the initial point (no step quantities)
+  int decide;              // 1: single GPU, run decide_step in the tail
+};
+
+constexpr int kPostThreads = 512;
+
+__global__ void __launch_bounds__(kPostThreads)
+k_post_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, int which, LmOptions opt,
+            Trace tr, PostArgs A) {
+  __shared__ double s_red[kPostThreads];
+  __shared__ int s_last;
+  if (which < 2 && st->done) return;
+  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
+  const ParamSet& ps = sel ? ps1 : ps0;
+  const int t = threadIdx.x;
+  if ((int)blockIdx.x < P.C) {
+    // 4 thread groups of 128 take every 4th slot; 4 loads in flight per thread
+    const int c = blockIdx.x, e = t & 127, grp = t >> 7;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (e < kCamRec) {
+      const double* part = ps.cam_part + e;
+      int sl = P.cam_slot_begin[c] + grp;
+      const int se = P.cam_slot_begin[c + 1];
+      for (; sl + 12 < se; sl += 16) {
+        s0 += part[(size_t)sl * kCamRec];
+        s1 += part[(size_t)(sl + 4) * kCamRec];
+        s2 += part[(size_t)(sl + 8) * kCamRec];
+        s3 += part[(size_t)(sl + 12) * kCamRec];
+      }
+      for (; sl < se; sl += 4) s0 += part[(size_t)sl * kCamRec];
+    }
+    s_red[t] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (t < kCamRec)
+      ps.comm[c * kCamRec + t] = (s_red[t] + s_red[t + 128]) + (s_red[t + 256] + s_red[t + 384]);
+  } else {
+    const int fb = blockIdx.x - P.C;
+    const int idx = fb * kPostThreads + t;
+    double gm = 0.0, xn2 = 0.0;
+    if (idx < P.F * 6) {
+      const int f = idx / 6, b = idx % 6;
+      double g = 0.0;
+      for (int p = P.frame_ptr[f]; p < P.frame_ptr[f + 1]; ++p)
+        g += ps.G[(size_t)P.frame_views[p] * kViewStride + kOffBI + b * 8 + 7];
+      const double x = ps.board_rt[idx];
+      const double projected = x + (-g);
+      gm = fabs(x - projected);
+      xn2 = x * x;
+    }
+    const double m = block_max(gm, s_red);
+    const double s = block_sum(xn2, s_red);
+    if (t == 0) { A.gmax_part[fb] = m; A.xn2_part[fb] = s; }
+  }
+  // ---- last block: combine ----------------------------------------------------------
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    const unsigned int n = atomicAdd(A.ticket, 1u);
+    s_last = (n == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double* extra = ps.comm + P.C * kCamRec;
+  for (int k = 0; k < 4; ++k) {
+    double s = 0.0;
+    if (!A.initial) {
+      for (int i = t; i < A.bs_nblk; i += kPostThreads) s += A.bs_part[k * A.bs_nblk + i];
+    } else if (k == 3) {
+      const volatile double* xp = A.xn2_part;
+      for (int i = t; i < A.fg_nblk; i += kPostThreads) s += xp[i];
+    }
+    const double tot = block_sum(s, s_red);
+    if (t == 0) extra[k] = tot;
+  }
+  {
+    double m = 0.0;
+    const volatile double* gp = A.gmax_part;
+    for (int i = t; i < A.fg_nblk; i += kPostThreads) m = fmax(m, gp[i]);
+    const double tot = block_max(m, s_red);
+    if (t == 0) ps.gmax[0] = tot;
+  }
+  __syncthreads();
+  if (t == 0) {
+    *A.ticket = 0u;
+    if (A.decide) { __threadfence(); decide_step(P, ps0, ps1, st, opt, tr); }
   }
 }
 

@@ -33,21 +33,23 @@ namespace tscm {
 constexpr int kNB = 6, kNC = 6, kNI = 7;
 constexpr int kCols = kNB + kNC + kNI + 1;  // 20
 
-// Per-view Gram record written by the evaluation kernel (doubles):
+// The 20x20 Gram matrix of [J | r] over a view's corners is kept in two records (doubles).
+// Per-VIEW record (what the Schur elimination of the view's frame needs):
 //   BB  0..20    6x6 upper triangle, row-major         -> V
 //   BC  21..56   6x6  [b][c]                           -> W (camera_rt part)
 //   BI  57..104  6x8  [b][i], i = 7 intrinsics then r  -> W (intrinsic part), g_e
-//   CC  105..125 6x6 upper triangle                    -> U
-//   CI  126..173 6x8  [c][i]                           -> U, g_c
-//   II  174..209 8x8 upper triangle                    -> U, g_c, r^T r
-//   210          cost  sum 1/2 rho(s)
-//   211          sum sqrt(s)  (mean Euclidean reprojection error read-out,
+//   105          padding
+// Per-CAMERA record (summed over all views of a camera; partial sums per (CTA, camera)):
+//   CC  0..20    6x6 upper triangle                    -> U
+//   CI  21..68   6x8  [c][i]                           -> U, g_c
+//   II  69..104  8x8 upper triangle                    -> U, g_c, r^T r
+//   105          cost  sum 1/2 rho(s)
+//   106          sum sqrt(s)  (mean Euclidean reprojection error read-out,
 //                multi_calib.cpp:273; s taken BEFORE the loss correction)
-constexpr int kOffBB = 0, kOffBC = 21, kOffBI = 57, kOffCC = 105, kOffCI = 126, kOffII = 174;
-constexpr int kOffCost = 210, kOffErr = 211;
-constexpr int kViewStride = 212;
-// Camera record (sum over a camera's views of entries 105..211).
-constexpr int kCamRec = kViewStride - kOffCC;  // 107
+constexpr int kOffBB = 0, kOffBC = 21, kOffBI = 57;
+constexpr int kViewStride = 106;
+constexpr int kCamCC = 0, kCamCI = 21, kCamII = 69, kCamCost = 105, kCamErr = 106;
+constexpr int kCamRec = 107;
 
 TSCM_HD constexpr int tri6(int i, int j) { return i * 6 - (i * (i - 1)) / 2 + (j - i); }   // i <= j
 TSCM_HD constexpr int tri8(int i, int j) { return i * 8 - (i * (i - 1)) / 2 + (j - i); }
@@ -177,17 +179,30 @@ TSCM_HD void loss_rho(int type, double a, double s, double rho[3]) {
 // Forward TS projection of a camera-frame point.  Returns the intermediate
 // quantities the Jacobian needs.
 struct TsForward {
-  double x, y, z, d1, d2, d3, z1, z2, D, iD, mx, my;
+  double x, y, z, d1, d2, d3, id1, id2, id3, z1, z2, D, iD, mx, my;
 };
+
+// d = sqrt(s) and 1/d.  On the device one rsqrt (MUFU seed + Newton, <= 1 ulp) yields both
+// (d = s * rsqrt(s), <= 2 ulp) instead of an IEEE sqrt followed by an IEEE division: the three
+// sphere distances sit on the projection's critical dependent chain.
+TSCM_HD void dist_and_inverse(double s, double& d, double& id) {
+#if defined(__CUDA_ARCH__)
+  id = rsqrt(s);
+  d = s * id;
+#else
+  d = sqrt(s);
+  id = 1.0 / d;
+#endif
+}
 
 TSCM_HD void ts_forward(const CamConst& c, const double P[3], TsForward& f) {
   f.x = P[0]; f.y = P[1]; f.z = P[2];
   const double rho2 = f.x * f.x + f.y * f.y;
-  f.d1 = sqrt(rho2 + f.z * f.z);
+  dist_and_inverse(rho2 + f.z * f.z, f.d1, f.id1);
   f.z1 = f.z + c.xi * f.d1;
-  f.d2 = sqrt(rho2 + f.z1 * f.z1);
+  dist_and_inverse(rho2 + f.z1 * f.z1, f.d2, f.id2);
   f.z2 = f.z1 + c.lam * f.d2;
-  f.d3 = sqrt(rho2 + f.z2 * f.z2);
+  dist_and_inverse(rho2 + f.z2 * f.z2, f.d3, f.id3);
   f.D = f.z2 + c.k * f.d3;
   f.iD = 1.0 / f.D;
   f.mx = f.x * f.iD;
@@ -228,7 +243,7 @@ TSCM_HD void obs_jacobian(const CamConst& c, const FrameConst& f, double X, doub
   o.Jv[19] = vo - (c.fy * t.my + c.cy);
 
   // grad D = (e x, e y, h)  (radial symmetry of the three-sphere chain)
-  const double id1 = 1.0 / t.d1, id2 = 1.0 / t.d2, id3 = 1.0 / t.d3;
+  const double id1 = t.id1, id2 = t.id2, id3 = t.id3;
   const double a1 = c.xi * id1;                       // grad z1 = (a1 x, a1 y, 1 + a1 z)
   const double g1 = 1.0 + a1 * t.z;
   const double b1 = (1.0 + t.z1 * a1) * id2;          // grad d2 = (b1 x, b1 y, c1)
@@ -349,7 +364,11 @@ TSCM_HD void chol6(double M[36]) {
     double d = M[j * 6 + j];
     TSCM_UNROLL
     for (int k = 0; k < j; ++k) d -= M[j * 6 + k] * M[j * 6 + k];
+#if defined(__CUDA_ARCH__)
+    const double inv = rsqrt(d);
+#else
     const double inv = 1.0 / sqrt(d);
+#endif
     M[j * 6 + j] = inv;
     TSCM_UNROLL
     for (int i = j + 1; i < 6; ++i) {
