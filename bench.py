@@ -263,7 +263,12 @@ def run_b200(args):
         }
         line["stage_ms"] = stages
 
-    # ---- end to end through the public one-shot C-ABI call with HOST buffers ----------
+    # ---- end to end through the public C-ABI with HOST buffers ------------------------------
+    # The call sequence a reference adapter makes for one calibration on a resident solver:
+    # upload observations (pinned host memory) and initial parameters, run the LM loop, read
+    # the parameters and the summary back.  Solver/communicator creation is outside the timed
+    # region (one per process); the one-shot tscm_solve(), which also pays allocation and
+    # teardown, is reported beside it at N = 1.
     solver.close()
     e2e_iters = args.steps
     pinned = torch.empty(problem.obs_xy.shape, dtype=torch.float64).pin_memory()
@@ -271,52 +276,54 @@ def run_b200(args):
     host_problem = capi.ProblemArrays(problem.board_xy, problem.view_camera, problem.view_frame,
                                       pinned.numpy(), problem.num_cameras, problem.num_frames,
                                       problem.fixed_camera)
-    if world == 1:
-        e_opt = fixed_iteration_options(e2e_iters)
-        capi.solve(host_problem, intr, cam_rt, board_rt, e_opt, device=local_rank)   # warm-up call
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        a, b, c, s = capi.solve(host_problem, intr, cam_rt, board_rt, e_opt, device=local_rank)
-        dt = time.perf_counter() - t0
-        assert s.num_iterations == e2e_iters + 1
-        h2d = problem.obs_xy.nbytes + intr.nbytes + cam_rt.nbytes + board_rt.nbytes + \
-            problem.view_camera.nbytes + problem.view_frame.nbytes + problem.board_xy.nbytes
-        d2h = a.nbytes + b.nbytes + c.nbytes + 5 * 8 * (e2e_iters + 1)
-        line["e2e"] = {
-            "value": total_obs * e2e_iters / dt / 1e9, "unit": UNIT,
-            "h2d_bytes_per_step": h2d / e2e_iters, "d2h_bytes_per_step": d2h / e2e_iters,
-            "lm_iterations_per_sec": e2e_iters / dt, "seconds_per_call": dt,
-            "what": f"one tscm_solve() call = {e2e_iters} LM iterations from pinned host buffers: "
-                    "solver creation, H2D of observations and parameters, transposition, "
-                    "iteration zero, the iterations, D2H of parameters and the trace, teardown; "
-                    "inputs are uploaded once per call, bytes are per call / steps",
-        }
-    else:
-        # each rank times its own resident-create + run from host buffers
-        t0 = time.perf_counter()
-        s2 = capi.Solver(host_problem, fixed_iteration_options(e2e_iters), device=local_rank)
+    e_opt = fixed_iteration_options(e2e_iters)
+    s2 = capi.Solver(host_problem, e_opt, device=local_rank)
+    if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         s2.attach_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
+
+    def one_call():
+        s2.set_observations(host_problem.obs_xy)
         s2.set_parameters(intr, cam_rt, board_rt)
-        res = s2.run()
-        s2.get_parameters()
-        dt = time.perf_counter() - t0
-        s2.close()
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        r = s2.run()
+        return r, s2.get_parameters()
+
+    one_call()                                   # warm-up call
+    barrier()
+    t0 = time.perf_counter()
+    res, (a, b, c) = one_call()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    s2.close()
+    tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        assert res.num_iterations == e2e_iters + 1
-        line["e2e"] = {
-            "value": total_obs * e2e_iters / dt / 1e9, "unit": UNIT,
-            "h2d_bytes_per_step": problem.obs_xy.nbytes / e2e_iters,
-            "d2h_bytes_per_step": (intr.nbytes + cam_rt.nbytes + board_rt.nbytes) / e2e_iters,
-            "lm_iterations_per_sec": e2e_iters / dt, "seconds_per_call": dt,
-            "what": "per rank: solver creation from host buffers, NCCL communicator, H2D, "
-                    f"{e2e_iters} LM iterations, D2H; max over ranks",
-        }
+    dt = float(tt.item())
+    assert res.num_iterations == e2e_iters + 1
+    h2d = problem.obs_xy.nbytes + intr.nbytes + cam_rt.nbytes + board_rt.nbytes
+    d2h = a.nbytes + b.nbytes + c.nbytes + 5 * 8 * (e2e_iters + 1)
+    line["e2e"] = {
+        "value": total_obs * e2e_iters / dt / 1e9, "unit": UNIT,
+        "h2d_bytes_per_step": h2d / e2e_iters, "d2h_bytes_per_step": d2h / e2e_iters,
+        "lm_iterations_per_sec": e2e_iters / dt, "seconds_per_call": dt,
+        "what": f"one calibration on a resident solver = {e2e_iters} LM iterations: H2D of the "
+                "observations (pinned host memory) and initial parameters, on-device transposition, "
+                "iteration zero, the iterations, D2H of parameters and trace; inputs are uploaded "
+                "once per call, bytes are per call / steps; max over ranks",
+    }
+    if world == 1:
+        capi.solve(host_problem, intr, cam_rt, board_rt, e_opt, device=local_rank)   # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        capi.solve(host_problem, intr, cam_rt, board_rt, e_opt, device=local_rank)
+        dt1 = time.perf_counter() - t0
+        line["e2e"]["one_shot_tscm_solve"] = {
+            "lm_iterations_per_sec": e2e_iters / dt1, "seconds_per_call": dt1,
+            "what": "tscm_solve(): additionally creates and destroys the solver (cudaMalloc/Free of "
+                    "~0.4 GB, index tables, CUDA graph capture) inside the timed region"}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

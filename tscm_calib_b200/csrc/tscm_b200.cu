@@ -124,6 +124,9 @@ struct tscm_solver {
   double* d_dbg_rhs = nullptr;
   SchurArgs schur{};
   Schur2Args schur2{};
+  SchurSplitArgs split{};
+  bool split_ok = false;
+  size_t split_smem = 0;
   bool schur2_ok = false;
   int schur2_nt = 0;
   size_t schur2_smem = 0;
@@ -271,7 +274,16 @@ int launch_eval_allreduce(tscm_solver* s, int which) {
 void launch_schur(tscm_solver* s, double radius_override) {
   SchurArgs a = s->schur;
   a.radius_override = radius_override;
-  if (s->schur2_ok) {
+  if (s->split_ok) {
+    SchurSplitArgs b = s->split;
+    b.a = a;
+    k_schur_frames<<<(s->F + 7) / 8, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
+    if (s->schur_ept == 1)
+      k_schur_update<1><<<s->schur_nblk, s->schur_nt, s->split_smem, s->stream>>>(s->P, s->d_state, b);
+    else
+      k_schur_update<2><<<s->schur_nblk, s->schur_nt, s->split_smem, s->stream>>>(s->P, s->d_state, b);
+    s->launches += 1;
+  } else if (s->schur2_ok) {
     Schur2Args b = s->schur2;
     b.a = a;
     k_schur2<<<s->schur_nblk, s->schur2_nt, s->schur2_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
@@ -333,7 +345,9 @@ int launch_iteration(tscm_solver* s) {
   return TSCM_OK;
 }
 
-int launches_per_iteration(const tscm_solver* s) { return s->num_ranks <= 1 ? 6 : 7; }
+int launches_per_iteration(const tscm_solver* s) {
+  return (s->num_ranks <= 1 ? 6 : 7) + (s->split_ok ? 1 : 0);
+}
 
 int ensure_graph(tscm_solver* s) {
   if (!s->graph_dirty && s->graph_exec) return TSCM_OK;
@@ -583,7 +597,7 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   {
     // per-frame column descriptors for the pipelined Schur kernel
     std::vector<int> col_ptr(F + 1, 0), col_src;
-    std::vector<short> col_g;
+    std::vector<short> col_g, col_sidx;
     for (int f = 0; f < F; ++f) {
       for (int q = frame_ptr[f]; q < frame_ptr[f + 1]; ++q) {
         const int v = frame_views[q], m = p->view_camera[v];
@@ -591,6 +605,7 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
         for (int k = 0; k < n; ++k) {
           col_src.push_back(v * 16 + (n == 13 ? k : k + 6));
           col_g.push_back((short)(live_off[m] + k));
+          col_sidx.push_back((short)(m * 13 + (n == 13 ? k : k + 6)));
         }
       }
       col_ptr[f + 1] = (int)col_src.size();
@@ -598,9 +613,22 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     TRY_RC(s->put(&s->schur2.col_ptr, col_ptr));
     TRY_RC(s->put(&s->schur2.col_src, col_src));
     TRY_RC(s->put(&s->schur2.col_g, col_g));
+    TRY_RC(s->put(&s->split.col_sidx, col_sidx));
     const int cons = (ntiles + 31) / 32 * 32;
     s->schur2_nt = kSchurFB * 32 + cons;
     s->schur2_smem = (size_t)(2 * (2 * kSchurFB * 6 * s->schur.NLp + kSchurFB * 6) + kSchurFB * 64) * sizeof(double);
+    // split form: materialise W_s, Y, z per frame (dense rows) when the rig's visibility is
+    // dense enough for that to be cheaper than staging inside one CTA
+    s->split.col_ptr = s->schur2.col_ptr; s->split.col_src = s->schur2.col_src; s->split.col_g = s->schur2.col_g;
+    s->split_smem = (size_t)(2 * (2 * kSchurFB * 6 * s->schur.NLp + kSchurFB * 6)) * sizeof(double);
+    const double fill = (double)col_src.size() / ((double)F * NL);
+    s->split_ok = fill >= 0.4 && s->split_smem <= (size_t)prop.sharedMemPerBlockOptin && V < (1 << 27) &&
+                  !getenv("TSCM_SCHUR_FUSED");
+    if (s->split_ok) {
+      TRY_RC(s->alloc(&s->split.Wg, (size_t)F * 6 * s->schur.NLp));
+      TRY_RC(s->alloc(&s->split.Yg, (size_t)F * 6 * s->schur.NLp));
+      TRY_RC(s->alloc(&s->split.zg, ((size_t)F + 8) * 6));
+    }
     s->schur2_ok = s->schur2_nt <= 640 && s->schur2_smem <= (size_t)prop.sharedMemPerBlockOptin &&
                    V < (1 << 27) && !getenv("TSCM_SCHUR_V1");
   }
@@ -626,6 +654,10 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     tscm_solver_destroy(s); return TSCM_ERR_UNSUPPORTED;
   }
   if (s->schur2_ok) TRY_RC(set_smem((const void*)k_schur2, s->schur2_smem));
+  if (s->split_ok) {
+    TRY_RC(set_smem((const void*)k_schur_update<1>, s->split_smem));
+    TRY_RC(set_smem((const void*)k_schur_update<2>, s->split_smem));
+  }
   TRY_RC(set_smem((const void*)k_schur<1, 512>, s->schur_smem));
   TRY_RC(set_smem((const void*)k_schur<2, 768>, s->schur_smem));
   TRY_RC(set_smem((const void*)k_solve<2>, s->solve_smem));

@@ -150,6 +150,9 @@ __device__ __forceinline__ void e3_load(const double* __restrict__ row, int lane
     for (int k = 0; k < 6; ++k) x[k] = row[(base + k) * 32 + lane];
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[6 + k] = row[(12 + k) * 32 + lane];
+    // roles 2 and 3 also own one row of BC each (load balance): they need B4 / B5
+    if (ROLE == 2) x[14] = row[4 * 32 + lane];
+    if (ROLE == 3) x[14] = row[5 * 32 + lane];
   }
 }
 
@@ -164,13 +167,17 @@ __device__ __forceinline__ constexpr bool e3_live(int row, int icol) {
 
 template <int ROLE, int ROW>
 __device__ __forceinline__ void e3_sweep(const double* x, double* __restrict__ acc) {
+  // slices (FMAs per sweep): role 0 = BB + BC rows 0-3 (45), role 1 = BI (36 live),
+  // role 2 = CC + II + BC row 4 (48 live), role 3 = CI + BC row 5 (42 live)
   if (ROLE == 0) {
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
 #pragma unroll
       for (int b = a; b < 6; ++b) acc[tri6(a, b)] = fma(x[a], x[b], acc[tri6(a, b)]);
+      if (a < 4) {
 #pragma unroll
-      for (int b = 0; b < 6; ++b) acc[21 + a * 6 + b] = fma(x[a], x[6 + b], acc[21 + a * 6 + b]);
+        for (int b = 0; b < 6; ++b) acc[21 + a * 6 + b] = fma(x[a], x[6 + b], acc[21 + a * 6 + b]);
+      }
     }
   } else if (ROLE == 2) {
 #pragma unroll
@@ -183,12 +190,18 @@ __device__ __forceinline__ void e3_sweep(const double* x, double* __restrict__ a
       for (int b = a; b < 8; ++b)
         if (e3_live(ROW, a) && e3_live(ROW, b))
           acc[21 + tri8(a, b)] = fma(x[6 + a], x[6 + b], acc[21 + tri8(a, b)]);
+#pragma unroll
+    for (int b = 0; b < 6; ++b) acc[59 + b] = fma(x[14], x[b], acc[59 + b]);      // BC row 4
   } else {
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
       for (int b = 0; b < 8; ++b)
         if (e3_live(ROW, b)) acc[a * 8 + b] = fma(x[a], x[6 + b], acc[a * 8 + b]);
+    if (ROLE == 3) {
+#pragma unroll
+      for (int b = 0; b < 6; ++b) acc[48 + b] = fma(x[14], x[b], acc[48 + b]);    // BC row 5
+    }
   }
 }
 
@@ -196,7 +209,7 @@ template <int ROLE>
 __device__ __forceinline__ void e3_consume_group(const double* __restrict__ buf, int lane,
                                                  double* __restrict__ acc) {
   constexpr int kRow = kE2Elems * 32;
-  double xu[14], xv[14];
+  double xu[15], xv[15];
   e3_load<ROLE>(buf, lane, xu);
   e3_load<ROLE>(buf + 20 * 32, lane, xv);
 #pragma unroll 1
@@ -278,9 +291,9 @@ k_eval3(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------ consumer ------------------------------------
-    double acc[59];
+    double acc[65];
 #pragma unroll
-    for (int i = 0; i < 59; ++i) acc[i] = 0.0;
+    for (int i = 0; i < 65; ++i) acc[i] = 0.0;
     for (int g = 0; g <= ngroups; ++g) {
       const long long tw0 = clock64();
       if (g > 0) {
@@ -304,7 +317,7 @@ k_eval3(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
       double* rec = s_rows + lane * kViewStride;
       if (warp == 0) {
 #pragma unroll
-        for (int i = 0; i < 57; ++i) rec[kOffBB + i] = acc[i];
+        for (int i = 0; i < 45; ++i) rec[kOffBB + i] = acc[i];     // BB, BC rows 0-3
       } else {
 #pragma unroll
         for (int i = 0; i < 48; ++i) rec[kOffBI + i] = acc[i];
@@ -313,6 +326,12 @@ k_eval3(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
     } else {
       // camera part: staged [entry][33] (conflict free both ways); summed over lanes below
       double* cs = s_rows + 32 * kViewStride;
+      double* rec = s_rows + lane * kViewStride;
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {       // the BC rows these roles own
+        if (warp == 2) rec[kOffBC + 4 * 6 + b] = acc[59 + b];
+        else rec[kOffBC + 5 * 6 + b] = acc[48 + b];
+      }
       if (warp == 2) {
 #pragma unroll
         for (int i = 0; i < 21; ++i) cs[(kCamCC + i) * 33 + lane] = acc[i];
@@ -871,6 +890,311 @@ k_schur2(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptio
     }
   }
   if (ct < NL) A.rpart[(size_t)blockIdx.x * NL + ct] = racc;
+}
+
+// ---------------------------------------------------------------------------
+// K3, split form (default for dense-ish visibility): the per-frame work and the
+// accumulation of S are separate kernels.
+//  k_schur_frames: one warp per frame with the whole GPU's occupancy hiding the
+//    dependent-load and FP64 latency chains (gather V / g_e, damp, 6x6 Cholesky,
+//    Y = V^-1 W_s, z); W_s, Y (6 x NLp rows per frame) and z go to global memory.
+//  k_schur_update: each CTA streams a contiguous range of frames through shared
+//    memory with TMA bulk copies (cp.async.bulk + mbarrier, two stages of 8 frames)
+//    and folds them into the 4x4 register tiles of S it owns.
+// ---------------------------------------------------------------------------
+// Column permutation of the materialised W_s / Y rows: the two low doubles of every 4-column
+// tile first, then the two high doubles, so that the update kernel's 16-byte operand loads
+// are contiguous across the lanes of a warp (no shared-memory bank conflicts).
+__host__ __device__ __forceinline__ int schur_perm(int col, int NLp) {
+  return ((col & 2) ? (NLp >> 1) : 0) + ((col >> 2) << 1) + (col & 1);
+}
+
+struct SchurSplitArgs {
+  SchurArgs a;
+  const int* col_ptr;      // [F+1]
+  const int* col_src;      // [ncol] view * 16 + kk
+  const short* col_g;      // [ncol] reduced (live) column
+  const short* col_sidx;   // [ncol] camera * 13 + kk (index into scale_c)
+  double* Wg;              // [F][6][NLp] scaled W rows, columns permuted (schur_perm)
+  double* Yg;              // [F][6][NLp] (V + D^2)^-1 W_s
+  double* zg;              // [Fpad8][6]   (V + D^2)^-1 g_s
+};
+
+__global__ void __launch_bounds__(256, 2)
+k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
+               SchurSplitArgs B) {
+  if (st->done) return;
+  __shared__ double s_scr[8][64];
+  const SchurArgs& A = B.a;
+  const ParamSet& ps = st->cur ? ps1 : ps0;
+  const double radius = A.radius_override > 0.0 ? A.radius_override : st->radius;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * 8 + warp;
+  if (f >= P.F) return;
+  const int NLp = A.NLp;
+  double* my = s_scr[warp];
+  double* Wf = B.Wg + (size_t)f * 6 * NLp;
+  double* Yf = B.Yg + (size_t)f * 6 * NLp;
+  const int p0 = P.frame_ptr[f], nv = P.frame_ptr[f + 1] - p0;
+  const int c0 = B.col_ptr[f], ncols = B.col_ptr[f + 1] - c0;
+  // cameras that do not see the frame contribute zero columns
+  if (ncols < P.NL) {
+    for (int i = lane; i < 6 * NLp; i += 32) { Wf[i] = 0.0; Yf[i] = 0.0; }
+    __syncwarp();
+  } else if (NLp > P.NL) {
+    for (int q = lane; q < 6 * (NLp - P.NL); q += 32) {
+      const int r = q / (NLp - P.NL), c = schur_perm(P.NL + q % (NLp - P.NL), NLp);
+      Wf[r * NLp + c] = 0.0; Yf[r * NLp + c] = 0.0;
+    }
+  }
+  const int vid = lane < nv ? P.frame_views[p0 + lane] : 0;
+  double se[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) se[i] = A.scale_e[f * 6 + i];
+  {
+    const int e = lane < 21 ? kOffBB + lane : kOffBI + (min(lane, 26) - 21) * 8 + 7;
+    double s0 = 0.0, s1 = 0.0;
+    int p = 0;
+    for (; p + 1 < nv; p += 2) {
+      const int va = __shfl_sync(0xffffffffu, vid, p), vb = __shfl_sync(0xffffffffu, vid, p + 1);
+      s0 += ps.G[(size_t)va * kViewStride + e];
+      s1 += ps.G[(size_t)vb * kViewStride + e];
+    }
+    if (p < nv) s0 += ps.G[(size_t)__shfl_sync(0xffffffffu, vid, p) * kViewStride + e];
+    if (lane < 27) my[lane] = s0 + s1;
+  }
+  __syncwarp();
+  double M[36], gs[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = i; j < 6; ++j) {
+      const double v = se[i] * se[j] * my[tri6(i, j)];
+      M[i * 6 + j] = v;
+      M[j * 6 + i] = v;
+    }
+    gs[i] = se[i] * my[21 + i];
+  }
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int j = i; j < 6; ++j) my[27 + tri6(i, j)] = M[i * 6 + j];
+      my[48 + i] = gs[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const double d = fmin(fmax(M[i * 6 + i], opt.min_lm_diagonal), opt.max_lm_diagonal);
+    const double D = sqrt(d / radius);
+    M[i * 6 + i] += D * D;
+  }
+  chol6(M);   // a failed pivot yields NaNs that the LM loop turns into an invalid step
+  double z[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) z[i] = gs[i];
+  chol6_solve(M, z);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) my[(i * (i + 1)) / 2 + j] = M[i * 6 + j];
+      my[21 + i] = z[i];
+      B.zg[(size_t)f * 6 + i] = z[i];
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < kFrameRec; i += 32) A.frame_rec[(size_t)i * A.Fpad + f] = my[i];
+  // columns of W_s and Y: up to kS2ColsPerLane per lane with every global load issued
+  // before the first use (two dependent levels: descriptors, then records), the rest
+  // (rigs with more than 9 cameras) in a plain loop
+  {
+    int csrc[kS2ColsPerLane], cg[kS2ColsPerLane];
+    double csc[kS2ColsPerLane];
+#pragma unroll
+    for (int r = 0; r < kS2ColsPerLane; ++r) {
+      const int col = lane + 32 * r;
+      const bool ok = col < ncols;
+      csrc[r] = ok ? B.col_src[c0 + col] : -1;
+      cg[r] = ok ? schur_perm(B.col_g[c0 + col], NLp) : 0;
+      csc[r] = ok ? A.scale_c[B.col_sidx[c0 + col]] : 0.0;
+    }
+    double raw[kS2ColsPerLane][6];
+#pragma unroll
+    for (int r = 0; r < kS2ColsPerLane; ++r) {
+      const int kk = csrc[r] & 15;
+      const double* Gv = ps.G + (size_t)(csrc[r] >= 0 ? (csrc[r] >> 4) : 0) * kViewStride;
+#pragma unroll
+      for (int q = 0; q < 6; ++q)
+        raw[r][q] = csrc[r] >= 0 ? (kk < 6 ? Gv[kOffBC + q * 6 + kk] : Gv[kOffBI + q * 8 + (kk - 6)]) : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < kS2ColsPerLane; ++r) {
+      if (csrc[r] >= 0) {
+        double w[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) w[q] = se[q] * raw[r][q] * csc[r];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) Wf[q * NLp + cg[r]] = w[q];
+        chol6_solve(M, w);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) Yf[q * NLp + cg[r]] = w[q];
+      }
+    }
+  }
+  for (int col = lane + 32 * kS2ColsPerLane; col < ncols; col += 32) {
+    const int src = B.col_src[c0 + col], g = schur_perm(B.col_g[c0 + col], NLp);
+    const int kk = src & 15;
+    const double sc = A.scale_c[B.col_sidx[c0 + col]];
+    const double* Gv = ps.G + (size_t)(src >> 4) * kViewStride;
+    double w[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const double rv = kk < 6 ? Gv[kOffBC + q * 6 + kk] : Gv[kOffBI + q * 8 + (kk - 6)];
+      w[q] = se[q] * rv * sc;
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) Wf[q * NLp + g] = w[q];
+    chol6_solve(M, w);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) Yf[q * NLp + g] = w[q];
+  }
+}
+
+// --- TMA bulk copy + mbarrier helpers (sm_90+/sm_100a) -----------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes,
+                                             unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int T>   // 4x4 tiles per thread
+__global__ void __launch_bounds__(T == 1 ? 512 : 768)
+k_schur_update(DeviceProblem P, const LmState* st, SchurSplitArgs B) {
+  if (st->done) return;
+  const SchurArgs& A = B.a;
+  extern __shared__ __align__(128) double s_mem[];
+  const int NL = P.NL, NLp = A.NLp, NT = blockDim.x;
+  const int rows_per_stage = kSchurFB * 6;
+  const int stage_doubles = 2 * rows_per_stage * NLp + rows_per_stage;   // Ws | Ys | zs
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  const int tid = threadIdx.x;
+  int tbi[T], tbj[T];
+  double acc[T][16];
+#pragma unroll
+  for (int k = 0; k < T; ++k) {
+    const int t = tid + k * NT;
+    tbi[k] = t < A.ntiles ? A.tile_bi[t] : -1;
+    tbj[k] = t < A.ntiles ? A.tile_bj[t] : 0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) acc[k][e] = 0.0;
+  }
+  double racc = 0.0;
+  const int f_begin = blockIdx.x * A.frames_per_block;
+  const int f_end = min(P.F, f_begin + A.frames_per_block);
+  const int nchunk = (f_end - f_begin + kSchurFB - 1) / kSchurFB;
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int c) {
+    const int f0 = f_begin + c * kSchurFB;
+    const int nf = min(kSchurFB, f_end - f0);
+    double* dst = s_mem + (c & 1) * stage_doubles;
+    const unsigned wbytes = (unsigned)(nf * 6 * NLp * sizeof(double));
+    const unsigned zbytes = (unsigned)(nf * 6 * sizeof(double));
+    mbar_expect_tx(&s_bar[c & 1], 2 * wbytes + zbytes);
+    tma_bulk_g2s(dst, B.Wg + (size_t)f0 * 6 * NLp, wbytes, &s_bar[c & 1]);
+    tma_bulk_g2s(dst + rows_per_stage * NLp, B.Yg + (size_t)f0 * 6 * NLp, wbytes, &s_bar[c & 1]);
+    tma_bulk_g2s(dst + 2 * rows_per_stage * NLp, B.zg + (size_t)f0 * 6, zbytes, &s_bar[c & 1]);
+  };
+  if (tid == 0 && nchunk > 0) issue(0);
+  for (int c = 0; c < nchunk; ++c) {
+    if (tid == 0 && c + 1 < nchunk) issue(c + 1);     // stage (c+1)&1 was released by the barrier below
+    mbar_wait(&s_bar[c & 1], (c >> 1) & 1);
+    const double* Ws = s_mem + (c & 1) * stage_doubles;
+    const double* Ys = Ws + rows_per_stage * NLp;
+    const double* zs = Ys + rows_per_stage * NLp;
+    const int rows = min(kSchurFB, f_end - (f_begin + c * kSchurFB)) * 6;
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+      if (tbi[k] >= 0) {
+        // operands of tile (bi, bj) in the permuted row: low pair at 2 b, high pair at NLp/2 + 2 b
+        const double* wl = Ws + 2 * tbi[k];
+        const double* yl = Ys + 2 * tbj[k];
+        const int hi = NLp >> 1;
+        for (int r0 = 0; r0 < rows; r0 += 3) {     // rows is a multiple of 6
+          double2 wa[3], wb[3], ya[3], yb[3];
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            const int o = (r0 + u) * NLp;
+            wa[u] = *reinterpret_cast<const double2*>(wl + o);
+            wb[u] = *reinterpret_cast<const double2*>(wl + o + hi);
+            ya[u] = *reinterpret_cast<const double2*>(yl + o);
+            yb[u] = *reinterpret_cast<const double2*>(yl + o + hi);
+          }
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            const double w[4] = {wa[u].x, wa[u].y, wb[u].x, wb[u].y};
+            const double y[4] = {ya[u].x, ya[u].y, yb[u].x, yb[u].y};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 4; ++b) acc[k][a * 4 + b] = fma(-w[a], y[b], acc[k][a * 4 + b]);
+          }
+        }
+      }
+    }
+    if (tid < NL) {
+      double a = racc;
+      const int pc = schur_perm(tid, NLp);
+      for (int r = 0; r < rows; ++r) a = fma(-Ws[r * NLp + pc], zs[r], a);
+      racc = a;
+    }
+    __syncthreads();
+  }
+  double* Sp = A.Spart + (size_t)blockIdx.x * P.Q;
+#pragma unroll
+  for (int k = 0; k < T; ++k) {
+    if (tbi[k] < 0) continue;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = 4 * tbi[k] + a, j = 4 * tbj[k] + b;
+        if (i <= j && j < NL) Sp[i * NL - (i * (i - 1)) / 2 + (j - i)] = acc[k][a * 4 + b];
+      }
+    }
+  }
+  if (tid < NL) A.rpart[(size_t)blockIdx.x * NL + tid] = racc;
 }
 
 // Sum the per-CTA partials: out = [S packed upper (Q) | rhs (NL)].
