@@ -39,3 +39,66 @@ extern "C" int hostmath_eval_jacobian(const tscm_problem* p, const double* intr,
   *cost = total;
   return 0;
 }
+
+
+// Per-view blocks through the moment formulation (what the evaluation kernel does) and
+// through the direct Gram of the full Jacobian rows; both written as [V][210] in the order
+// BB 21 | BC 36 | BI 48 | CC 21 | CI 48 | II 36.
+extern "C" int hostmath_view_blocks(const tscm_problem* p, const double* intr, const double* cam_rt,
+                                    const double* board_rt, int loss_type, double loss_scale,
+                                    double* via_moments, double* direct) {
+  using namespace tscm;
+  const int K = p->corners_per_board;
+  for (int v = 0; v < p->num_views; ++v) {
+    const int m = p->view_camera[v], i = p->view_frame[v];
+    CamConst cc; FrameConst fc; ViewConst vc;
+    make_cam_const(cam_rt + 6 * m, intr + 9 * m, m != p->fixed_camera, cc);
+    make_frame_const(board_rt + 6 * i, fc);
+    make_view_const(cc, fc, vc);
+    double mom[108] = {0}, II[36] = {0};
+    double G[20][20] = {{0}};
+    for (int j = 0; j < K; ++j) {
+      const size_t o = (size_t)v * K + j;
+      const double X = p->board_xy[2 * j], Y = p->board_xy[2 * j + 1];
+      ObsCompact oc;
+      obs_compact(cc, vc, X, Y, p->obs_xy[2 * o], p->obs_xy[2 * o + 1], oc);
+      double err;
+      obs_compact_loss(loss_type, loss_scale, oc, &err, true);
+      const double mu[3] = {X, Y, 1.0};
+      double q[6];
+      int e = 0;
+      for (int a = 0; a < 3; ++a) for (int b = a; b < 3; ++b) q[e++] = oc.au[a] * oc.au[b] + oc.av[a] * oc.av[b];
+      for (int mm = 0; mm < 3; ++mm) for (int nn = mm; nn < 3; ++nn)
+        for (int k = 0; k < 6; ++k) mom[mom_pair(mm, nn) * 6 + k] += mu[mm] * mu[nn] * q[k];
+      for (int mm = 0; mm < 3; ++mm) for (int k = 0; k < 3; ++k) for (int ii = 0; ii < 8; ++ii)
+        mom[36 + (mm * 3 + k) * 8 + ii] += mu[mm] * (oc.au[k] * oc.ju[ii] + oc.av[k] * oc.jv[ii]);
+      for (int a = 0; a < 8; ++a) for (int b = a; b < 8; ++b)
+        II[tri8(a, b)] += oc.ju[a] * oc.ju[b] + oc.jv[a] * oc.jv[b];
+      // direct
+      ObsRow row;
+      obs_jacobian<true, true, true>(cc, fc, X, Y, p->obs_xy[2 * o], p->obs_xy[2 * o + 1], row);
+      obs_apply_loss<0, 19>(loss_type, loss_scale, row, &err);
+      for (int a = 0; a < 20; ++a) for (int b = 0; b < 20; ++b)
+        G[a][b] += row.Ju[a] * row.Ju[b] + row.Jv[a] * row.Jv[b];
+    }
+    double cols[12][9];
+    for (int a = 0; a < 12; ++a) view_column_vectors(cc, fc, a, cols[a]);
+    double E[12][12], X[12][8];
+    for (int b = 0; b < 12; ++b) {
+      double oe[12], ox[8];
+      view_blocks_column(&cols[0][0], 9, b, [&](int k) { return mom[k]; }, oe, ox);
+      for (int a = 0; a <= b; ++a) E[a][b] = oe[a];
+      for (int ii = 0; ii < 8; ++ii) X[b][ii] = ox[ii];
+    }
+    double* out = via_moments + (size_t)v * 210;
+    double* ref = direct + (size_t)v * 210;
+    int k = 0;
+    for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b) { out[k] = E[a][b]; ref[k++] = G[a][b]; }
+    for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) { out[k] = E[a][6 + b]; ref[k++] = G[a][6 + b]; }
+    for (int a = 0; a < 6; ++a) for (int b = 0; b < 8; ++b) { out[k] = X[a][b]; ref[k++] = G[a][12 + b]; }
+    for (int a = 0; a < 6; ++a) for (int b = a; b < 6; ++b) { out[k] = E[6 + a][6 + b]; ref[k++] = G[6 + a][6 + b]; }
+    for (int a = 0; a < 6; ++a) for (int b = 0; b < 8; ++b) { out[k] = X[6 + a][b]; ref[k++] = G[6 + a][12 + b]; }
+    for (int a = 0; a < 8; ++a) for (int b = a; b < 8; ++b) { out[k] = II[tri8(a, b)]; ref[k++] = G[12 + a][12 + b]; }
+  }
+  return 0;
+}

@@ -131,7 +131,9 @@ struct tscm_solver {
   int schur2_nt = 0;
   size_t schur2_smem = 0;
   int schur_nblk = 0, schur_nt = 256, schur_ept = 20;
-  size_t schur_smem = 0, solve_smem = 0, eval3_smem = 0;
+  size_t schur_smem = 0, solve_smem = 0, eval3_smem = 0, eval4_smem = 0;
+  int eval_variant = 4;
+  int want_err = 0;   // accumulate sum sqrt(s) (reprojection read-out only)
   int prof = 0;
   int bs_nblk = 0, fg_nblk = 0;
   // graph of one LM iteration
@@ -223,11 +225,16 @@ int validate_problem(const tscm_problem* p) {
   return TSCM_OK;
 }
 
-// The residual + Jacobian + normal-equation kernel (warp-specialised k_eval3).
+// The residual + Jacobian + normal-equation kernel: k_eval4 (moment form, default) or
+// k_eval3 (rank-1 sweeps of full Jacobian rows; TSCM_EVAL_VARIANT=3, kept for A/B timing).
 void launch_eval_kernel(tscm_solver* s, int which) {
   const DeviceProblem& P = s->P;
-  k_eval3<<<(P.V + 31) / 32, kE3Threads, s->eval3_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state,
-                                                                    which, s->lm, s->prof);
+  if (s->eval_variant == 3)
+    k_eval3<<<(P.V + 31) / 32, kE3Threads, s->eval3_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state,
+                                                                      which, s->lm, s->prof);
+  else
+    k_eval4<<<(P.V + 31) / 32, kE3Threads, s->eval4_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state,
+                                                                      which, s->lm, s->want_err);
 }
 
 // which: 0 = current, 1 = candidate (relative to st->cur); 2/3 = absolute set 0/1.
@@ -324,7 +331,8 @@ void launch_solve(tscm_solver* s, double radius_override, bool debug) {
 
 void launch_backsub(tscm_solver* s) {
   k_backsub<<<s->bs_nblk, kBacksubThreads, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state,
-                                                          s->schur, s->d_yc, s->d_bs_part, s->bs_nblk);
+                                                          s->schur, s->d_yc, s->d_bs_part, s->bs_nblk,
+                                                          s->split_ok ? s->split.Wg : nullptr);
   s->launches += 1;
 }
 
@@ -588,6 +596,14 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   if (const char* pv = getenv("TSCM_PROF")) s->prof = atoi(pv);
   s->eval3_smem = (size_t)(2 * kE3Group * kE2Elems * 32 + 2 * K) * sizeof(double) +
                   (size_t)C * sizeof(CamConst);
+  {
+    const size_t main_d = (size_t)2 * kE3Group * kE4Elems * 32;
+    const size_t epi_d = (size_t)kE4Mom * 33 + 32 * 108 + 32 * kViewStride + (size_t)kCamRec * 33;
+    const size_t kpad = ((size_t)K + kE3Group - 1) / kE3Group * kE3Group;
+    s->eval4_smem = (std::max(main_d, epi_d) + kFcElems * 32 + 5 * kpad + (kpad & 1)) * sizeof(double) +
+                    (size_t)C * sizeof(CamConst);
+  }
+  if (const char* ev = getenv("TSCM_EVAL_VARIANT")) s->eval_variant = atoi(ev) == 3 ? 3 : 4;
   TRY_RC(s->alloc(&s->schur.frame_rec, (size_t)kFrameRec * s->schur.Fpad));
   TRY_RC(s->alloc(&s->d_Spart, (size_t)s->schur_nblk * P.Q));
   TRY_RC(s->alloc(&s->d_rpart, (size_t)s->schur_nblk * NL));
@@ -664,6 +680,7 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   TRY_RC(set_smem((const void*)k_solve<4>, s->solve_smem));
   TRY_RC(set_smem((const void*)k_solve<7>, s->solve_smem));
   TRY_RC(set_smem((const void*)k_eval3, s->eval3_smem));
+  TRY_RC(set_smem((const void*)k_eval4, s->eval4_smem));
 
   TRY_RC(tscm_solver_set_observations(s, p->obs_xy));
 #undef TRY_RC
@@ -889,9 +906,11 @@ int tscm_solver_reprojection_error(tscm_solver* s, double* per_camera, double* o
   // Read-out uses the plain (loss-free) residuals, like multi_calib.cpp:235-283.
   LmOptions saved = s->lm;
   s->lm.loss_type = 0;
+  s->want_err = 1;
   launch_evaluation(s, 2 + cur, 1);
   rc = launch_eval_allreduce(s, 2 + cur);
   s->lm = saved;
+  s->want_err = 0;
   if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   CUDA_TRY(cudaGetLastError());

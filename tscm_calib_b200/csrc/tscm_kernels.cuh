@@ -375,6 +375,264 @@ k_eval3(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
   }
 }
 
+// ---------------------------------------------------------------------------
+// K1+K2, moment form (default).  Same warp-specialised skeleton as k_eval3 — a CTA owns 32
+// views (lane = view), 8 producer warps, 4 consumer warps, double-buffered rows, one barrier
+// per group of 8 corners — but built on the moment formulation of tscm_math.cuh:
+//  * a producer evaluates only the projection, At = -d(u,v)/dP (2x3), the intrinsic rows and
+//    the residual of its corner (24 doubles published instead of 42; no 2x12 extrinsic chain);
+//  * consumer 0 accumulates the 36 second moments M[m][n] of At^T At, consumers 1..3 the 24
+//    entries of N[m] = sum mu_m At^T [J_I | r] for m = X, Y, 1 plus a third of II each;
+//  * once per view, all 384 threads rebuild the 12x12 / 12x8 extrinsic blocks from the
+//    moments (thread = (view, column), view_blocks_column) and write the per-view record and
+//    the per-(CTA, camera) partial record exactly as k_eval3 does.
+// ~48 % fewer FP64 instructions per corner than k_eval3 on the busiest sub-partition.
+// ---------------------------------------------------------------------------
+constexpr int kE4Elems = 24;     // au[3] av[3] ju[8] jv[8] 1/2rho sqrt(s)
+constexpr int kE4Mom = 108;      // M 36 | N 72
+constexpr int kFcElems = 27;
+
+// live intrinsic columns of a residual row (see e3_live)
+template <int ROLE>
+__device__ __forceinline__ void e4_consume(const double* __restrict__ row, int lane,
+                                           const double* __restrict__ mu, double* __restrict__ acc) {
+  // row elements: au 0..2, av 3..5, ju 6..13, jv 14..21, cost 22, err 23
+  double au[3], av[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { au[k] = row[k * 32 + lane]; av[k] = row[(3 + k) * 32 + lane]; }
+  if (ROLE == 0) {
+    double q[6];
+    q[0] = fma(av[0], av[0], au[0] * au[0]); q[1] = fma(av[0], av[1], au[0] * au[1]);
+    q[2] = fma(av[0], av[2], au[0] * au[2]); q[3] = fma(av[1], av[1], au[1] * au[1]);
+    q[4] = fma(av[1], av[2], au[1] * au[2]); q[5] = fma(av[2], av[2], au[2] * au[2]);
+    // pairs 00 01 02 11 12 22 <-> weights X^2, XY, X, Y^2, Y, 1   (mu = X, Y, X^2, XY, Y^2)
+    const double w[5] = {mu[2], mu[3], mu[0], mu[4], mu[1]};
+#pragma unroll
+    for (int pr = 0; pr < 5; ++pr)
+#pragma unroll
+      for (int e = 0; e < 6; ++e) acc[pr * 6 + e] = fma(w[pr], q[e], acc[pr * 6 + e]);
+#pragma unroll
+    for (int e = 0; e < 6; ++e) acc[30 + e] += q[e];
+    acc[36] += row[22 * 32 + lane];
+    acc[37] += row[23 * 32 + lane];
+  } else {
+    double ju[8], jv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ju[i] = row[(6 + i) * 32 + lane]; jv[i] = row[(14 + i) * 32 + lane]; }
+    if (ROLE < 3) {
+      const double m = mu[ROLE - 1];      // X or Y
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { au[k] *= m; av[k] *= m; }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (e3_live(0, i)) acc[k * 8 + i] = fma(au[k], ju[i], acc[k * 8 + i]);
+        if (e3_live(1, i)) acc[k * 8 + i] = fma(av[k], jv[i], acc[k * 8 + i]);
+      }
+    // this role's third of II (tri8 entries 12 (ROLE-1) .. 12 ROLE - 1)
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = a; b < 8; ++b) {
+        constexpr int lo = 12 * (ROLE - 1);
+        const int e = tri8(a, b);
+        if (e >= lo && e < lo + 12) {
+          if (e3_live(0, a) && e3_live(0, b)) acc[24 + e - lo] = fma(ju[a], ju[b], acc[24 + e - lo]);
+          if (e3_live(1, a) && e3_live(1, b)) acc[24 + e - lo] = fma(jv[a], jv[b], acc[24 + e - lo]);
+        }
+      }
+  }
+}
+
+__global__ void __launch_bounds__(kE3Threads, 1)
+k_eval4(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which, LmOptions opt,
+        int want_err) {
+  if (which < 2 && st->done) return;
+  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
+  const ParamSet& ps = sel ? ps1 : ps0;
+  extern __shared__ __align__(16) double s_mem[];
+  constexpr int kBuf = kE3Group * kE4Elems * 32;
+  // main-loop layout: rows [2][8][24][32]; epilogue layout (re-uses the rows region):
+  // moments [108][33] | colvecs [32][108] | view records [32][106] | camera staging [107][33]
+  constexpr int kMainDoubles = 2 * kBuf;
+  constexpr int kEpiDoubles = kE4Mom * 33 + 32 * 108 + 32 * kViewStride + kCamRec * 33;
+  constexpr int kRegion = kMainDoubles > kEpiDoubles ? kMainDoubles : kEpiDoubles;
+  double* s_rows = s_mem;
+  double* s_fc = s_mem + kRegion;                                     // [27][32]
+  double* s_mu = s_fc + kFcElems * 32;                                // [Kpad][5], Kpad = K rounded up to 8
+  const int Kpad = (P.K + kE3Group - 1) / kE3Group * kE3Group;
+  CamConst* s_cam = reinterpret_cast<CamConst*>(s_mu + 5 * Kpad + (Kpad & 1));   // [C]
+  for (int j = threadIdx.x; j < Kpad; j += blockDim.x) {
+    const double X = j < P.K ? P.board_xy[2 * j] : 0.0, Y = j < P.K ? P.board_xy[2 * j + 1] : 0.0;
+    s_mu[5 * j] = X; s_mu[5 * j + 1] = Y; s_mu[5 * j + 2] = X * X; s_mu[5 * j + 3] = X * Y; s_mu[5 * j + 4] = Y * Y;
+  }
+  {
+    const int n = P.C * (int)(sizeof(CamConst) / sizeof(double));
+    const double* src = reinterpret_cast<const double*>(ps.cam);
+    double* dst = reinterpret_cast<double*>(s_cam);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v0 = blockIdx.x * 32 + lane;
+  const bool valid = v0 < P.V;
+  const int v = valid ? v0 : P.V - 1;
+  if (warp == kE3Consumers) {
+    FrameConst fc;
+    make_frame_const(ps.board_rt + 6 * P.view_frame[v], fc);
+    const double* fp = reinterpret_cast<const double*>(&fc);
+#pragma unroll
+    for (int e = 0; e < kFcElems; ++e) s_fc[e * 32 + lane] = fp[e];
+  }
+  __syncthreads();
+  const int ngroups = (P.K + kE3Group - 1) / kE3Group;
+
+  if (warp >= kE3Consumers) {
+    // ------------------------------ producer ------------------------------------
+    const int p = warp - kE3Consumers;
+    const CamConst& cc = s_cam[P.view_camera[v]];
+    const double2* obs = P.obsT + v;
+    ViewConst vc;
+    {
+      FrameConst fc;
+      double* fp = reinterpret_cast<double*>(&fc);
+#pragma unroll
+      for (int e = 0; e < kFcElems; ++e) fp[e] = s_fc[e * 32 + lane];
+      make_view_const(cc, fc, vc);
+    }
+    for (int g = 0; g <= ngroups; ++g) {
+      if (g < ngroups) {
+        const int j = g * kE3Group + p;
+        double* mine = s_rows + (g & 1) * kBuf + p * (kE4Elems * 32);
+        if (j < P.K && valid) {
+          const double2 uv = obs[(size_t)j * P.Vpad];
+          ObsCompact o;
+          obs_compact(cc, vc, s_mu[5 * j], s_mu[5 * j + 1], uv.x, uv.y, o);
+          double err;
+          const double half_rho = obs_compact_loss(opt.loss_type, opt.loss_scale, o, &err, want_err != 0);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { mine[k * 32 + lane] = o.au[k]; mine[(3 + k) * 32 + lane] = o.av[k]; }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { mine[(6 + k) * 32 + lane] = o.ju[k]; mine[(14 + k) * 32 + lane] = o.jv[k]; }
+          mine[22 * 32 + lane] = half_rho;
+          mine[23 * 32 + lane] = err;
+        } else {
+#pragma unroll
+          for (int k = 0; k < kE4Elems; ++k) mine[k * 32 + lane] = 0.0;
+        }
+      }
+      __syncthreads();
+    }
+  } else {
+    // ------------------------------ consumer ------------------------------------
+    double acc[38];
+#pragma unroll
+    for (int i = 0; i < 38; ++i) acc[i] = 0.0;
+    for (int g = 0; g <= ngroups; ++g) {
+      if (g > 0) {
+        const double* buf = s_rows + ((g - 1) & 1) * kBuf;
+        const double* mu = s_mu + 5 * (g - 1) * kE3Group;
+        if (warp == 0) {
+#pragma unroll 2
+          for (int o = 0; o < kE3Group; ++o) e4_consume<0>(buf + o * (kE4Elems * 32), lane, mu + 5 * o, acc);
+        } else if (warp == 1) {
+#pragma unroll 2
+          for (int o = 0; o < kE3Group; ++o) e4_consume<1>(buf + o * (kE4Elems * 32), lane, mu + 5 * o, acc);
+        } else if (warp == 2) {
+#pragma unroll 2
+          for (int o = 0; o < kE3Group; ++o) e4_consume<2>(buf + o * (kE4Elems * 32), lane, mu + 5 * o, acc);
+        } else {
+#pragma unroll 2
+          for (int o = 0; o < kE3Group; ++o) e4_consume<3>(buf + o * (kE4Elems * 32), lane, mu + 5 * o, acc);
+        }
+      }
+      __syncthreads();
+    }
+    // moments -> shared [entry][33]; II, cost, err straight to the camera staging area
+    double* mom = s_rows;
+    double* cs = s_rows + kE4Mom * 33 + 32 * 108 + 32 * kViewStride;
+    if (warp == 0) {
+#pragma unroll
+      for (int i = 0; i < 36; ++i) mom[i * 33 + lane] = acc[i];
+      cs[kCamCost * 33 + lane] = acc[36];
+      cs[kCamErr * 33 + lane] = acc[37];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 24; ++i) mom[(36 + (warp - 1) * 24 + i) * 33 + lane] = acc[i];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) cs[(kCamII + 12 * (warp - 1) + i) * 33 + lane] = acc[24 + i];
+    }
+  }
+  // (the staging writes above touch the rows region: every warp is past the last barrier of
+  // the main loop, and the last group consumed lives in buffer (ngroups-1)&1 — the moments
+  // area overlaps it, so synchronise before anyone reads and after everyone consumed)
+  __syncthreads();
+  double* mom = s_rows;
+  double* colv = s_rows + kE4Mom * 33;                 // [32][12][9]
+  double* recs = colv + 32 * 108;                      // [32][106]
+  double* cs = recs + 32 * kViewStride;                // [107][33]
+  {
+    // column vectors: thread (view, column)
+    const int vw = threadIdx.x / 12, b = threadIdx.x % 12;
+    if (vw < 32) {
+      const int gv = min(blockIdx.x * 32 + vw, P.V - 1);
+      FrameConst fc;
+      double* fp = reinterpret_cast<double*>(&fc);
+#pragma unroll
+      for (int e = 0; e < kFcElems; ++e) fp[e] = s_fc[e * 32 + vw];
+      view_column_vectors(s_cam[P.view_camera[gv]], fc, b, colv + (vw * 12 + b) * 9);
+    }
+  }
+  __syncthreads();
+  {
+    const int vw = threadIdx.x / 12, b = threadIdx.x % 12;
+    if (vw < 32) {
+      double oe[12], ox[8];
+      const double* mv = mom + vw;
+      view_blocks_column(colv + vw * 108, 9, b, [mv](int k) { return mv[k * 33]; }, oe, ox);
+      double* rec = recs + vw * kViewStride;
+      if (b < 6) {
+        for (int a = 0; a <= b; ++a) rec[kOffBB + tri6(a, b)] = oe[a];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rec[kOffBI + b * 8 + i] = ox[i];
+        if (b == 0) rec[kViewStride - 1] = 0.0;
+      } else {
+        const int c = b - 6;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) rec[kOffBC + a * 6 + c] = oe[a];
+        for (int a = 0; a <= c; ++a) cs[(kCamCC + tri6(a, c)) * 33 + vw] = oe[6 + a];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cs[(kCamCI + c * 8 + i) * 33 + vw] = ox[i];
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kCamRec) {
+    const double* c1 = cs + threadIdx.x * 33;
+    const int nv = min(32, P.V - blockIdx.x * 32);
+    const int* vc = P.view_camera + blockIdx.x * 32;
+    int slot = P.blk_slot[blockIdx.x];
+    int l = 0;
+    while (l < nv) {
+      const int c = vc[l];
+      double s0 = 0.0, s1 = 0.0;
+      int k = l;
+      for (; k + 1 < nv && vc[k + 1] == c; k += 2) { s0 += c1[k]; s1 += c1[k + 1]; }
+      if (k < nv && vc[k] == c) { s0 += c1[k]; ++k; }
+      ps.cam_part[(size_t)slot * kCamRec + threadIdx.x] = s0 + s1;
+      ++slot;
+      l = k;
+    }
+  }
+  {
+    const int nv = min(32, P.V - blockIdx.x * 32);
+    double* dst = ps.G + (size_t)blockIdx.x * 32 * kViewStride;
+    const int n = nv * kViewStride;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = recs[i];
+  }
+}
+
 // Inspection kernel: one thread per observation, full residual + Jacobian rows
 // in the reference's column order (camera_rt 6, chessboard_rt 6, intrinsic 9).
 __global__ void k_eval_rows(DeviceProblem P, ParamSet ps, LmOptions opt, double* residuals,
@@ -1429,20 +1687,46 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
     __syncthreads();
   }
   tk2 = clock64();
-  // Back-substitution by warp 0: x_j = (rhs'_j - sum_{i>j} A[i][j] x_i) / d_j; column j is
-  // contiguous, the sum is a warp dot product.
+  // Back-substitution by warp 0, four columns per step: the four dot products
+  // sum_{i >= j+4} A[i][j+c] x_i are reduced together (their shuffle chains interleave), then
+  // the 4x4 unit-triangular tail is solved by substitution.  x_j = (rhs'_j - sum) / d_j.
   if (warp == 0) {
-    for (int j = NL - 1; j >= 0; --j) {
-      const int cp = COLPTR(j) - j;
-      double s0 = 0.0;
+    for (int jb = ((NL - 1) >> 2) << 2; jb >= 0; jb -= 4) {
+      const int nb = min(4, NL - jb);
+      double sacc[4] = {0.0, 0.0, 0.0, 0.0};
+      const int i0 = jb + nb;
 #pragma unroll
-      for (int bb = 0; bb < AMAX; ++bb) {
-        const int i = j + 1 + lane + 32 * bb;
-        if (i < NL) s0 = fma(L[cp + i], x[i], s0);
+      for (int c = 0; c < 4; ++c) {
+        if (c < nb) {
+          const int cp = COLPTR(jb + c) - (jb + c);
+#pragma unroll
+          for (int bb = 0; bb < AMAX; ++bb) {
+            const int i = i0 + lane + 32 * bb;
+            if (i < NL) sacc[c] = fma(L[cp + i], x[i], sacc[c]);
+          }
+        }
       }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-      if (lane == 0) x[j] = (L[cp + NL] - s0) * dinv[j];
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sacc[c] += __shfl_xor_sync(0xffffffffu, sacc[c], o);
+      }
+      if (lane == 0) {
+        double xs[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int c = 3; c >= 0; --c) {
+          if (c < nb) {
+            const int j = jb + c;
+            const int cp = COLPTR(j) - j;
+            double t = L[cp + NL] - sacc[c];
+#pragma unroll
+            for (int d = 3; d > 0; --d)
+              if (d > c && d < nb) t = fma(-L[cp + jb + d], xs[d], t);
+            xs[c] = t * dinv[j];
+            x[j] = xs[c];
+          }
+        }
+      }
       __syncwarp();
     }
   }
@@ -1514,9 +1798,17 @@ constexpr int kBacksubThreads = 256;
 
 __global__ void __launch_bounds__(kBacksubThreads)
 k_backsub(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, SchurArgs A,
-          const double* __restrict__ y_c, double* __restrict__ part /*[4][nblk]*/, int nblk) {
+          const double* __restrict__ y_c, double* __restrict__ part /*[4][nblk]*/, int nblk,
+          const double* __restrict__ Wg /* materialised, permuted W_s rows or nullptr */) {
   __shared__ double s_red[kBacksubThreads];
+  __shared__ double s_yp[224];
   if (st->done) return;
+  if (Wg) {
+    for (int i = threadIdx.x; i < A.NLp; i += kBacksubThreads) s_yp[i] = 0.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.NL; i += kBacksubThreads) s_yp[schur_perm(i, A.NLp)] = y_c[i];
+    __syncthreads();
+  }
   const int sel = st->cur;
   const ParamSet& ps = sel ? ps1 : ps0;
   const ParamSet& pc = sel ? ps0 : ps1;
@@ -1529,7 +1821,15 @@ k_backsub(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, SchurA
     for (int i = 0; i < 6; ++i) se[i] = A.scale_e[f * 6 + i];
     // w = W_s y_c : lanes stride over the frame's live columns
     double w[6] = {0, 0, 0, 0, 0, 0};
-    const int p0 = P.frame_ptr[f], nv = P.frame_ptr[f + 1] - p0;
+    const int p0 = P.frame_ptr[f], nv = Wg ? 0 : P.frame_ptr[f + 1] - p0;
+    if (Wg) {
+      const double* Wf = Wg + (size_t)f * 6 * A.NLp;
+      for (int c = lane; c < A.NLp; c += 32) {
+        const double yv = s_yp[c];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) w[r] = fma(Wf[r * A.NLp + c], yv, w[r]);
+      }
+    }
     for (int p = 0; p < nv; ++p) {
       const int v = P.frame_views[p0 + p];
       const int m = P.view_camera[v];
@@ -1549,7 +1849,7 @@ k_backsub(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, SchurA
     for (int r = 0; r < 6; ++r) {
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1) w[r] += __shfl_xor_sync(0xffffffffu, w[r], s);
-      w[r] *= se[r];
+      if (!Wg) w[r] *= se[r];     // the materialised rows are already scaled
     }
     if (lane == 0) {
       double Lm[36], z[6], Vs[21], gs[6];

@@ -313,6 +313,175 @@ TSCM_HD void obs_jacobian(const CamConst& c, const FrameConst& f, double X, doub
   }
 }
 
+// ---------------------------------------------------------------------------
+// Moment formulation of the per-view normal-equation blocks.
+//
+// Camera-frame point of board corner (X, Y, 0):  P = X m1 + Y m2 + T  (per-view m1, m2, T).
+// Every extrinsic column of dP/dparams is affine in (X, Y):
+//      g_a(X, Y) = X c0[a] + Y c1[a] + c2[a]          a = 0..11  (w_f, t_f, w_c, t_c)
+// and the residual Jacobian is  J = [ At G | J_I ],  At = -d(u,v)/dP  (2x3).  Hence
+//      J_ext^T J_ext   = sum_{m,n} C_m^T  M[m][n]  C_n ,   M[m][n] = sum_j mu_m mu_n At_j^T At_j
+//      J_ext^T [J_I|r] = sum_m     C_m^T  N[m]         ,   N[m]    = sum_j mu_m At_j^T [J_I | r]_j
+// with mu = (X, Y, 1).  Per corner only At (6 numbers), the intrinsic rows and r are
+// evaluated and 36 + 72 moment sums are updated; the 12x12 / 12x8 blocks are rebuilt once
+// per view from the moments (view_blocks_column).
+// ---------------------------------------------------------------------------
+struct ViewConst {
+  double m1[3], m2[3], T[3];
+};
+
+TSCM_HD void make_view_const(const CamConst& c, const FrameConst& f, ViewConst& v) {
+  TSCM_UNROLL
+  for (int i = 0; i < 3; ++i) {
+    v.m1[i] = c.R[3 * i] * f.r1[0] + c.R[3 * i + 1] * f.r1[1] + c.R[3 * i + 2] * f.r1[2];
+    v.m2[i] = c.R[3 * i] * f.r2[0] + c.R[3 * i + 1] * f.r2[1] + c.R[3 * i + 2] * f.r2[2];
+    v.T[i] = c.R[3 * i] * f.t[0] + c.R[3 * i + 1] * f.t[1] + c.R[3 * i + 2] * f.t[2] + c.t[i];
+  }
+}
+
+// Compact per-observation row: At rows (au, av), intrinsic rows + residual (ju, jv; [7] = r).
+struct ObsCompact {
+  double au[3], av[3];
+  double ju[8], jv[8];
+};
+
+TSCM_HD void obs_compact(const CamConst& c, const ViewConst& vc, double X, double Y, double uo,
+                         double vo, ObsCompact& o) {
+  double P[3];
+  TSCM_UNROLL
+  for (int i = 0; i < 3; ++i) P[i] = X * vc.m1[i] + Y * vc.m2[i] + vc.T[i];
+  TsForward t;
+  ts_forward(c, P, t);
+  o.ju[7] = uo - (c.fx * t.mx + c.cx);
+  o.jv[7] = vo - (c.fy * t.my + c.cy);
+  const double a1 = c.xi * t.id1;
+  const double g1 = 1.0 + a1 * t.z;
+  const double b1 = (1.0 + t.z1 * a1) * t.id2;
+  const double c1 = t.z1 * g1 * t.id2;
+  const double a2 = a1 + c.lam * b1;
+  const double g2 = g1 + c.lam * c1;
+  const double b2 = (1.0 + t.z2 * a2) * t.id3;
+  const double c2 = t.z2 * g2 * t.id3;
+  const double e = a2 + c.k * b2;
+  const double h = g2 + c.k * c2;
+  const double fu = c.fx * t.iD, fv = c.fy * t.iD;
+  // At = -A
+  o.au[0] = -fu * (1.0 - t.mx * e * t.x); o.au[1] = fu * t.mx * e * t.y; o.au[2] = fu * t.mx * h;
+  o.av[0] = fv * t.my * e * t.x; o.av[1] = -fv * (1.0 - t.my * e * t.y); o.av[2] = fv * t.my * h;
+  const double d2xi = t.z1 * t.d1 * t.id2;
+  const double z2xi = t.d1 + c.lam * d2xi;
+  const double Dxi = z2xi + c.k * (t.z2 * z2xi * t.id3);
+  const double Dlam = t.d2 + c.k * (t.z2 * t.d2 * t.id3);
+  const double Dal = t.d3 * c.dk;
+  const double ex = fu * t.mx, ey = fv * t.my;
+  o.ju[0] = -t.mx; o.jv[0] = 0.0;
+  o.ju[1] = 0.0;   o.jv[1] = -t.my;
+  o.ju[2] = -1.0;  o.jv[2] = 0.0;
+  o.ju[3] = 0.0;   o.jv[3] = -1.0;
+  o.ju[4] = ex * Dxi;  o.jv[4] = ey * Dxi;
+  o.ju[5] = ex * Dlam; o.jv[5] = ey * Dlam;
+  o.ju[6] = ex * Dal;  o.jv[6] = ey * Dal;
+}
+
+// Loss correction of a compact row (Huber / Cauchy have rho'' <= 0, so Ceres' Corrector
+// reduces to a uniform scaling by sqrt(rho') of J and r — corrector.cc, alpha == 0 branch;
+// structural zeros of the rows are preserved).  Returns 1/2 rho(s); *err = sqrt(s) (raw).
+TSCM_HD double obs_compact_loss(int loss_type, double loss_scale, ObsCompact& o, double* err,
+                                bool want_err) {
+  const double ru = o.ju[7], rv = o.jv[7];
+  const double s = ru * ru + rv * rv;
+  *err = want_err ? sqrt(s) : 0.0;
+  if (loss_type == 0) return 0.5 * s;
+  double rho[3];
+  loss_rho(loss_type, loss_scale, s, rho);
+  const double w = sqrt(rho[1]);
+  TSCM_UNROLL
+  for (int k = 0; k < 3; ++k) { o.au[k] *= w; o.av[k] *= w; }
+  TSCM_UNROLL
+  for (int k = 0; k < 8; ++k) { o.ju[k] *= w; o.jv[k] *= w; }
+  return 0.5 * rho[0];
+}
+
+// The three coefficient vectors of extrinsic column a (0..2 w_f, 3..5 t_f, 6..8 w_c, 9..11 t_c):
+// out[m*3 + i] = c_m[a][i].
+TSCM_HD void view_column_vectors(const CamConst& c, const FrameConst& f, int a, double out[9]) {
+  TSCM_UNROLL
+  for (int i = 0; i < 9; ++i) out[i] = 0.0;
+  if (a < 3) {            // w_f[b]:  X R_c d1[b] + Y R_c d2[b]
+    for (int i = 0; i < 3; ++i) {
+      out[i] = c.R[3 * i] * f.d1[a][0] + c.R[3 * i + 1] * f.d1[a][1] + c.R[3 * i + 2] * f.d1[a][2];
+      out[3 + i] = c.R[3 * i] * f.d2[a][0] + c.R[3 * i + 1] * f.d2[a][1] + c.R[3 * i + 2] * f.d2[a][2];
+    }
+  } else if (a < 6) {     // t_f[k]:  R_c[:, k]
+    for (int i = 0; i < 3; ++i) out[6 + i] = c.R[3 * i + (a - 3)];
+  } else if (c.free_rt) {
+    if (a < 9) {          // w_c[b]:  dR_c[b] (X r1 + Y r2 + t_f)
+      const double* D = c.dR[a - 6];
+      for (int i = 0; i < 3; ++i) {
+        out[i] = D[3 * i] * f.r1[0] + D[3 * i + 1] * f.r1[1] + D[3 * i + 2] * f.r1[2];
+        out[3 + i] = D[3 * i] * f.r2[0] + D[3 * i + 1] * f.r2[1] + D[3 * i + 2] * f.r2[2];
+        out[6 + i] = D[3 * i] * f.t[0] + D[3 * i + 1] * f.t[1] + D[3 * i + 2] * f.t[2];
+      }
+    } else {              // t_c[k]:  e_k
+      out[6 + (a - 9)] = 1.0;
+    }
+  }
+}
+
+// Moment layouts.  M: 6 (m<=n pairs: 00 01 02 11 12 22) x 6 (sym 3x3: 00 01 02 11 12 22) = 36;
+// N: 3 (m) x 3 (k) x 8 (i) = 72.
+TSCM_HD constexpr int mom_pair(int m, int n) {   // m <= n
+  return m == 0 ? n : (m == 1 ? 2 + n : 5);
+}
+TSCM_HD double sym3(const double* q, int i, int j) {   // q: 00 01 02 11 12 22
+  const int a = i < j ? i : j, b = i < j ? j : i;
+  return q[a == 0 ? b : (a == 1 ? 2 + b : 5)];
+}
+
+// Column b of the per-view blocks from the moments.  cols: [12][9] coefficient vectors of
+// all columns (view_column_vectors), ld = stride between columns.
+//   outE[a] = E[a][b] for a = 0..b     (upper triangle of J_ext^T J_ext)
+//   outX[i] = X[b][i] for i = 0..7     (row b of J_ext^T [J_I | r])
+template <typename MomLoad>
+TSCM_HD void view_blocks_column(const double* cols, int ld, int b, MomLoad mom, double* outE,
+                                double* outX) {
+  const double* cb = cols + b * ld;
+  // h_m = sum_n M[m][n] c_n[b]
+  double h[3][3];
+  TSCM_UNROLL
+  for (int m = 0; m < 3; ++m) {
+    TSCM_UNROLL
+    for (int i = 0; i < 3; ++i) h[m][i] = 0.0;
+    TSCM_UNROLL
+    for (int n = 0; n < 3; ++n) {
+      const int pr = m <= n ? mom_pair(m, n) : mom_pair(n, m);
+      double q[6];
+      TSCM_UNROLL
+      for (int e = 0; e < 6; ++e) q[e] = mom(pr * 6 + e);
+      TSCM_UNROLL
+      for (int i = 0; i < 3; ++i)
+        h[m][i] += sym3(q, i, 0) * cb[3 * n] + sym3(q, i, 1) * cb[3 * n + 1] + sym3(q, i, 2) * cb[3 * n + 2];
+    }
+  }
+  for (int a = 0; a <= b; ++a) {
+    const double* ca = cols + a * ld;
+    double s = 0.0;
+    TSCM_UNROLL
+    for (int m = 0; m < 3; ++m)
+      s += ca[3 * m] * h[m][0] + ca[3 * m + 1] * h[m][1] + ca[3 * m + 2] * h[m][2];
+    outE[a] = s;
+  }
+  TSCM_UNROLL
+  for (int i = 0; i < 8; ++i) {
+    double s = 0.0;
+    TSCM_UNROLL
+    for (int m = 0; m < 3; ++m)
+      s += cb[3 * m] * mom(36 + (m * 3 + 0) * 8 + i) + cb[3 * m + 1] * mom(36 + (m * 3 + 1) * 8 + i) +
+           cb[3 * m + 2] * mom(36 + (m * 3 + 2) * 8 + i);
+    outX[i] = s;
+  }
+}
+
 // Loss correction of one observation's rows (ResidualBlock::Evaluate order:
 // Jacobian first with the uncorrected residual, then the residual).  Returns
 // 1/2 rho(s); *err receives sqrt(s) of the raw residual.
