@@ -48,6 +48,22 @@ ALG_BYTES_PER_OBS_EVAL = 24.0   # J-pass with per-view blocks 
 ALG_FLOPS_PER_OBS_EVAL = 1060.0  # forward 130 + Jacobian 250 + outer products 680
 
 
+def captured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture
+    (profiles/r*_traffic.json, written by tools/make_profile_summary.py); None if absent."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json"))):
+        try:
+            with open(path) as f:
+                d = json.load(f)
+            if kernel in d:
+                best = d[kernel]["dram_bytes"]
+        except Exception:
+            pass
+    return best
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -246,17 +262,18 @@ def run_b200(args):
         hbm_peak, how = measured_peaks()
         achieved = n_obs * ALG_BYTES_PER_OBS_EVAL / (ms_eval * 1e-3) / 1e9
         line["roofline"] = {
-            "kernel": "k_eval3", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "kernel": "k_eval4", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": captured_traffic("k_eval4"),
             "peak_source": how, "ms_per_launch": ms_eval,
             "algorithmic_bytes_per_observation": ALG_BYTES_PER_OBS_EVAL,
-            "note": "k_eval is FP64-pipe bound (arithmetic intensity ~44 flop/B vs machine "
-                    "balance ~5.7 flop/B); see roofline_fp64",
+            "note": "k_eval4 is FP64-pipe bound (arithmetic intensity ~44 flop/B vs machine "
+                    "balance ~5.3 flop/B); see roofline_fp64.  traffic = DRAM bytes of one launch "
+                    "from the committed ncu capture (profiles/)",
         }
         fp64_peak = capi.device_fp64_peak(local_rank)
         tf = n_obs * ALG_FLOPS_PER_OBS_EVAL / (ms_eval * 1e-3) / 1e12
         line["roofline_fp64"] = {
-            "kernel": "k_eval3", "bound": "fp64", "achieved": tf, "peak": fp64_peak,
+            "kernel": "k_eval4", "bound": "fp64", "achieved": tf, "peak": fp64_peak,
             "unit": "TFLOP/s", "frac": tf / fp64_peak,
             "peak_source": "measured in this run (DFMA microbenchmark, tscm_device_fp64_peak)",
             "algorithmic_flops_per_observation": ALG_FLOPS_PER_OBS_EVAL,

@@ -413,41 +413,61 @@ ParallelFor(L.V, num_threads, [&](int, int vb, int ve) {
     }
   }
 
-  // out += J^T vec (vec has 2N entries).
+  // out += J^T vec (vec has 2N entries).  Frames are dealt to the threads (disjoint pose
+  // segments of `out`); the camera part goes through per-thread accumulators that are
+  // added in thread order.
   void JtVec(const std::vector<double>& jac, const std::vector<double>& vec,
              std::vector<double>& out) const {
-    for (int v = 0; v < L.V; ++v) {
-      const int m = p->view_camera[v], i = p->view_frame[v];
-      const int coff = L.n_e + L.cam_off[m], rts = L.cam_rt_sz[m];
-      for (int j = 0; j < L.K; ++j) {
-        const double* Jr = &jac[((size_t)v * L.K + j) * 2 * kJ];
-        for (int a = 0; a < 2; ++a) {
-          const double rv = vec[((size_t)v * L.K + j) * 2 + a];
-          const double* row = Jr + a * kJ;
-          if (rts) for (int k = 0; k < 6; ++k) out[coff + k] += row[k] * rv;
-          for (int k = 0; k < 6; ++k) out[6 * i + k] += row[6 + k] * rv;
-          for (int k = 0; k < 9; ++k) out[coff + rts + k] += row[12 + k] * rv;
+    const int nt = std::max(1, num_threads);
+    std::vector<std::vector<double>> cam(nt, std::vector<double>(L.n_c, 0.0));
+    ParallelFor(L.F, nt, [&](int t, int fb, int fe) {
+      double* cacc = cam[t].data();
+      for (int i = fb; i < fe; ++i) {
+        for (int v : L.frame_views[i]) {
+          const int m = p->view_camera[v];
+          const int coff = L.cam_off[m], rts = L.cam_rt_sz[m];
+          for (int j = 0; j < L.K; ++j) {
+            const double* Jr = &jac[((size_t)v * L.K + j) * 2 * kJ];
+            for (int a = 0; a < 2; ++a) {
+              const double rv = vec[((size_t)v * L.K + j) * 2 + a];
+              const double* row = Jr + a * kJ;
+              if (rts) for (int k = 0; k < 6; ++k) cacc[coff + k] += row[k] * rv;
+              for (int k = 0; k < 6; ++k) out[6 * i + k] += row[6 + k] * rv;
+              for (int k = 0; k < 9; ++k) cacc[coff + rts + k] += row[12 + k] * rv;
+            }
+          }
         }
       }
-    }
+    });
+    for (int t = 0; t < nt; ++t)
+      for (int k = 0; k < L.n_c; ++k) out[L.n_e + k] += cam[t][k];
   }
 
   // SparseMatrix::SquaredColumnNorm
   void SquaredColumnNorm(const std::vector<double>& jac, std::vector<double>& out) const {
     out.assign(L.n, 0.0);
-    for (int v = 0; v < L.V; ++v) {
-      const int m = p->view_camera[v], i = p->view_frame[v];
-      const int coff = L.n_e + L.cam_off[m], rts = L.cam_rt_sz[m];
-      for (int j = 0; j < L.K; ++j) {
-        const double* Jr = &jac[((size_t)v * L.K + j) * 2 * kJ];
-        for (int a = 0; a < 2; ++a) {
-          const double* row = Jr + a * kJ;
-          if (rts) for (int k = 0; k < 6; ++k) out[coff + k] += row[k] * row[k];
-          for (int k = 0; k < 6; ++k) out[6 * i + k] += row[6 + k] * row[6 + k];
-          for (int k = 0; k < 9; ++k) out[coff + rts + k] += row[12 + k] * row[12 + k];
+    const int nt = std::max(1, num_threads);
+    std::vector<std::vector<double>> cam(nt, std::vector<double>(L.n_c, 0.0));
+    ParallelFor(L.F, nt, [&](int t, int fb, int fe) {
+      double* cacc = cam[t].data();
+      for (int i = fb; i < fe; ++i) {
+        for (int v : L.frame_views[i]) {
+          const int m = p->view_camera[v];
+          const int coff = L.cam_off[m], rts = L.cam_rt_sz[m];
+          for (int j = 0; j < L.K; ++j) {
+            const double* Jr = &jac[((size_t)v * L.K + j) * 2 * kJ];
+            for (int a = 0; a < 2; ++a) {
+              const double* row = Jr + a * kJ;
+              if (rts) for (int k = 0; k < 6; ++k) cacc[coff + k] += row[k] * row[k];
+              for (int k = 0; k < 6; ++k) out[6 * i + k] += row[6 + k] * row[6 + k];
+              for (int k = 0; k < 9; ++k) cacc[coff + rts + k] += row[12 + k] * row[12 + k];
+            }
+          }
         }
       }
-    }
+    });
+    for (int t = 0; t < nt; ++t)
+      for (int k = 0; k < L.n_c; ++k) out[L.n_e + k] += cam[t][k];
   }
 
   // SparseMatrix::ScaleColumns
@@ -472,25 +492,32 @@ ParallelFor(L.V, num_threads, [&](int, int vb, int ve) {
   // model_residuals = J * step; returns -(m . (r + m/2))  (ComputeTrustRegionStep).
   double ModelCostChange(const std::vector<double>& jac, const std::vector<double>& res,
                          const std::vector<double>& step) const {
-    double acc = 0.0;
-    for (int i = 0; i < L.F; ++i) {
-      for (int v : L.frame_views[i]) {
-        const int m = p->view_camera[v];
-        const int coff = L.n_e + L.cam_off[m], rts = L.cam_rt_sz[m];
-        for (int j = 0; j < L.K; ++j) {
-          const double* Jr = &jac[((size_t)v * L.K + j) * 2 * kJ];
-          for (int a = 0; a < 2; ++a) {
-            const double* row = Jr + a * kJ;
-            double mr = 0.0;
-            if (rts) for (int k = 0; k < 6; ++k) mr += row[k] * step[coff + k];
-            for (int k = 0; k < 6; ++k) mr += row[6 + k] * step[6 * i + k];
-            for (int k = 0; k < 9; ++k) mr += row[12 + k] * step[coff + rts + k];
-            const double r = res[((size_t)v * L.K + j) * 2 + a];
-            acc += mr * (r + mr / 2.0);
+    const int nt = std::max(1, num_threads);
+    std::vector<double> part(nt, 0.0);
+    ParallelFor(L.F, nt, [&](int t, int fb, int fe) {
+      double acc = 0.0;
+      for (int i = fb; i < fe; ++i) {
+        for (int v : L.frame_views[i]) {
+          const int m = p->view_camera[v];
+          const int coff = L.n_e + L.cam_off[m], rts = L.cam_rt_sz[m];
+          for (int j = 0; j < L.K; ++j) {
+            const double* Jr = &jac[((size_t)v * L.K + j) * 2 * kJ];
+            for (int a = 0; a < 2; ++a) {
+              const double* row = Jr + a * kJ;
+              double mr = 0.0;
+              if (rts) for (int k = 0; k < 6; ++k) mr += row[k] * step[coff + k];
+              for (int k = 0; k < 6; ++k) mr += row[6 + k] * step[6 * i + k];
+              for (int k = 0; k < 9; ++k) mr += row[12 + k] * step[coff + rts + k];
+              const double r = res[((size_t)v * L.K + j) * 2 + a];
+              acc += mr * (r + mr / 2.0);
+            }
           }
         }
       }
-    }
+      part[t] = acc;
+    });
+    double acc = 0.0;
+    for (int t = 0; t < nt; ++t) acc += part[t];
     return -acc;
   }
 };

@@ -227,8 +227,6 @@ __global__ void __launch_bounds__(kE3Threads, 1)
 k_eval3(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which, LmOptions opt,
         int prof) {
   if (which < 2 && st->done) return;
-  const long long t_start = clock64();
-  long long t_work = 0;
   const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
   const ParamSet& ps = sel ? ps1 : ps0;
   extern __shared__ __align__(16) double s_mem[];
@@ -263,7 +261,6 @@ k_eval3(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
     FrameConst fc;
     make_frame_const(ps.board_rt + 6 * P.view_frame[v], fc);
     for (int g = 0; g <= ngroups; ++g) {
-      const long long tw0 = clock64();
       if (g < ngroups) {
         const int j = g * kE3Group + p;
         double* mine = s_rows + (g & 1) * kBuf + p * (kE2Elems * 32);
@@ -282,12 +279,8 @@ k_eval3(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
           for (int k = 0; k < kE2Elems; ++k) mine[k * 32 + lane] = 0.0;
         }
       }
-      t_work += clock64() - tw0;
       __syncthreads();
     }
-    if (prof && blockIdx.x == 0 && lane == 0 && (p == 0 || p == 5))
-      printf("k_eval3 producer %d: work %lld cycles over %d groups, total %lld\n", p, t_work, ngroups,
-             clock64() - t_start);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------ consumer ------------------------------------
@@ -295,7 +288,6 @@ k_eval3(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
 #pragma unroll
     for (int i = 0; i < 65; ++i) acc[i] = 0.0;
     for (int g = 0; g <= ngroups; ++g) {
-      const long long tw0 = clock64();
       if (g > 0) {
         const double* buf = s_rows + ((g - 1) & 1) * kBuf;
         if (warp == 0) e3_consume_group<0>(buf, lane, acc);
@@ -303,12 +295,8 @@ k_eval3(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
         else if (warp == 2) e3_consume_group<2>(buf, lane, acc);
         else e3_consume_group<3>(buf, lane, acc);
       }
-      t_work += clock64() - tw0;
       __syncthreads();
     }
-    if (prof && blockIdx.x == 0 && lane == 0)
-      printf("k_eval3 consumer %d: work %lld cycles over %d groups, total %lld\n", warp, t_work,
-             ngroups, clock64() - t_start);
     // View part (BB | BC | BI) -> per-view record staged in shared memory (the row buffers
     // are free now); camera part (CC | CI | II | cost | err) -> summed over the lanes that
     // share a camera with a fixed-order butterfly and written as one partial per
@@ -424,24 +412,34 @@ __device__ __forceinline__ void e4_consume(const double* __restrict__ row, int l
 #pragma unroll
       for (int k = 0; k < 3; ++k) { au[k] *= m; av[k] *= m; }
     }
+    // two passes (u terms, then v terms): consecutive FMAs on one accumulator are a whole
+    // pass apart, so the ~24-cycle FP64 latency never stalls the warp
 #pragma unroll
     for (int k = 0; k < 3; ++k)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 8; ++i)
         if (e3_live(0, i)) acc[k * 8 + i] = fma(au[k], ju[i], acc[k * 8 + i]);
-        if (e3_live(1, i)) acc[k * 8 + i] = fma(av[k], jv[i], acc[k * 8 + i]);
-      }
-    // this role's third of II (tri8 entries 12 (ROLE-1) .. 12 ROLE - 1)
+    constexpr int lo = 12 * (ROLE - 1);   // this role's third of II: tri8 entries lo .. lo + 11
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
       for (int b = a; b < 8; ++b) {
-        constexpr int lo = 12 * (ROLE - 1);
         const int e = tri8(a, b);
-        if (e >= lo && e < lo + 12) {
-          if (e3_live(0, a) && e3_live(0, b)) acc[24 + e - lo] = fma(ju[a], ju[b], acc[24 + e - lo]);
-          if (e3_live(1, a) && e3_live(1, b)) acc[24 + e - lo] = fma(jv[a], jv[b], acc[24 + e - lo]);
-        }
+        if (e >= lo && e < lo + 12 && e3_live(0, a) && e3_live(0, b))
+          acc[24 + e - lo] = fma(ju[a], ju[b], acc[24 + e - lo]);
+      }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (e3_live(1, i)) acc[k * 8 + i] = fma(av[k], jv[i], acc[k * 8 + i]);
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = a; b < 8; ++b) {
+        const int e = tri8(a, b);
+        if (e >= lo && e < lo + 12 && e3_live(1, a) && e3_live(1, b))
+          acc[24 + e - lo] = fma(jv[a], jv[b], acc[24 + e - lo]);
       }
   }
 }
@@ -501,16 +499,21 @@ k_eval4(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
       for (int e = 0; e < kFcElems; ++e) fp[e] = s_fc[e * 32 + lane];
       make_view_const(cc, fc, vc);
     }
+    // the observation of the NEXT group is requested before the current corner is evaluated,
+    // so its ~700-cycle global-load latency hides behind the projection's FP64 chain
+    double2 uv_next = make_double2(0.0, 0.0);
+    if (p < P.K && valid) uv_next = obs[(size_t)p * P.Vpad];
     for (int g = 0; g <= ngroups; ++g) {
       if (g < ngroups) {
         const int j = g * kE3Group + p;
         double* mine = s_rows + (g & 1) * kBuf + p * (kE4Elems * 32);
+        const double2 uv = uv_next;
+        if (j + kE3Group < P.K && valid) uv_next = obs[(size_t)(j + kE3Group) * P.Vpad];
         if (j < P.K && valid) {
-          const double2 uv = obs[(size_t)j * P.Vpad];
           ObsCompact o;
           obs_compact(cc, vc, s_mu[5 * j], s_mu[5 * j + 1], uv.x, uv.y, o);
           double err;
-          const double half_rho = obs_compact_loss(opt.loss_type, opt.loss_scale, o, &err, want_err != 0);
+          const double half_rho = obs_compact_loss(opt.loss_type, opt.loss_scale, o, &err, (want_err & 1) != 0);
 #pragma unroll
           for (int k = 0; k < 3; ++k) { mine[k * 32 + lane] = o.au[k]; mine[(3 + k) * 32 + lane] = o.av[k]; }
 #pragma unroll
@@ -593,7 +596,8 @@ k_eval4(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
       view_blocks_column(colv + vw * 108, 9, b, [mv](int k) { return mv[k * 33]; }, oe, ox);
       double* rec = recs + vw * kViewStride;
       if (b < 6) {
-        for (int a = 0; a <= b; ++a) rec[kOffBB + tri6(a, b)] = oe[a];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) if (a <= b) rec[kOffBB + tri6(a, b)] = oe[a];
 #pragma unroll
         for (int i = 0; i < 8; ++i) rec[kOffBI + b * 8 + i] = ox[i];
         if (b == 0) rec[kViewStride - 1] = 0.0;
@@ -601,7 +605,8 @@ k_eval4(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
         const int c = b - 6;
 #pragma unroll
         for (int a = 0; a < 6; ++a) rec[kOffBC + a * 6 + c] = oe[a];
-        for (int a = 0; a <= c; ++a) cs[(kCamCC + tri6(a, c)) * 33 + vw] = oe[6 + a];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) if (a <= c) cs[(kCamCC + tri6(a, c)) * 33 + vw] = oe[6 + a];
 #pragma unroll
         for (int i = 0; i < 8; ++i) cs[(kCamCI + c * 8 + i) * 33 + vw] = ox[i];
       }

@@ -440,7 +440,7 @@ TSCM_HD double sym3(const double* q, int i, int j) {   // q: 00 01 02 11 12 22
 
 // Column b of the per-view blocks from the moments.  cols: [12][9] coefficient vectors of
 // all columns (view_column_vectors), ld = stride between columns.
-//   outE[a] = E[a][b] for a = 0..b     (upper triangle of J_ext^T J_ext)
+//   outE[a] = E[a][b] for a = 0..11    (use a <= b: upper triangle of J_ext^T J_ext)
 //   outX[i] = X[b][i] for i = 0..7     (row b of J_ext^T [J_I | r])
 template <typename MomLoad>
 TSCM_HD void view_blocks_column(const double* cols, int ld, int b, MomLoad mom, double* outE,
@@ -463,7 +463,10 @@ TSCM_HD void view_blocks_column(const double* cols, int ld, int b, MomLoad mom, 
         h[m][i] += sym3(q, i, 0) * cb[3 * n] + sym3(q, i, 1) * cb[3 * n + 1] + sym3(q, i, 2) * cb[3 * n + 2];
     }
   }
-  for (int a = 0; a <= b; ++a) {
+  // all 12 rows are evaluated (fixed trip count: the 12 dot products interleave instead of
+  // running as one dependent chain after another); the caller uses rows a <= b only
+  TSCM_UNROLL
+  for (int a = 0; a < 12; ++a) {
     const double* ca = cols + a * ld;
     double s = 0.0;
     TSCM_UNROLL
