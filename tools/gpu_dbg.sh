@@ -1,5 +1,5 @@
 #!/bin/bash
-TSCM_PROF=1 python - <<'PY'
+TSCM_PROF=2 python - <<'PY'
 import os, sys
 sys.path.insert(0, os.getcwd())
 from tscm_calib_b200 import capi, synth

@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -456,6 +457,12 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
                        tscm_solver** out) {
   if (!out) { set_error("out is NULL"); return TSCM_ERR_INVALID_ARGUMENT; }
   *out = nullptr;
+  const auto t_create0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!getenv("TSCM_PROF")) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_create0).count();
+    std::fprintf(stderr, "[tscm create] %-28s %8.2f ms\n", what, ms);
+  };
   int rc = validate_problem(p);
   if (rc) return rc;
   int ndev = 0;
@@ -471,6 +478,7 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     return TSCM_ERR_NO_DEVICE;
   }
+  lap("validate + device query");
   tscm_solver* s = new tscm_solver();
   s->device = device;
   s->sm_count = prop.multiProcessorCount;
@@ -539,6 +547,7 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   std::vector<short> tile_bi, tile_bj;
   for (int bi = 0; bi < nb; ++bi) for (int bj = bi; bj < nb; ++bj) { tile_bi.push_back((short)bi); tile_bj.push_back((short)bj); }
   const int ntiles = (int)tile_bi.size();
+  lap("index tables (host)");
 #define TRY_RC(x) do { rc = (x); if (rc) { tscm_solver_destroy(s); return rc; } } while (0)
   std::vector<double> board(p->board_xy, p->board_xy + 2 * (size_t)K);
   std::vector<int> vcam(p->view_camera, p->view_camera + V), vfrm(p->view_frame, p->view_frame + V);
@@ -556,6 +565,7 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   TRY_RC(s->put(&P.blk_slot, blk_slot));
   TRY_RC(s->put(&P.cam_slot_begin, cam_slot_begin));
 
+  lap("table upload");
   // ---- buffers --------------------------------------------------------------
   TRY_RC(s->alloc(&s->d_obs_in, (size_t)V * K));
   TRY_RC(s->alloc(&s->d_obsT, (size_t)P.Vpad * K));
@@ -593,7 +603,7 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
                   kSchurFB * 32 * sizeof(int);
   s->solve_smem = (size_t)((NL + 1) * (NL + 2) / 2 + 4 * NL + 4 + 4 * (NL + 1) + 2 * kSolveThreads + 8) * sizeof(double) +
                   (size_t)2 * NL * sizeof(short) + 16;
-  if (const char* pv = getenv("TSCM_PROF")) s->prof = atoi(pv);
+  if (const char* pv = getenv("TSCM_PROF")) s->prof = atoi(pv) >= 2 ? 1 : 0;   // 2: in-kernel cycle printf
   s->eval3_smem = (size_t)(2 * kE3Group * kE2Elems * 32 + 2 * K) * sizeof(double) +
                   (size_t)C * sizeof(CamConst);
   {
@@ -659,6 +669,7 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   TRY_RC(s->alloc(&s->d_dbg_rhs, (size_t)NL));
   TRY_RC(ensure_trace(s, std::min(s->options.max_num_iterations, 1 << 16) + 2));
 
+  lap("buffers");
   auto set_smem = [&](const void* fn, size_t bytes) -> int {
     if (bytes > 48 * 1024)
       CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -682,7 +693,9 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   TRY_RC(set_smem((const void*)k_eval3, s->eval3_smem));
   TRY_RC(set_smem((const void*)k_eval4, s->eval4_smem));
 
+  lap("kernel attributes");
   TRY_RC(tscm_solver_set_observations(s, p->obs_xy));
+  lap("observations H2D + transpose");
 #undef TRY_RC
   *out = s;
   return TSCM_OK;
@@ -800,13 +813,26 @@ int tscm_solver_run(tscm_solver* s, tscm_summary* summary) {
 
 int tscm_solve(const tscm_problem* problem, const tscm_options* options, double* intrinsics,
                double* cam_rt, double* board_rt, tscm_summary* summary, int device) {
+  const bool prof = getenv("TSCM_PROF") != nullptr;
+  auto now = []() { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  const auto t0 = now();
   tscm_solver* s = nullptr;
   int rc = tscm_solver_create(problem, options, device, &s);
   if (rc) return rc;
+  const auto t1 = now();
   rc = tscm_solver_set_parameters(s, intrinsics, cam_rt, board_rt);
+  const auto t2 = now();
   if (!rc) rc = tscm_solver_run(s, summary);
+  const auto t3 = now();
   if (!rc) rc = tscm_solver_get_parameters(s, intrinsics, cam_rt, board_rt);
+  const auto t4 = now();
   tscm_solver_destroy(s);
+  if (prof)
+    std::fprintf(stderr, "[tscm_solve] create %.2f  set %.2f  run %.2f  get %.2f  destroy %.2f ms\n",
+                 ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
   return rc;
 }
 

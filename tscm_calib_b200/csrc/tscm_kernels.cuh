@@ -1591,7 +1591,9 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
     __syncthreads();
   }
   tk1 = clock64();
+  long long tp0 = 0, tp1 = 0, tp2 = 0;
   for (int j = 0; j < NL; j += kSolveNB) {
+    const long long ta = clock64();
     const int nb = min(kSolveNB, NL - j);
     // ---- pivot block (every thread, redundantly) -------------------------------
     const int c0 = COLPTR(j), c1 = COLPTR(j + 1), c2 = COLPTR(j + 2), c3 = COLPTR(j + 3);
@@ -1612,6 +1614,7 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
     const double d3 = fma(-w32, l32, fma(-w31, l31, fma(-t30, l30, t33))), i3 = fast_rcp(d3);
     const double g0 = i0, g1 = nb > 1 ? i1 : 0.0, g2 = nb > 2 ? i2 : 0.0, g3 = nb > 3 ? i3 : 0.0;
     __syncthreads();   // everyone has read the pivot block before it is rewritten
+    const long long tb = clock64();
     if (tid == 0) {
       dinv[j] = i0;
       bool ok = d0 > 0.0;
@@ -1630,6 +1633,8 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
       Pb[i] = p0; Pb[n1 + i] = p1; Pb[2 * n1 + i] = p2; Pb[3 * n1 + i] = p3;
     }
     __syncthreads();
+    const long long tc = clock64();
+    tp0 += tb - ta; tp1 += tc - tb;
     // ---- rank-4 update of the trailing triangle ---------------------------------
     const int base = j + nb;
     if (base < NL) {
@@ -1690,6 +1695,7 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
       }
     }
     __syncthreads();
+    tp2 += clock64() - tc;
   }
   tk2 = clock64();
   // Back-substitution by warp 0, four columns per step: the four dot products
@@ -1790,8 +1796,8 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
     st->cam_lin = t_lin; st->cam_quad = t_quad; st->cam_dn2 = t_dn2; st->cam_xn2 = t_xn2;
     st->solve_ok = s_ok;
     if (prof)
-      printf("k_solve cycles: assemble %lld  ldlt %lld  backsub %lld  tail %lld\n", tk1 - tk0,
-             tk2 - tk1, tk3 - tk2, clock64() - tk3);
+      printf("k_solve cycles: assemble %lld  ldlt %lld (pivot %lld panel %lld trailing %lld)  backsub %lld  tail %lld\n",
+             tk1 - tk0, tk2 - tk1, tp0, tp1, tp2, tk3 - tk2, clock64() - tk3);
   }
 }
 
