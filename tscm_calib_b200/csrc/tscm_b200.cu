@@ -20,6 +20,7 @@
 
 #include "../../include/tscm.h"
 #include "tscm_kernels.cuh"
+#include "tscm_eval5.cuh"
 
 namespace {
 
@@ -117,6 +118,8 @@ struct tscm_solver {
   double* d_rpart = nullptr;
   double* d_Sr = nullptr;
   double* d_yc = nullptr;
+  double* d_mom = nullptr;       // [ntiles][188][32] moments of the evaluation in flight (k_eval5 -> k_view_blocks)
+  double* d_fcg = nullptr;       // [ntiles][27][32] frame constants of the evaluation in flight
   double* d_bs_part = nullptr;
   double* d_gmax_part = nullptr;
   double* d_xn2_part = nullptr;
@@ -132,8 +135,8 @@ struct tscm_solver {
   int schur2_nt = 0;
   size_t schur2_smem = 0;
   int schur_nblk = 0, schur_nt = 256, schur_ept = 20;
-  size_t schur_smem = 0, solve_smem = 0, eval3_smem = 0, eval4_smem = 0;
-  int eval_variant = 4;
+  size_t schur_smem = 0, solve_smem = 0, eval3_smem = 0, eval4_smem = 0, eval5_smem = 0;
+  int eval_variant = 5;
   int want_err = 0;   // accumulate sum sqrt(s) (reprojection read-out only)
   int prof = 0;
   int bs_nblk = 0, fg_nblk = 0;
@@ -230,7 +233,14 @@ int validate_problem(const tscm_problem* p) {
 // k_eval3 (rank-1 sweeps of full Jacobian rows; TSCM_EVAL_VARIANT=3, kept for A/B timing).
 void launch_eval_kernel(tscm_solver* s, int which) {
   const DeviceProblem& P = s->P;
-  if (s->eval_variant == 3)
+  if (s->eval_variant == 5) {
+    const int ntiles = (P.V + 31) / 32;
+    k_eval5<<<std::min(ntiles, s->sm_count), kE5Threads, s->eval5_smem, s->stream>>>(
+        P, s->ps[0], s->ps[1], s->d_state, which, s->lm, s->want_err, s->d_mom, s->d_fcg);
+    k_view_blocks<<<ntiles, kVbThreads, vb_smem_bytes(), s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which,
+                                                                      s->d_mom, s->d_fcg);
+    s->launches += 1;
+  } else if (s->eval_variant == 3)
     k_eval3<<<(P.V + 31) / 32, kE3Threads, s->eval3_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state,
                                                                       which, s->lm, s->prof);
   else
@@ -355,7 +365,7 @@ int launch_iteration(tscm_solver* s) {
 }
 
 int launches_per_iteration(const tscm_solver* s) {
-  return (s->num_ranks <= 1 ? 6 : 7) + (s->split_ok ? 1 : 0);
+  return (s->num_ranks <= 1 ? 6 : 7) + (s->split_ok ? 1 : 0) + (s->eval_variant == 5 ? 1 : 0);
 }
 
 int ensure_graph(tscm_solver* s) {
@@ -613,7 +623,14 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     s->eval4_smem = (std::max(main_d, epi_d) + kFcElems * 32 + 5 * kpad + (kpad & 1)) * sizeof(double) +
                     (size_t)C * sizeof(CamConst);
   }
-  if (const char* ev = getenv("TSCM_EVAL_VARIANT")) s->eval_variant = atoi(ev) == 3 ? 3 : 4;
+  // k_eval5 (persistent, mbarrier-pipelined) is the default; it needs ~214 KB of shared
+  // memory plus the camera table, so very large rigs fall back to k_eval4.
+  s->eval5_smem = e5_smem_bytes(K, C);
+  if (const char* ev = getenv("TSCM_EVAL_VARIANT")) {
+    const int v = atoi(ev);
+    s->eval_variant = v == 3 ? 3 : (v == 4 ? 4 : 5);
+  }
+  if (s->eval_variant == 5 && s->eval5_smem > (size_t)prop.sharedMemPerBlockOptin) s->eval_variant = 4;
   TRY_RC(s->alloc(&s->schur.frame_rec, (size_t)kFrameRec * s->schur.Fpad));
   TRY_RC(s->alloc(&s->d_Spart, (size_t)s->schur_nblk * P.Q));
   TRY_RC(s->alloc(&s->d_rpart, (size_t)s->schur_nblk * NL));
@@ -692,6 +709,13 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   TRY_RC(set_smem((const void*)k_solve<7>, s->solve_smem));
   TRY_RC(set_smem((const void*)k_eval3, s->eval3_smem));
   TRY_RC(set_smem((const void*)k_eval4, s->eval4_smem));
+  if (s->eval_variant == 5) {
+    TRY_RC(set_smem((const void*)k_eval5, s->eval5_smem));
+    TRY_RC(set_smem((const void*)k_view_blocks, vb_smem_bytes()));
+    const size_t ntiles = ((size_t)V + 31) / 32;
+    TRY_RC(s->alloc(&s->d_mom, ntiles * kE5MomEntries * 32));
+    TRY_RC(s->alloc(&s->d_fcg, ntiles * kFcElems * 32));
+  }
 
   lap("kernel attributes");
   TRY_RC(tscm_solver_set_observations(s, p->obs_xy));

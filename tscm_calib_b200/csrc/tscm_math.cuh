@@ -442,6 +442,50 @@ TSCM_HD double sym3(const double* q, int i, int j) {   // q: 00 01 02 11 12 22
 // all columns (view_column_vectors), ld = stride between columns.
 //   outE[a] = E[a][b] for a = 0..11    (use a <= b: upper triangle of J_ext^T J_ext)
 //   outX[i] = X[b][i] for i = 0..7     (row b of J_ext^T [J_I | r])
+//
+// view_blocks_column_g is the same computation with the coefficient vectors behind an
+// accessor col(a, k) (k = 0..8), for layouts that are not [12][ld] in memory (k_eval5 keeps
+// them lane-interleaved in shared memory).
+template <typename ColLoad, typename MomLoad>
+TSCM_HD void view_blocks_column_g(ColLoad col, int b, MomLoad mom, double* outE, double* outX) {
+  double cb[9];
+  TSCM_UNROLL
+  for (int k = 0; k < 9; ++k) cb[k] = col(b, k);
+  double h[3][3];
+  TSCM_UNROLL
+  for (int m = 0; m < 3; ++m) {
+    TSCM_UNROLL
+    for (int i = 0; i < 3; ++i) h[m][i] = 0.0;
+    TSCM_UNROLL
+    for (int n = 0; n < 3; ++n) {
+      const int pr = m <= n ? mom_pair(m, n) : mom_pair(n, m);
+      double q[6];
+      TSCM_UNROLL
+      for (int e = 0; e < 6; ++e) q[e] = mom(pr * 6 + e);
+      TSCM_UNROLL
+      for (int i = 0; i < 3; ++i)
+        h[m][i] += sym3(q, i, 0) * cb[3 * n] + sym3(q, i, 1) * cb[3 * n + 1] + sym3(q, i, 2) * cb[3 * n + 2];
+    }
+  }
+  TSCM_UNROLL
+  for (int a = 0; a < 12; ++a) {
+    double s = 0.0;
+    TSCM_UNROLL
+    for (int m = 0; m < 3; ++m)
+      s += col(a, 3 * m) * h[m][0] + col(a, 3 * m + 1) * h[m][1] + col(a, 3 * m + 2) * h[m][2];
+    outE[a] = s;
+  }
+  TSCM_UNROLL
+  for (int i = 0; i < 8; ++i) {
+    double s = 0.0;
+    TSCM_UNROLL
+    for (int m = 0; m < 3; ++m)
+      s += cb[3 * m] * mom(36 + (m * 3 + 0) * 8 + i) + cb[3 * m + 1] * mom(36 + (m * 3 + 1) * 8 + i) +
+           cb[3 * m + 2] * mom(36 + (m * 3 + 2) * 8 + i);
+    outX[i] = s;
+  }
+}
+
 template <typename MomLoad>
 TSCM_HD void view_blocks_column(const double* cols, int ld, int b, MomLoad mom, double* outE,
                                 double* outX) {
