@@ -313,7 +313,7 @@ void launch_schur(tscm_solver* s, double radius_override) {
     k_schur<2, 768><<<s->schur_nblk, s->schur_nt, s->schur_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
                                                                              s->d_state, s->lm, a);
   const int n = s->P.Q + s->P.NL;
-  k_reduce_s<<<(n + 255) / 256, 256, 0, s->stream>>>(s->P, s->d_state, s->d_Spart, s->d_rpart,
+  k_reduce_s<<<(n + 31) / 32, kReduceThreads, 0, s->stream>>>(s->P, s->d_state, s->d_Spart, s->d_rpart,
                                                     s->schur_nblk, s->d_Sr);
   s->launches += 2;
 }

@@ -680,30 +680,32 @@ __global__ void k_transpose_obs(const double2* __restrict__ in, double2* __restr
   }
 }
 
-// Block-wide deterministic sum / max helpers (blockDim.x <= 1024, power of 2).
-__device__ __forceinline__ double block_sum(double v, double* s_red) {
-  const int t = threadIdx.x;
-  s_red[t] = v;
+// Block-wide deterministic sum / max helpers (blockDim.x a multiple of 32, <= 1024; s_red
+// holds >= 33 doubles).  Warp shuffles, one shared-memory hop, two barriers: the fixed
+// butterfly order makes the result independent of scheduling.
+template <typename Op>
+__device__ __forceinline__ double block_reduce(double v, double* s_red, Op op, double identity) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if (lane == 0) s_red[warp] = v;
   __syncthreads();
-  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
-    if (t < s) s_red[t] += s_red[t + s];
-    __syncthreads();
+  if (warp == 0) {
+    double w = lane < nw ? s_red[lane] : identity;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = op(w, __shfl_xor_sync(0xffffffffu, w, o));
+    if (lane == 0) s_red[32] = w;
   }
-  const double r = s_red[0];
+  __syncthreads();
+  const double r = s_red[32];
   __syncthreads();
   return r;
 }
+__device__ __forceinline__ double block_sum(double v, double* s_red) {
+  return block_reduce(v, s_red, [](double a, double b) { return a + b; }, 0.0);
+}
 __device__ __forceinline__ double block_max(double v, double* s_red) {
-  const int t = threadIdx.x;
-  s_red[t] = v;
-  __syncthreads();
-  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
-    if (t < s) s_red[t] = fmax(s_red[t], s_red[t + s]);
-    __syncthreads();
-  }
-  const double r = s_red[0];
-  __syncthreads();
-  return r;
+  return block_reduce(v, s_red, [](double a, double b) { return fmax(a, b); }, 0.0);
 }
 
 // ---------------------------------------------------------------------------
@@ -1460,24 +1462,40 @@ k_schur_update(DeviceProblem P, const LmState* st, SchurSplitArgs B) {
   if (tid < NL) A.rpart[(size_t)blockIdx.x * NL + tid] = racc;
 }
 
-// Sum the per-CTA partials: out = [S packed upper (Q) | rhs (NL)].
-__global__ void k_reduce_s(DeviceProblem P, const LmState* st, const double* __restrict__ Spart,
-                           const double* __restrict__ rpart, int nblk, double* __restrict__ out) {
+// Sum the per-CTA partials: out = [S packed upper (Q) | rhs (NL)].  A CTA owns 32 consecutive
+// entries; its 8 warps each sum every 8th partial (4 loads in flight per thread, 256-byte
+// coalesced rows) and the 8 warp sums are added in a fixed order: ~5 dependent L2 round
+// trips instead of the 37 of a one-thread-per-entry sum.
+constexpr int kReduceThreads = 256;
+__global__ void __launch_bounds__(kReduceThreads)
+k_reduce_s(DeviceProblem P, const LmState* st, const double* __restrict__ Spart,
+           const double* __restrict__ rpart, int nblk, double* __restrict__ out) {
   if (st->done) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.Q + P.NL) return;
-  const double* src = i < P.Q ? Spart + i : rpart + (i - P.Q);
-  const size_t stride = i < P.Q ? P.Q : P.NL;
+  __shared__ double s_part[8][33];
+  const int e = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + e;
+  const bool ok = i < P.Q + P.NL;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int b = 0;
-  for (; b + 3 < nblk; b += 4) {
-    s0 += src[(size_t)b * stride];
-    s1 += src[(size_t)(b + 1) * stride];
-    s2 += src[(size_t)(b + 2) * stride];
-    s3 += src[(size_t)(b + 3) * stride];
+  if (ok) {
+    const double* src = i < P.Q ? Spart + i : rpart + (i - P.Q);
+    const size_t stride = i < P.Q ? P.Q : P.NL;
+    int b = part;
+    for (; b + 24 < nblk; b += 32) {
+      s0 += src[(size_t)b * stride];
+      s1 += src[(size_t)(b + 8) * stride];
+      s2 += src[(size_t)(b + 16) * stride];
+      s3 += src[(size_t)(b + 24) * stride];
+    }
+    for (; b < nblk; b += 8) s0 += src[(size_t)b * stride];
   }
-  for (; b < nblk; ++b) s0 += src[(size_t)b * stride];
-  out[i] = (s0 + s1) + (s2 + s3);
+  s_part[part][e] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (part == 0 && ok) {
+    double t = s_part[0][e];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) t += s_part[q][e];
+    out[i] = t;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1698,47 +1716,44 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
     tp2 += clock64() - tc;
   }
   tk2 = clock64();
-  // Back-substitution by warp 0, four columns per step: the four dot products
-  // sum_{i >= j+4} A[i][j+c] x_i are reduced together (their shuffle chains interleave), then
-  // the 4x4 unit-triangular tail is solved by substitution.  x_j = (rhs'_j - sum) / d_j.
-  if (warp == 0) {
+  // Back-substitution, row-owner form: thread i keeps r_i = rhs'_i - sum_{j solved} A'[j][i] x_j
+  // in a register.  Per block of 4 columns (right to left): the owners publish their r_j,
+  // one thread solves the 4x4 unit-triangular tail (x_j = (r_j - ...) / d_j), then every row
+  // above the block folds the 4 new x_j in with 4 FMAs on 4 consecutive entries of its own
+  // column.  Two barriers and ~15 dependent FP64 operations per 4 columns (the previous
+  // warp-0 form reduced four dot products through shuffles per block: 3x the latency).
+  {
+    const bool own = tid < NL;
+    double r = own ? L[COLPTR(tid) - tid + NL] : 0.0;
     for (int jb = ((NL - 1) >> 2) << 2; jb >= 0; jb -= 4) {
       const int nb = min(4, NL - jb);
-      double sacc[4] = {0.0, 0.0, 0.0, 0.0};
-      const int i0 = jb + nb;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < nb) {
-          const int cp = COLPTR(jb + c) - (jb + c);
-#pragma unroll
-          for (int bb = 0; bb < AMAX; ++bb) {
-            const int i = i0 + lane + 32 * bb;
-            if (i < NL) sacc[c] = fma(L[cp + i], x[i], sacc[c]);
-          }
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) sacc[c] += __shfl_xor_sync(0xffffffffu, sacc[c], o);
-      }
-      if (lane == 0) {
+      if (own && tid >= jb && tid < jb + nb) x[tid] = r;
+      __syncthreads();
+      if (tid == 0) {
         double xs[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int c = 3; c >= 0; --c) {
           if (c < nb) {
             const int j = jb + c;
             const int cp = COLPTR(j) - j;
-            double t = L[cp + NL] - sacc[c];
+            double t = x[j];
 #pragma unroll
             for (int d = 3; d > 0; --d)
               if (d > c && d < nb) t = fma(-L[cp + jb + d], xs[d], t);
             xs[c] = t * dinv[j];
-            x[j] = xs[c];
           }
         }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (c < nb) x[jb + c] = xs[c];
       }
-      __syncwarp();
+      __syncthreads();
+      if (own && tid < jb) {
+        const double* col = L + COLPTR(tid) - tid + jb;     // A'[jb + c][tid], c = 0..3
+        double acc = r;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (c < nb) acc = fma(-col[c], x[jb + c], acc);
+        r = acc;
+      }
     }
   }
   __syncthreads();
