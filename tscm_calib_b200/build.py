@@ -32,12 +32,14 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_cuda(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into tscm_calib_b200/libtscm_b200.so for sm_100a."""
-    if not force and not needs_build():
-        return LIB
+def build_cuda(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """Compile csrc/*.cu into tscm_calib_b200/libtscm_b200.so for sm_100a.
+    defines / out: A/B builds of tuning macros into another path (tools/ab_build.py)."""
+    lib = out or LIB
+    if not force and not defines and not needs_build():
+        return lib
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+          ["-D" + d for d in defines] + ["-o", lib] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     env = dict(os.environ)
     # nvcc must use the distribution g++ (the image's $CXX lacks some specs)
     env.pop("CXX", None)
@@ -47,7 +49,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return lib
 
 
 HOST = os.path.join(_HERE, "host")

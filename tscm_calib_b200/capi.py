@@ -207,7 +207,7 @@ def load_library(path: str | None = None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("TSCM_LIB_PATH") or LIB_PATH   # TSCM_LIB_PATH: A/B builds (tools/)
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`."

@@ -611,7 +611,8 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   s->schur.Fpad = (F + 31) / 32 * 32;
   s->schur_smem = (size_t)(2 * kSchurFB * 6 * s->schur.NLp + kSchurFB * 6 + kSchurFB * 64) * sizeof(double) +
                   kSchurFB * 32 * sizeof(int);
-  s->solve_smem = (size_t)((NL + 1) * (NL + 2) / 2 + 4 * NL + 4 + 4 * (NL + 1) + 2 * kSolveThreads + 8) * sizeof(double) +
+  s->solve_smem = (size_t)((NL + 1) * (NL + 2) / 2 + 4 * NL + 4 + 4 * (NL + 1) + 2 * kSolveThreads + 8 +
+                           C * kCamRec) * sizeof(double) +
                   (size_t)2 * NL * sizeof(short) + 16;
   if (const char* pv = getenv("TSCM_PROF")) s->prof = atoi(pv) >= 2 ? 1 : 0;   // 2: in-kernel cycle printf
   s->eval3_smem = (size_t)(2 * kE3Group * kE2Elems * 32 + 2 * K) * sizeof(double) +

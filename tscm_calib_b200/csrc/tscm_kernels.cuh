@@ -1271,23 +1271,24 @@ k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, L
   }
   __syncwarp();
   for (int i = lane; i < kFrameRec; i += 32) A.frame_rec[(size_t)i * A.Fpad + f] = my[i];
-  // columns of W_s and Y: up to kS2ColsPerLane per lane with every global load issued
-  // before the first use (two dependent levels: descriptors, then records), the rest
-  // (rigs with more than 9 cameras) in a plain loop
-  {
-    int csrc[kS2ColsPerLane], cg[kS2ColsPerLane];
-    double csc[kS2ColsPerLane];
+  // columns of W_s and Y: four per lane and round, with every global load of a round issued
+  // before the first use (two dependent levels: descriptors, then records).  The Cholesky
+  // factor is read from shared memory (packed, written above).
+  constexpr int kCols = 4;
+  for (int base = 0; base < ncols; base += 32 * kCols) {
+    int csrc[kCols], cg[kCols];
+    double csc[kCols];
 #pragma unroll
-    for (int r = 0; r < kS2ColsPerLane; ++r) {
-      const int col = lane + 32 * r;
+    for (int r = 0; r < kCols; ++r) {
+      const int col = base + lane + 32 * r;
       const bool ok = col < ncols;
       csrc[r] = ok ? B.col_src[c0 + col] : -1;
       cg[r] = ok ? schur_perm(B.col_g[c0 + col], NLp) : 0;
       csc[r] = ok ? A.scale_c[B.col_sidx[c0 + col]] : 0.0;
     }
-    double raw[kS2ColsPerLane][6];
+    double raw[kCols][6];
 #pragma unroll
-    for (int r = 0; r < kS2ColsPerLane; ++r) {
+    for (int r = 0; r < kCols; ++r) {
       const int kk = csrc[r] & 15;
       const double* Gv = ps.G + (size_t)(csrc[r] >= 0 ? (csrc[r] >> 4) : 0) * kViewStride;
 #pragma unroll
@@ -1295,35 +1296,18 @@ k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, L
         raw[r][q] = csrc[r] >= 0 ? (kk < 6 ? Gv[kOffBC + q * 6 + kk] : Gv[kOffBI + q * 8 + (kk - 6)]) : 0.0;
     }
 #pragma unroll
-    for (int r = 0; r < kS2ColsPerLane; ++r) {
+    for (int r = 0; r < kCols; ++r) {
       if (csrc[r] >= 0) {
         double w[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) w[q] = se[q] * raw[r][q] * csc[r];
 #pragma unroll
         for (int q = 0; q < 6; ++q) Wf[q * NLp + cg[r]] = w[q];
-        chol6_solve(M, w);
+        chol6_solve_packed(my, w);
 #pragma unroll
         for (int q = 0; q < 6; ++q) Yf[q * NLp + cg[r]] = w[q];
       }
     }
-  }
-  for (int col = lane + 32 * kS2ColsPerLane; col < ncols; col += 32) {
-    const int src = B.col_src[c0 + col], g = schur_perm(B.col_g[c0 + col], NLp);
-    const int kk = src & 15;
-    const double sc = A.scale_c[B.col_sidx[c0 + col]];
-    const double* Gv = ps.G + (size_t)(src >> 4) * kViewStride;
-    double w[6];
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      const double rv = kk < 6 ? Gv[kOffBC + q * 6 + kk] : Gv[kOffBI + q * 8 + (kk - 6)];
-      w[q] = se[q] * rv * sc;
-    }
-#pragma unroll
-    for (int q = 0; q < 6; ++q) Wf[q * NLp + g] = w[q];
-    chol6_solve(M, w);
-#pragma unroll
-    for (int q = 0; q < 6; ++q) Yf[q * NLp + g] = w[q];
   }
 }
 
@@ -1562,7 +1546,8 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
   double* Pb = dinv + NL + 4;              // [4][n1] panel P[c][i]
   double* dummy = Pb + 4 * n1;             // [kSolveThreads] sink for masked lanes
   double* s_red = dummy + kSolveThreads;   // [kSolveThreads]
-  short* s_cam = reinterpret_cast<short*>(s_red + kSolveThreads);   // [NL]
+  double* s_comm = s_red + kSolveThreads;  // [C][kCamRec] camera records of the current point
+  short* s_cam = reinterpret_cast<short*>(s_comm + P.C * kCamRec);   // [NL]
   short* s_kk = s_cam + NL;                                         // [NL]
   __shared__ int s_ok;
 #define COLPTR(k) ((k) * n1 - ((k) * ((k) - 1)) / 2)
@@ -1572,32 +1557,44 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
     s_cam[i] = (short)c; s_kk[i] = (short)kk;
     sc[i] = scale_c[c * 13 + kk];
   }
+  for (int i = tid; i < P.C * kCamRec; i += kSolveThreads) s_comm[i] = ps.comm[i];
   __syncthreads();
-  // assemble: column k by warp, rows along lanes (Sr is packed upper row-major: row k, col i)
-  for (int k = warp; k < NL; k += kWarps) {
-    const int qb = k * NL - (k * (k - 1)) / 2 - k;   // q(k, i) = qb + i
-    const int cp = COLPTR(k) - k;
-    const int ck = s_cam[k], kkk = s_kk[k];
-    const double* U = ps.comm + ck * kCamRec;
-    const double sk = sc[k];
-    for (int i = k + lane; i < NL; i += 32) {
-      double v = Sr[qb + i];
+  // assemble: one thread per packed entry q = (k, i), k <= i, four global loads in flight
+  // per thread (Sr and the index tables are L2-resident; the camera records sit in shared
+  // memory), instead of a warp walking a column with two dependent global loads per step
+  for (int q0 = tid; q0 < P.Q; q0 += 4 * kSolveThreads) {
+    double v[4];
+    int kk_[4], ii_[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * kSolveThreads;
+      const bool ok = q < P.Q;
+      v[u] = ok ? Sr[q] : 0.0;
+      kk_[u] = ok ? P.q_i[q] : -1;
+      ii_[u] = ok ? P.q_j[q] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (kk_[u] < 0) continue;
+      const int k = kk_[u], i = ii_[u];
+      const int ck = s_cam[k];
+      double val = v[u];
       if (s_cam[i] == ck) {
-        const double us = sk * sc[i] * cam_block(U, kkk, s_kk[i]);
-        v += us;
+        const double us = sc[k] * sc[i] * cam_block(s_comm + ck * kCamRec, s_kk[k], s_kk[i]);
+        val += us;
         if (i == k) {
           const double d = fmin(fmax(us, opt.min_lm_diagonal), opt.max_lm_diagonal);
           const double D = sqrt(d / radius);
-          v += D * D;
+          val += D * D;
         }
       }
-      L[cp + i] = v;
+      L[COLPTR(k) - k + i] = val;
     }
-    if (lane == 0) {
-      const double g = sk * cam_grad(U, kkk);
-      gsv[k] = g;
-      L[cp + NL] = Sr[P.Q + k] + g;          // augmented row = rhs
-    }
+  }
+  for (int k = tid; k < NL; k += kSolveThreads) {
+    const double g = sc[k] * cam_grad(s_comm + s_cam[k] * kCamRec, s_kk[k]);
+    gsv[k] = g;
+    L[COLPTR(k) - k + NL] = Sr[P.Q + k] + g;          // augmented row = rhs
   }
   __syncthreads();
   if (dbg_lhs) {
@@ -1769,7 +1766,7 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
     dn2 += delta * delta;
     // quad: y^T U_s y restricted to this row (both triangles)
     const int ci = s_cam[i];
-    const double* U = ps.comm + ci * kCamRec;
+    const double* U = s_comm + ci * kCamRec;
     const int o0 = P.live_off[ci], n = P.live_off[ci + 1] - o0;
     const int ki = s_kk[i];
     double row = 0.0;

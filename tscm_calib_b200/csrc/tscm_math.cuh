@@ -613,4 +613,23 @@ TSCM_HD void chol6_solve(const double L[36], double b[6]) {
   }
 }
 
+// chol6_solve with the factor stored packed (row i at i(i+1)/2, reciprocal diagonal), e.g. in
+// shared memory: the 36-double register copy of the factor does not have to stay live.
+TSCM_HD void chol6_solve_packed(const double* Lp, double b[6]) {
+  TSCM_UNROLL
+  for (int i = 0; i < 6; ++i) {
+    double s = b[i];
+    TSCM_UNROLL
+    for (int k = 0; k < i; ++k) s -= Lp[(i * (i + 1)) / 2 + k] * b[k];
+    b[i] = s * Lp[(i * (i + 1)) / 2 + i];
+  }
+  TSCM_UNROLL
+  for (int i = 5; i >= 0; --i) {
+    double s = b[i];
+    TSCM_UNROLL
+    for (int k = i + 1; k < 6; ++k) s -= Lp[(k * (k + 1)) / 2 + i] * b[k];
+    b[i] = s * Lp[(i * (i + 1)) / 2 + i];
+  }
+}
+
 }  // namespace tscm
