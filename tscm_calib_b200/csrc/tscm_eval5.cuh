@@ -48,8 +48,11 @@ constexpr int kE5Threads = 32 * (kE5Consumers + kE5Producers);   // 512
 #define TSCM_E5_DEPTH 4
 #endif
 constexpr int kE5Depth = TSCM_E5_DEPTH;                      // ring slots per producer warp
-// published row: au 0..2 | av 3..5 | live u-row intrinsic entries 6..11 | live v-row 12..17 |
-// 1/2 rho 18 | sqrt(s) 19   (structural zeros of the intrinsic rows are never stored)
+// published row = 10 double2 per lane (structural zeros of the intrinsic rows are never stored):
+//   u group  0 (au0 au1) | 1 (au2 ju0) | 2 (ju1 ju2) | 3 (ju3 ju4) | 4 (ju5 1/2rho)
+//   v group  5 (av0 av1) | 6 (av2 jv0) | 7 (jv1 jv2) | 8 (jv3 jv4) | 9 (jv5 sqrt(s))
+// ju/jv indexed by live column (e5_live_col); a consumer slice reads one group with five
+// 16-byte loads
 constexpr int kE5Elems = 20;
 constexpr int kE5Slot = kE5Elems * 32;           // doubles per slot: [20][32]
 // moment buffer of a tile: M 36 | Nu [9][6] | Nv [9][6] | IIu 21 | IIv 21 | cost | err, x 32 lanes
@@ -94,10 +97,11 @@ __host__ __device__ constexpr int e5_live_tri(int a, int b) { return tri6(e5_liv
 template <int W>
 __device__ __forceinline__ void e5_consume(const double* __restrict__ row, int lane,
                                            const double* __restrict__ mu, double* __restrict__ acc) {
+  const double2* __restrict__ row2 = reinterpret_cast<const double2*>(row) + lane;
   if (W < 2) {
-    double au[3], av[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { au[k] = row[k * 32 + lane]; av[k] = row[(3 + k) * 32 + lane]; }
+    const double2 u0 = row2[0 * 32], u1 = row2[1 * 32], v0 = row2[5 * 32], v1 = row2[6 * 32];
+    const double2 ce = row2[(W == 0 ? 4 : 9) * 32];      // .y = 1/2 rho (W = 0) or sqrt(s) (W = 1)
+    const double au[3] = {u0.x, u0.y, u1.x}, av[3] = {v0.x, v0.y, v1.x};
     double q[6];
     q[0] = fma(av[0], av[0], au[0] * au[0]); q[1] = fma(av[0], av[1], au[0] * au[1]);
     q[2] = fma(av[0], av[2], au[0] * au[2]); q[3] = fma(av[1], av[1], au[1] * au[1]);
@@ -109,7 +113,6 @@ __device__ __forceinline__ void e5_consume(const double* __restrict__ row, int l
       for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
         for (int e = 0; e < 6; ++e) acc[pr * 6 + e] = fma(w[pr], q[e], acc[pr * 6 + e]);
-      acc[18] += row[18 * 32 + lane];
     } else {
       const double w[2] = {mu[4], mu[1]};
 #pragma unroll
@@ -118,15 +121,14 @@ __device__ __forceinline__ void e5_consume(const double* __restrict__ row, int l
         for (int e = 0; e < 6; ++e) acc[pr * 6 + e] = fma(w[pr], q[e], acc[pr * 6 + e]);
 #pragma unroll
       for (int e = 0; e < 6; ++e) acc[12 + e] += q[e];
-      acc[18] += row[19 * 32 + lane];
     }
+    acc[18] += ce.y;
   } else {
     constexpr int m = (W - 2) / 2, r = (W - 2) % 2;
-    double a[3], j[6];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) a[k] = row[(3 * r + k) * 32 + lane];
-#pragma unroll
-    for (int li = 0; li < 6; ++li) j[li] = row[(6 + 6 * r + li) * 32 + lane];
+    const double2 p0 = row2[(5 * r + 0) * 32], p1 = row2[(5 * r + 1) * 32], p2 = row2[(5 * r + 2) * 32],
+                  p3 = row2[(5 * r + 3) * 32], p4 = row2[(5 * r + 4) * 32];
+    double a[3] = {p0.x, p0.y, p1.x};
+    const double j[6] = {p1.y, p2.x, p2.y, p3.x, p3.y, p4.x};
     if (m < 2) {
       const double s = mu[m];      // X or Y
 #pragma unroll
@@ -392,27 +394,21 @@ k_eval5(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
       return (j < P.K && tile < ntiles && vv < P.V) ? P.obsT[(size_t)j * P.Vpad + vv] : make_double2(0.0, 0.0);
     };
     auto store_row = [&](double* mine, const ObsCompact& o, double half_rho, double err, bool ok) {
-      if (__all_sync(0xffffffffu, ok)) {       // every tile but the last, every real corner
+      double2* m2 = reinterpret_cast<double2*>(mine) + lane;
+      const double ju[6] = {o.ju[e5_live_col(0, 0)], o.ju[e5_live_col(0, 1)], o.ju[e5_live_col(0, 2)],
+                            o.ju[e5_live_col(0, 3)], o.ju[e5_live_col(0, 4)], o.ju[e5_live_col(0, 5)]};
+      const double jv[6] = {o.jv[e5_live_col(1, 0)], o.jv[e5_live_col(1, 1)], o.jv[e5_live_col(1, 2)],
+                            o.jv[e5_live_col(1, 3)], o.jv[e5_live_col(1, 4)], o.jv[e5_live_col(1, 5)]};
+      double2 pr[10] = {make_double2(o.au[0], o.au[1]), make_double2(o.au[2], ju[0]), make_double2(ju[1], ju[2]),
+                        make_double2(ju[3], ju[4]), make_double2(ju[5], half_rho),
+                        make_double2(o.av[0], o.av[1]), make_double2(o.av[2], jv[0]), make_double2(jv[1], jv[2]),
+                        make_double2(jv[3], jv[4]), make_double2(jv[5], err)};
+      if (!__all_sync(0xffffffffu, ok)) {      // last tile / padding corner: zero rows
 #pragma unroll
-        for (int q = 0; q < 3; ++q) { mine[q * 32 + lane] = o.au[q]; mine[(3 + q) * 32 + lane] = o.av[q]; }
-#pragma unroll
-        for (int li = 0; li < 6; ++li) {
-          mine[(6 + li) * 32 + lane] = o.ju[e5_live_col(0, li)];
-          mine[(12 + li) * 32 + lane] = o.jv[e5_live_col(1, li)];
-        }
-        mine[18 * 32 + lane] = half_rho;
-        mine[19 * 32 + lane] = err;
-      } else {
-#pragma unroll
-        for (int q = 0; q < 3; ++q) { mine[q * 32 + lane] = ok ? o.au[q] : 0.0; mine[(3 + q) * 32 + lane] = ok ? o.av[q] : 0.0; }
-#pragma unroll
-        for (int li = 0; li < 6; ++li) {
-          mine[(6 + li) * 32 + lane] = ok ? o.ju[e5_live_col(0, li)] : 0.0;
-          mine[(12 + li) * 32 + lane] = ok ? o.jv[e5_live_col(1, li)] : 0.0;
-        }
-        mine[18 * 32 + lane] = ok ? half_rho : 0.0;
-        mine[19 * 32 + lane] = ok ? err : 0.0;
+        for (int q = 0; q < 10; ++q) if (!ok) pr[q] = make_double2(0.0, 0.0);
       }
+#pragma unroll
+      for (int q = 0; q < 10; ++q) m2[q * 32] = pr[q];
     };
     double2 uvA = fetch(blockIdx.x, p), uvB = fetch(blockIdx.x, p + kE5Producers);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
