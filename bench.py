@@ -239,8 +239,8 @@ def run_b200(args):
                    "observations_per_gpu": int(problem.num_observations),
                    "step": "one LM iteration (Schur + reduced solve + back-substitution + "
                            "residual/Jacobian/normal-equation pass + accept/reject)",
-                   "l2": "per-step working set (observations 56 MB + two 68 MB Gram-record "
-                         "buffers) exceeds the 126 MB L2; no explicit flush",
+                   "l2": "per-step working set (observations 56 MB, moment buffer 60 MB, per-view "
+                         "records 2 x 34 MB, Schur rows 48 MB) exceeds the 126 MB L2; no explicit flush",
                    "parallelism": f"frames sharded over {world} GPU(s), NCCL all-reduce of the "
                                   "reduced camera system" if world > 1 else "single GPU"},
         "lm_iterations_per_sec": it_per_s,
@@ -248,11 +248,19 @@ def run_b200(args):
         "clocks": clocks,
     }
 
-    # ---- roofline of the dominant kernel (k_eval), timed alone with CUDA events ---------
+    # ---- roofline of the dominant kernel, timed alone with CUDA events ----------------------
+    # The J-pass (residual + analytic Jacobian + normal-equation blocks) is two kernels:
+    # k_eval5 (persistent, per-view moments; the dominant kernel of the iteration) and
+    # k_view_blocks (per-view blocks from the moments).  TSCM_EVAL_VARIANT=4 selects the
+    # older single-kernel form k_eval4, for which stage 7 is empty.
     # (every rank runs the same stage sequence: the set-up in front of a timed stage
     # contains collectives; only rank 0 reports)
+    variant = os.environ.get("TSCM_EVAL_VARIANT", "5")
+    main_kernel = "k_eval5" if variant not in ("3", "4") else "k_eval" + variant
     solver.time_stage(0, 3)
-    ms_eval = solver.time_stage(0, 20)
+    ms_pass = solver.time_stage(0, 20)
+    ms_main = solver.time_stage(6, 20)
+    ms_blocks = solver.time_stage(7, 20) if main_kernel == "k_eval5" else 0.0
     stages = {}
     for sid, name in ((5, "evaluation_pass"), (1, "schur"), (2, "reduced_solve"), (3, "backsub")):
         solver.time_stage(sid, 2)
@@ -260,23 +268,26 @@ def run_b200(args):
     if rank == 0:
         n_obs = problem.num_observations
         hbm_peak, how = measured_peaks()
-        achieved = n_obs * ALG_BYTES_PER_OBS_EVAL / (ms_eval * 1e-3) / 1e9
+        achieved = n_obs * ALG_BYTES_PER_OBS_EVAL / (ms_main * 1e-3) / 1e9
         line["roofline"] = {
-            "kernel": "k_eval4", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": captured_traffic("k_eval4"),
-            "peak_source": how, "ms_per_launch": ms_eval,
+            "kernel": main_kernel, "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+            "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": captured_traffic(main_kernel),
+            "peak_source": how, "ms_per_launch": ms_main,
             "algorithmic_bytes_per_observation": ALG_BYTES_PER_OBS_EVAL,
-            "note": "k_eval4 is FP64-pipe bound (arithmetic intensity ~44 flop/B vs machine "
+            "note": f"{main_kernel} is FP64-pipe bound (arithmetic intensity ~44 flop/B vs machine "
                     "balance ~5.3 flop/B); see roofline_fp64.  traffic = DRAM bytes of one launch "
                     "from the committed ncu capture (profiles/)",
         }
         fp64_peak = capi.device_fp64_peak(local_rank)
-        tf = n_obs * ALG_FLOPS_PER_OBS_EVAL / (ms_eval * 1e-3) / 1e12
+        tf = n_obs * ALG_FLOPS_PER_OBS_EVAL / (ms_pass * 1e-3) / 1e12
         line["roofline_fp64"] = {
-            "kernel": "k_eval4", "bound": "fp64", "achieved": tf, "peak": fp64_peak,
-            "unit": "TFLOP/s", "frac": tf / fp64_peak,
+            "kernel": main_kernel + ("+k_view_blocks" if ms_blocks else ""), "bound": "fp64",
+            "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
             "peak_source": "measured in this run (DFMA microbenchmark, tscm_device_fp64_peak)",
             "algorithmic_flops_per_observation": ALG_FLOPS_PER_OBS_EVAL,
+            "ms_per_pass": ms_pass, "ms_main_kernel": ms_main, "ms_view_blocks": ms_blocks,
+            "note": "SURVEY 8(d)'s 1,060 flop/observation J-pass (projection, Jacobian, normal-equation "
+                    "blocks) over the time of the whole pass (both kernels)",
         }
         line["stage_ms"] = stages
 
@@ -348,7 +359,7 @@ def run_b200(args):
         threads = os.cpu_count() or 1
         frames = args.cpu_frames
         sp = synth.config(3, num_frames=frames)
-        iters = 3
+        iters = args.cpu_iterations      # ~10-20 s of CPU work on 16 host threads
         dt = time_oracle(sp.problem, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt, iters,
                          threads)
         line["cpu_baseline"] = {
@@ -374,8 +385,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--frames", type=int, default=5000, help="frames of config 3 (per GPU if weak)")
-    ap.add_argument("--cpu-frames", type=int, default=1000, help="cpu_baseline sample size")
-    ap.add_argument("--reference-frames", type=int, default=500, help="--impl reference sample size")
+    ap.add_argument("--cpu-iterations", type=int, default=30, help="cpu_baseline LM iterations")
+    ap.add_argument("--cpu-frames", type=int, default=5000, help="cpu_baseline sample size (frames)")
+    ap.add_argument("--reference-frames", type=int, default=5000, help="--impl reference sample size (frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -185,7 +185,9 @@ int tscm_solver_reprojection_error(tscm_solver* solver, double* per_camera, doub
  * stage: 0 = residual+Jacobian+normal-equation kernel, 1 = Schur elimination,
  *        2 = reduced solve, 3 = back-substitution, 4 = whole LM iterations (iteration
  *        zero, then `repeats` replays of the iteration graph; fails if the loop
- *        terminates early), 5 = whole evaluation pass (kernel + reductions). */
+ *        terminates early), 5 = whole evaluation pass (kernels + reductions),
+ *        6 / 7 = the two kernels of stage 0 on their own (k_eval5: moments of every view;
+ *        k_view_blocks: per-view blocks from the moments). */
 int tscm_solver_time_stage(tscm_solver* solver, int stage, int repeats, double* ms_per_launch);
 /* Number of kernels launched by this solver since creation. */
 int64_t tscm_solver_launch_count(const tscm_solver* solver);

@@ -231,15 +231,20 @@ int validate_problem(const tscm_problem* p) {
 
 // The residual + Jacobian + normal-equation kernel: k_eval4 (moment form, default) or
 // k_eval3 (rank-1 sweeps of full Jacobian rows; TSCM_EVAL_VARIANT=3, kept for A/B timing).
-void launch_eval_kernel(tscm_solver* s, int which) {
+// part: 0 = the whole pass, 1 = k_eval5 only, 2 = k_view_blocks only (stage timing).
+void launch_eval_kernel(tscm_solver* s, int which, int part = 0) {
   const DeviceProblem& P = s->P;
   if (s->eval_variant == 5) {
     const int ntiles = (P.V + 31) / 32;
-    k_eval5<<<std::min(ntiles, s->sm_count), kE5Threads, s->eval5_smem, s->stream>>>(
-        P, s->ps[0], s->ps[1], s->d_state, which, s->lm, s->want_err, s->d_mom, s->d_fcg);
-    k_view_blocks<<<ntiles, kVbThreads, vb_smem_bytes(), s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which,
-                                                                      s->d_mom, s->d_fcg);
-    s->launches += 1;
+    if (part != 2)
+      k_eval5<<<std::min(ntiles, s->sm_count), kE5Threads, s->eval5_smem, s->stream>>>(
+          P, s->ps[0], s->ps[1], s->d_state, which, s->lm, s->want_err, s->d_mom, s->d_fcg);
+    if (part != 1)
+      k_view_blocks<<<ntiles, kVbThreads, vb_smem_bytes(), s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which,
+                                                                        s->d_mom, s->d_fcg);
+    if (part == 0) s->launches += 1;
+  } else if (part == 2) {
+    return;
   } else if (s->eval_variant == 3)
     k_eval3<<<(P.V + 31) / 32, kE3Threads, s->eval3_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state,
                                                                       which, s->lm, s->prof);
@@ -1011,6 +1016,8 @@ int tscm_solver_time_stage(tscm_solver* s, int stage, int repeats, double* ms_pe
         case 2: launch_solve(s, 0.0, false); break;
         case 3: launch_backsub(s); break;
         case 5: launch_evaluation(s, 3, 0); break;
+        case 6: launch_eval_kernel(s, 3, 1); s->launches += 1; break;
+        case 7: launch_eval_kernel(s, 3, 2); s->launches += 1; break;
         default: s->lm = saved; set_error("unknown stage %d", stage); return TSCM_ERR_INVALID_ARGUMENT;
       }
     }
