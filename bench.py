@@ -198,11 +198,7 @@ def run_b200(args):
     opt = fixed_iteration_options(total_iters + 8)
     solver = capi.Solver(problem, opt, device=local_rank)
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        solver.attach_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        capi.attach_ranks(solver, rank, world)
     solver.set_parameters(intr, cam_rt, board_rt)
 
     def barrier():
@@ -241,8 +237,11 @@ def run_b200(args):
                            "residual/Jacobian/normal-equation pass + accept/reject)",
                    "l2": "per-step working set (observations 56 MB, moment buffer 60 MB, per-view "
                          "records 2 x 34 MB, Schur rows 48 MB) exceeds the 126 MB L2; no explicit flush",
-                   "parallelism": f"frames sharded over {world} GPU(s), NCCL all-reduce of the "
-                                  "reduced camera system" if world > 1 else "single GPU"},
+                   "parallelism": (f"frames sharded over {world} GPU(s); the reduced camera system and "
+                                   "the evaluation record are exchanged by "
+                                   + ("this library's kernels over NVLink peer memory (CUDA IPC)"
+                                      if os.environ.get("TSCM_P2P", "1") != "0" and world <= 8
+                                      else "NCCL all-reduce")) if world > 1 else "single GPU"},
         "lm_iterations_per_sec": it_per_s,
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -307,11 +306,7 @@ def run_b200(args):
     e_opt = fixed_iteration_options(e2e_iters)
     s2 = capi.Solver(host_problem, e_opt, device=local_rank)
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        s2.attach_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
+        capi.attach_ranks(s2, rank, world)
 
     def one_call():
         s2.set_observations(host_problem.obs_xy)

@@ -162,6 +162,15 @@ int tscm_comm_unique_id(void* unique_id_128);
 int tscm_solver_attach_comm(tscm_solver* solver, int rank, int num_ranks,
                             const void* unique_id_128);
 
+/* Multi-GPU on one NVLink/NVSwitch node (preferred): the two exchange steps of an LM
+ * iteration run inside this library's own kernels over peer memory instead of NCCL.  Every
+ * rank exports the 64-byte CUDA-IPC handle of its mailbox, the host gathers the handles of
+ * all ranks (rank order, 64 bytes each) and hands them to every rank.  At most 8 ranks.
+ * Either attach call makes the solver a rank of a sharded solve; with both, peer memory is
+ * used. */
+int tscm_solver_p2p_export(tscm_solver* solver, void* handle_64);
+int tscm_solver_p2p_attach(tscm_solver* solver, int rank, int num_ranks, const void* handles);
+
 /* ---- inspection entry points (used by the parity tests and the bench) ---- */
 
 /* One residual + analytic-Jacobian pass at the current device parameters.

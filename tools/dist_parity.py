@@ -17,11 +17,7 @@ for cfg, frames in ((2, 200), (3, 600)):
     opt = capi.default_options()
     prob, fr = synth.shard_frames(sp, rank, world)
     s = capi.Solver(prob, opt, device=local)
-    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
-    dist.broadcast(uid, 0)
-    s.attach_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))
+    capi.attach_ranks(s, rank, world)
     s.set_parameters(sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt[fr])
     res = s.run()
     intr, cam_rt, board_rt = s.get_parameters()

@@ -237,6 +237,10 @@ def load_library(path: str | None = None):
     lib.tscm_comm_unique_id.restype = C.c_int
     lib.tscm_solver_attach_comm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.tscm_solver_attach_comm.restype = C.c_int
+    lib.tscm_solver_p2p_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tscm_solver_p2p_export.restype = C.c_int
+    lib.tscm_solver_p2p_attach.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.tscm_solver_p2p_attach.restype = C.c_int
     lib.tscm_solver_eval_jacobian.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
     lib.tscm_solver_eval_jacobian.restype = C.c_int
     lib.tscm_solver_reduced_size.argtypes = [C.c_void_p]
@@ -265,7 +269,7 @@ EXPORTED_SYMBOLS = [
     "tscm_options_init", "tscm_solve", "tscm_solver_create", "tscm_solver_destroy",
     "tscm_solver_set_options", "tscm_solver_set_parameters", "tscm_solver_get_parameters",
     "tscm_solver_set_observations", "tscm_solver_run", "tscm_comm_unique_id",
-    "tscm_solver_attach_comm", "tscm_solver_eval_jacobian", "tscm_solver_reduced_size",
+    "tscm_solver_attach_comm", "tscm_solver_p2p_export", "tscm_solver_p2p_attach", "tscm_solver_eval_jacobian", "tscm_solver_reduced_size",
     "tscm_solver_reduced_system", "tscm_solver_reprojection_error", "tscm_solver_time_stage",
     "tscm_solver_launch_count", "tscm_device_fp64_peak", "tscm_last_error", "tscm_version",
 ]
@@ -339,6 +343,18 @@ class Solver:
         b = C.create_string_buffer(unique_id, 128)
         check(self.lib.tscm_solver_attach_comm(self.h, rank, num_ranks, b), self.lib)
 
+    def p2p_export(self) -> bytes:
+        """64-byte CUDA-IPC handle of this rank's exchange mailbox."""
+        b = C.create_string_buffer(64)
+        check(self.lib.tscm_solver_p2p_export(self.h, b), self.lib)
+        return b.raw
+
+    def p2p_attach(self, rank: int, num_ranks: int, handles: bytes):
+        """handles: the p2p_export() of every rank, concatenated in rank order."""
+        assert len(handles) == 64 * num_ranks
+        b = C.create_string_buffer(handles, len(handles))
+        check(self.lib.tscm_solver_p2p_attach(self.h, rank, num_ranks, b), self.lib)
+
     def eval_jacobian(self, want_jacobian=True):
         N = self.problem.num_observations
         r = np.zeros((N, 2))
@@ -400,3 +416,25 @@ def solve(problem: ProblemArrays, intrinsics, cam_rt, board_rt, options: TscmOpt
     check(lib.tscm_solve(C.byref(problem.c), C.byref(options), _dp(a), _dp(b), _dp(c),
                          C.byref(buf.c), device), lib)
     return a, b, c, buf.result()
+
+
+def attach_ranks(solver: "Solver", rank: int, world: int, use_p2p: bool | None = None):
+    """Make `solver` one rank of a frame-sharded solve inside an initialised
+    torch.distributed NCCL process group (one process per GPU of one node).
+    Peer-memory exchange (tscm_p2p.cuh) when world <= 8 unless TSCM_P2P=0; NCCL otherwise."""
+    import torch
+    import torch.distributed as dist
+    if use_p2p is None:
+        use_p2p = os.environ.get("TSCM_P2P", "1") != "0" and world <= 8
+    if use_p2p:
+        mine = torch.frombuffer(bytearray(solver.p2p_export()), dtype=torch.uint8).cuda()
+        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine)
+        solver.p2p_attach(rank, world, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+        dist.barrier()      # every rank has mapped every mailbox before the first exchange
+    else:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        solver.attach_comm(rank, world, bytes(uid.cpu().numpy().tobytes()))

@@ -21,6 +21,7 @@
 #include "../../include/tscm.h"
 #include "tscm_kernels.cuh"
 #include "tscm_eval5.cuh"
+#include "tscm_p2p.cuh"
 
 namespace {
 
@@ -147,6 +148,14 @@ struct tscm_solver {
   // comm
   NcclApi::Comm comm = nullptr;
   int rank = 0, num_ranks = 1;
+  // NVLink peer-memory exchange (tscm_p2p.cuh): mailbox of this rank, IPC mappings of the peers
+  bool p2p_on = false;
+  double* d_mailbox = nullptr;
+  unsigned long long* d_p2p_seq = nullptr;
+  unsigned int* d_p2p_ticket = nullptr;
+  int* d_p2p_err = nullptr;
+  void* p2p_peer[kP2PMaxRanks] = {};
+  P2PArgs p2p{};
   int64_t launches = 0;
   // host copies needed later
   int C = 0, F = 0, K = 0, V = 0;
@@ -277,8 +286,14 @@ void launch_evaluation(tscm_solver* s, int which, int initial, bool prep = true,
 // Global sums of the evaluation record.  The record lives in ps[sel].comm; the
 // selection is only known on the device, so both candidates are reduced when
 // `which` is relative (they are tiny: C*107+4 doubles).
-int launch_eval_allreduce(tscm_solver* s, int which) {
+int launch_eval_allreduce(tscm_solver* s, int which, bool decide = false) {
   if (s->num_ranks <= 1) return TSCM_OK;
+  if (s->p2p_on) {
+    k_xchg_eval<<<1, kXchgThreads, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, which, s->lm,
+                                                    s->trace, s->p2p, decide ? 1 : 0);
+    s->launches += 1;
+    return TSCM_OK;
+  }
   NcclApi& n = nccl();
   const size_t cnt = (size_t)s->P.C * kCamRec + kCommExtra;
   n.GroupStart();
@@ -318,13 +333,17 @@ void launch_schur(tscm_solver* s, double radius_override) {
     k_schur<2, 768><<<s->schur_nblk, s->schur_nt, s->schur_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
                                                                              s->d_state, s->lm, a);
   const int n = s->P.Q + s->P.NL;
-  k_reduce_s<<<(n + 31) / 32, kReduceThreads, 0, s->stream>>>(s->P, s->d_state, s->d_Spart, s->d_rpart,
-                                                    s->schur_nblk, s->d_Sr);
+  if (s->p2p_on && s->num_ranks > 1)
+    k_reduce_s_p2p<<<(n + 31) / 32, kReduceThreads, 0, s->stream>>>(s->P, s->d_state, s->d_Spart, s->d_rpart,
+                                                                    s->schur_nblk, s->d_Sr, s->p2p);
+  else
+    k_reduce_s<<<(n + 31) / 32, kReduceThreads, 0, s->stream>>>(s->P, s->d_state, s->d_Spart, s->d_rpart,
+                                                                s->schur_nblk, s->d_Sr);
   s->launches += 2;
 }
 
 int launch_schur_allreduce(tscm_solver* s) {
-  if (s->num_ranks <= 1) return TSCM_OK;
+  if (s->num_ranks <= 1 || s->p2p_on) return TSCM_OK;   // P2P: exchanged inside k_reduce_s_p2p
   NcclApi& n = nccl();
   int rc = n.AllReduce(s->d_Sr, s->d_Sr, (size_t)s->P.Q + s->P.NL, kNcclFloat64, kNcclSum, s->comm, s->stream);
   if (rc) { set_error("ncclAllReduce(S) failed: %d", rc); return TSCM_ERR_COMM; }
@@ -361,10 +380,12 @@ int launch_iteration(tscm_solver* s) {
   const bool single = s->num_ranks <= 1;
   launch_evaluation(s, 1, 0, /*prep=*/false, /*decide=*/single);
   if (!single) {
-    rc = launch_eval_allreduce(s, 1);
+    rc = launch_eval_allreduce(s, 1, /*decide=*/true);
     if (rc) return rc;
-    k_decide<<<1, 32, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, s->trace);
-    s->launches += 1;
+    if (!s->p2p_on) {
+      k_decide<<<1, 32, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, s->trace);
+      s->launches += 1;
+    }
   }
   return TSCM_OK;
 }
@@ -685,6 +706,19 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   s->bs_nblk = (F + kBacksubThreads / 32 - 1) / (kBacksubThreads / 32);
   s->fg_nblk = (F * 6 + kPostThreads - 1) / kPostThreads;
   TRY_RC(s->alloc(&s->d_ticket, 1));
+  {
+    // mailbox of the peer-memory exchange (tiny; allocated always so that its IPC handle can
+    // be exported right after creation)
+    const int nwords = P.Q + NL;
+    s->p2p.nA = (nwords + 31) / 32 * 32;
+    s->p2p.nctaA = (nwords + 31) / 32;
+    s->p2p.nB = (C * kCamRec + kCommExtra + 1 + 31) / 32 * 32;
+    TRY_RC(s->alloc(&s->d_mailbox, p2p_mailbox_words(s->p2p.nA, s->p2p.nctaA, s->p2p.nB)));
+    TRY_RC(s->alloc(&s->d_p2p_seq, 2));
+    TRY_RC(s->alloc(&s->d_p2p_ticket, 1));
+    TRY_RC(s->alloc(&s->d_p2p_err, 1));
+    s->p2p.seq = s->d_p2p_seq; s->p2p.ticket = s->d_p2p_ticket; s->p2p.err = s->d_p2p_err;
+  }
   TRY_RC(s->alloc(&s->d_bs_part, (size_t)4 * s->bs_nblk));
   TRY_RC(s->alloc(&s->d_gmax_part, (size_t)s->fg_nblk));
   TRY_RC(s->alloc(&s->d_xn2_part, (size_t)s->fg_nblk));
@@ -738,6 +772,8 @@ void tscm_solver_destroy(tscm_solver* s) {
   if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
   if (s->graph) cudaGraphDestroy(s->graph);
   if (s->comm && nccl().ok) nccl().CommDestroy(s->comm);
+  for (int r = 0; r < kP2PMaxRanks; ++r)
+    if (s->p2p_peer[r]) cudaIpcCloseMemHandle(s->p2p_peer[r]);
   for (void* p : s->owned) cudaFree(p);
   if (s->h_state) cudaFreeHost(s->h_state);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -814,6 +850,11 @@ int tscm_solver_run(tscm_solver* s, tscm_summary* summary) {
   }
   if ((rc = fetch_state(s))) return rc;
   CUDA_TRY(cudaGetLastError());
+  if (s->p2p_on) {
+    int perr = 0;
+    CUDA_TRY(cudaMemcpy(&perr, s->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (perr) { set_error("peer-memory exchange timed out waiting for another rank"); return TSCM_ERR_COMM; }
+  }
   const LmState& st = *s->h_state;
   if (summary) {
     summary->termination_type = st.done ? st.termination : TSCM_NO_CONVERGENCE;
@@ -886,6 +927,41 @@ int tscm_solver_attach_comm(tscm_solver* s, int rank, int num_ranks, const void*
   int rc = n.CommInitRank(&s->comm, num_ranks, id, rank);
   if (rc) { set_error("ncclCommInitRank failed: %d", rc); return TSCM_ERR_COMM; }
   s->rank = rank; s->num_ranks = num_ranks;
+  s->graph_dirty = true;
+  return TSCM_OK;
+}
+
+int tscm_solver_p2p_export(tscm_solver* s, void* handle_64) {
+  if (!s || !handle_64) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));      // the mailbox is zeroed before anyone maps it
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, s->d_mailbox));
+  std::memcpy(handle_64, &h, 64);
+  return TSCM_OK;
+}
+
+int tscm_solver_p2p_attach(tscm_solver* s, int rank, int num_ranks, const void* handles) {
+  if (!s || !handles || rank < 0 || rank >= num_ranks) { set_error("bad p2p arguments"); return TSCM_ERR_INVALID_ARGUMENT; }
+  if (num_ranks > kP2PMaxRanks) { set_error("peer-memory exchange supports at most %d ranks", kP2PMaxRanks); return TSCM_ERR_INVALID_ARGUMENT; }
+  CUDA_TRY(cudaSetDevice(s->device));
+  for (int r = 0; r < num_ranks; ++r) {
+    if (r == rank) { s->p2p.mb[r] = s->d_mailbox; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char*)handles + 64 * r, 64);
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
+      return TSCM_ERR_COMM;
+    }
+    s->p2p_peer[r] = ptr;
+    s->p2p.mb[r] = static_cast<double*>(ptr);
+  }
+  s->p2p.rank = rank; s->p2p.world = num_ranks;
+  s->rank = rank; s->num_ranks = num_ranks;
+  s->p2p_on = true;
   s->graph_dirty = true;
   return TSCM_OK;
 }
