@@ -204,6 +204,35 @@ int64_t tscm_solver_launch_count(const tscm_solver* solver);
  * denominator of the FP64 roofline this FP64-bound path is judged against. */
 int tscm_device_fp64_peak(int device, double* tflops);
 
+/* ---- remap tables --------------------------------------------------
+ * The per-pixel loops that fill CV_32FC1 lookup tables through the TS projection:
+ *   TripleSphereCamera::undistort             /root/reference/TS.cpp:284-306
+ *   TripleSphereCamera::undistort_chessboard  /root/reference/TS.cpp:308-330 (mapx/mapy part)
+ *   Remap::init_remap                         /root/reference/EpipolarRectify/rectify.cpp:86-199
+ * One job = one rectangular block of the output maps: for block pixel (i, j)
+ *   ray  = ((j - ray_cx)/ray_fx, (i - ray_cy)/ray_fy, 1)        TS.cpp:293-295, rectify.cpp:98
+ *   P    = matrix * ray                                         rectify.cpp:99, TS.cpp:321-322
+ *   (u,v)= TS projection of P with skew b, c                    TS.cpp:332-344
+ *          or (-1,-1) when cutoff_w2 > 0 and Z <= -cutoff_w2*|P| rectify.cpp:7,28
+ *   mapx[row0+i][col0+j] = (float)(u + offset_x), mapy likewise rectify.cpp:113-114
+ * Results are bit-identical to those loops evaluated in IEEE double without FMA
+ * contraction.  Host pointers; mapx/mapy are map_height x map_width floats, pixels not
+ * covered by any job are left untouched.  At most 64 jobs per call. */
+typedef struct tscm_remap_job {
+  double intrinsics[TSCM_INTRINSIC_SIZE]; /* source camera {fx,fy,cx,cy,xi,lambda,alpha,b,c} */
+  double matrix[9];                       /* row-major 3x3 */
+  double ray_fx, ray_fy, ray_cx, ray_cy;
+  double offset_x, offset_y;
+  double cutoff_w2;                       /* 0 = none (TS.cpp); 0.42399 in rectify.cpp:7 */
+  int32_t width, height;                  /* block size */
+  int32_t row0, col0;                     /* block origin in the maps */
+} tscm_remap_job;
+
+/* kernel_ms (may be NULL): device time of the table kernel, CUDA events. */
+int tscm_remap_tables(const tscm_remap_job* jobs, int32_t num_jobs, int32_t map_width,
+                      int32_t map_height, float* mapx, float* mapy, int device,
+                      double* kernel_ms);
+
 const char* tscm_last_error(void);
 const char* tscm_version(void);
 

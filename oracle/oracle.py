@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 
 from tscm_calib_b200.capi import (ProblemArrays, SummaryBuffers, TscmOptions, TscmProblem,
-                                  TscmSummary, _dp, c_double_p, default_options)
+                                  TscmRemapJob, TscmSummary, _dp, c_double_p, default_options)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtscm_oracle.so")
@@ -21,7 +21,7 @@ _lib = None
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("tscm_oracle.cpp", "tscm_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("tscm_oracle.cpp", "tscm_oracle.h", "remap_oracle.c")]
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return LIB_PATH
@@ -58,6 +58,9 @@ def load():
     lib.tscm_oracle_reprojection_error.restype = C.c_int
     lib.tscm_oracle_project.argtypes = [c_double_p, c_double_p, C.c_int, c_double_p]
     lib.tscm_oracle_project.restype = None
+    lib.tscm_oracle_remap_tables.argtypes = [P(TscmRemapJob), C.c_int32, C.c_int32, C.c_int32,
+                                             P(C.c_float), P(C.c_float)]
+    lib.tscm_oracle_remap_tables.restype = C.c_int
     _lib = lib
     return lib
 
@@ -146,3 +149,15 @@ def project(intrinsic9, pts):
     uv = np.zeros((p.shape[0], 2))
     lib.tscm_oracle_project(_dp(a), _dp(p), p.shape[0], _dp(uv))
     return uv
+
+
+def remap_tables(jobs, map_size):
+    """CPU restatement of the reference's remap-table loops (remap_oracle.c)."""
+    lib = load()
+    W, H = int(map_size[0]), int(map_size[1])
+    mapx, mapy = np.zeros((H, W), dtype=np.float32), np.zeros((H, W), dtype=np.float32)
+    arr = (TscmRemapJob * len(jobs))(*jobs)
+    rc = lib.tscm_oracle_remap_tables(arr, len(jobs), W, H, mapx.ctypes.data_as(C.POINTER(C.c_float)),
+                                      mapy.ctypes.data_as(C.POINTER(C.c_float)))
+    assert rc == 0
+    return mapx, mapy

@@ -45,6 +45,26 @@ def hostmath():
 
 
 @pytest.fixture(scope="session")
+def hostinit():
+    """C wrappers (tests/hostmath/hostinit.cpp) around the C++ TripleSphereCamera adapter."""
+    from tscm_calib_b200 import build as tbuild
+    tbuild.build_cuda()
+    here = os.path.join(ROOT, "tests", "hostmath")
+    host = os.path.join(ROOT, "tscm_calib_b200", "host")
+    out = os.path.join(here, "libhostinit.so")
+    srcs = [os.path.join(here, "hostinit.cpp"), os.path.join(host, "ts_camera.cpp")]
+    deps = srcs + [os.path.join(host, "ts_camera.h"), os.path.join(host, "cv_compat.h"),
+                   os.path.join(ROOT, "include", "tscm.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        env = dict(os.environ)
+        env.pop("CXX", None)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out] + srcs +
+                       ["-L" + os.path.join(ROOT, "tscm_calib_b200"), "-ltscm_b200",
+                        "-Wl,-rpath," + os.path.join(ROOT, "tscm_calib_b200")], check=True, env=env)
+    return ctypes.CDLL(out)
+
+
+@pytest.fixture(scope="session")
 def oracle():
     from oracle import oracle as o
     o.build()

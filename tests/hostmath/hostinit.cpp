@@ -1,0 +1,113 @@
+// Test-only C wrappers around the C++ drop-in adapter (tscm_calib_b200/host/ts_camera.*), so
+// that pytest can drive TripleSphereCamera's cold-start initialisation (TS.cpp:36-52,110-203),
+// the cv shim's solveZ / solvePnPRansac, the full calibrate() and the remap tables through
+// ctypes.  Not part of the product library.
+#include <cstring>
+#include <vector>
+
+#include "../../tscm_calib_b200/host/ts_camera.h"
+
+namespace {
+std::vector<std::vector<cv::Point2d>> unpack(const double* px, const unsigned char* has, int F, int K) {
+  std::vector<std::vector<cv::Point2d>> pixels(F);
+  for (int i = 0; i < F; ++i) {
+    if (!has[i]) continue;                      // empty vector = no detection (main.cpp:33-37)
+    pixels[i].resize(K);
+    std::memcpy((void*)pixels[i].data(), px + (size_t)i * K * 2, sizeof(double) * 2 * K);
+  }
+  return pixels;
+}
+std::vector<cv::Point3d> board(int W, int H, double square) {   // main.cpp:12-18
+  std::vector<cv::Point3d> w;
+  for (int j = 0; j < W * H; ++j) w.push_back(cv::Point3d((j % W) * square, (j / W) * square, 0.0));
+  return w;
+}
+void export_state(TripleSphereCamera& cam, int F, const unsigned char* has, double* intr9, double* Rt) {
+  const double v[9] = {cam.fx(), cam.fy(), cam.cx(), cam.cy(), cam.xi(), cam.lamda(), cam.alpha(), cam.b(), cam.c()};
+  std::memcpy(intr9, v, sizeof(v));
+  for (int i = 0; i < F; ++i) {
+    if (!has[i]) continue;
+    cv::Mat M = cam.Rt(i);
+    for (int k = 0; k < 9; ++k) Rt[(size_t)i * 9 + k] = M.at<double>(k / 3, k % 3);
+  }
+}
+}  // namespace
+
+extern "C" {
+
+void hostinit_solve_z(const double* A, int rows, int cols, double* z) {
+  cv::Mat M(rows, cols), out;
+  for (int i = 0; i < rows * cols; ++i) M.at<double>(i / cols, i % cols) = A[i];
+  cv::SVD::solveZ(M, out);
+  for (int i = 0; i < cols; ++i) z[i] = out.at<double>(i, 0);
+}
+
+int hostinit_solve_pnp(const double* obj_xyz, const double* img_xy, int n, double* rvec, double* tvec) {
+  std::vector<cv::Point3d> o(n);
+  std::vector<cv::Point2d> p(n);
+  for (int i = 0; i < n; ++i) { o[i] = cv::Point3d(obj_xyz[3 * i], obj_xyz[3 * i + 1], obj_xyz[3 * i + 2]); p[i] = cv::Point2d(img_xy[2 * i], img_xy[2 * i + 1]); }
+  cv::Mat r, t;
+  if (!cv::solvePnPRansac(o, p, cv::Mat::eye(3, 3, cv::CV_64F), cv::Mat::zeros(4, 0, cv::CV_64F), r, t)) return 1;
+  for (int k = 0; k < 3; ++k) { rvec[k] = r.at<double>(k, 0); tvec[k] = t.at<double>(k, 0); }
+  return 0;
+}
+
+// TS.cpp:36-52 from scratch (guess7 == NULL) or from given intrinsics.
+int hostinit_initial_guess(const double* px, const unsigned char* has, int F, int W, int H, double square,
+                           int img_w, int img_h, const double* guess7, double* intr9, double* Rt) {
+  TripleSphereCamera cam = guess7 ? TripleSphereCamera(guess7[0], guess7[1], guess7[2], guess7[3], guess7[4], guess7[5], guess7[6])
+                                  : TripleSphereCamera();
+  std::vector<bool> hb(F);
+  for (int i = 0; i < F; ++i) hb[i] = has[i] != 0;
+  const bool ok = cam.initial_guess(unpack(px, has, F, W * H), hb, board(W, H, square), cv::Size(img_w, img_h), cv::Size(W, H));
+  export_state(cam, F, has, intr9, Rt);
+  return ok ? 0 : 1;
+}
+
+// The whole TripleSphereCamera::calibrate (TS.cpp:30-108): cold start + refinement on the GPU.
+// summary4 = {termination, iterations, initial cost, final cost}.
+int hostinit_calibrate(const double* px, const unsigned char* has, int F, int W, int H, double square,
+                       int img_w, int img_h, const double* guess7, double* intr9, double* Rt,
+                       double* summary4) {
+  TripleSphereCamera cam = guess7 ? TripleSphereCamera(guess7[0], guess7[1], guess7[2], guess7[3], guess7[4], guess7[5], guess7[6])
+                                  : TripleSphereCamera();
+  cam.device = 0;
+  std::vector<bool> hb(F);
+  for (int i = 0; i < F; ++i) hb[i] = has[i] != 0;
+  const bool ok = cam.calibrate(unpack(px, has, F, W * H), hb, board(W, H, square), cv::Size(img_w, img_h), cv::Size(W, H));
+  export_state(cam, F, has, intr9, Rt);
+  const tscm_summary& s = cam.last_summary();
+  summary4[0] = s.termination_type; summary4[1] = s.num_iterations; summary4[2] = s.initial_cost; summary4[3] = s.final_cost;
+  return ok ? 0 : 1;
+}
+
+// TS.cpp:284-306 and 308-326 through the adapter.
+int hostinit_undistort(const double* intr9, double fx, double fy, double cx, double cy, int w, int h,
+                       float* mapx, float* mapy) {
+  TripleSphereCamera cam(intr9[0], intr9[1], intr9[2], intr9[3], intr9[4], intr9[5], intr9[6]);
+  cam.device = 0;
+  cv::Mat mx, my;
+  cam.undistort(fx, fy, cx, cy, cv::Size(w, h), mx, my);
+  if (mx.empty() || mx.rows != h || mx.cols != w) return 1;
+  std::memcpy(mapx, mx.ptr<float>(), sizeof(float) * (size_t)w * h);
+  std::memcpy(mapy, my.ptr<float>(), sizeof(float) * (size_t)w * h);
+  return 0;
+}
+
+int hostinit_undistort_chessboard(const double* intr9, const double* Rt9, int W, int H, double square,
+                                  float* mapx, float* mapy, int* out_w, int* out_h) {
+  TripleSphereCamera cam(intr9[0], intr9[1], intr9[2], intr9[3], intr9[4], intr9[5], intr9[6]);
+  cam.device = 0;
+  cv::Mat M(3, 3);
+  for (int k = 0; k < 9; ++k) M.at<double>(k / 3, k % 3) = Rt9[k];
+  cam.setRt(std::vector<cv::Mat>{M});
+  cam.setHasChessboard(std::vector<bool>{true});
+  cv::Mat mx, my;
+  if (!cam.undistort_chessboard_maps(0, cv::Size(W, H), square, mx, my)) return 1;
+  *out_w = mx.cols; *out_h = mx.rows;
+  std::memcpy(mapx, mx.ptr<float>(), sizeof(float) * (size_t)mx.cols * mx.rows);
+  std::memcpy(mapy, my.ptr<float>(), sizeof(float) * (size_t)mx.cols * mx.rows);
+  return 0;
+}
+
+}  // extern "C"

@@ -76,6 +76,19 @@ class TscmSummary(C.Structure):
     ]
 
 
+class TscmRemapJob(C.Structure):
+    """tscm_remap_job (include/tscm.h): one block of a remap table."""
+    _fields_ = [
+        ("intrinsics", C.c_double * 9),
+        ("matrix", C.c_double * 9),
+        ("ray_fx", C.c_double), ("ray_fy", C.c_double), ("ray_cx", C.c_double), ("ray_cy", C.c_double),
+        ("offset_x", C.c_double), ("offset_y", C.c_double),
+        ("cutoff_w2", C.c_double),
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("row0", C.c_int32), ("col0", C.c_int32),
+    ]
+
+
 def default_options(**overrides) -> TscmOptions:
     """ceres::Solver::Options defaults in force at TS.cpp:271-274 /
     multi_calib.cpp:209-212 (same values tscm_options_init() writes)."""
@@ -255,6 +268,9 @@ def load_library(path: str | None = None):
     lib.tscm_solver_launch_count.restype = C.c_int64
     lib.tscm_device_fp64_peak.argtypes = [C.c_int, c_double_p]
     lib.tscm_device_fp64_peak.restype = C.c_int
+    lib.tscm_remap_tables.argtypes = [P(TscmRemapJob), C.c_int32, C.c_int32, C.c_int32,
+                                      P(C.c_float), P(C.c_float), C.c_int, c_double_p]
+    lib.tscm_remap_tables.restype = C.c_int
     lib.tscm_last_error.argtypes = []
     lib.tscm_last_error.restype = C.c_char_p
     lib.tscm_version.argtypes = []
@@ -271,7 +287,8 @@ EXPORTED_SYMBOLS = [
     "tscm_solver_set_observations", "tscm_solver_run", "tscm_comm_unique_id",
     "tscm_solver_attach_comm", "tscm_solver_p2p_export", "tscm_solver_p2p_attach", "tscm_solver_eval_jacobian", "tscm_solver_reduced_size",
     "tscm_solver_reduced_system", "tscm_solver_reprojection_error", "tscm_solver_time_stage",
-    "tscm_solver_launch_count", "tscm_device_fp64_peak", "tscm_last_error", "tscm_version",
+    "tscm_solver_launch_count", "tscm_device_fp64_peak", "tscm_remap_tables",
+    "tscm_last_error", "tscm_version",
 ]
 
 
@@ -394,6 +411,35 @@ def device_fp64_peak(device: int = -1) -> float:
     v = C.c_double()
     check(lib.tscm_device_fp64_peak(device, C.byref(v)), lib)
     return v.value
+
+
+def remap_job(intrinsics, matrix, ray, size, origin=(0, 0), offset=(0.0, 0.0), cutoff_w2=0.0) -> TscmRemapJob:
+    """ray = (fx, fy, cx, cy) of the output pixel grid; size = (width, height);
+    origin = (row0, col0) of the block in the maps."""
+    j = TscmRemapJob()
+    j.intrinsics[:] = [float(v) for v in np.asarray(intrinsics, dtype=np.float64).reshape(9)]
+    j.matrix[:] = [float(v) for v in np.asarray(matrix, dtype=np.float64).reshape(9)]
+    j.ray_fx, j.ray_fy, j.ray_cx, j.ray_cy = (float(v) for v in ray)
+    j.offset_x, j.offset_y = float(offset[0]), float(offset[1])
+    j.cutoff_w2 = float(cutoff_w2)
+    j.width, j.height = int(size[0]), int(size[1])
+    j.row0, j.col0 = int(origin[0]), int(origin[1])
+    return j
+
+
+def remap_tables(jobs, map_size, device: int = -1, mapx=None, mapy=None):
+    """tscm_remap_tables(): fill CV_32FC1 tables (map_size = (width, height)) on the GPU.
+    Returns (mapx, mapy, kernel_ms)."""
+    lib = load_library()
+    W, H = int(map_size[0]), int(map_size[1])
+    mapx = np.zeros((H, W), dtype=np.float32) if mapx is None else mapx
+    mapy = np.zeros((H, W), dtype=np.float32) if mapy is None else mapy
+    assert mapx.shape == (H, W) and mapy.shape == (H, W) and mapx.dtype == np.float32
+    arr = (TscmRemapJob * len(jobs))(*jobs)
+    ms = C.c_double()
+    check(lib.tscm_remap_tables(arr, len(jobs), W, H, mapx.ctypes.data_as(C.POINTER(C.c_float)),
+                                mapy.ctypes.data_as(C.POINTER(C.c_float)), device, C.byref(ms)), lib)
+    return mapx, mapy, ms.value
 
 
 def comm_unique_id() -> bytes:

@@ -22,6 +22,7 @@
 #include "tscm_kernels.cuh"
 #include "tscm_eval5.cuh"
 #include "tscm_p2p.cuh"
+#include "tscm_remap.cuh"
 
 namespace {
 
@@ -1127,6 +1128,101 @@ int tscm_solver_time_stage(tscm_solver* s, int stage, int repeats, double* ms_pe
     }
   }
   return TSCM_OK;
+}
+
+// Remap tables: TS.cpp:284-330, rectify.cpp:86-199 as one batched kernel.
+int tscm_remap_tables(const tscm_remap_job* jobs, int32_t num_jobs, int32_t map_width,
+                      int32_t map_height, float* mapx, float* mapy, int device, double* kernel_ms) {
+  if (!jobs || !mapx || !mapy || num_jobs <= 0 || map_width <= 0 || map_height <= 0) {
+    set_error("bad remap arguments"); return TSCM_ERR_INVALID_ARGUMENT;
+  }
+  if (num_jobs > kRemapMaxJobs) {
+    set_error("%d remap jobs exceed the per-call limit of %d", num_jobs, kRemapMaxJobs);
+    return TSCM_ERR_INVALID_ARGUMENT;
+  }
+  std::vector<RemapBatch> hb(1);
+  RemapBatch& B = hb[0];
+  std::memset(&B, 0, sizeof(B));
+  int64_t total = 0;
+  for (int k = 0; k < num_jobs; ++k) {
+    const tscm_remap_job& j = jobs[k];
+    if (j.width <= 0 || j.height <= 0 || j.row0 < 0 || j.col0 < 0 ||
+        (int64_t)j.row0 + j.height > map_height || (int64_t)j.col0 + j.width > map_width) {
+      set_error("remap job %d: block %dx%d at (%d,%d) does not fit the %dx%d maps", k, j.width, j.height,
+                j.col0, j.row0, map_width, map_height);
+      return TSCM_ERR_INVALID_ARGUMENT;
+    }
+    if (j.ray_fx == 0.0 || j.ray_fy == 0.0) { set_error("remap job %d: zero ray focal length", k); return TSCM_ERR_INVALID_ARGUMENT; }
+    RemapJobDev& d = B.job[k];
+    std::memcpy(d.intr, j.intrinsics, sizeof(d.intr));
+    std::memcpy(d.M, j.matrix, sizeof(d.M));
+    d.ray_fx = j.ray_fx; d.ray_fy = j.ray_fy; d.ray_cx = j.ray_cx; d.ray_cy = j.ray_cy;
+    d.offset_x = j.offset_x; d.offset_y = j.offset_y; d.cutoff_w2 = j.cutoff_w2;
+    d.width = j.width; d.height = j.height; d.row0 = j.row0; d.col0 = j.col0;
+    d.first_pixel = total;
+    total += (int64_t)j.width * j.height;
+  }
+  B.num_jobs = num_jobs; B.map_width = map_width; B.total_pixels = total;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: remap tables have no CPU fallback");
+    return TSCM_ERR_NO_DEVICE;
+  }
+  if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major < 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    return TSCM_ERR_NO_DEVICE;
+  }
+  const size_t map_bytes = (size_t)map_width * map_height * sizeof(float);
+  RemapBatch* d_batch = nullptr;
+  float *d_x = nullptr, *d_y = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int rc = TSCM_OK;
+  auto cleanup = [&]() {
+    cudaFree(d_batch); cudaFree(d_x); cudaFree(d_y);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  };
+#define REMAP_TRY(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      cleanup(); return TSCM_ERR_CUDA;                                                    \
+    }                                                                                     \
+  } while (0)
+  REMAP_TRY(cudaMalloc((void**)&d_batch, sizeof(RemapBatch)));
+  REMAP_TRY(cudaMalloc((void**)&d_x, map_bytes));
+  REMAP_TRY(cudaMalloc((void**)&d_y, map_bytes));
+  REMAP_TRY(cudaMemcpy(d_batch, &B, sizeof(RemapBatch), cudaMemcpyHostToDevice));
+  REMAP_TRY(cudaEventCreate(&e0));
+  REMAP_TRY(cudaEventCreate(&e1));
+  // one wave of resident CTAs (8 x 256 threads per SM), grid-stride over the pixels
+  const int64_t want = (total + 255) / 256;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)prop.multiProcessorCount * 8);
+  REMAP_TRY(cudaEventRecord(e0, 0));
+  k_remap_tables<<<grid, 256>>>(d_batch, d_x, d_y);
+  REMAP_TRY(cudaEventRecord(e1, 0));
+  REMAP_TRY(cudaGetLastError());
+  for (int k = 0; k < num_jobs && rc == TSCM_OK; ++k) {   // only the blocks that were written
+    const tscm_remap_job& j = jobs[k];
+    const size_t o = (size_t)j.row0 * map_width + j.col0, pitch = (size_t)map_width * sizeof(float);
+    REMAP_TRY(cudaMemcpy2D(mapx + o, pitch, d_x + o, pitch, (size_t)j.width * sizeof(float), j.height, cudaMemcpyDeviceToHost));
+    REMAP_TRY(cudaMemcpy2D(mapy + o, pitch, d_y + o, pitch, (size_t)j.width * sizeof(float), j.height, cudaMemcpyDeviceToHost));
+  }
+  REMAP_TRY(cudaEventSynchronize(e1));
+  if (kernel_ms) {
+    float ms = 0.f;
+    REMAP_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    *kernel_ms = ms;
+  }
+#undef REMAP_TRY
+  cleanup();
+  return rc;
 }
 
 int64_t tscm_solver_launch_count(const tscm_solver* s) { return s ? s->launches : 0; }

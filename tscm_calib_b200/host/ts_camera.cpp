@@ -1,5 +1,6 @@
-// ts_camera.cpp — see ts_camera.h.  The only compute here is parameter packing; the
-// refinement itself is tscm_solve().
+// ts_camera.cpp — see ts_camera.h.  Host side: parameter packing and the cold-start
+// initialisation (small dense linear algebra, as in the reference); the refinement is
+// tscm_solve(), the remap tables are tscm_remap_tables().
 #include "ts_camera.h"
 
 #include <cmath>
@@ -40,19 +41,12 @@ TripleSphereCamera::TripleSphereCamera(double fx, double fy, double cx, double c
 
 bool TripleSphereCamera::calibrate(const std::vector<std::vector<cv::Point2d>> pixels,
                                    std::vector<bool> has_chessboard,
-                                   const std::vector<cv::Point3d>& worlds, const cv::Size /*img_size*/,
-                                   const cv::Size /*chessboard_num*/) {
-  pixels_ = pixels;
-  has_chessboard_ = has_chessboard;
+                                   const std::vector<cv::Point3d>& worlds, const cv::Size img_size,
+                                   const cv::Size chessboard_num) {
   const size_t img_num = pixels.size();
+  if (has_chessboard.size() != img_num) return false;
+  if (!initial_guess(pixels, has_chessboard, worlds, img_size, chessboard_num)) return false;   // TS.cpp:41-52
   rt_.assign(img_num, std::vector<double>(TSCM_POSE_SIZE, 0.0));
-  if (!has_init_guess_ || Rt_.size() != img_num) {
-    // estimate_focal / estimate_extrinsic (TS.cpp:48,52) are the reference's OpenCV code.
-    std::cout << "[tscm] calibrate() needs an initial guess: intrinsics via the 7-argument "
-                 "constructor and per-frame [r1 r2 t] via setRt(); cold-start initialisation "
-                 "stays in the reference (TS.cpp:110-203)" << std::endl;
-    return false;
-  }
   const double packed[TSCM_INTRINSIC_SIZE] = {fx_, fy_, cx_, cy_, xi_, lamda_, alpha_, b_, c_};  // TS.cpp:53-61
   intrinsic_.assign(packed, packed + TSCM_INTRINSIC_SIZE);
   // [r1 r2 t] -> angle-axis + t, through single-precision r1, r2 like TS.cpp:66-72 (cv::Vec3f).
@@ -86,6 +80,106 @@ bool TripleSphereCamera::calibrate(const std::vector<std::vector<cv::Point2d>> p
     }
   }
   return status;
+}
+
+// TS.cpp:36-52: the state calibrate() is in when it reaches the parameter packing.
+bool TripleSphereCamera::initial_guess(const std::vector<std::vector<cv::Point2d>>& pixels,
+                                       std::vector<bool> has_chessboard,
+                                       const std::vector<cv::Point3d>& worlds, const cv::Size img_size,
+                                       const cv::Size chessboard_num) {
+  pixels_ = pixels;
+  has_chessboard_ = has_chessboard;
+  const size_t img_num = pixels.size();
+  Rt_.resize(img_num);
+  if (!has_init_guess_) {
+    cx_ = img_size.width / 2 - 0.5;     // integer halves, as TS.cpp:43-44
+    cy_ = img_size.height / 2 - 0.5;
+    xi_ = 0.0;
+    lamda_ = 0.0;
+    alpha_ = 0.5;
+    estimate_focal(pixels, worlds, img_size, chessboard_num);
+    std::cout << "[initialize] focal:" << fx_ << ", cx:" << cx_ << ", cy:" << cy_ << ", xi:" << xi_
+              << ", lamda:" << lamda_ << ", alpha:" << alpha_ << std::endl;
+    if (fx_ == 0) return false;
+  }
+  estimate_extrinsic(pixels, worlds, chessboard_num);
+  return true;
+}
+
+// TS.cpp:110-168.  With xi = lamda = 0, alpha = 0.5 a board row (a 3-D line) images as a
+// circle x^2 + y^2 - 2 f (nx/nz) x - 2 f (ny/nz) y - f^2 = 0 around the principal point; the
+// null vector of [x y 1/2 -(x^2+y^2)/2] per row gives the focal length.
+void TripleSphereCamera::estimate_focal(const std::vector<std::vector<cv::Point2d>>& pixels,
+                                        const std::vector<cv::Point3d>& /*worlds*/, cv::Size /*img_size*/,
+                                        const cv::Size chessboard_num) {
+  double focal = 0;
+  int total_num = 0;
+  const int W = chessboard_num.width, H = chessboard_num.height;
+  for (size_t k = 0; k < pixels.size(); ++k) {
+    if (pixels[k].size() == 0) continue;
+    for (int i = 0; i < H; ++i) {
+      cv::Mat P(W, 4);
+      for (int j = 0; j < W; ++j) {
+        const double x = pixels[k][i * W + j].x - cx_, y = pixels[k][i * W + j].y - cy_;
+        P.at<double>(j, 0) = x;
+        P.at<double>(j, 1) = y;
+        P.at<double>(j, 2) = 0.5;
+        P.at<double>(j, 3) = -0.5 * (x * x + y * y);
+      }
+      cv::Mat C;
+      cv::SVD::solveZ(P, C);
+      const double c1 = C.at<double>(0), c2 = C.at<double>(1), c3 = C.at<double>(2), c4 = C.at<double>(3);
+      const double t = c1 * c1 + c2 * c2 + c3 * c4;
+      if (t < 0) continue;
+      const double d = std::sqrt(1 / t);
+      const double nx = c1 * d, ny = c2 * d;
+      if (nx * nx + ny * ny > 0.95) continue;
+      const double nz = std::sqrt(1 - nx * nx - ny * ny);
+      focal += std::fabs(c3 * d / nz);
+      total_num++;
+    }
+  }
+  if (total_num > 0) focal /= total_num;
+  else std::cout << "焦距估计失败" << std::endl;      // the reference's message (TS.cpp:165)
+  fx_ = fy_ = focal;
+}
+
+// TS.cpp:170-203.  Corners are lifted to the unit sphere, rotated so that a central corner
+// looks down +z, projected to the normalised plane, and the board pose comes from
+// solvePnPRansac with an identity camera matrix; the pose is rotated back and stored in the
+// [r1 r2 t] form.
+void TripleSphereCamera::estimate_extrinsic(const std::vector<std::vector<cv::Point2d>>& pixels,
+                                            const std::vector<cv::Point3d>& worlds,
+                                            const cv::Size chessboard_num) {
+  for (size_t k = 0; k < pixels.size(); ++k) {
+    if (has_chessboard_[k] == false) continue;
+    const std::vector<cv::Point2d>& pixel = pixels[k];
+    cv::Mat transform = cv::Mat::eye(3, 3, cv::CV_64F);
+    const cv::Point3d p = get_unit_sphere_coordinate(pixel[pixel.size() / 2 - chessboard_num.width / 2 - 1], transform);
+    const double alpha_angle = std::atan2(p.x, p.z);
+    const double beta_angle = std::asin(p.y);
+    cv::Mat R1 = (cv::Mat_<double>(3, 3) << std::cos(alpha_angle), 0, -std::sin(alpha_angle),
+                                            0, 1, 0,
+                                            std::sin(alpha_angle), 0, std::cos(alpha_angle));
+    cv::Mat R2 = (cv::Mat_<double>(3, 3) << 1, 0, 0,
+                                            0, std::cos(beta_angle), -std::sin(beta_angle),
+                                            0, std::sin(beta_angle), std::cos(beta_angle));
+    transform = R2 * R1;
+    std::vector<cv::Point2d> pixels_normalize;
+    for (size_t i = 0; i < pixel.size(); ++i) {
+      const cv::Point3d q = get_unit_sphere_coordinate(pixel[i], transform);
+      pixels_normalize.push_back(cv::Point2d(q.x / q.z, q.y / q.z));
+    }
+    cv::Mat rvec, tvec, Rt;
+    cv::solvePnPRansac(worlds, pixels_normalize, cv::Mat::eye(3, 3, cv::CV_64F), cv::Mat::zeros(4, 0, cv::CV_64F), rvec, tvec);
+    cv::Rodrigues(rvec, Rt);
+    Rt = transform.t() * Rt;
+    tvec = transform.t() * tvec;
+    Rt.at<double>(0, 2) = tvec.at<double>(0);
+    Rt.at<double>(1, 2) = tvec.at<double>(1);
+    Rt.at<double>(2, 2) = tvec.at<double>(2);
+    Rt_[k] = Rt;
+  }
 }
 
 // Replaces TS.cpp:247-282: one residual block per corner of every frame with a board
@@ -174,3 +268,45 @@ double TripleSphereCamera::ReprojectError(const std::vector<cv::Point2d>& pixels
   }
   return error;
 }
+
+namespace {
+// One block covering the whole table, through the CUDA kernel (no CPU path).
+bool fill_tables(const double intr[9], const cv::Mat& M, double rfx, double rfy, double rcx, double rcy,
+                 cv::Size size, int device, cv::Mat& mapx, cv::Mat& mapy) {
+  mapx = cv::Mat(size, cv::CV_32FC1);
+  mapy = cv::Mat(size, cv::CV_32FC1);
+  tscm_remap_job job;
+  std::memset(&job, 0, sizeof(job));
+  std::memcpy(job.intrinsics, intr, sizeof(job.intrinsics));
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) job.matrix[3 * r + c] = M.at<double>(r, c);
+  job.ray_fx = rfx; job.ray_fy = rfy; job.ray_cx = rcx; job.ray_cy = rcy;
+  job.width = size.width; job.height = size.height;
+  const int rc = tscm_remap_tables(&job, 1, size.width, size.height, mapx.ptr<float>(), mapy.ptr<float>(), device, nullptr);
+  if (rc != TSCM_OK) std::cout << "[tscm] remap tables failed: " << tscm_last_error() << std::endl;
+  return rc == TSCM_OK;
+}
+}  // namespace
+
+void TripleSphereCamera::undistort(double fx, double fy, double cx, double cy, cv::Size img_size, cv::Mat& mapx,
+                                   cv::Mat& mapy) {
+  const double intr[9] = {fx_, fy_, cx_, cy_, xi_, lamda_, alpha_, b_, c_};
+  fill_tables(intr, cv::Mat::eye(3, 3, cv::CV_64F), fx, fy, cx, cy, img_size, device, mapx, mapy);
+}
+
+bool TripleSphereCamera::undistort_chessboard_maps(int index, cv::Size chessboard, double chessboard_size,
+                                                   cv::Mat& mapx, cv::Mat& mapy) {
+  if (index < 0 || index >= (int)has_chessboard_.size() || has_chessboard_[index] == false) return false;
+  const cv::Size img_size((int)((chessboard.width + 1) * chessboard_size), (int)((chessboard.height + 1) * chessboard_size));
+  const double intr[9] = {fx_, fy_, cx_, cy_, xi_, lamda_, alpha_, b_, c_};
+  // P = Rt * (j - size, i - size, 1)   (TS.cpp:321-322)
+  return fill_tables(intr, Rt_[index], 1.0, 1.0, chessboard_size, chessboard_size, img_size, device, mapx, mapy);
+}
+
+#ifdef TSCM_USE_OPENCV
+cv::Mat TripleSphereCamera::undistort_chessboard(cv::Mat src, int index, cv::Size chessboard, double chessboard_size) {
+  cv::Mat dst, mapx, mapy;
+  if (!undistort_chessboard_maps(index, chessboard, chessboard_size, mapx, mapy)) return dst;
+  cv::remap(src, dst, mapx, mapy, cv::INTER_LINEAR);
+  return dst;
+}
+#endif

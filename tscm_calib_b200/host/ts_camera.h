@@ -5,11 +5,13 @@
 // refinement() (TS.cpp:247-282): instead of building a ceres::Problem and calling
 // ceres::Solve it hands the same arrays to tscm_solve() (include/tscm.h).
 //
-// Out of scope (stays the reference's CPU/OpenCV code): the cold-start
-// initialisation estimate_focal / estimate_extrinsic (SVD::solveZ, solvePnPRansac).  Here
-// calibrate() therefore needs an initial guess: intrinsics through the 7-argument
-// constructor and per-frame [r1 r2 t] matrices through setRt(), exactly the state the
-// reference's second calibrate() call (main.cpp:129, warm start) begins from.
+// The cold-start initialisation is host C++ like the reference's:
+// estimate_focal (TS.cpp:110-168, circle fit through cv::SVD::solveZ) and
+// estimate_extrinsic (TS.cpp:170-203, cv::solvePnPRansac on unit-sphere-normalised
+// corners).  With real OpenCV (TSCM_USE_OPENCV) those two calls are OpenCV's; otherwise the
+// shim's restatements in cv_compat.h are used (same minimisers, not bit-identical).
+// The remap tables of undistort / undistort_chessboard (TS.cpp:284-330, §8f #4) are filled
+// by the CUDA kernel behind tscm_remap_tables().
 #pragma once
 
 #include <vector>
@@ -35,6 +37,21 @@ class TripleSphereCamera {
   // TS.h:58-69 — summed Euclidean reprojection error of one board under (R, t).
   double ReprojectError(const std::vector<cv::Point2d>& pixels, const std::vector<cv::Point3d>& worlds,
                         cv::Mat R, cv::Mat t);
+  // TS.cpp:284-306 — CV_32FC1 lookup tables of a pinhole (fx, fy, cx, cy) view, on the GPU.
+  void undistort(double fx, double fy, double cx, double cy, cv::Size img_size, cv::Mat& mapx, cv::Mat& mapy);
+  // TS.cpp:308-326 — the tables of the fronto-parallel board image of frame `index` (false
+  // if the frame has no board, where the reference returns an empty image).
+  bool undistort_chessboard_maps(int index, cv::Size chessboard, double chessboard_size, cv::Mat& mapx,
+                                 cv::Mat& mapy);
+#ifdef TSCM_USE_OPENCV
+  // TS.cpp:308-330 — tables as above, then cv::remap (OpenCV's own).
+  cv::Mat undistort_chessboard(cv::Mat src, int index, cv::Size chessboard, double chessboard_size);
+#endif
+  // The cold-start part of calibrate() on its own (TS.cpp:41-52): default intrinsics,
+  // estimate_focal, estimate_extrinsic.  False when the focal estimate fails (TS.cpp:50).
+  bool initial_guess(const std::vector<std::vector<cv::Point2d>>& pixels, std::vector<bool> has_chessboard,
+                     const std::vector<cv::Point3d>& worlds, const cv::Size img_size,
+                     const cv::Size chessboard_num);
 
   double cx() { return cx_; }
   double cy() { return cy_; }
@@ -60,6 +77,10 @@ class TripleSphereCamera {
   int device = -1;
 
  private:
+  void estimate_focal(const std::vector<std::vector<cv::Point2d>>& pixels, const std::vector<cv::Point3d>& worlds,
+                      cv::Size img_size, const cv::Size chessboard_num);
+  void estimate_extrinsic(const std::vector<std::vector<cv::Point2d>>& pixels,
+                          const std::vector<cv::Point3d>& worlds, const cv::Size chessboard_num);
   bool refinement(const std::vector<std::vector<cv::Point2d>>& pixels, const std::vector<cv::Point3d>& worlds);
 
   bool has_init_guess_;
