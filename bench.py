@@ -365,6 +365,18 @@ def run_b200(args):
                       f"(dual-number autodiff, dense Schur), {threads} threads, {dt:.1f} s",
             "lm_iterations_per_sec_at_3.52M": sp.num_observations * iters / dt / 3.52e6,
         }
+        # the reference never sets Solver::Options::num_threads (Ceres default 1): the same
+        # port on ONE thread is the faithful picture of what a reference user runs today
+        sp1 = synth.config(3, num_frames=max(1, frames // 10))
+        it1 = max(2, iters // 10)
+        dt1 = time_oracle(sp1.problem, sp1.init_intrinsics, sp1.init_cam_rt, sp1.init_board_rt, it1, 1)
+        line["cpu_baseline_single_thread"] = {
+            "value": sp1.num_observations * it1 / dt1 / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{sp1.problem.num_frames} of 5000 frames of config 3 ({sp1.num_observations} "
+                      f"observations), {it1} LM iterations, 1 thread (Ceres' default num_threads, which the "
+                      f"reference leaves in force), {dt1:.1f} s",
+            "lm_iterations_per_sec_at_3.52M": sp1.num_observations * it1 / dt1 / 3.52e6,
+        }
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

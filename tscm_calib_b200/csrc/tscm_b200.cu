@@ -22,6 +22,7 @@
 #include "tscm_kernels.cuh"
 #include "tscm_eval5.cuh"
 #include "tscm_p2p.cuh"
+#include "tscm_schur_pairs.cuh"
 #include "tscm_remap.cuh"
 
 namespace {
@@ -133,6 +134,8 @@ struct tscm_solver {
   SchurSplitArgs split{};
   bool split_ok = false;
   size_t split_smem = 0;
+  bool pairs_ok = false;         // sparse visibility: per-camera-pair Schur update (tscm_schur_pairs.cuh)
+  PairArgs pairs{};
   bool schur2_ok = false;
   int schur2_nt = 0;
   size_t schur2_smem = 0;
@@ -322,6 +325,13 @@ void launch_schur(tscm_solver* s, double radius_override) {
     else
       k_schur_update<2><<<s->schur_nblk, s->schur_nt, s->split_smem, s->stream>>>(s->P, s->d_state, b);
     s->launches += 1;
+  } else if (s->pairs_ok) {
+    SchurSplitArgs b = s->split;
+    b.a = a;
+    k_schur_frames<<<(s->F + 7) / 8, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
+    k_schur_pairs<<<s->sm_count, kPairWarps * 32, kPairSmem, s->stream>>>(s->d_state, s->pairs);
+    k_reduce_pairs<<<s->pairs.npairs, kPairReduceGroups * kPairPart, 0, s->stream>>>(s->P, s->d_state, s->pairs);
+    s->launches += 2;
   } else if (s->schur2_ok) {
     Schur2Args b = s->schur2;
     b.a = a;
@@ -334,12 +344,13 @@ void launch_schur(tscm_solver* s, double radius_override) {
     k_schur<2, 768><<<s->schur_nblk, s->schur_nt, s->schur_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
                                                                              s->d_state, s->lm, a);
   const int n = s->P.Q + s->P.NL;
+  const int nparts = s->pairs_ok ? 1 : s->schur_nblk;   // k_reduce_pairs leaves one complete partial
   if (s->p2p_on && s->num_ranks > 1)
     k_reduce_s_p2p<<<(n + 31) / 32, kReduceThreads, 0, s->stream>>>(s->P, s->d_state, s->d_Spart, s->d_rpart,
-                                                                    s->schur_nblk, s->d_Sr, s->p2p);
+                                                                    nparts, s->d_Sr, s->p2p);
   else
     k_reduce_s<<<(n + 31) / 32, kReduceThreads, 0, s->stream>>>(s->P, s->d_state, s->d_Spart, s->d_rpart,
-                                                                s->schur_nblk, s->d_Sr);
+                                                                nparts, s->d_Sr);
   s->launches += 2;
 }
 
@@ -392,7 +403,7 @@ int launch_iteration(tscm_solver* s) {
 }
 
 int launches_per_iteration(const tscm_solver* s) {
-  return (s->num_ranks <= 1 ? 6 : 7) + (s->split_ok ? 1 : 0) + (s->eval_variant == 5 ? 1 : 0);
+  return (s->num_ranks <= 1 ? 6 : 7) + (s->split_ok ? 1 : (s->pairs_ok ? 2 : 0)) + (s->eval_variant == 5 ? 1 : 0);
 }
 
 int ensure_graph(tscm_solver* s) {
@@ -702,6 +713,52 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     }
     s->schur2_ok = s->schur2_nt <= 640 && s->schur2_smem <= (size_t)prop.sharedMemPerBlockOptin &&
                    V < (1 << 27) && !getenv("TSCM_SCHUR_V1");
+    // Sparse visibility with a reduced system too wide for the fused kernel (BASELINE config 4):
+    // per-camera-pair update on per-view blocks.  TSCM_SCHUR_PAIRS=1 forces it (parity tests),
+    // =0 disables it.
+    const char* pe = getenv("TSCM_SCHUR_PAIRS");
+    const bool want_pairs = pe ? atoi(pe) != 0 : (!s->split_ok && !s->schur2_ok);
+    if (want_pairs && V < (1 << 27) && kPairSmem <= (size_t)prop.sharedMemPerBlockOptin) {
+      std::vector<int2> ent;
+      std::vector<int> item_begin, pair_item;
+      std::vector<short> pair_a, pair_b, loff(C + 1);
+      for (int m = 0; m <= C; ++m) loff[m] = (short)live_off[m];
+      // view of camera m in frame f (or -1)
+      std::vector<int> view_of((size_t)C * F, -1);
+      for (int v = 0; v < V; ++v) view_of[(size_t)p->view_camera[v] * F + p->view_frame[v]] = v;
+      for (int a2 = 0; a2 < C; ++a2)
+        for (int b2 = a2; b2 < C; ++b2) {
+          pair_a.push_back((short)a2); pair_b.push_back((short)b2);
+          pair_item.push_back((int)item_begin.size());
+          int in_item = 0;
+          const int* va = &view_of[(size_t)a2 * F];
+          const int* vb = &view_of[(size_t)b2 * F];
+          for (int f = 0; f < F; ++f) {
+            if (va[f] < 0 || vb[f] < 0) continue;
+            if (in_item == 0) item_begin.push_back((int)ent.size());
+            ent.push_back(make_int2(va[f], vb[f]));
+            if (++in_item == kPairChunk) in_item = 0;
+          }
+        }
+      pair_item.push_back((int)item_begin.size());
+      const int nitems = (int)item_begin.size();
+      item_begin.push_back((int)ent.size());
+      s->pairs.nitems = nitems;
+      s->pairs.npairs = (int)pair_a.size();
+      TRY_RC(s->put(&s->pairs.ent, ent));
+      TRY_RC(s->put(&s->pairs.item_begin, item_begin));
+      TRY_RC(s->put(&s->pairs.pair_item, pair_item));
+      TRY_RC(s->put(&s->pairs.pair_a, pair_a));
+      TRY_RC(s->put(&s->pairs.pair_b, pair_b));
+      TRY_RC(s->put(&s->pairs.live_off, loff));
+      TRY_RC(s->alloc(&s->pairs.part, (size_t)std::max(1, nitems) * kPairPart));
+      TRY_RC(s->alloc(&s->split.Wv, (size_t)V * 96));
+      TRY_RC(s->alloc(&s->split.Yv, (size_t)V * 96));
+      s->pairs.Wv = s->split.Wv; s->pairs.Yv = s->split.Yv;
+      s->pairs.Sout = s->d_Spart; s->pairs.rout = s->d_rpart;
+      s->split_ok = false; s->schur2_ok = false;
+      s->pairs_ok = true;
+    }
   }
   TRY_RC(s->alloc(&s->d_yc, (size_t)NL));
   s->bs_nblk = (F + kBacksubThreads / 32 - 1) / (kBacksubThreads / 32);
@@ -739,6 +796,7 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     tscm_solver_destroy(s); return TSCM_ERR_UNSUPPORTED;
   }
   if (s->schur2_ok) TRY_RC(set_smem((const void*)k_schur2, s->schur2_smem));
+  if (s->pairs_ok) TRY_RC(set_smem((const void*)k_schur_pairs, kPairSmem));
   if (s->split_ok) {
     TRY_RC(set_smem((const void*)k_schur_update<1>, s->split_smem));
     TRY_RC(set_smem((const void*)k_schur_update<2>, s->split_smem));

@@ -1183,7 +1183,14 @@ struct SchurSplitArgs {
   double* Wg;              // [F][6][NLp] scaled W rows, columns permuted (schur_perm)
   double* Yg;              // [F][6][NLp] (V + D^2)^-1 W_s
   double* zg;              // [Fpad8][6]   (V + D^2)^-1 g_s
+  // sparse-visibility form (k_schur_pairs): per-VIEW 6 x 16 blocks instead of dense rows
+  double* Wv;              // [V][6][16] scaled W_s block of the view's camera, column c at c
+  double* Yv;              // [V][6][16] (V + D^2)^-1 W_s, column c at pair_pos(c); z at pair_pos(13)
 };
+
+// Column c (0..13) of a view's Y block sits at c + (c >= 7): two 8-double halves of 7 columns
+// each, so that a lane of k_schur_pairs reads its 7 operands with aligned 16-byte loads.
+__host__ __device__ __forceinline__ int pair_pos(int c) { return c + (c >= 7 ? 1 : 0); }
 
 __global__ void __launch_bounds__(256, 2)
 k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
@@ -1198,12 +1205,15 @@ k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, L
   if (f >= P.F) return;
   const int NLp = A.NLp;
   double* my = s_scr[warp];
-  double* Wf = B.Wg + (size_t)f * 6 * NLp;
-  double* Yf = B.Yg + (size_t)f * 6 * NLp;
+  const bool compact = B.Wv != nullptr;
+  double* Wf = compact ? nullptr : B.Wg + (size_t)f * 6 * NLp;
+  double* Yf = compact ? nullptr : B.Yg + (size_t)f * 6 * NLp;
   const int p0 = P.frame_ptr[f], nv = P.frame_ptr[f + 1] - p0;
   const int c0 = B.col_ptr[f], ncols = B.col_ptr[f + 1] - c0;
   // cameras that do not see the frame contribute zero columns
-  if (ncols < P.NL) {
+  if (compact) {
+    // per-view blocks: nothing to clear (padding was zeroed at allocation and is never written)
+  } else if (ncols < P.NL) {
     for (int i = lane; i < 6 * NLp; i += 32) { Wf[i] = 0.0; Yf[i] = 0.0; }
     __syncwarp();
   } else if (NLp > P.NL) {
@@ -1266,8 +1276,13 @@ k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, L
 #pragma unroll
       for (int j = 0; j <= i; ++j) my[(i * (i + 1)) / 2 + j] = M[i * 6 + j];
       my[21 + i] = z[i];
-      B.zg[(size_t)f * 6 + i] = z[i];
+      if (!compact) B.zg[(size_t)f * 6 + i] = z[i];
     }
+  }
+  if (compact && lane < nv) {
+    // z rides along as column 13 of every view's Y block: W_a^T z falls out of the diagonal pairs
+#pragma unroll
+    for (int i = 0; i < 6; ++i) B.Yv[(size_t)vid * 96 + i * 16 + pair_pos(13)] = z[i];
   }
   __syncwarp();
   for (int i = lane; i < kFrameRec; i += 32) A.frame_rec[(size_t)i * A.Fpad + f] = my[i];
@@ -1301,11 +1316,21 @@ k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, L
         double w[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) w[q] = se[q] * raw[r][q] * csc[r];
+        if (compact) {
+          double* Wb = B.Wv + (size_t)(csrc[r] >> 4) * 96 + (csrc[r] & 15);
+          double* Yb = B.Yv + (size_t)(csrc[r] >> 4) * 96 + pair_pos(csrc[r] & 15);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) Wf[q * NLp + cg[r]] = w[q];
-        chol6_solve_packed(my, w);
+          for (int q = 0; q < 6; ++q) Wb[q * 16] = w[q];
+          chol6_solve_packed(my, w);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) Yf[q * NLp + cg[r]] = w[q];
+          for (int q = 0; q < 6; ++q) Yb[q * 16] = w[q];
+        } else {
+#pragma unroll
+          for (int q = 0; q < 6; ++q) Wf[q * NLp + cg[r]] = w[q];
+          chol6_solve_packed(my, w);
+#pragma unroll
+          for (int q = 0; q < 6; ++q) Yf[q * NLp + cg[r]] = w[q];
+        }
       }
     }
   }

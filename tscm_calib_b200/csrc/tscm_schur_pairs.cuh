@@ -1,0 +1,175 @@
+// tscm_schur_pairs.cuh — Schur complement update for SPARSE visibility (ring rigs, BASELINE
+// config 4: 16 cameras, every frame seen by ~6 of them).
+//
+// Replaces (Ceres) SchurEliminator::Eliminate's outer products  S -= sum_f W_f^T (V_f + D^2)^-1 W_f
+// where W_f only has columns for the cameras that see frame f.  The dense-row kernels
+// (k_schur / k_schur_update) multiply full NL-wide rows, i.e. mostly zeros at 39 % visibility
+// and NL = 202.  Here the product is organised by CAMERA PAIR: block (a, b) of S is
+//     S_ab = - sum over frames seen by both a and b of  W_a^T Y_b ,   Y = (V + D^2)^-1 W
+// a 13 x 13 block with a 6-deep inner dimension per frame.  k_schur_frames (compact form)
+// leaves one 6 x 16 W block and one 6 x 16 Y block per VIEW in HBM (768 B each, z as an extra
+// Y column so that rhs_a = -sum W_a^T z falls out of the diagonal pairs).
+//
+// k_schur_pairs: one WARP per work item = (pair, <= kPairChunk consecutive common frames).
+//   The two blocks of every entry stream through a per-warp 4-stage shared-memory ring with
+//   cp.async (16 B per lane, 3 per entry); lane = (row i of W_a^T, half h of the Y columns)
+//   keeps 7 accumulators in registers for the whole item: per entry and lane 6 x (1 LDS.64 +
+//   4 LDS.128 + 7 DFMA).  No atomics: the item's 13 x 14 partial goes to its own slot.
+// k_reduce_pairs: CTA per pair sums the pair's item partials in item order (4 thread groups,
+//   4 loads in flight) and scatters into the packed upper S / rhs that k_reduce_s and k_solve
+//   consume.  Deterministic: fixed item boundaries, fixed summation order.
+//
+// Bound: FP64 pipe (42 DFMA per 1.5 KB streamed = 3.6 flop/B is below the machine balance of
+// 5.3 flop/B only nominally: most blocks are re-read from L2 by the other pairs of the frame).
+#pragma once
+
+#include "tscm_kernels.cuh"
+
+namespace tscm {
+
+constexpr int kPairChunk = 128;    // entries per work item
+constexpr int kPairStages = 4;
+constexpr int kPairWarps = 16;
+constexpr int kPairPart = 208;     // 13 rows x 16 positions per item partial
+constexpr size_t kPairSmem = (size_t)kPairWarps * kPairStages * 192 * sizeof(double);
+
+struct PairArgs {
+  const double* Wv;        // [V][96]
+  const double* Yv;        // [V][96]
+  const int2* ent;         // [nent] (view of camera a, view of camera b) per common frame
+  const int* item_begin;   // [nitems + 1] entry range of an item
+  int nitems;
+  double* part;            // [nitems][kPairPart]
+  // reduction
+  const int* pair_item;    // [npairs + 1] item range of a pair
+  const short* pair_a;     // [npairs]
+  const short* pair_b;     // [npairs]
+  const short* live_off;   // [C + 1] first live column of a camera
+  int npairs;
+  double* Sout;            // [Q] packed upper
+  double* rout;            // [NL]
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kPairWarps * 32, 1)
+k_schur_pairs(const LmState* st, PairArgs A) {
+  if (st->done) return;
+  extern __shared__ __align__(128) double s_ring[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* ring = s_ring + (size_t)warp * kPairStages * 192;
+  const int i = min(lane >> 1, 12), h = lane & 1;
+  const int nwarps = gridDim.x * kPairWarps;
+  for (int item = blockIdx.x * kPairWarps + warp; item < A.nitems; item += nwarps) {
+    const int e0 = A.item_begin[item], n = A.item_begin[item + 1] - e0;
+    double acc[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) acc[q] = 0.0;
+    // entry descriptors: lane l holds entry (32 * block + l) of the item
+    const int2 cur = lane < n ? A.ent[e0 + lane] : make_int2(0, 0);
+    const int2 nxt = 32 + lane < n ? A.ent[e0 + 32 + lane] : make_int2(0, 0);
+    // Descriptor bookkeeping: the producer side runs kPairStages - 1 entries ahead of the
+    // consumer, so it may already need the next 32-entry block: `pcur` / `pnxt` follow it.
+    int2 pcur = cur, pnxt = nxt;
+    int pblock = 0;                    // 32-entry block `pcur` belongs to
+    auto produce = [&](int e) {
+      if (e < n) {
+        if ((e >> 5) != pblock) {      // warp-uniform
+          pcur = pnxt;
+          pblock = e >> 5;
+          const int q = (pblock + 1) * 32 + lane;
+          pnxt = q < n ? A.ent[e0 + q] : make_int2(0, 0);
+        }
+        const int va = __shfl_sync(0xffffffffu, pcur.x, e & 31);
+        const int vb = __shfl_sync(0xffffffffu, pcur.y, e & 31);
+        double* dst = ring + (e % kPairStages) * 192;
+        const double* wsrc = A.Wv + (size_t)va * 96;
+        const double* ysrc = A.Yv + (size_t)vb * 96;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int c = lane + 32 * r;                 // 16-byte chunk 0..95 of [W | Y]
+          cp_async16(dst + 2 * c, c < 48 ? wsrc + 2 * c : ysrc + 2 * (c - 48));
+        }
+      }
+      cp_async_commit();               // always: keeps the group count in step with the entry index
+    };
+    __syncwarp();                      // the previous item's last reads of the ring are done
+#pragma unroll
+    for (int e = 0; e < kPairStages - 1; ++e) produce(e);
+    for (int e = 0; e < n; ++e) {
+      produce(e + kPairStages - 1);    // overwrites the stage consumed at e - 1 (ordered by the syncwarp below)
+      cp_async_wait<kPairStages - 1>();
+      __syncwarp();                    // every lane's copies of entry e have landed
+      const double* Wb = ring + (e % kPairStages) * 192;
+      const double2* Yb = reinterpret_cast<const double2*>(Wb + 96 + h * 8);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const double w = Wb[k * 16 + i];
+        const double2 y0 = Yb[k * 8 + 0], y1 = Yb[k * 8 + 1], y2 = Yb[k * 8 + 2], y3 = Yb[k * 8 + 3];
+        acc[0] = fma(w, y0.x, acc[0]);
+        acc[1] = fma(w, y0.y, acc[1]);
+        acc[2] = fma(w, y1.x, acc[2]);
+        acc[3] = fma(w, y1.y, acc[3]);
+        acc[4] = fma(w, y2.x, acc[4]);
+        acc[5] = fma(w, y2.y, acc[5]);
+        acc[6] = fma(w, y3.x, acc[6]);
+      }
+      __syncwarp();                    // stage e % kPairStages may be refilled from the next iteration on
+    }
+    cp_async_wait<0>();
+    if (lane < 26) {
+      double* out = A.part + (size_t)item * kPairPart + i * 16 + h * 8;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) out[q] = acc[q];
+    }
+  }
+}
+
+constexpr int kPairReduceGroups = 4;
+
+__global__ void __launch_bounds__(kPairReduceGroups * kPairPart)
+k_reduce_pairs(DeviceProblem P, const LmState* st, PairArgs A) {
+  if (st->done) return;
+  __shared__ double s_sum[kPairReduceGroups][kPairPart];
+  const int pr = blockIdx.x;
+  const int t = threadIdx.x % kPairPart, grp = threadIdx.x / kPairPart;
+  const int it0 = A.pair_item[pr], it1 = A.pair_item[pr + 1];
+  const double* src = A.part + t;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int it = it0 + grp;
+  for (; it + 3 * kPairReduceGroups < it1; it += 4 * kPairReduceGroups) {
+    s0 += src[(size_t)it * kPairPart];
+    s1 += src[(size_t)(it + kPairReduceGroups) * kPairPart];
+    s2 += src[(size_t)(it + 2 * kPairReduceGroups) * kPairPart];
+    s3 += src[(size_t)(it + 3 * kPairReduceGroups) * kPairPart];
+  }
+  for (; it < it1; it += kPairReduceGroups) s0 += src[(size_t)it * kPairPart];
+  s_sum[grp][t] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (grp != 0) return;
+  const double total = (s_sum[0][t] + s_sum[1][t]) + (s_sum[2][t] + s_sum[3][t]);
+  const int i = t >> 4, pos = t & 15;
+  if (pos == 7 || pos == 15) return;                  // padding of the two column halves
+  const int c = pos > 7 ? pos - 1 : pos;              // inverse of pair_pos
+  const int a = A.pair_a[pr], b = A.pair_b[pr];
+  const int na = A.live_off[a + 1] - A.live_off[a], nb = A.live_off[b + 1] - A.live_off[b];
+  const int li = na == 13 ? i : i - 6;                // the fixed camera keeps its 7 intrinsics only
+  if (li < 0) return;
+  const int gi = A.live_off[a] + li;
+  if (c == 13) {                                      // W_a^T z
+    if (a == b) A.rout[gi] = -total;
+    return;
+  }
+  const int lj = nb == 13 ? c : c - 6;
+  if (lj < 0) return;
+  const int gj = A.live_off[b] + lj;
+  if (gi > gj) return;                                // lower triangle of a diagonal pair
+  A.Sout[gi * P.NL - (gi * (gi - 1)) / 2 + (gj - gi)] = -total;
+}
+
+}  // namespace tscm

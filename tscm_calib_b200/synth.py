@@ -366,3 +366,61 @@ def shard_frames(sp: SyntheticProblem, rank: int, world: int):
     local = ProblemArrays(p.board_xy, p.view_camera[sel], p.view_frame[sel] - lo, p.obs_xy[sel],
                           p.num_cameras, hi - lo, fixed_camera=p.fixed_camera)
     return local, np.arange(lo, hi)
+
+
+def concat_frames(parts) -> SyntheticProblem:
+    """One problem from several frame batches of the SAME rig (same `seed`, different
+    `frame_seed`): frames are renumbered batch after batch and the views re-sorted
+    camera-major / frame-minor as tscm_problem requires."""
+    first = parts[0]
+    C = first.problem.num_cameras
+    cams, frames, obs, off = [], [], [], 0
+    for sp in parts:
+        assert np.array_equal(sp.gt_intrinsics, first.gt_intrinsics) and np.array_equal(sp.gt_cam_rt, first.gt_cam_rt)
+        cams.append(sp.problem.view_camera)
+        frames.append(sp.problem.view_frame + off)
+        obs.append(sp.problem.obs_xy)
+        off += sp.problem.num_frames
+    cams, frames, obs = np.concatenate(cams), np.concatenate(frames), np.concatenate(obs, axis=0)
+    order = np.argsort(cams, kind="stable")          # frames already increase within a camera
+    prob = ProblemArrays(first.problem.board_xy, cams[order], frames[order], obs[order], C, off,
+                         fixed_camera=first.problem.fixed_camera)
+    return SyntheticProblem(prob, first.gt_intrinsics, first.gt_cam_rt,
+                            np.concatenate([sp.gt_board_rt for sp in parts], axis=0),
+                            first.init_intrinsics, first.init_cam_rt,
+                            np.concatenate([sp.init_board_rt for sp in parts], axis=0),
+                            np.concatenate([sp.visible for sp in parts], axis=1), first.name)
+
+
+def _config_batch(args):
+    """Worker of config_batched: plain arrays (a ProblemArrays holds ctypes pointers and
+    cannot cross a process boundary)."""
+    idx, kw = args
+    sp = config(idx, **kw)
+    p = sp.problem
+    return (p.board_xy, p.view_camera, p.view_frame, p.obs_xy, p.num_cameras, p.num_frames,
+            p.fixed_camera, sp.gt_intrinsics, sp.gt_cam_rt, sp.gt_board_rt, sp.init_intrinsics,
+            sp.init_cam_rt, sp.init_board_rt, sp.visible, sp.name)
+
+
+def _unpack_batch(t) -> SyntheticProblem:
+    return SyntheticProblem(ProblemArrays(t[0], t[1], t[2], t[3], t[4], t[5], fixed_camera=t[6]), *t[7:])
+
+
+def config_batched(idx: int, num_frames: int, batch: int = 10000, processes: int = 1, **kw) -> SyntheticProblem:
+    """config(idx) with `num_frames` frames drawn in batches of `batch` (bounded host memory:
+    config 4 at its full 100,000 frames would need tens of GB in one piece), optionally in
+    parallel processes."""
+    jobs, left, k = [], num_frames, 0
+    while left > 0:
+        n = min(batch, left)
+        jobs.append((idx, dict(kw, num_frames=n, frame_seed=k)))
+        left -= n
+        k += 1
+    if processes > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(processes, len(jobs))) as pool:
+            parts = [_unpack_batch(t) for t in pool.map(_config_batch, jobs)]
+    else:
+        parts = [_unpack_batch(_config_batch(j)) for j in jobs]
+    return parts[0] if len(parts) == 1 else concat_frames(parts)
