@@ -12,7 +12,11 @@ local = int(os.environ.get("LOCAL_RANK", rank))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for cfg, frames in ((2, 200), (3, 600)):
+# config 4 = 16-camera ring, sparse visibility: the per-camera-pair Schur path on every rank
+CASES = ((2, 200), (3, 600), (4, 2000))
+if os.environ.get("DIST_CFGS"):
+    CASES = tuple(c for c in CASES if str(c[0]) in os.environ["DIST_CFGS"].split(","))
+for cfg, frames in CASES:
     sp = synth.config(cfg, num_frames=frames)
     opt = capi.default_options()
     prob, fr = synth.shard_frames(sp, rank, world)

@@ -127,6 +127,7 @@ struct tscm_solver {
   double* d_gmax_part = nullptr;
   double* d_xn2_part = nullptr;
   unsigned int* d_ticket = nullptr;
+  double* d_comm_stage = nullptr;   // NCCL fallback: staged evaluation record (+ gmax)
   double* d_dbg_lhs = nullptr;
   double* d_dbg_rhs = nullptr;
   SchurArgs schur{};
@@ -298,18 +299,21 @@ int launch_eval_allreduce(tscm_solver* s, int which, bool decide = false) {
     s->launches += 1;
     return TSCM_OK;
   }
+  // The record of the set the device selects is staged through a fixed buffer: only that
+  // record may be summed (the current point's is already global).
   NcclApi& n = nccl();
-  const size_t cnt = (size_t)s->P.C * kCamRec + kCommExtra;
+  const int cnt = s->P.C * kCamRec + kCommExtra;
+  const int blocks = (cnt + 1 + 255) / 256;
+  k_comm_stage<<<blocks, 256, 0, s->stream>>>(s->ps[0], s->ps[1], s->d_state, which, cnt, s->d_comm_stage, 0);
   n.GroupStart();
-  for (int sel = 0; sel < 2; ++sel) {
-    if (which >= 2 && sel != which - 2) continue;
-    int rc = n.AllReduce(s->ps[sel].comm, s->ps[sel].comm, cnt, kNcclFloat64, kNcclSum, s->comm, s->stream);
-    if (rc) { set_error("ncclAllReduce(sum) failed: %d", rc); n.GroupEnd(); return TSCM_ERR_COMM; }
-    rc = n.AllReduce(s->ps[sel].gmax, s->ps[sel].gmax, 1, kNcclFloat64, kNcclMax, s->comm, s->stream);
-    if (rc) { set_error("ncclAllReduce(max) failed: %d", rc); n.GroupEnd(); return TSCM_ERR_COMM; }
-  }
-  int rc = n.GroupEnd();
+  int rc = n.AllReduce(s->d_comm_stage, s->d_comm_stage, (size_t)cnt, kNcclFloat64, kNcclSum, s->comm, s->stream);
+  if (rc) { set_error("ncclAllReduce(sum) failed: %d", rc); n.GroupEnd(); return TSCM_ERR_COMM; }
+  rc = n.AllReduce(s->d_comm_stage + cnt, s->d_comm_stage + cnt, 1, kNcclFloat64, kNcclMax, s->comm, s->stream);
+  if (rc) { set_error("ncclAllReduce(max) failed: %d", rc); n.GroupEnd(); return TSCM_ERR_COMM; }
+  rc = n.GroupEnd();
   if (rc) { set_error("ncclGroupEnd failed: %d", rc); return TSCM_ERR_COMM; }
+  k_comm_stage<<<blocks, 256, 0, s->stream>>>(s->ps[0], s->ps[1], s->d_state, which, cnt, s->d_comm_stage, 1);
+  s->launches += 2;
   return TSCM_OK;
 }
 
@@ -329,9 +333,14 @@ void launch_schur(tscm_solver* s, double radius_override) {
     SchurSplitArgs b = s->split;
     b.a = a;
     k_schur_frames<<<(s->F + 7) / 8, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
-    k_schur_pairs<<<s->sm_count, kPairWarps * 32, kPairSmem, s->stream>>>(s->d_state, s->pairs);
+    k_pair_blocks<<<(s->V * 16 + 255) / 256, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, b);
+#ifdef TSCM_PAIR_SINGLE
+    k_schur_pairs<<<TSCM_PAIR_MINB * s->sm_count, kPairWarps * 32, kPairSmem, s->stream>>>(s->d_state, s->pairs);
+#else
+    k_schur_pairs2<<<s->sm_count, kPairWarps * 32, kPair2Smem, s->stream>>>(s->d_state, s->pairs);
+#endif
     k_reduce_pairs<<<s->pairs.npairs, kPairReduceGroups * kPairPart, 0, s->stream>>>(s->P, s->d_state, s->pairs);
-    s->launches += 2;
+    s->launches += 3;
   } else if (s->schur2_ok) {
     Schur2Args b = s->schur2;
     b.a = a;
@@ -403,7 +412,7 @@ int launch_iteration(tscm_solver* s) {
 }
 
 int launches_per_iteration(const tscm_solver* s) {
-  return (s->num_ranks <= 1 ? 6 : 7) + (s->split_ok ? 1 : (s->pairs_ok ? 2 : 0)) + (s->eval_variant == 5 ? 1 : 0);
+  return (s->num_ranks <= 1 ? 6 : (s->p2p_on ? 7 : 9)) + (s->split_ok ? 1 : (s->pairs_ok ? 3 : 0)) + (s->eval_variant == 5 ? 1 : 0);
 }
 
 int ensure_graph(tscm_solver* s) {
@@ -718,9 +727,9 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     // =0 disables it.
     const char* pe = getenv("TSCM_SCHUR_PAIRS");
     const bool want_pairs = pe ? atoi(pe) != 0 : (!s->split_ok && !s->schur2_ok);
-    if (want_pairs && V < (1 << 27) && kPairSmem <= (size_t)prop.sharedMemPerBlockOptin) {
-      std::vector<int2> ent;
-      std::vector<int> item_begin, pair_item;
+    if (want_pairs && V < (1 << 27) && kPair2Smem <= (size_t)prop.sharedMemPerBlockOptin) {
+      std::vector<int2> ent, raw_range;
+      std::vector<int> raw_pair, raw_first, pair_item;
       std::vector<short> pair_a, pair_b, loff(C + 1);
       for (int m = 0; m <= C; ++m) loff[m] = (short)live_off[m];
       // view of camera m in frame f (or -1)
@@ -728,32 +737,53 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
       for (int v = 0; v < V; ++v) view_of[(size_t)p->view_camera[v] * F + p->view_frame[v]] = v;
       for (int a2 = 0; a2 < C; ++a2)
         for (int b2 = a2; b2 < C; ++b2) {
+          const int pr = (int)pair_a.size();
           pair_a.push_back((short)a2); pair_b.push_back((short)b2);
-          pair_item.push_back((int)item_begin.size());
           int in_item = 0;
           const int* va = &view_of[(size_t)a2 * F];
           const int* vb = &view_of[(size_t)b2 * F];
           for (int f = 0; f < F; ++f) {
             if (va[f] < 0 || vb[f] < 0) continue;
-            if (in_item == 0) item_begin.push_back((int)ent.size());
+            if (in_item == 0) {
+              raw_range.push_back(make_int2((int)ent.size(), (int)ent.size()));
+              raw_pair.push_back(pr);
+              raw_first.push_back(f);
+            }
             ent.push_back(make_int2(va[f], vb[f]));
+            raw_range.back().y = (int)ent.size();
             if (++in_item == kPairChunk) in_item = 0;
           }
         }
-      pair_item.push_back((int)item_begin.size());
-      const int nitems = (int)item_begin.size();
-      item_begin.push_back((int)ent.size());
+      // items in the order of the first frame they touch (stable: a pair's items keep their order)
+      const int nitems = (int)raw_range.size();
+      std::vector<int> order(nitems);
+      for (int k = 0; k < nitems; ++k) order[k] = k;
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return raw_first[x] < raw_first[y]; });
+      std::vector<int2> item_range(nitems);
+      std::vector<std::vector<int>> items_of(pair_a.size());
+      for (int pos = 0; pos < nitems; ++pos) {
+        item_range[pos] = raw_range[order[pos]];
+        items_of[raw_pair[order[pos]]].push_back(pos);
+      }
+      std::vector<int> pair_items;
+      for (size_t pr = 0; pr < pair_a.size(); ++pr) {
+        pair_item.push_back((int)pair_items.size());
+        pair_items.insert(pair_items.end(), items_of[pr].begin(), items_of[pr].end());
+      }
+      pair_item.push_back((int)pair_items.size());
       s->pairs.nitems = nitems;
       s->pairs.npairs = (int)pair_a.size();
       TRY_RC(s->put(&s->pairs.ent, ent));
-      TRY_RC(s->put(&s->pairs.item_begin, item_begin));
+      TRY_RC(s->put(&s->pairs.item_range, item_range));
       TRY_RC(s->put(&s->pairs.pair_item, pair_item));
+      TRY_RC(s->put(&s->pairs.pair_items, pair_items));
       TRY_RC(s->put(&s->pairs.pair_a, pair_a));
       TRY_RC(s->put(&s->pairs.pair_b, pair_b));
       TRY_RC(s->put(&s->pairs.live_off, loff));
       TRY_RC(s->alloc(&s->pairs.part, (size_t)std::max(1, nitems) * kPairPart));
       TRY_RC(s->alloc(&s->split.Wv, (size_t)V * 96));
       TRY_RC(s->alloc(&s->split.Yv, (size_t)V * 96));
+      TRY_RC(s->alloc(&s->split.fact, (size_t)F * 32));
       s->pairs.Wv = s->split.Wv; s->pairs.Yv = s->split.Yv;
       s->pairs.Sout = s->d_Spart; s->pairs.rout = s->d_rpart;
       s->split_ok = false; s->schur2_ok = false;
@@ -777,6 +807,7 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     TRY_RC(s->alloc(&s->d_p2p_err, 1));
     s->p2p.seq = s->d_p2p_seq; s->p2p.ticket = s->d_p2p_ticket; s->p2p.err = s->d_p2p_err;
   }
+  TRY_RC(s->alloc(&s->d_comm_stage, (size_t)C * kCamRec + kCommExtra + 8));
   TRY_RC(s->alloc(&s->d_bs_part, (size_t)4 * s->bs_nblk));
   TRY_RC(s->alloc(&s->d_gmax_part, (size_t)s->fg_nblk));
   TRY_RC(s->alloc(&s->d_xn2_part, (size_t)s->fg_nblk));
@@ -796,7 +827,10 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     tscm_solver_destroy(s); return TSCM_ERR_UNSUPPORTED;
   }
   if (s->schur2_ok) TRY_RC(set_smem((const void*)k_schur2, s->schur2_smem));
-  if (s->pairs_ok) TRY_RC(set_smem((const void*)k_schur_pairs, kPairSmem));
+  if (s->pairs_ok) {
+    TRY_RC(set_smem((const void*)k_schur_pairs, kPairSmem));
+    TRY_RC(set_smem((const void*)k_schur_pairs2, kPair2Smem));
+  }
   if (s->split_ok) {
     TRY_RC(set_smem((const void*)k_schur_update<1>, s->split_smem));
     TRY_RC(set_smem((const void*)k_schur_update<2>, s->split_smem));

@@ -1186,13 +1186,18 @@ struct SchurSplitArgs {
   // sparse-visibility form (k_schur_pairs): per-VIEW 6 x 16 blocks instead of dense rows
   double* Wv;              // [V][6][16] scaled W_s block of the view's camera, column c at c
   double* Yv;              // [V][6][16] (V + D^2)^-1 W_s, column c at pair_pos(c); z at pair_pos(13)
+  double* fact;            // [F][32] packed Cholesky factor (21, reciprocal diagonal) | z (6): the
+                           // per-frame result k_pair_blocks applies to every view of the frame
 };
 
 // Column c (0..13) of a view's Y block sits at c + (c >= 7): two 8-double halves of 7 columns
 // each, so that a lane of k_schur_pairs reads its 7 operands with aligned 16-byte loads.
 __host__ __device__ __forceinline__ int pair_pos(int c) { return c + (c >= 7 ? 1 : 0); }
 
-__global__ void __launch_bounds__(256, 2)
+#ifndef TSCM_SF_MINB
+#define TSCM_SF_MINB 2
+#endif
+__global__ void __launch_bounds__(256, TSCM_SF_MINB)
 k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
                SchurSplitArgs B) {
   if (st->done) return;
@@ -1279,13 +1284,14 @@ k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, L
       if (!compact) B.zg[(size_t)f * 6 + i] = z[i];
     }
   }
-  if (compact && lane < nv) {
-    // z rides along as column 13 of every view's Y block: W_a^T z falls out of the diagonal pairs
-#pragma unroll
-    for (int i = 0; i < 6; ++i) B.Yv[(size_t)vid * 96 + i * 16 + pair_pos(13)] = z[i];
-  }
   __syncwarp();
   for (int i = lane; i < kFrameRec; i += 32) A.frame_rec[(size_t)i * A.Fpad + f] = my[i];
+  if (compact) {
+    // sparse-visibility form: the per-view blocks are written by k_pair_blocks (one thread per
+    // block column, no per-frame serial chain in front of the 1.5 KB of stores per view)
+    if (lane < 27) B.fact[(size_t)f * 32 + lane] = my[lane];
+    return;
+  }
   // columns of W_s and Y: four per lane and round, with every global load of a round issued
   // before the first use (two dependent levels: descriptors, then records).  The Cholesky
   // factor is read from shared memory (packed, written above).
@@ -1316,24 +1322,62 @@ k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, L
         double w[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) w[q] = se[q] * raw[r][q] * csc[r];
-        if (compact) {
-          double* Wb = B.Wv + (size_t)(csrc[r] >> 4) * 96 + (csrc[r] & 15);
-          double* Yb = B.Yv + (size_t)(csrc[r] >> 4) * 96 + pair_pos(csrc[r] & 15);
 #pragma unroll
-          for (int q = 0; q < 6; ++q) Wb[q * 16] = w[q];
-          chol6_solve_packed(my, w);
+        for (int q = 0; q < 6; ++q) Wf[q * NLp + cg[r]] = w[q];
+        chol6_solve_packed(my, w);
 #pragma unroll
-          for (int q = 0; q < 6; ++q) Yb[q * 16] = w[q];
-        } else {
-#pragma unroll
-          for (int q = 0; q < 6; ++q) Wf[q * NLp + cg[r]] = w[q];
-          chol6_solve_packed(my, w);
-#pragma unroll
-          for (int q = 0; q < 6; ++q) Yf[q * NLp + cg[r]] = w[q];
-        }
+        for (int q = 0; q < 6; ++q) Yf[q * NLp + cg[r]] = w[q];
       }
     }
   }
+}
+
+// Per-view blocks of the sparse-visibility Schur form: thread = (view, block column 0..15).
+// Columns 0..12 are the camera's [rt 6 | intr 7] columns of the scaled W_s (a fixed camera's rt
+// columns stay zero), Y = (V + D^2)^-1 W_s through the frame's packed factor, column 13 of Y
+// carries z; every thread stores its whole column so that each 768-byte block is rewritten
+// completely (full 128-byte rows, padding included).
+__global__ void __launch_bounds__(256)
+k_pair_blocks(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, SchurSplitArgs B) {
+  if (st->done) return;
+  const ParamSet& ps = st->cur ? ps1 : ps0;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = t >> 4, c = t & 15;
+  if (v >= P.V) return;
+  const int m = P.view_camera[v], f = P.view_frame[v];
+  const bool free_rt = P.live_off[m + 1] - P.live_off[m] == 13;
+  const bool live = c < 13 && (free_rt || c >= 6);
+  const double* Lp = B.fact + (size_t)f * 32;
+  double w[6];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) w[q] = 0.0;
+  if (live) {
+    const double csc = B.a.scale_c[m * 13 + c];
+    const double* Gv = ps.G + (size_t)v * kViewStride;
+    const double* se = B.a.scale_e + (size_t)f * 6;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      const double raw = c < 6 ? Gv[kOffBC + q * 6 + c] : Gv[kOffBI + q * 8 + (c - 6)];
+      w[q] = se[q] * raw * csc;
+    }
+  }
+  double* Wb = B.Wv + (size_t)v * 96 + c;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) Wb[q * 16] = w[q];
+  if (live) {
+    double L[21];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) L[i] = Lp[i];
+    chol6_solve_packed(L, w);
+  } else if (c == 13) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) w[q] = Lp[21 + q];
+  }
+  // positions: columns 0..13 at pair_pos(c); the two padding slots (7, 15) take threads 14, 15
+  const int pos = c < 14 ? pair_pos(c) : (c == 14 ? 7 : 15);
+  double* Yb = B.Yv + (size_t)v * 96 + pos;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) Yb[q * 16] = w[q];
 }
 
 // --- TMA bulk copy + mbarrier helpers (sm_90+/sm_100a) -----------------------------------
@@ -2199,6 +2243,23 @@ k_post_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, int which,
   if (t == 0) {
     *A.ticket = 0u;
     if (A.decide) { __threadfence(); decide_step(P, ps0, ps1, st, opt, tr); }
+  }
+}
+
+// NCCL fallback of the evaluation exchange: the record to all-reduce lives in the parameter
+// set the DEVICE selects (st->cur), so it is staged through a fixed buffer.  (All-reducing both
+// sets in place would sum the current point's already-global record a second time — harmless
+// after an accepted step, which replaces it, but wrong after a REJECTED one.)
+// dir 0: ps[sel].comm, gmax -> stage[0..n), stage[n]; dir 1: back.
+__global__ void k_comm_stage(ParamSet ps0, ParamSet ps1, const LmState* st, int which, int n,
+                             double* __restrict__ stage, int dir) {
+  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
+  const ParamSet& ps = sel ? ps1 : ps0;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    if (dir == 0) stage[i] = ps.comm[i]; else ps.comm[i] = stage[i];
+  } else if (i == n) {
+    if (dir == 0) stage[n] = ps.gmax[0]; else ps.gmax[0] = stage[n];
   }
 }
 
