@@ -296,6 +296,22 @@ def test_pair_schur_is_deterministic_and_agrees_with_dense_rows(monkeypatch):
         np.testing.assert_allclose(x, y, rtol=1e-7, atol=1e-9)
 
 
+def test_dense_rows_from_pair_frames_kernels_are_bit_identical(monkeypatch):
+    """TSCM_SPLIT_FRAMES8=1: the dense W_s / Y rows produced by k_pair_frames + k_pair_blocks
+    (8 lanes per frame, thread per column) instead of the warp-per-frame k_schur_frames: same
+    arithmetic and summation order, so the whole solve is bit-identical."""
+    sp = synth.config(3, num_frames=200)
+    opt = capi.default_options()
+    init = (sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt)
+    monkeypatch.setenv("TSCM_SPLIT_FRAMES8", "0")
+    a0, b0, c0, s0 = capi.solve(sp.problem, *init, opt)
+    monkeypatch.setenv("TSCM_SPLIT_FRAMES8", "1")
+    a1, b1, c1, s1 = capi.solve(sp.problem, *init, opt)
+    np.testing.assert_array_equal(s0.cost, s1.cost)
+    for x, y in ((a0, a1), (b0, b1), (c0, c1)):
+        np.testing.assert_array_equal(x, y)
+
+
 def test_errors_are_reported_not_swallowed():
     sp = synth.config(1)
     s = capi.Solver(sp.problem)

@@ -13,7 +13,7 @@ PY
 }
 for lib in ${LIBS:-default chunk32 minb1 sf3}; do
   if [ "$lib" = default ]; then unset TSCM_LIB_PATH; else export TSCM_LIB_PATH=$PWD/build_ab/libtscm_$lib.so; fi
-  timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_schur_frames|k_schur_pairs|k_reduce_pairs' -c 30 --csv --log-file gpurun_out/ab_$lib.csv python tools/stress_cfg4.py --frames ${FRAMES:-40000} --timed-iterations 3 --out gpurun_out/stress_ab_$lib.json > gpurun_out/ab_$lib.log 2>&1
+  timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_schur_frames|k_pair_blocks|k_schur_pairs|k_reduce_pairs' -c 30 --csv --log-file gpurun_out/ab_$lib.csv python tools/stress_cfg4.py --frames ${FRAMES:-40000} --timed-iterations 3 --out gpurun_out/stress_ab_$lib.json > gpurun_out/ab_$lib.log 2>&1
   summ gpurun_out/ab_$lib.csv
 done
 unset TSCM_LIB_PATH

@@ -29,19 +29,36 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "stress_cfg4.json"))
     a = ap.parse_args()
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # strong scaling: the 10,000-frame batches of the same problem are dealt to the ranks
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t0 = time.time()
-    sp = synth.config_batched(4, a.frames, batch=10000, processes=a.processes)
+    sp = synth.config_batched(4, a.frames, batch=10000, processes=max(1, a.processes // world),
+                              rank=rank, world=world)
     p = sp.problem
     t_gen = time.time() - t0
     N = p.num_observations
+    if world > 1:
+        tn = torch.tensor([N], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tn)
+        N = int(tn.item())
     print(f"generated {p.num_cameras} cameras x {p.num_frames} frames: {p.num_views} views, {N} observations "
           f"({N * 16 / 1e6:.0f} MB) in {t_gen:.1f} s", flush=True)
 
     t0 = time.time()
-    s = capi.Solver(p, capi.default_options(), device=0)
+    s = capi.Solver(p, capi.default_options(), device=local)
+    if world > 1:
+        capi.attach_ranks(s, rank, world)
     t_create = time.time() - t0
-    res = {"workload": "config4: 16-camera ring x %d frames x 88 corners, visibility masks" % p.num_frames,
-           "num_views": int(p.num_views), "observations": int(N), "residuals": int(2 * N),
+    res = {"workload": "config4: 16-camera ring x %d frames x 88 corners, visibility masks" % a.frames,
+           "n_gpus": world, "scaling": "strong", "frames_this_rank": int(p.num_frames),
+           "num_views_this_rank": int(p.num_views), "observations": int(N), "residuals": int(2 * N),
            "visible_fraction": float(p.num_views) / (p.num_cameras * p.num_frames),
            "reduced_size": int(s.reduced_size()), "generate_s": t_gen, "solver_create_s": t_create}
 
@@ -54,7 +71,7 @@ def main():
     r1, wall1, x1 = solve()
     r2, wall2, x2 = solve()
     acc = r1.cost[(r1.step_flags & 2) != 0]
-    per, overall, rms = s.reprojection_error()
+    per, overall, rms = s.reprojection_error() if world == 1 else (None, float("nan"), float(np.sqrt(2 * r1.final_cost / N)))
     res.update({
         "termination": r1.termination, "iterations": int(r1.num_iterations),
         "successful_steps": int(r1.num_successful_steps), "initial_cost": float(r1.initial_cost),
@@ -73,18 +90,29 @@ def main():
     s.set_parameters(sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt)
     ms = s.time_stage(4, a.timed_iterations)
     stages = {}
-    for name, st in (("evaluation_pass", 5), ("schur", 1), ("reduced_solve", 2), ("backsub", 3)):
-        stages[name] = s.time_stage(st, 5)
+    if world == 1:
+        for name, st in (("evaluation_pass", 5), ("schur", 1), ("reduced_solve", 2), ("backsub", 3)):
+            stages[name] = s.time_stage(st, 5)
+    else:
+        tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)       # device-timed, max over ranks
+        ms = float(tm.item())
     res.update({"ms_per_lm_iteration": ms, "lm_iterations_per_sec": 1e3 / ms,
-                "gobs_per_sec": N / ms / 1e6, "stage_ms": stages,
-                "fp64_tflops_algorithmic_1060_flop_per_obs": N * 1060.0 / (stages["evaluation_pass"] * 1e-3) / 1e12})
+                "gobs_per_sec": N / ms / 1e6, "stage_ms": stages})
+    if world == 1:
+        res["fp64_tflops_algorithmic_1060_flop_per_obs"] = N * 1060.0 / (stages["evaluation_pass"] * 1e-3) / 1e12
     ok = (res["cost_monotone_over_accepted_steps"] and res["repeat_solve_bit_identical"] and
           res["termination"] == "CONVERGENCE" and 0.12 < res["rms_px"] < 0.16)
     res["properties_ok"] = bool(ok)
-    os.makedirs(os.path.dirname(a.out), exist_ok=True)
-    with open(a.out, "w") as f:
-        json.dump(res, f, indent=1)
-    print(json.dumps(res))
+    if rank == 0:
+        os.makedirs(os.path.dirname(a.out), exist_ok=True)
+        with open(a.out, "w") as f:
+            json.dump(res, f, indent=1)
+        print(json.dumps(res))
+    s.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
 

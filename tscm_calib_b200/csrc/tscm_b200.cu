@@ -135,6 +135,7 @@ struct tscm_solver {
   SchurSplitArgs split{};
   bool split_ok = false;
   size_t split_smem = 0;
+  bool split_frames8 = false;    // dense rows produced by k_pair_frames + k_pair_blocks
   bool pairs_ok = false;         // sparse visibility: per-camera-pair Schur update (tscm_schur_pairs.cuh)
   PairArgs pairs{};
   bool schur2_ok = false;
@@ -323,7 +324,14 @@ void launch_schur(tscm_solver* s, double radius_override) {
   if (s->split_ok) {
     SchurSplitArgs b = s->split;
     b.a = a;
-    k_schur_frames<<<(s->F + 7) / 8, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
+    if (s->split_frames8) {
+      // per-frame chain with 8 lanes per frame, then the rows with one thread per column
+      k_pair_frames<<<(s->F + 31) / 32, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
+      k_pair_blocks<<<(s->V * 16 + 255) / 256, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, b);
+      s->launches += 1;
+    } else {
+      k_schur_frames<<<(s->F + 7) / 8, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
+    }
     if (s->schur_ept == 1)
       k_schur_update<1><<<s->schur_nblk, s->schur_nt, s->split_smem, s->stream>>>(s->P, s->d_state, b);
     else
@@ -332,7 +340,7 @@ void launch_schur(tscm_solver* s, double radius_override) {
   } else if (s->pairs_ok) {
     SchurSplitArgs b = s->split;
     b.a = a;
-    k_schur_frames<<<(s->F + 7) / 8, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
+    k_pair_frames<<<(s->F + 31) / 32, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
     k_pair_blocks<<<(s->V * 16 + 255) / 256, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, b);
 #ifdef TSCM_PAIR_SINGLE
     k_schur_pairs<<<TSCM_PAIR_MINB * s->sm_count, kPairWarps * 32, kPairSmem, s->stream>>>(s->d_state, s->pairs);
@@ -412,7 +420,7 @@ int launch_iteration(tscm_solver* s) {
 }
 
 int launches_per_iteration(const tscm_solver* s) {
-  return (s->num_ranks <= 1 ? 6 : (s->p2p_on ? 7 : 9)) + (s->split_ok ? 1 : (s->pairs_ok ? 3 : 0)) + (s->eval_variant == 5 ? 1 : 0);
+  return (s->num_ranks <= 1 ? 6 : (s->p2p_on ? 7 : 9)) + (s->split_ok ? (s->split_frames8 ? 2 : 1) : (s->pairs_ok ? 3 : 0)) + (s->eval_variant == 5 ? 1 : 0);
 }
 
 int ensure_graph(tscm_solver* s) {
@@ -719,6 +727,9 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
       TRY_RC(s->alloc(&s->split.Wg, (size_t)F * 6 * s->schur.NLp));
       TRY_RC(s->alloc(&s->split.Yg, (size_t)F * 6 * s->schur.NLp));
       TRY_RC(s->alloc(&s->split.zg, ((size_t)F + 8) * 6));
+      TRY_RC(s->alloc(&s->split.fact, (size_t)F * 32));
+      const char* f8 = getenv("TSCM_SPLIT_FRAMES8");
+      s->split_frames8 = f8 ? atoi(f8) != 0 : false;   // measured on config 3: -6 us of kernel time, +1 launch: no net gain
     }
     s->schur2_ok = s->schur2_nt <= 640 && s->schur2_smem <= (size_t)prop.sharedMemPerBlockOptin &&
                    V < (1 << 27) && !getenv("TSCM_SCHUR_V1");

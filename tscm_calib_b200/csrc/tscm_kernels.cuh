@@ -1210,15 +1210,12 @@ k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, L
   if (f >= P.F) return;
   const int NLp = A.NLp;
   double* my = s_scr[warp];
-  const bool compact = B.Wv != nullptr;
-  double* Wf = compact ? nullptr : B.Wg + (size_t)f * 6 * NLp;
-  double* Yf = compact ? nullptr : B.Yg + (size_t)f * 6 * NLp;
+  double* Wf = B.Wg + (size_t)f * 6 * NLp;
+  double* Yf = B.Yg + (size_t)f * 6 * NLp;
   const int p0 = P.frame_ptr[f], nv = P.frame_ptr[f + 1] - p0;
   const int c0 = B.col_ptr[f], ncols = B.col_ptr[f + 1] - c0;
   // cameras that do not see the frame contribute zero columns
-  if (compact) {
-    // per-view blocks: nothing to clear (padding was zeroed at allocation and is never written)
-  } else if (ncols < P.NL) {
+  if (ncols < P.NL) {
     for (int i = lane; i < 6 * NLp; i += 32) { Wf[i] = 0.0; Yf[i] = 0.0; }
     __syncwarp();
   } else if (NLp > P.NL) {
@@ -1281,17 +1278,11 @@ k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, L
 #pragma unroll
       for (int j = 0; j <= i; ++j) my[(i * (i + 1)) / 2 + j] = M[i * 6 + j];
       my[21 + i] = z[i];
-      if (!compact) B.zg[(size_t)f * 6 + i] = z[i];
+      B.zg[(size_t)f * 6 + i] = z[i];
     }
   }
   __syncwarp();
   for (int i = lane; i < kFrameRec; i += 32) A.frame_rec[(size_t)i * A.Fpad + f] = my[i];
-  if (compact) {
-    // sparse-visibility form: the per-view blocks are written by k_pair_blocks (one thread per
-    // block column, no per-frame serial chain in front of the 1.5 KB of stores per view)
-    if (lane < 27) B.fact[(size_t)f * 32 + lane] = my[lane];
-    return;
-  }
   // columns of W_s and Y: four per lane and round, with every global load of a round issued
   // before the first use (two dependent levels: descriptors, then records).  The Cholesky
   // factor is read from shared memory (packed, written above).
@@ -1332,6 +1323,97 @@ k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, L
   }
 }
 
+// Per-frame part of the sparse-visibility Schur form: V_s + D^2 -> Cholesky -> z, frame record
+// and packed factor.  EIGHT lanes per frame (four frames per warp): the chain frame -> views ->
+// 27 sums -> 6 x 6 factorisation is pure latency, so what counts is frames in flight per warp
+// instruction (k_schur_frames, one warp per frame, spent 138 us on 40,000 frames here).  Same
+// arithmetic and summation order as k_schur_frames.
+__global__ void __launch_bounds__(256, 2)
+k_pair_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
+              SchurSplitArgs B) {
+  if (st->done) return;
+  __shared__ double s_rec[32][kFrameRec + 2];
+  const SchurArgs& A = B.a;
+  const ParamSet& ps = st->cur ? ps1 : ps0;
+  const double radius = A.radius_override > 0.0 ? A.radius_override : st->radius;
+  const int lane = threadIdx.x & 31, g = lane & 7, grp = threadIdx.x >> 3;   // grp: 0..31 in the CTA
+  const int f = blockIdx.x * 32 + grp;
+  const bool active = f < P.F;
+  const int fc = active ? f : P.F - 1;
+  const int p0 = P.frame_ptr[fc], nv = P.frame_ptr[fc + 1] - p0;
+  // lane g sums entries g, g + 8, g + 16, g + 24 (< 27) of [BB 21 | g_e 6] over the frame's views
+  int eidx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int e = min(g + 8 * j, 26);
+    eidx[j] = e < 21 ? kOffBB + e : kOffBI + (e - 21) * 8 + 7;
+  }
+  double s0[4] = {0.0, 0.0, 0.0, 0.0}, s1[4] = {0.0, 0.0, 0.0, 0.0};
+  int p = 0;
+  for (; p + 1 < nv; p += 2) {
+    const size_t va = (size_t)P.frame_views[p0 + p] * kViewStride, vb = (size_t)P.frame_views[p0 + p + 1] * kViewStride;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s0[j] += ps.G[va + eidx[j]]; s1[j] += ps.G[vb + eidx[j]]; }
+  }
+  if (p < nv) {
+    const size_t va = (size_t)P.frame_views[p0 + p] * kViewStride;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s0[j] += ps.G[va + eidx[j]];
+  }
+  double my[27];
+  const int gbase = lane & ~7;
+#pragma unroll
+  for (int e = 0; e < 27; ++e) my[e] = __shfl_sync(0xffffffffu, s0[e >> 3] + s1[e >> 3], gbase + (e & 7));
+  double se[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) se[i] = A.scale_e[fc * 6 + i];
+  double M[36], gs[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = i; j < 6; ++j) {
+      const double v = se[i] * se[j] * my[tri6(i, j)];
+      M[i * 6 + j] = v;
+      M[j * 6 + i] = v;
+    }
+    gs[i] = se[i] * my[21 + i];
+  }
+  double* rec = s_rec[grp];
+  if (g == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int j = i; j < 6; ++j) rec[27 + tri6(i, j)] = M[i * 6 + j];
+      rec[48 + i] = gs[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const double d = fmin(fmax(M[i * 6 + i], opt.min_lm_diagonal), opt.max_lm_diagonal);
+    const double D = sqrt(d / radius);
+    M[i * 6 + i] += D * D;
+  }
+  chol6(M);   // a failed pivot yields NaNs that the LM loop turns into an invalid step
+  double z[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) z[i] = gs[i];
+  chol6_solve(M, z);
+  if (g == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) rec[(i * (i + 1)) / 2 + j] = M[i * 6 + j];
+      rec[21 + i] = z[i];
+    }
+  }
+  __syncwarp();
+  if (active) {
+    for (int i = g; i < kFrameRec; i += 8) A.frame_rec[(size_t)i * A.Fpad + f] = rec[i];
+    for (int i = g; i < 27; i += 8) B.fact[(size_t)f * 32 + i] = rec[i];
+    if (B.Wv == nullptr && g < 6) B.zg[(size_t)f * 6 + g] = rec[21 + g];   // dense-row form
+  }
+}
+
 // Per-view blocks of the sparse-visibility Schur form: thread = (view, block column 0..15).
 // Columns 0..12 are the camera's [rt 6 | intr 7] columns of the scaled W_s (a fixed camera's rt
 // columns stay zero), Y = (V + D^2)^-1 W_s through the frame's packed factor, column 13 of Y
@@ -1360,6 +1442,23 @@ k_pair_blocks(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, Sc
       const double raw = c < 6 ? Gv[kOffBC + q * 6 + c] : Gv[kOffBI + q * 8 + (c - 6)];
       w[q] = se[q] * raw * csc;
     }
+  }
+  if (B.Wv == nullptr) {
+    // dense-row form (k_schur_update): rows [F][6][NLp], columns permuted (schur_perm); columns
+    // of cameras that do not see the frame were zeroed at allocation and are never written
+    if (!live) return;
+    const int col = schur_perm(P.live_off[m] + (free_rt ? c : c - 6), B.a.NLp);
+    double* Wr = B.Wg + (size_t)f * 6 * B.a.NLp + col;
+    double* Yr = B.Yg + (size_t)f * 6 * B.a.NLp + col;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) Wr[q * B.a.NLp] = w[q];
+    double L[21];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) L[i] = Lp[i];
+    chol6_solve_packed(L, w);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) Yr[q * B.a.NLp] = w[q];
+    return;
   }
   double* Wb = B.Wv + (size_t)v * 96 + c;
 #pragma unroll
@@ -1985,6 +2084,7 @@ k_backsub(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, SchurA
     part[2 * nblk + blockIdx.x] = t2; part[3 * nblk + blockIdx.x] = t3;
   }
 }
+
 
 // ---------------------------------------------------------------------------
 // K5: trust-region bookkeeping.  The comm record of an evaluated parameter set holds the

@@ -407,14 +407,17 @@ def _unpack_batch(t) -> SyntheticProblem:
     return SyntheticProblem(ProblemArrays(t[0], t[1], t[2], t[3], t[4], t[5], fixed_camera=t[6]), *t[7:])
 
 
-def config_batched(idx: int, num_frames: int, batch: int = 10000, processes: int = 1, **kw) -> SyntheticProblem:
+def config_batched(idx: int, num_frames: int, batch: int = 10000, processes: int = 1, rank: int = 0,
+                   world: int = 1, **kw) -> SyntheticProblem:
     """config(idx) with `num_frames` frames drawn in batches of `batch` (bounded host memory:
     config 4 at its full 100,000 frames would need tens of GB in one piece), optionally in
-    parallel processes."""
+    parallel processes.  With world > 1 a rank keeps batches rank, rank + world, ... only: the
+    union over the ranks is the same set of frames as the single-rank problem."""
     jobs, left, k = [], num_frames, 0
     while left > 0:
         n = min(batch, left)
-        jobs.append((idx, dict(kw, num_frames=n, frame_seed=k)))
+        if k % world == rank:
+            jobs.append((idx, dict(kw, num_frames=n, frame_seed=k)))
         left -= n
         k += 1
     if processes > 1 and len(jobs) > 1:
