@@ -66,3 +66,31 @@ def test_shard_frames_partitions_everything():
         np.testing.assert_array_equal(np.concatenate(seen_frames), np.arange(p.num_frames))
         sizes = [len(f) for f in seen_frames]
         assert max(sizes) - min(sizes) <= 0.25 * p.num_frames / world + 2
+
+
+def test_batched_generation_concatenates_frame_batches():
+    """config_batched: frames drawn batch by batch for one common rig (what the config-4
+    stress run and the weak-scaling bench use); serial and parallel generation agree, views
+    stay camera-major / frame-minor, and a rank's share is a subset of the same frames."""
+    sp = synth.config_batched(4, 500, batch=200, processes=1)
+    par = synth.config_batched(4, 500, batch=200, processes=2)
+    p = sp.problem
+    np.testing.assert_array_equal(p.obs_xy, par.problem.obs_xy)
+    assert p.num_frames == 500 and sp.visible.shape == (16, 500) and sp.init_board_rt.shape == (500, 6)
+    key = p.view_camera.astype(np.int64) * p.num_frames + p.view_frame
+    assert np.all(np.diff(key) > 0)
+    assert len(np.unique(p.view_frame)) == 500                  # every frame is seen by a camera
+    cams, frames = np.nonzero(sp.visible)
+    np.testing.assert_array_equal(cams, p.view_camera)
+    np.testing.assert_array_equal(frames, p.view_frame)
+    # the first batch is config(4) with frame_seed 0; the rig is common to all batches
+    first = synth.config(4, num_frames=200, frame_seed=0)
+    np.testing.assert_array_equal(sp.gt_board_rt[:200], first.gt_board_rt)
+    np.testing.assert_array_equal(sp.gt_intrinsics, first.gt_intrinsics)
+    # ranks of a strong-scaling run take alternate batches: together, the same frames
+    r0 = synth.config_batched(4, 500, batch=200, rank=0, world=2)
+    r1 = synth.config_batched(4, 500, batch=200, rank=1, world=2)
+    assert r0.problem.num_frames == 300 and r1.problem.num_frames == 200
+    np.testing.assert_array_equal(r0.gt_board_rt, np.concatenate([sp.gt_board_rt[:200], sp.gt_board_rt[400:]]))
+    np.testing.assert_array_equal(r1.gt_board_rt, sp.gt_board_rt[200:400])
+    assert r0.problem.num_observations + r1.problem.num_observations == p.num_observations

@@ -26,6 +26,9 @@ def main():
     ap.add_argument("--frames", type=int, default=100000)
     ap.add_argument("--processes", type=int, default=min(10, os.cpu_count() or 1))
     ap.add_argument("--timed-iterations", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=0,
+                    help="frames per generated batch (batches are dealt round-robin to the ranks); "
+                         "default: about 10,000, adjusted so that every rank gets the same number")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "stress_cfg4.json"))
     a = ap.parse_args()
 
@@ -38,8 +41,11 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if a.batch <= 0:
+        per_rank = max(1, round(a.frames / (10000.0 * world)))       # batches per rank
+        a.batch = -(-a.frames // (per_rank * world))
     t0 = time.time()
-    sp = synth.config_batched(4, a.frames, batch=10000, processes=max(1, a.processes // world),
+    sp = synth.config_batched(4, a.frames, batch=a.batch, processes=max(1, a.processes // world),
                               rank=rank, world=world)
     p = sp.problem
     t_gen = time.time() - t0
@@ -57,7 +63,7 @@ def main():
         capi.attach_ranks(s, rank, world)
     t_create = time.time() - t0
     res = {"workload": "config4: 16-camera ring x %d frames x 88 corners, visibility masks" % a.frames,
-           "n_gpus": world, "scaling": "strong", "frames_this_rank": int(p.num_frames),
+           "n_gpus": world, "scaling": "strong", "frames_this_rank": int(p.num_frames), "batch": int(a.batch),
            "num_views_this_rank": int(p.num_views), "observations": int(N), "residuals": int(2 * N),
            "visible_fraction": float(p.num_views) / (p.num_cameras * p.num_frames),
            "reduced_size": int(s.reduced_size()), "generate_s": t_gen, "solver_create_s": t_create}
