@@ -52,8 +52,10 @@ def hostinit():
     here = os.path.join(ROOT, "tests", "hostmath")
     host = os.path.join(ROOT, "tscm_calib_b200", "host")
     out = os.path.join(here, "libhostinit.so")
-    srcs = [os.path.join(here, "hostinit.cpp"), os.path.join(host, "ts_camera.cpp")]
+    srcs = [os.path.join(here, "hostinit.cpp"), os.path.join(host, "ts_camera.cpp"),
+            os.path.join(host, "multi_calib_b200.cpp")]
     deps = srcs + [os.path.join(host, "ts_camera.h"), os.path.join(host, "cv_compat.h"),
+                   os.path.join(host, "multi_calib_b200.h"),
                    os.path.join(ROOT, "include", "tscm.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         env = dict(os.environ)

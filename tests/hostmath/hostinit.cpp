@@ -5,6 +5,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../tscm_calib_b200/host/multi_calib_b200.h"
 #include "../../tscm_calib_b200/host/ts_camera.h"
 
 namespace {
@@ -107,6 +108,86 @@ int hostinit_undistort_chessboard(const double* intr9, const double* Rt9, int W,
   *out_w = mx.cols; *out_h = mx.rows;
   std::memcpy(mapx, mx.ptr<float>(), sizeof(float) * (size_t)mx.cols * mx.rows);
   std::memcpy(mapy, my.ptr<float>(), sizeof(float) * (size_t)mx.cols * mx.rows);
+  return 0;
+}
+
+// MultiCalib's pose-graph initialisation (multi_calib.cpp:6-153) from per-camera mono results:
+// px [C][F][K][2], has [C][F], intr [C][9], Rt [C][F][9] (each camera's [r1 r2 t] board poses).
+// Outputs per camera / per board: R (9), t (3), rt_ (6); board_init[F] = is_initial().
+int hostinit_pose_graph(int C, int F, int W, int H, double square, const double* px, const unsigned char* has,
+                        const double* intr, const double* Rt, double* cam_R, double* cam_t, double* cam_rt,
+                        double* board_R, double* board_t, double* board_rt, unsigned char* board_init) {
+  const int K = W * H;
+  std::vector<TripleSphereCamera> cams;
+  for (int m = 0; m < C; ++m) {
+    const double* in = intr + 9 * m;
+    TripleSphereCamera cam(in[0], in[1], in[2], in[3], in[4], in[5], in[6]);
+    std::vector<bool> hb(F);
+    std::vector<cv::Mat> Rts(F);
+    for (int i = 0; i < F; ++i) {
+      hb[i] = has[(size_t)m * F + i] != 0;
+      cv::Mat M(3, 3);
+      for (int k = 0; k < 9; ++k) M.at<double>(k / 3, k % 3) = Rt[((size_t)m * F + i) * 9 + k];
+      Rts[i] = M;
+    }
+    cam.setRt(Rts);
+    cam.setHasChessboard(hb);
+    cam.setPixels(unpack(px + (size_t)m * F * K * 2, has + (size_t)m * F, F, K));
+    cams.push_back(cam);
+  }
+  MultiCalib calib(cams, board(W, H, square));
+  if ((int)calib.cameras_.size() != C || (int)calib.chessboards_.size() != F) return 1;
+  for (int m = 0; m < C; ++m) {
+    if (!calib.cameras_[m].is_initial()) return 2;
+    cv::Mat R = calib.cameras_[m].R(), t = calib.cameras_[m].t();
+    for (int k = 0; k < 9; ++k) cam_R[9 * m + k] = R.at<double>(k / 3, k % 3);
+    for (int k = 0; k < 3; ++k) cam_t[3 * m + k] = t.at<double>(k, 0);
+    for (int k = 0; k < 6; ++k) cam_rt[6 * m + k] = calib.cameras_[m].rt_[k];
+  }
+  for (int i = 0; i < F; ++i) {
+    board_init[i] = calib.chessboards_[i].is_initial() ? 1 : 0;
+    if (!board_init[i]) continue;
+    cv::Mat R = calib.chessboards_[i].R(), t = calib.chessboards_[i].t();
+    for (int k = 0; k < 9; ++k) board_R[9 * i + k] = R.at<double>(k / 3, k % 3);
+    for (int k = 0; k < 3; ++k) board_t[3 * i + k] = t.at<double>(k, 0);
+    for (int k = 0; k < 6; ++k) board_rt[6 * i + k] = calib.chessboards_[i].rt_[k];
+  }
+  return 0;
+}
+
+// The reference's whole flow from corners only (main.cpp:57-129,283-289): per camera a cold-start
+// mono calibration (TS.cpp:30-108, refinement on the GPU), the pose graph (multi_calib.cpp:6-153),
+// the joint refinement (multi_calib.cpp:155-283, on the GPU).
+// summary5 = {mono calibrations that converged, termination, iterations, final cost, mean error}.
+int hostinit_full_pipeline(int C, int F, int W, int H, double square, int img_w, int img_h, const double* px,
+                           const unsigned char* has, double* intr, double* cam_rt, double* board_rt,
+                           double* summary5) {
+  const int K = W * H;
+  const std::vector<cv::Point3d> worlds = board(W, H, square);
+  std::vector<TripleSphereCamera> cams;
+  int converged = 0;
+  for (int m = 0; m < C; ++m) {
+    TripleSphereCamera cam;
+    cam.device = 0;
+    std::vector<bool> hb(F);
+    for (int i = 0; i < F; ++i) hb[i] = has[(size_t)m * F + i] != 0;
+    if (cam.calibrate(unpack(px + (size_t)m * F * K * 2, has + (size_t)m * F, F, K), hb, worlds,
+                      cv::Size(img_w, img_h), cv::Size(W, H)))
+      ++converged;
+    cams.push_back(cam);
+  }
+  MultiCalib calib(cams, worlds);
+  calib.device = 0;
+  calib.calibrate();
+  for (int m = 0; m < C; ++m) {
+    std::memcpy(intr + 9 * m, calib.cameras_[m].intrinsic_.data(), 72);
+    std::memcpy(cam_rt + 6 * m, calib.cameras_[m].rt_.data(), 48);
+  }
+  for (int i = 0; i < F; ++i)
+    if (calib.chessboards_[i].is_initial()) std::memcpy(board_rt + 6 * i, calib.chessboards_[i].rt_.data(), 48);
+  const tscm_summary& s = calib.last_summary();
+  summary5[0] = converged; summary5[1] = s.termination_type; summary5[2] = s.num_iterations;
+  summary5[3] = s.final_cost; summary5[4] = calib.average_reprojection_error;
   return 0;
 }
 

@@ -43,7 +43,10 @@ MultiCalib_camera::MultiCalib_camera(double cx, double cy, double fx, double fy,
   has_chessboard_ = has_chessboard;
   pixel_coordinates_ = pixel_coordinates;
   is_initial_ = true;
-  update_param();
+  // R_, t_ stay the matrices that were handed in (multi_calib.h:20-21): the pose-graph chain
+  // composes them as they are, not their re-orthogonalised Rodrigues round trip
+  intrinsic_matrix_ = cv::Mat(1, 9);
+  for (int k = 0; k < 9; ++k) intrinsic_matrix_.at<double>(0, k) = intrinsic_[k];
 }
 
 void MultiCalib_camera::update_param() {
