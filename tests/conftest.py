@@ -38,7 +38,8 @@ def hostmath():
     """Host build of csrc/tscm_math.cuh (the kernels' per-observation arithmetic)."""
     src = os.path.join(ROOT, "tests", "hostmath", "hostmath.cpp")
     out = os.path.join(ROOT, "tests", "hostmath", "libhostmath.so")
-    deps = [src, os.path.join(ROOT, "tscm_calib_b200", "csrc", "tscm_math.cuh")]
+    deps = [src, os.path.join(ROOT, "tscm_calib_b200", "csrc", "tscm_math.cuh"),
+            os.path.join(ROOT, "tscm_calib_b200", "csrc", "tscm_pair_lists.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, src], check=True)
     return ctypes.CDLL(out)

@@ -102,3 +102,21 @@ extern "C" int hostmath_view_blocks(const tscm_problem* p, const double* intr, c
   }
   return 0;
 }
+
+
+// Work lists of the per-camera-pair Schur update (csrc/tscm_pair_lists.h), for the CPU tests.
+#include "../../tscm_calib_b200/csrc/tscm_pair_lists.h"
+extern "C" int hostmath_pair_lists(int C, int F, int V, const int* view_camera, const int* view_frame, int chunk,
+                                   int cap_ent, int cap_items, int* sizes /*[2]: entries, items*/,
+                                   int* ent /*[cap_ent][2]*/, int* item_range /*[cap_items][2]*/,
+                                   int* pair_item /*[npairs + 1]*/, int* pair_items /*[cap_items]*/) {
+  const tscm::PairLists L = tscm::build_pair_lists(C, F, V, view_camera, view_frame, chunk);
+  sizes[0] = (int)L.ent.size();
+  sizes[1] = (int)L.item_range.size();
+  if ((int)L.ent.size() > cap_ent || (int)L.item_range.size() > cap_items) return 1;
+  for (size_t k = 0; k < L.ent.size(); ++k) { ent[2 * k] = L.ent[k].view_a; ent[2 * k + 1] = L.ent[k].view_b; }
+  for (size_t k = 0; k < L.item_range.size(); ++k) { item_range[2 * k] = L.item_range[k].begin; item_range[2 * k + 1] = L.item_range[k].end; }
+  for (size_t k = 0; k < L.pair_item.size(); ++k) pair_item[k] = L.pair_item[k];
+  for (size_t k = 0; k < L.pair_items.size(); ++k) pair_items[k] = L.pair_items[k];
+  return 0;
+}

@@ -23,6 +23,7 @@
 #include "tscm_eval5.cuh"
 #include "tscm_p2p.cuh"
 #include "tscm_schur_pairs.cuh"
+#include "tscm_pair_lists.h"
 #include "tscm_remap.cuh"
 
 namespace {
@@ -739,57 +740,19 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     const char* pe = getenv("TSCM_SCHUR_PAIRS");
     const bool want_pairs = pe ? atoi(pe) != 0 : (!s->split_ok && !s->schur2_ok);
     if (want_pairs && V < (1 << 27) && kPair2Smem <= (size_t)prop.sharedMemPerBlockOptin) {
-      std::vector<int2> ent, raw_range;
-      std::vector<int> raw_pair, raw_first, pair_item;
-      std::vector<short> pair_a, pair_b, loff(C + 1);
+      static_assert(sizeof(PairEntry) == sizeof(int2) && sizeof(PairRange) == sizeof(int2), "int2 layout");
+      const PairLists lists = build_pair_lists(C, F, V, p->view_camera, p->view_frame, kPairChunk);
+      std::vector<short> loff(C + 1);
       for (int m = 0; m <= C; ++m) loff[m] = (short)live_off[m];
-      // view of camera m in frame f (or -1)
-      std::vector<int> view_of((size_t)C * F, -1);
-      for (int v = 0; v < V; ++v) view_of[(size_t)p->view_camera[v] * F + p->view_frame[v]] = v;
-      for (int a2 = 0; a2 < C; ++a2)
-        for (int b2 = a2; b2 < C; ++b2) {
-          const int pr = (int)pair_a.size();
-          pair_a.push_back((short)a2); pair_b.push_back((short)b2);
-          int in_item = 0;
-          const int* va = &view_of[(size_t)a2 * F];
-          const int* vb = &view_of[(size_t)b2 * F];
-          for (int f = 0; f < F; ++f) {
-            if (va[f] < 0 || vb[f] < 0) continue;
-            if (in_item == 0) {
-              raw_range.push_back(make_int2((int)ent.size(), (int)ent.size()));
-              raw_pair.push_back(pr);
-              raw_first.push_back(f);
-            }
-            ent.push_back(make_int2(va[f], vb[f]));
-            raw_range.back().y = (int)ent.size();
-            if (++in_item == kPairChunk) in_item = 0;
-          }
-        }
-      // items in the order of the first frame they touch (stable: a pair's items keep their order)
-      const int nitems = (int)raw_range.size();
-      std::vector<int> order(nitems);
-      for (int k = 0; k < nitems; ++k) order[k] = k;
-      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return raw_first[x] < raw_first[y]; });
-      std::vector<int2> item_range(nitems);
-      std::vector<std::vector<int>> items_of(pair_a.size());
-      for (int pos = 0; pos < nitems; ++pos) {
-        item_range[pos] = raw_range[order[pos]];
-        items_of[raw_pair[order[pos]]].push_back(pos);
-      }
-      std::vector<int> pair_items;
-      for (size_t pr = 0; pr < pair_a.size(); ++pr) {
-        pair_item.push_back((int)pair_items.size());
-        pair_items.insert(pair_items.end(), items_of[pr].begin(), items_of[pr].end());
-      }
-      pair_item.push_back((int)pair_items.size());
+      const int nitems = (int)lists.item_range.size();
       s->pairs.nitems = nitems;
-      s->pairs.npairs = (int)pair_a.size();
-      TRY_RC(s->put(&s->pairs.ent, ent));
-      TRY_RC(s->put(&s->pairs.item_range, item_range));
-      TRY_RC(s->put(&s->pairs.pair_item, pair_item));
-      TRY_RC(s->put(&s->pairs.pair_items, pair_items));
-      TRY_RC(s->put(&s->pairs.pair_a, pair_a));
-      TRY_RC(s->put(&s->pairs.pair_b, pair_b));
+      s->pairs.npairs = (int)lists.pair_a.size();
+      TRY_RC(s->put(reinterpret_cast<const PairEntry**>(&s->pairs.ent), lists.ent));
+      TRY_RC(s->put(reinterpret_cast<const PairRange**>(&s->pairs.item_range), lists.item_range));
+      TRY_RC(s->put(&s->pairs.pair_item, lists.pair_item));
+      TRY_RC(s->put(&s->pairs.pair_items, lists.pair_items));
+      TRY_RC(s->put(&s->pairs.pair_a, lists.pair_a));
+      TRY_RC(s->put(&s->pairs.pair_b, lists.pair_b));
       TRY_RC(s->put(&s->pairs.live_off, loff));
       TRY_RC(s->alloc(&s->pairs.part, (size_t)std::max(1, nitems) * kPairPart));
       TRY_RC(s->alloc(&s->split.Wv, (size_t)V * 96));
