@@ -43,6 +43,21 @@ void hostinit_solve_z(const double* A, int rows, int cols, double* z) {
   for (int i = 0; i < cols; ++i) z[i] = out.at<double>(i, 0);
 }
 
+// cv::Rodrigues of the shim: dir 0 = 3-vector -> 3x3, dir 1 = 3x3 -> 3-vector.
+void hostinit_rodrigues(const double* in, int dir, double* out) {
+  if (dir == 0) {
+    cv::Mat v(3, 1), R;
+    for (int k = 0; k < 3; ++k) v.at<double>(k, 0) = in[k];
+    cv::Rodrigues(v, R);
+    for (int k = 0; k < 9; ++k) out[k] = R.at<double>(k / 3, k % 3);
+  } else {
+    cv::Mat R(3, 3), v;
+    for (int k = 0; k < 9; ++k) R.at<double>(k / 3, k % 3) = in[k];
+    cv::Rodrigues(R, v);
+    for (int k = 0; k < 3; ++k) out[k] = v.at<double>(k, 0);
+  }
+}
+
 int hostinit_solve_pnp(const double* obj_xyz, const double* img_xy, int n, double* rvec, double* tvec) {
   std::vector<cv::Point3d> o(n);
   std::vector<cv::Point2d> p(n);
