@@ -106,79 +106,97 @@ bool TripleSphereCamera::initial_guess(const std::vector<std::vector<cv::Point2d
   return true;
 }
 
-// TS.cpp:110-168.  With xi = lamda = 0, alpha = 0.5 a board row (a 3-D line) images as a
-// circle x^2 + y^2 - 2 f (nx/nz) x - 2 f (ny/nz) y - f^2 = 0 around the principal point; the
-// null vector of [x y 1/2 -(x^2+y^2)/2] per row gives the focal length.
+namespace {
+
+// Focal length from ONE board row (TS.cpp:127-158).  With xi = lamda = 0, alpha = 0.5 the
+// model is the unified sphere model with unit mirror parameter, under which a 3-D line images
+// as the circle  x^2 + y^2 - 2 f (nx/nz) x - 2 f (ny/nz) y - f^2 = 0  (n = unit normal of the
+// line's plane through the centre).  The row's corners, relative to the principal point, give
+// the design matrix [x  y  1/2  -(x^2 + y^2)/2]; its null vector c fixes f = |c3 / (|..| nz)|.
+// Rows whose plane is too oblique (nx^2 + ny^2 > 0.95) or whose fit is not a real circle are
+// skipped; returns false for those.
+bool focal_from_board_row(const cv::Point2d* row, int count, double cx, double cy, double* focal) {
+  cv::Mat design(count, 4);
+  for (int j = 0; j < count; ++j) {
+    const double x = row[j].x - cx, y = row[j].y - cy;
+    design.at<double>(j, 0) = x;
+    design.at<double>(j, 1) = y;
+    design.at<double>(j, 2) = 0.5;
+    design.at<double>(j, 3) = -0.5 * (x * x + y * y);
+  }
+  cv::Mat nullvec;
+  cv::SVD::solveZ(design, nullvec);
+  const double c[4] = {nullvec.at<double>(0), nullvec.at<double>(1), nullvec.at<double>(2), nullvec.at<double>(3)};
+  const double scale2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[3];
+  if (scale2 < 0) return false;
+  const double inv_norm = std::sqrt(1 / scale2);
+  const double nx = c[0] * inv_norm, ny = c[1] * inv_norm;
+  const double oblique = nx * nx + ny * ny;
+  if (oblique > 0.95) return false;
+  *focal = std::fabs(c[2] * inv_norm / std::sqrt(1 - oblique));
+  return true;
+}
+
+// Rotation that turns the viewing ray p (unit vector) onto +z: first about y by the azimuth,
+// then about x by the elevation (TS.cpp:179-187).
+cv::Mat rotation_facing(const cv::Point3d& p) {
+  const double az = std::atan2(p.x, p.z), el = std::asin(p.y);
+  cv::Mat about_y = (cv::Mat_<double>(3, 3) << std::cos(az), 0, -std::sin(az),
+                                               0, 1, 0,
+                                               std::sin(az), 0, std::cos(az));
+  cv::Mat about_x = (cv::Mat_<double>(3, 3) << 1, 0, 0,
+                                               0, std::cos(el), -std::sin(el),
+                                               0, std::sin(el), std::cos(el));
+  return about_x * about_y;
+}
+
+}  // namespace
+
+// TS.cpp:110-168: mean of the per-row focal estimates over every frame with corners.
 void TripleSphereCamera::estimate_focal(const std::vector<std::vector<cv::Point2d>>& pixels,
                                         const std::vector<cv::Point3d>& /*worlds*/, cv::Size /*img_size*/,
                                         const cv::Size chessboard_num) {
-  double focal = 0;
-  int total_num = 0;
-  const int W = chessboard_num.width, H = chessboard_num.height;
-  for (size_t k = 0; k < pixels.size(); ++k) {
-    if (pixels[k].size() == 0) continue;
-    for (int i = 0; i < H; ++i) {
-      cv::Mat P(W, 4);
-      for (int j = 0; j < W; ++j) {
-        const double x = pixels[k][i * W + j].x - cx_, y = pixels[k][i * W + j].y - cy_;
-        P.at<double>(j, 0) = x;
-        P.at<double>(j, 1) = y;
-        P.at<double>(j, 2) = 0.5;
-        P.at<double>(j, 3) = -0.5 * (x * x + y * y);
-      }
-      cv::Mat C;
-      cv::SVD::solveZ(P, C);
-      const double c1 = C.at<double>(0), c2 = C.at<double>(1), c3 = C.at<double>(2), c4 = C.at<double>(3);
-      const double t = c1 * c1 + c2 * c2 + c3 * c4;
-      if (t < 0) continue;
-      const double d = std::sqrt(1 / t);
-      const double nx = c1 * d, ny = c2 * d;
-      if (nx * nx + ny * ny > 0.95) continue;
-      const double nz = std::sqrt(1 - nx * nx - ny * ny);
-      focal += std::fabs(c3 * d / nz);
-      total_num++;
+  double sum = 0;
+  int rows_used = 0;
+  for (const std::vector<cv::Point2d>& frame : pixels) {
+    if (frame.empty()) continue;                        // no detection in this image
+    for (int r = 0; r < chessboard_num.height; ++r) {
+      double f;
+      if (!focal_from_board_row(&frame[(size_t)r * chessboard_num.width], chessboard_num.width, cx_, cy_, &f)) continue;
+      sum += f;
+      ++rows_used;
     }
   }
-  if (total_num > 0) focal /= total_num;
-  else std::cout << "焦距估计失败" << std::endl;      // the reference's message (TS.cpp:165)
-  fx_ = fy_ = focal;
+  if (rows_used == 0) std::cout << "焦距估计失败" << std::endl;      // the reference's message (TS.cpp:165)
+  fx_ = fy_ = rows_used > 0 ? sum / rows_used : 0.0;
 }
 
-// TS.cpp:170-203.  Corners are lifted to the unit sphere, rotated so that a central corner
-// looks down +z, projected to the normalised plane, and the board pose comes from
-// solvePnPRansac with an identity camera matrix; the pose is rotated back and stored in the
-// [r1 r2 t] form.
+// TS.cpp:170-203.  Per frame: the corners are lifted to the unit sphere with the current
+// intrinsics, the sphere is turned so that a corner near the board centre looks down +z, the
+// rays are projected to the normalised plane z = 1 and the board pose follows from
+// solvePnPRansac with an identity camera matrix; turned back, it is kept in the [r1 r2 t] form.
 void TripleSphereCamera::estimate_extrinsic(const std::vector<std::vector<cv::Point2d>>& pixels,
                                             const std::vector<cv::Point3d>& worlds,
                                             const cv::Size chessboard_num) {
+  const cv::Mat identity = cv::Mat::eye(3, 3, cv::CV_64F);
   for (size_t k = 0; k < pixels.size(); ++k) {
-    if (has_chessboard_[k] == false) continue;
-    const std::vector<cv::Point2d>& pixel = pixels[k];
-    cv::Mat transform = cv::Mat::eye(3, 3, cv::CV_64F);
-    const cv::Point3d p = get_unit_sphere_coordinate(pixel[pixel.size() / 2 - chessboard_num.width / 2 - 1], transform);
-    const double alpha_angle = std::atan2(p.x, p.z);
-    const double beta_angle = std::asin(p.y);
-    cv::Mat R1 = (cv::Mat_<double>(3, 3) << std::cos(alpha_angle), 0, -std::sin(alpha_angle),
-                                            0, 1, 0,
-                                            std::sin(alpha_angle), 0, std::cos(alpha_angle));
-    cv::Mat R2 = (cv::Mat_<double>(3, 3) << 1, 0, 0,
-                                            0, std::cos(beta_angle), -std::sin(beta_angle),
-                                            0, std::sin(beta_angle), std::cos(beta_angle));
-    transform = R2 * R1;
-    std::vector<cv::Point2d> pixels_normalize;
-    for (size_t i = 0; i < pixel.size(); ++i) {
-      const cv::Point3d q = get_unit_sphere_coordinate(pixel[i], transform);
-      pixels_normalize.push_back(cv::Point2d(q.x / q.z, q.y / q.z));
+    if (!has_chessboard_[k]) continue;
+    const std::vector<cv::Point2d>& corners = pixels[k];
+    const size_t centre = corners.size() / 2 - chessboard_num.width / 2 - 1;        // TS.cpp:177
+    const cv::Mat facing = rotation_facing(get_unit_sphere_coordinate(corners[centre], identity));
+    std::vector<cv::Point2d> plane(corners.size());
+    for (size_t i = 0; i < corners.size(); ++i) {
+      const cv::Point3d ray = get_unit_sphere_coordinate(corners[i], facing);
+      plane[i] = cv::Point2d(ray.x / ray.z, ray.y / ray.z);
     }
-    cv::Mat rvec, tvec, Rt;
-    cv::solvePnPRansac(worlds, pixels_normalize, cv::Mat::eye(3, 3, cv::CV_64F), cv::Mat::zeros(4, 0, cv::CV_64F), rvec, tvec);
-    cv::Rodrigues(rvec, Rt);
-    Rt = transform.t() * Rt;
-    tvec = transform.t() * tvec;
-    Rt.at<double>(0, 2) = tvec.at<double>(0);
-    Rt.at<double>(1, 2) = tvec.at<double>(1);
-    Rt.at<double>(2, 2) = tvec.at<double>(2);
-    Rt_[k] = Rt;
+    cv::Mat rvec, tvec, pose;
+    cv::solvePnPRansac(worlds, plane, identity, cv::Mat::zeros(4, 0, cv::CV_64F), rvec, tvec);
+    cv::Rodrigues(rvec, pose);
+    const cv::Mat back = facing.t();
+    pose = back * pose;
+    const cv::Mat t = back * tvec;
+    for (int r = 0; r < 3; ++r) pose.at<double>(r, 2) = t.at<double>(r);
+    Rt_[k] = pose;
   }
 }
 
