@@ -205,3 +205,49 @@ def test_iteration_cap_and_trace_bookkeeping(oracle):
     assert s.num_successful_steps + s.num_unsuccessful_steps == 4
     assert s.step_flags[0] == 3 and s.cost[0] == s.initial_cost
     assert s.final_cost == s.cost.min()
+
+
+def test_analytic_jacobian_matches_jets_on_extreme_geometry(oracle, hostmath):
+    """The hand-derived Jacobian against Jet autodiff away from the comfortable configs:
+    the 16-camera ring (incidence up to 110 degrees, boards near the image border), intrinsics
+    pushed to the edge of the model's range, near-zero and near-pi rotations, and a board almost
+    on the optical axis (r -> 0, where d(u, v)/dP loses its usual scale)."""
+    rng = np.random.default_rng(314)
+    sp = synth.config(4, num_frames=120)
+    p = sp.problem
+    worst = 0.0
+    for trial in range(4):
+        intr = sp.init_intrinsics.copy()
+        cam_rt = sp.init_cam_rt.copy()
+        board_rt = sp.init_board_rt.copy()
+        if trial == 1:      # strong mirror terms
+            intr[:, 4] = rng.uniform(-0.45, 0.3, len(intr))
+            intr[:, 5] = rng.uniform(-0.25, 0.25, len(intr))
+            intr[:, 6] = rng.uniform(0.35, 0.75, len(intr))
+        if trial == 2:      # rotations at the Taylor branch and close to pi
+            board_rt[::3, :3] = rng.normal(0, 1e-9, (len(board_rt[::3]), 3))
+            ax = rng.normal(0, 1, (len(board_rt[1::3]), 3))
+            board_rt[1::3, :3] = ax / np.linalg.norm(ax, axis=1, keepdims=True) * (np.pi - 1e-4)
+        if trial == 3:      # far and very near boards
+            board_rt[::2, 3:] *= 6.0
+            board_rt[1::2, 3:] *= 0.3
+        r0, J0, c0 = oracle.eval_jacobian(p, intr, cam_rt, board_rt)
+        r, J, c = hostmath_eval(hostmath, p, intr, cam_rt, board_rt)
+        ok = np.isfinite(J0).all(axis=(1, 2)) & np.isfinite(r0).all(axis=1)
+        assert ok.mean() > 0.9                                  # (points behind the mirror give NaN in both)
+        np.testing.assert_array_equal(np.isfinite(J).all(axis=(1, 2)), ok)
+        scale = np.maximum(np.abs(J0[ok]).max(axis=2, keepdims=True), 1.0)   # per residual row
+        err = float(np.max(np.abs(J[ok] - J0[ok]) / scale))
+        worst = max(worst, err)
+        assert err < 1e-10, (trial, err)
+        np.testing.assert_allclose(r[ok], r0[ok], rtol=1e-12, atol=1e-9)
+    # a board centred on the optical axis of camera 0, 400 mm away, facing it
+    K = p.corners_per_board
+    one = capi.ProblemArrays(p.board_xy - p.board_xy.mean(axis=0), np.zeros(1, np.int32), np.zeros(1, np.int32),
+                             np.full((K, 2), 600.0), 1, 1, 0)
+    intr1 = sp.gt_intrinsics[:1].copy()
+    pose = np.array([[1e-3, -2e-3, 0.3, 0.0, 0.0, 400.0]])
+    r0, J0, _ = oracle.eval_jacobian(one, intr1, np.zeros((1, 6)), pose)
+    r, J, _ = hostmath_eval(hostmath, one, intr1, np.zeros((1, 6)), pose)
+    scale = np.maximum(np.abs(J0).max(axis=2, keepdims=True), 1.0)
+    assert np.max(np.abs(J - J0) / scale) < 1e-10
