@@ -251,3 +251,33 @@ def test_analytic_jacobian_matches_jets_on_extreme_geometry(oracle, hostmath):
     r, J, _ = hostmath_eval(hostmath, one, intr1, np.zeros((1, 6)), pose)
     scale = np.maximum(np.abs(J0).max(axis=2, keepdims=True), 1.0)
     assert np.max(np.abs(J - J0) / scale) < 1e-10
+
+
+@pytest.mark.parametrize("case", ["cfg2", "ring", "cfg5-huber"])
+def test_moment_formulation_equals_direct_gram(hostmath, case):
+    """The per-view normal-equation blocks rebuilt from the 36 + 108 moment sums (what k_eval5 +
+    k_view_blocks do) against the direct Gram of the Jacobian rows [J | r] of the
+    same view: BB, BC, BI, CC, CI, II — 210 entries per view."""
+    loss, scale = 0, 1.0
+    if case == "cfg2":
+        sp = synth.config(2, num_frames=40)
+    elif case == "ring":
+        sp = synth.config(4, num_frames=60)
+    else:
+        sp, loss = synth.config(5, num_frames=40), capi.LOSS["huber"]
+    p = sp.problem
+    a = np.ascontiguousarray(sp.init_intrinsics)
+    b = np.ascontiguousarray(sp.init_cam_rt)
+    c = np.ascontiguousarray(sp.init_board_rt)
+    mom, direct = np.zeros((p.num_views, 210)), np.zeros((p.num_views, 210))
+    rc = hostmath.hostmath_view_blocks(C.byref(p.c), _dp(a), _dp(b), _dp(c), loss, C.c_double(scale),
+                                       _dp(mom), _dp(direct))
+    assert rc == 0
+    # entries of one block live on very different scales (rotation vs translation vs focal
+    # columns): compare against the geometric mean of the two diagonal entries involved
+    assert np.isfinite(direct).all() and np.isfinite(mom).all()
+    blocks = [(0, 21), (21, 57), (57, 105), (105, 126), (126, 174), (174, 210)]   # BB BC BI CC CI II
+    for lo, hi in blocks:
+        ref = direct[:, lo:hi]
+        scale_b = np.abs(ref).max(axis=1, keepdims=True) + 1e-300
+        assert np.max(np.abs(mom[:, lo:hi] - ref) / scale_b) < 1e-11, (case, lo)
