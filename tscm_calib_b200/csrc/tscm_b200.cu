@@ -343,11 +343,7 @@ void launch_schur(tscm_solver* s, double radius_override) {
     b.a = a;
     k_pair_frames<<<(s->F + 31) / 32, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
     k_pair_blocks<<<(s->V * 16 + 255) / 256, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, b);
-#ifdef TSCM_PAIR_SINGLE
-    k_schur_pairs<<<TSCM_PAIR_MINB * s->sm_count, kPairWarps * 32, kPairSmem, s->stream>>>(s->d_state, s->pairs);
-#else
     k_schur_pairs2<<<s->sm_count, kPairWarps * 32, kPair2Smem, s->stream>>>(s->d_state, s->pairs);
-#endif
     k_reduce_pairs<<<s->pairs.npairs, kPairReduceGroups * kPairPart, 0, s->stream>>>(s->P, s->d_state, s->pairs);
     s->launches += 3;
   } else if (s->schur2_ok) {
@@ -801,10 +797,7 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
     tscm_solver_destroy(s); return TSCM_ERR_UNSUPPORTED;
   }
   if (s->schur2_ok) TRY_RC(set_smem((const void*)k_schur2, s->schur2_smem));
-  if (s->pairs_ok) {
-    TRY_RC(set_smem((const void*)k_schur_pairs, kPairSmem));
-    TRY_RC(set_smem((const void*)k_schur_pairs2, kPair2Smem));
-  }
+  if (s->pairs_ok) TRY_RC(set_smem((const void*)k_schur_pairs2, kPair2Smem));
   if (s->split_ok) {
     TRY_RC(set_smem((const void*)k_schur_update<1>, s->split_smem));
     TRY_RC(set_smem((const void*)k_schur_update<2>, s->split_smem));

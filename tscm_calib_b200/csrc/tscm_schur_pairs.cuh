@@ -10,11 +10,11 @@
 // leaves one 6 x 16 W block and one 6 x 16 Y block per VIEW in HBM (768 B each, z as an extra
 // Y column so that rhs_a = -sum W_a^T z falls out of the diagonal pairs).
 //
-// k_schur_pairs: one WARP per work item = (pair, <= kPairChunk consecutive common frames).
+// k_schur_pairs2: one WARP per work item = (pair, <= kPairChunk consecutive common frames).
 //   The two blocks of every entry stream through a per-warp 4-stage shared-memory ring with
-//   cp.async (16 B per lane, 3 per entry); lane = (row i of W_a^T, half h of the Y columns)
-//   keeps 7 accumulators in registers for the whole item: per entry and lane 6 x (1 LDS.64 +
-//   4 LDS.128 + 7 DFMA).  No atomics: the item's 13 x 14 partial goes to its own slot.
+//   cp.async (16 B per lane, 3 per entry); the half-warps take alternate entries and a lane =
+//   (row pair of W_a^T, half of the Y columns) keeps 14 accumulators in registers for the whole
+//   item.  No atomics: the item's 13 x 14 partial goes to its own slot.
 // k_reduce_pairs: CTA per pair sums the pair's item partials in item order (4 thread groups,
 //   4 loads in flight) and scatters into the packed upper S / rhs that k_reduce_s and k_solve
 //   consume.  Deterministic: fixed item boundaries, fixed summation order.
@@ -30,14 +30,9 @@ namespace tscm {
 #ifndef TSCM_PAIR_CHUNK
 #define TSCM_PAIR_CHUNK 128
 #endif
-#ifndef TSCM_PAIR_MINB
-#define TSCM_PAIR_MINB 2
-#endif
 constexpr int kPairChunk = TSCM_PAIR_CHUNK;    // entries per work item
-constexpr int kPairStages = 4;
 constexpr int kPairWarps = 16;
 constexpr int kPairPart = 208;     // 13 rows x 16 positions per item partial
-constexpr size_t kPairSmem = (size_t)kPairWarps * kPairStages * 192 * sizeof(double);   // 96 KB: 2 CTAs per SM
 
 struct PairArgs {
   const double* Wv;        // [V][96]
@@ -66,84 +61,11 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(kPairWarps * 32, TSCM_PAIR_MINB)
-k_schur_pairs(const LmState* st, PairArgs A) {
-  if (st->done) return;
-  extern __shared__ __align__(128) double s_ring[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* ring = s_ring + (size_t)warp * kPairStages * 192;
-  const int i = min(lane >> 1, 12), h = lane & 1;
-  const int nwarps = gridDim.x * kPairWarps;
-  for (int item = blockIdx.x * kPairWarps + warp; item < A.nitems; item += nwarps) {
-    const int2 range = A.item_range[item];
-    const int e0 = range.x, n = range.y - range.x;
-    double acc[7];
-#pragma unroll
-    for (int q = 0; q < 7; ++q) acc[q] = 0.0;
-    // entry descriptors: lane l holds entry (32 * block + l) of the item
-    const int2 cur = lane < n ? A.ent[e0 + lane] : make_int2(0, 0);
-    const int2 nxt = 32 + lane < n ? A.ent[e0 + 32 + lane] : make_int2(0, 0);
-    // Descriptor bookkeeping: the producer side runs kPairStages - 1 entries ahead of the
-    // consumer, so it may already need the next 32-entry block: `pcur` / `pnxt` follow it.
-    int2 pcur = cur, pnxt = nxt;
-    int pblock = 0;                    // 32-entry block `pcur` belongs to
-    auto produce = [&](int e) {
-      if (e < n) {
-        if ((e >> 5) != pblock) {      // warp-uniform
-          pcur = pnxt;
-          pblock = e >> 5;
-          const int q = (pblock + 1) * 32 + lane;
-          pnxt = q < n ? A.ent[e0 + q] : make_int2(0, 0);
-        }
-        const int va = __shfl_sync(0xffffffffu, pcur.x, e & 31);
-        const int vb = __shfl_sync(0xffffffffu, pcur.y, e & 31);
-        double* dst = ring + (e % kPairStages) * 192;
-        const double* wsrc = A.Wv + (size_t)va * 96;
-        const double* ysrc = A.Yv + (size_t)vb * 96;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const int c = lane + 32 * r;                 // 16-byte chunk 0..95 of [W | Y]
-          cp_async16(dst + 2 * c, c < 48 ? wsrc + 2 * c : ysrc + 2 * (c - 48));
-        }
-      }
-      cp_async_commit();               // always: keeps the group count in step with the entry index
-    };
-    __syncwarp();                      // the previous item's last reads of the ring are done
-#pragma unroll
-    for (int e = 0; e < kPairStages - 1; ++e) produce(e);
-    for (int e = 0; e < n; ++e) {
-      produce(e + kPairStages - 1);    // overwrites the stage consumed at e - 1 (ordered by the syncwarp below)
-      cp_async_wait<kPairStages - 1>();
-      __syncwarp();                    // every lane's copies of entry e have landed
-      const double* Wb = ring + (e % kPairStages) * 192;
-      const double2* Yb = reinterpret_cast<const double2*>(Wb + 96 + h * 8);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const double w = Wb[k * 16 + i];
-        const double2 y0 = Yb[k * 8 + 0], y1 = Yb[k * 8 + 1], y2 = Yb[k * 8 + 2], y3 = Yb[k * 8 + 3];
-        acc[0] = fma(w, y0.x, acc[0]);
-        acc[1] = fma(w, y0.y, acc[1]);
-        acc[2] = fma(w, y1.x, acc[2]);
-        acc[3] = fma(w, y1.y, acc[3]);
-        acc[4] = fma(w, y2.x, acc[4]);
-        acc[5] = fma(w, y2.y, acc[5]);
-        acc[6] = fma(w, y3.x, acc[6]);
-      }
-      __syncwarp();                    // stage e % kPairStages may be refilled from the next iteration on
-    }
-    cp_async_wait<0>();
-    if (lane < 26) {
-      double* out = A.part + (size_t)item * kPairPart + i * 16 + h * 8;
-#pragma unroll
-      for (int q = 0; q < 7; ++q) out[q] = acc[q];
-    }
-  }
-}
-
 // Two entries per step: the half-warps take entry 2s and 2s + 1, a lane owns TWO rows of
-// W_a^T (one 16-byte load) x 7 columns = 14 accumulators, i.e. 5 LDS.128 per 14 DFMA instead
-// of 5 loads per 7: the single-entry form above is bound by the shared-memory instruction
-// queue (mio_throttle 22 %, LSU pipe 66-88 % busy, FP64 pipe 36 %).
+// W_a^T (one 16-byte load) x 7 columns = 14 accumulators, i.e. 5 LDS.128 per 14 DFMA.  (The
+// first version — one entry per step, one row x 7 columns per lane, 5 loads per 7 DFMA — was
+// bound by the shared-memory instruction queue: mio_throttle 22 %, LSU pipe 66-88 % busy,
+// FP64 pipe 36 %, 262 us against 200 us on 40,000 frames of config 4; it is in the history.)
 constexpr int kPair2Stages = 4;
 constexpr size_t kPair2Smem = (size_t)kPairWarps * kPair2Stages * 384 * sizeof(double);   // 192 KB
 
