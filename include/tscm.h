@@ -35,6 +35,7 @@
 #ifndef TSCM_H_
 #define TSCM_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -102,11 +103,18 @@ typedef struct tscm_options {
   int32_t loss_type;                        /* TSCM_LOSS_NONE */
   double loss_scale;                        /* `a` of HuberLoss(a)/CauchyLoss(a) */
   int32_t parameter_tolerance_needs_successful_step;
-                                            /* 0: Ceres <= 2.0 (test on every valid step);
-                                               1: Ceres >= 2.1 */
+                                            /* 0: Ceres <= 2.0 (parameter and function tolerance are
+                                               tested on every valid step);
+                                               1: Ceres >= 2.1 (both tests only after at least one
+                                               successful step) */
   int32_t disable_tolerances;               /* 1: fixed-iteration timing mode — run exactly
                                                max_num_iterations LM iterations */
   int32_t verbose;                          /* 1: print BriefReport() line (TS.cpp:280) */
+  int32_t num_gpus;                         /* 0 or 1: one GPU.  N > 1: the frames are sharded over the
+                                               N devices [device, device + N) of this process
+                                               (peer access between them is required).
+                                               The reference is single-process, so this is how
+                                               MultiCalib::calibrate() reaches more than one GPU. */
 } tscm_options;
 
 typedef struct tscm_summary {
@@ -132,10 +140,23 @@ void tscm_options_init(tscm_options* options);
 /* One-shot solve: the call a reference adapter makes instead of ceres::Solve.
  * Host pointers in, parameters updated in place (as Ceres does through the raw
  * double* it was handed: TS.cpp:266-267, multi_calib.cpp:182-184).  Uses CUDA
- * device `device` (-1 = current device). */
+ * device `device` (-1 = current device); options->num_gpus > 1 shards the frames over
+ * the devices [device, device + num_gpus).
+ *
+ * The solver built for a problem STRUCTURE (device, C, F, K, the view lists, the board and
+ * fixed_camera) is kept after the call, so that the next tscm_solve() on the same structure
+ * — a re-calibration with new detections, another LM run from a different start — only
+ * uploads observations and parameters: no allocation, no index tables, no graph capture.
+ * tscm_cache_configure(0) disables this, tscm_cache_release() frees what is held.  Observations
+ * staged in memory from tscm_host_alloc() (page-locked) upload at full PCIe rate. */
 int tscm_solve(const tscm_problem* problem, const tscm_options* options,
                double* intrinsics, double* cam_rt, double* board_rt,
                tscm_summary* summary, int device);
+void tscm_cache_configure(int32_t max_solvers);   /* default 1; 0 = no caching */
+void tscm_cache_release(void);
+/* Page-locked host memory for observation staging (cudaHostAlloc / cudaFreeHost). */
+void* tscm_host_alloc(size_t bytes);
+void tscm_host_free(void* p);
 
 /* Resident solver: observations stay in HBM between solves. */
 typedef struct tscm_solver tscm_solver;
@@ -162,14 +183,19 @@ int tscm_comm_unique_id(void* unique_id_128);
 int tscm_solver_attach_comm(tscm_solver* solver, int rank, int num_ranks,
                             const void* unique_id_128);
 
-/* Multi-GPU on one NVLink/NVSwitch node (preferred): the two exchange steps of an LM
- * iteration run inside this library's own kernels over peer memory instead of NCCL.  Every
- * rank exports the 64-byte CUDA-IPC handle of its mailbox, the host gathers the handles of
- * all ranks (rank order, 64 bytes each) and hands them to every rank.  At most 8 ranks.
+/* Multi-GPU on one NVLink/NVSwitch node, one PROCESS per GPU (preferred over NCCL): the two
+ * exchange steps of an LM iteration run inside this library's own kernels over peer memory.
+ * Every rank exports the 64-byte CUDA-IPC handle of its mailbox, the host gathers the handles
+ * of all ranks (rank order, 64 bytes each) and hands them to every rank.  At most 8 ranks.
  * Either attach call makes the solver a rank of a sharded solve; with both, peer memory is
- * used. */
+ * used.  The host must put a barrier between the attach calls of all ranks and the first
+ * tscm_solver_run(), and every rank must make the same sequence of calls: an exchange waits
+ * for its peers on the device and gives up after `tscm_solver_set_exchange_timeout` seconds
+ * (default 10 s), which ends the solve with TSCM_FAILURE and returns TSCM_ERR_COMM.
+ * (Inside ONE process use tscm_options.num_gpus instead: no IPC, same kernels.) */
 int tscm_solver_p2p_export(tscm_solver* solver, void* handle_64);
 int tscm_solver_p2p_attach(tscm_solver* solver, int rank, int num_ranks, const void* handles);
+int tscm_solver_set_exchange_timeout(tscm_solver* solver, double seconds);
 
 /* ---- inspection entry points (used by the parity tests and the bench) ---- */
 
@@ -198,6 +224,13 @@ int tscm_solver_reprojection_error(tscm_solver* solver, double* per_camera, doub
  *        6 / 7 = the two kernels of stage 0 on their own (k_eval5: moments of every view;
  *        k_view_blocks: per-view blocks from the moments). */
 int tscm_solver_time_stage(tscm_solver* solver, int stage, int repeats, double* ms_per_launch);
+/* Schur-elimination form (test hook: the default, 0 = chosen from the visibility pattern, is
+ * what every production call uses): 1 = dense rows (k_schur_frames + k_schur_update), 2 = fused
+ * producer/consumer CTA (k_schur2), 3 = per-camera-pair (k_pair_* + k_schur_pairs2).  Returns
+ * TSCM_ERR_UNSUPPORTED when the form cannot hold this problem. */
+int tscm_solver_set_schur_form(tscm_solver* solver, int form);
+/* bit 0: creation / solve phase timings on stderr; bit 1: in-kernel cycle counts of k_solve. */
+void tscm_set_debug(int32_t flags);
 /* Number of kernels launched by this solver since creation. */
 int64_t tscm_solver_launch_count(const tscm_solver* solver);
 /* Measured FP64 FMA throughput of the device (TFLOP/s, FMA = 2 flops): the

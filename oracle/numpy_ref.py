@@ -395,7 +395,7 @@ def solve(P: Problem, intr, cam_rt, board_rt, max_num_iterations=50, function_to
         if (not ptol_needs_success or one_success) and \
                 step_norm <= parameter_tolerance * (x_norm + parameter_tolerance):
             S.termination = "CONVERGENCE"; break
-        if abs(x_cost - cand) <= function_tolerance * x_cost:
+        if (not ptol_needs_success or one_success) and abs(x_cost - cand) <= function_tolerance * x_cost:
             S.termination = "CONVERGENCE"; break
         rho = -DBL_MAX if cand >= DBL_MAX else (x_cost - cand) / model_cost_change
         if rho > min_relative_decrease:

@@ -21,7 +21,8 @@ _lib = None
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("tscm_oracle.cpp", "tscm_oracle.h", "remap_oracle.c")]
+    src = [os.path.join(_HERE, f) for f in ("tscm_oracle.cpp", "tscm_oracle.h", "remap_oracle.c",
+                                            os.path.join("..", "include", "tscm.h"))]
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in src)):
         return LIB_PATH

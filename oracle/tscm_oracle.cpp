@@ -897,7 +897,9 @@ int tscm_oracle_solve(const tscm_problem* problem, const tscm_options* options,
     // FunctionToleranceReached
     {
       const double cost_change = x_cost - candidate_cost;
-      if (!o.disable_tolerances && std::fabs(cost_change) <= o.function_tolerance * x_cost) {
+      // Ceres >= 2.1 gates this test on atleast_one_successful_step as well
+      const bool armed = !o.parameter_tolerance_needs_successful_step || atleast_one_successful_step;
+      if (!o.disable_tolerances && armed && std::fabs(cost_change) <= o.function_tolerance * x_cost) {
         termination = TSCM_CONVERGENCE; returned = true; break;
       }
     }

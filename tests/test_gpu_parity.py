@@ -233,20 +233,15 @@ def test_sixteen_camera_ring_uses_wide_schur_path(oracle):
     assert_same_solve(s, s0, (a, b, c), (a0, b0, c0))
 
 
-@pytest.fixture
-def forced_pairs(monkeypatch):
-    """TSCM_SCHUR_PAIRS=1: the per-camera-pair Schur kernels (sparse-visibility path,
-    csrc/tscm_schur_pairs.cuh) on problems that would otherwise take the dense-row kernels."""
-    monkeypatch.setenv("TSCM_SCHUR_PAIRS", "1")
-
-
 @pytest.mark.parametrize("case", ["cfg2", "ragged", "ring16"])
-def test_pair_schur_reduced_system_matches_oracle(oracle, forced_pairs, case):
-    """S and rhs from k_schur_frames (per-view blocks) -> k_schur_pairs -> k_reduce_pairs."""
+def test_pair_schur_reduced_system_matches_oracle(oracle, case):
+    """S and rhs from k_pair_frames / k_pair_blocks (per-view blocks) -> k_schur_pairs2 ->
+    k_reduce_pairs (csrc/tscm_schur_pairs.cuh), forced on problems that would otherwise take the
+    dense-row kernels (tscm_solver_set_schur_form)."""
     sp = {"cfg2": lambda: synth.config(2),
           "ragged": lambda: synth.generate(num_cameras=4, num_frames=60, board=(7, 5), rig="calib", seed=71),
           "ring16": lambda: synth.config(4, num_frames=700)}[case]()   # > 128 common frames per pair: several items
-    s = capi.Solver(sp.problem)
+    s = capi.Solver(sp.problem, schur_form="pairs")
     s.set_parameters(sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt)
     for radius in (1e4, 3.0):
         lhs, rhs = s.reduced_system(radius)
@@ -261,8 +256,9 @@ def test_pair_schur_reduced_system_matches_oracle(oracle, forced_pairs, case):
     s.close()
 
 
+@pytest.mark.parametrize("form", ["pairs", "fused", "rows"])
 @pytest.mark.parametrize("case", ["cfg2", "cfg5-huber", "ragged"])
-def test_pair_schur_solve_matches_oracle(oracle, forced_pairs, case):
+def test_every_schur_form_solves_like_the_oracle(oracle, case, form):
     if case == "cfg2":
         sp, opt = synth.config(2), capi.default_options()
     elif case == "cfg5-huber":
@@ -271,22 +267,20 @@ def test_pair_schur_solve_matches_oracle(oracle, forced_pairs, case):
         sp = synth.generate(num_cameras=4, num_frames=60, board=(7, 5), rig="calib", seed=71)
         opt = capi.default_options()
     init = (sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt)
-    a, b, c, s = capi.solve(sp.problem, *init, opt)
+    a, b, c, s = capi.solve_resident(sp.problem, *init, opt, schur_form=form)
     a0, b0, c0, s0 = oracle.solve(sp.problem, *init, opt)
     assert_same_solve(s, s0, (a, b, c), (a0, b0, c0))
 
 
-def test_pair_schur_is_deterministic_and_agrees_with_dense_rows(monkeypatch):
+def test_pair_schur_is_deterministic_and_agrees_with_dense_rows():
     """Same problem through the dense-row kernels and through the pair kernels: iteration
     counts equal, costs to round-off; the pair path twice: bit-identical."""
-    sp = synth.config(4, num_frames=1500)
+    sp = synth.config(3, num_frames=400)
     opt = capi.default_options(max_num_iterations=12)
     init = (sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt)
-    monkeypatch.setenv("TSCM_SCHUR_PAIRS", "0")
-    a0, b0, c0, s0 = capi.solve(sp.problem, *init, opt)
-    monkeypatch.setenv("TSCM_SCHUR_PAIRS", "1")
-    a1, b1, c1, s1 = capi.solve(sp.problem, *init, opt)
-    a2, b2, c2, s2 = capi.solve(sp.problem, *init, opt)
+    a0, b0, c0, s0 = capi.solve_resident(sp.problem, *init, opt, schur_form="rows")
+    a1, b1, c1, s1 = capi.solve_resident(sp.problem, *init, opt, schur_form="pairs")
+    a2, b2, c2, s2 = capi.solve_resident(sp.problem, *init, opt, schur_form="pairs")
     np.testing.assert_array_equal(s1.cost, s2.cost)
     for x, y in ((a1, a2), (b1, b2), (c1, c2)):
         np.testing.assert_array_equal(x, y)
@@ -294,22 +288,6 @@ def test_pair_schur_is_deterministic_and_agrees_with_dense_rows(monkeypatch):
     np.testing.assert_allclose(s1.cost, s0.cost, rtol=1e-10)
     for x, y in ((a1, a0), (b1, b0), (c1, c0)):
         np.testing.assert_allclose(x, y, rtol=1e-7, atol=1e-9)
-
-
-def test_dense_rows_from_pair_frames_kernels_are_bit_identical(monkeypatch):
-    """TSCM_SPLIT_FRAMES8=1: the dense W_s / Y rows produced by k_pair_frames + k_pair_blocks
-    (8 lanes per frame, thread per column) instead of the warp-per-frame k_schur_frames: same
-    arithmetic and summation order, so the whole solve is bit-identical."""
-    sp = synth.config(3, num_frames=200)
-    opt = capi.default_options()
-    init = (sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt)
-    monkeypatch.setenv("TSCM_SPLIT_FRAMES8", "0")
-    a0, b0, c0, s0 = capi.solve(sp.problem, *init, opt)
-    monkeypatch.setenv("TSCM_SPLIT_FRAMES8", "1")
-    a1, b1, c1, s1 = capi.solve(sp.problem, *init, opt)
-    np.testing.assert_array_equal(s0.cost, s1.cost)
-    for x, y in ((a0, a1), (b0, b1), (c0, c1)):
-        np.testing.assert_array_equal(x, y)
 
 
 def test_errors_are_reported_not_swallowed():

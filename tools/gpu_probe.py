@@ -1,0 +1,46 @@
+"""One GPU-box visit worth of diagnostics for the host/solve rewrite: k_solve cycle counts,
+one-shot tscm_solve() phase timings (cold and cached), creation time at config 3 / config 4."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from tscm_calib_b200 import capi, synth
+
+what = sys.argv[1:] or ["solve_cycles", "oneshot", "cfg4_create"]
+if "solve_cycles" in what:
+    capi.set_debug(2)
+    for cfg, frames in ((3, 96), (4, 160)):
+        sp = synth.config(cfg, num_frames=frames)
+        opt = capi.default_options(max_num_iterations=2)
+        a, b, c, s = capi.solve(sp.problem, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt, opt)
+        print("cfg", cfg, s.termination, s.cost, flush=True)
+    capi.set_debug(0)
+if "oneshot" in what:
+    capi.set_debug(1)
+    sp = synth.config(3)
+    obs = capi.pinned_array(sp.problem.obs_xy.shape)
+    obs[...] = sp.problem.obs_xy
+    hp = capi.ProblemArrays(sp.problem.board_xy, sp.problem.view_camera, sp.problem.view_frame, obs,
+                            sp.problem.num_cameras, sp.problem.num_frames, sp.problem.fixed_camera)
+    opt = capi.default_options(max_num_iterations=20, disable_tolerances=1)
+    for tag, prob in (("pinned", hp), ("pageable", sp.problem)):
+        capi.cache_release()
+        for rep in range(3):
+            t = time.perf_counter()
+            capi.solve(prob, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt, opt)
+            dt = time.perf_counter() - t
+            print(f"one-shot {tag} rep {rep}: {dt*1e3:.2f} ms -> {20/dt:.0f} it/s", flush=True)
+    capi.set_debug(0)
+if "cfg4_create" in what:
+    capi.set_debug(1)
+    capi.cache_release()
+    t = time.perf_counter()
+    sp = synth.config(4, num_frames=int(os.environ.get("CFG4_FRAMES", "100000")))
+    print(f"synth config 4: {time.perf_counter()-t:.1f} s, views {sp.problem.num_views}", flush=True)
+    opt = capi.default_options(max_num_iterations=5, disable_tolerances=1)
+    for rep in range(2):
+        t = time.perf_counter()
+        s = capi.Solver(sp.problem, opt); t1 = time.perf_counter()
+        s.set_parameters(sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt); t2 = time.perf_counter()
+        r = s.run(); t3 = time.perf_counter()
+        s.close(); t4 = time.perf_counter()
+        print(f"cfg4 rep {rep}: create {1e3*(t1-t):.1f} set {1e3*(t2-t1):.1f} run(5 it) {1e3*(t3-t2):.1f} destroy {1e3*(t4-t3):.1f} ms", flush=True)

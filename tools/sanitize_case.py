@@ -1,0 +1,21 @@
+"""Small solves for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): every kernel of the LM
+iteration graph runs at least twice, on sizes a sanitizer finishes in a minute.
+  python tools/sanitize_case.py dense|pairs|mono|robust
+"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from tscm_calib_b200 import capi, synth
+
+case = sys.argv[1] if len(sys.argv) > 1 else "dense"
+if case == "dense":      # config 3 shape: k_eval5, k_view_blocks, k_schur_frames, k_schur_update, k_solve, ...
+    sp, opt = synth.config(3, num_frames=96), capi.default_options(max_num_iterations=4)
+elif case == "pairs":    # 16-camera ring, sparse visibility: k_pair_frames, k_pair_blocks, k_schur_pairs2, k_reduce_pairs
+    sp, opt = synth.config(4, num_frames=160), capi.default_options(max_num_iterations=4)
+elif case == "mono":
+    sp, opt = synth.config(1), capi.default_options(max_num_iterations=4)
+else:                    # robust loss, ragged visibility (config 5)
+    sp, opt = synth.config(5, num_frames=60), capi.default_options(max_num_iterations=4, loss_type="huber", loss_scale=1.0)
+a, b, c, s = capi.solve(sp.problem, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt, opt)
+print(case, s.termination, s.num_iterations, s.cost)
+assert np.all(np.isfinite(s.cost)) and s.cost[-1] < s.cost[0]

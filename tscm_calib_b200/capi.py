@@ -55,6 +55,7 @@ class TscmOptions(C.Structure):
         ("parameter_tolerance_needs_successful_step", C.c_int32),
         ("disable_tolerances", C.c_int32),
         ("verbose", C.c_int32),
+        ("num_gpus", C.c_int32),
     ]
 
 
@@ -110,6 +111,7 @@ def default_options(**overrides) -> TscmOptions:
     o.parameter_tolerance_needs_successful_step = 0
     o.disable_tolerances = 0
     o.verbose = 0
+    o.num_gpus = 1
     for k, v in overrides.items():
         if k == "loss_type" and isinstance(v, str):
             v = LOSS[v]
@@ -232,6 +234,20 @@ def load_library(path: str | None = None):
     lib.tscm_solve.argtypes = [P(TscmProblem), P(TscmOptions), c_double_p, c_double_p,
                                c_double_p, P(TscmSummary), C.c_int]
     lib.tscm_solve.restype = C.c_int
+    lib.tscm_cache_configure.argtypes = [C.c_int32]
+    lib.tscm_cache_configure.restype = None
+    lib.tscm_cache_release.argtypes = []
+    lib.tscm_cache_release.restype = None
+    lib.tscm_host_alloc.argtypes = [C.c_size_t]
+    lib.tscm_host_alloc.restype = C.c_void_p
+    lib.tscm_host_free.argtypes = [C.c_void_p]
+    lib.tscm_host_free.restype = None
+    lib.tscm_solver_set_exchange_timeout.argtypes = [C.c_void_p, C.c_double]
+    lib.tscm_solver_set_exchange_timeout.restype = C.c_int
+    lib.tscm_solver_set_schur_form.argtypes = [C.c_void_p, C.c_int]
+    lib.tscm_solver_set_schur_form.restype = C.c_int
+    lib.tscm_set_debug.argtypes = [C.c_int32]
+    lib.tscm_set_debug.restype = None
     lib.tscm_solver_create.argtypes = [P(TscmProblem), P(TscmOptions), C.c_int, P(C.c_void_p)]
     lib.tscm_solver_create.restype = C.c_int
     lib.tscm_solver_destroy.argtypes = [C.c_void_p]
@@ -288,8 +304,12 @@ EXPORTED_SYMBOLS = [
     "tscm_solver_attach_comm", "tscm_solver_p2p_export", "tscm_solver_p2p_attach", "tscm_solver_eval_jacobian", "tscm_solver_reduced_size",
     "tscm_solver_reduced_system", "tscm_solver_reprojection_error", "tscm_solver_time_stage",
     "tscm_solver_launch_count", "tscm_device_fp64_peak", "tscm_remap_tables",
-    "tscm_last_error", "tscm_version",
+    "tscm_last_error", "tscm_version", "tscm_cache_configure", "tscm_cache_release",
+    "tscm_host_alloc", "tscm_host_free", "tscm_solver_set_exchange_timeout",
+    "tscm_solver_set_schur_form", "tscm_set_debug",
 ]
+
+SCHUR_FORM = {"auto": 0, "rows": 1, "fused": 2, "pairs": 3}
 
 
 class TscmError(RuntimeError):
@@ -306,7 +326,8 @@ def check(rc: int, lib=None):
 class Solver:
     """Resident solver handle (observations stay in HBM)."""
 
-    def __init__(self, problem: ProblemArrays, options: TscmOptions | None = None, device: int = -1):
+    def __init__(self, problem: ProblemArrays, options: TscmOptions | None = None, device: int = -1,
+                 schur_form: str | int | None = None):
         self.lib = load_library()
         self.problem = problem
         self.options = options or default_options()
@@ -314,6 +335,16 @@ class Solver:
         check(self.lib.tscm_solver_create(C.byref(problem.c), C.byref(self.options), device,
                                           C.byref(h)), self.lib)
         self.h = h
+        if schur_form is not None:
+            self.set_schur_form(schur_form)
+
+    def set_schur_form(self, form):
+        """Test hook (tscm_solver_set_schur_form): 'auto' | 'rows' | 'fused' | 'pairs'."""
+        f = SCHUR_FORM[form] if isinstance(form, str) else int(form)
+        check(self.lib.tscm_solver_set_schur_form(self.h, f), self.lib)
+
+    def set_exchange_timeout(self, seconds: float):
+        check(self.lib.tscm_solver_set_exchange_timeout(self.h, float(seconds)), self.lib)
 
     def close(self):
         if getattr(self, "h", None):
@@ -464,14 +495,60 @@ def solve(problem: ProblemArrays, intrinsics, cam_rt, board_rt, options: TscmOpt
     return a, b, c, buf.result()
 
 
+def solve_resident(problem: ProblemArrays, intrinsics, cam_rt, board_rt, options: TscmOptions | None = None,
+                   device: int = -1, schur_form=None):
+    """The same solve through a resident Solver handle (create / set / run / get / destroy),
+    optionally with a forced Schur form.  Returns (intr, cam_rt, board_rt, summary)."""
+    s = Solver(problem, options, device=device, schur_form=schur_form)
+    try:
+        s.set_parameters(intrinsics, cam_rt, board_rt)
+        res = s.run()
+        a, b, c = s.get_parameters()
+    finally:
+        s.close()
+    return a, b, c, res
+
+
+def set_debug(flags: int):
+    load_library().tscm_set_debug(int(flags))
+
+
+def cache_release():
+    load_library().tscm_cache_release()
+
+
+def cache_configure(max_solvers: int):
+    load_library().tscm_cache_configure(int(max_solvers))
+
+
+def pinned_array(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array over page-locked memory from tscm_host_alloc() (kept alive by the array)."""
+    lib = load_library()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib.tscm_host_alloc(max(1, n))
+    if not p:
+        raise TscmError("tscm_host_alloc failed")
+
+    class _Owner:
+        def __init__(self, ptr): self.ptr = ptr
+        def __del__(self):
+            try:
+                lib.tscm_host_free(self.ptr)
+            except Exception:
+                pass
+    buf = (C.c_char * max(1, n)).from_address(p)
+    buf._owner = _Owner(p)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
 def attach_ranks(solver: "Solver", rank: int, world: int, use_p2p: bool | None = None):
     """Make `solver` one rank of a frame-sharded solve inside an initialised
     torch.distributed NCCL process group (one process per GPU of one node).
-    Peer-memory exchange (tscm_p2p.cuh) when world <= 8 unless TSCM_P2P=0; NCCL otherwise."""
+    Peer-memory exchange (tscm_p2p.cuh) when world <= 8 unless use_p2p=False; NCCL otherwise."""
     import torch
     import torch.distributed as dist
     if use_p2p is None:
-        use_p2p = os.environ.get("TSCM_P2P", "1") != "0" and world <= 8
+        use_p2p = world <= 8
     if use_p2p:
         mine = torch.frombuffer(bytearray(solver.p2p_export()), dtype=torch.uint8).cuda()
         allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]

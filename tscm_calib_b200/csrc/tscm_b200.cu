@@ -4,16 +4,27 @@
 // replays it, and reads back the summary.  There is no CPU fallback.
 //
 // Replaces: ceres::Solve at /root/reference/TS.cpp:278 and multi_calib.cpp:216.
+//
+// Host-side structure:
+//   * one tscm_solver per device ("shard"): every buffer lives in ONE arena allocation, every
+//     static index table in ONE uploaded blob, so that creating a solver is a handful of CUDA
+//     calls;
+//   * a group solver (tscm_options.num_gpus > 1) owns one shard per device of this process and
+//     drives them from the calling thread; the shards exchange through the peer-memory kernels
+//     of tscm_p2p.cuh over directly mapped peer pointers;
+//   * tscm_solve() keeps the solver of the last problem structure (tscm_cache_configure).
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -21,6 +32,7 @@
 #include "../../include/tscm.h"
 #include "tscm_kernels.cuh"
 #include "tscm_eval5.cuh"
+#include "tscm_solve.cuh"
 #include "tscm_p2p.cuh"
 #include "tscm_schur_pairs.cuh"
 #include "tscm_pair_lists.h"
@@ -29,6 +41,7 @@
 namespace {
 
 thread_local std::string g_last_error;
+int g_debug = 0;     // tscm_set_debug(): bit 0 phase timings on stderr, bit 1 k_solve cycle counts
 
 void set_error(const char* fmt, ...) {
   char buf[1024];
@@ -47,6 +60,16 @@ void set_error(const char* fmt, ...) {
       return TSCM_ERR_CUDA;                                                           \
     }                                                                                 \
   } while (0)
+#define RC_TRY(expr)            \
+  do {                          \
+    const int rc_ = (expr);     \
+    if (rc_) return rc_;        \
+  } while (0)
+
+using Clock = std::chrono::steady_clock;
+double ms_since(Clock::time_point t0) {
+  return std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+}
 
 // ---------------------------------------------------------------------------
 // NCCL through dlopen: the process that hosts us (PyTorch) already carries an
@@ -88,33 +111,105 @@ NcclApi& nccl() {
   return api;
 }
 
-template <typename T>
-int upload(T** dst, const std::vector<T>& src) {
-  const size_t bytes = std::max<size_t>(1, src.size()) * sizeof(T);
-  CUDA_TRY(cudaMalloc((void**)dst, bytes));
-  if (!src.empty()) CUDA_TRY(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+// Device properties are queried once per device (cudaGetDeviceProperties costs ~2 ms).
+struct DeviceInfo {
+  bool queried = false;
+  int major = 0, minor = 0, sm_count = 0;
+  size_t smem_optin = 0;
+};
+int device_info(int device, DeviceInfo* out) {
+  static std::mutex mu;
+  static DeviceInfo table[64];
+  std::lock_guard<std::mutex> lock(mu);
+  if (device < 0 || device >= 64) { set_error("device %d out of range", device); return TSCM_ERR_INVALID_ARGUMENT; }
+  DeviceInfo& d = table[device];
+  if (!d.queried) {
+    CUDA_TRY(cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, device));
+    int optin = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    d.smem_optin = (size_t)optin;
+    d.queried = true;
+  }
+  *out = d;
   return TSCM_OK;
 }
+
+// All device buffers of a solver: requests are collected, then served by one cudaMalloc and
+// zeroed by one memset.
+struct Arena {
+  struct Req { void** slot; size_t bytes, off; };
+  std::vector<Req> reqs;
+  size_t total = 0;
+  char* base = nullptr;
+  template <typename T>
+  void want(T** slot, size_t n) {
+    size_t b = std::max<size_t>(1, n) * sizeof(T);
+    b = (b + 255) & ~(size_t)255;
+    reqs.push_back(Req{reinterpret_cast<void**>(slot), b, total});
+    total += b;
+  }
+  int commit(cudaStream_t st) {
+    CUDA_TRY(cudaMalloc((void**)&base, std::max<size_t>(256, total)));
+    CUDA_TRY(cudaMemsetAsync(base, 0, std::max<size_t>(256, total), st));
+    for (const Req& r : reqs) *r.slot = base + r.off;
+    return TSCM_OK;
+  }
+};
+// Static index tables: appended on the host, uploaded with one copy.
+struct Blob {
+  struct Fix { const void** slot; size_t off; };
+  std::vector<char> bytes;
+  std::vector<Fix> fixes;
+  char* d_base = nullptr;
+  template <typename T>
+  void add(const T** slot, const T* data, size_t n) {
+    const size_t off = (bytes.size() + 15) & ~(size_t)15;
+    bytes.resize(off + std::max<size_t>(1, n) * sizeof(T));
+    if (n) std::memcpy(bytes.data() + off, data, n * sizeof(T));
+    fixes.push_back(Fix{reinterpret_cast<const void**>(slot), off});
+  }
+  template <typename T>
+  void add(const T** slot, const std::vector<T>& v) { add(slot, v.data(), v.size()); }
+  int upload(cudaStream_t st) {
+    CUDA_TRY(cudaMemcpyAsync(d_base, bytes.data(), bytes.size(), cudaMemcpyHostToDevice, st));
+    for (const Fix& f : fixes) *f.slot = d_base + f.off;
+    CUDA_TRY(cudaStreamSynchronize(st));      // `bytes` is pageable and about to go away
+    return TSCM_OK;
+  }
+};
 
 }  // namespace
 
 using namespace tscm;
 
+enum { kSchurAuto = 0, kSchurRows = 1, kSchurFused = 2, kSchurPairs = 3 };
+
+// A run of consecutive views of one camera: where a shard's observations sit in the caller's array.
+struct ObsSegment { int dst_view, src_view, count; };
+
 struct tscm_solver {
   int device = 0;
   int sm_count = 148;
+  size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
   tscm_options options{};
   LmOptions lm{};
   DeviceProblem P{};
   ParamSet ps[2]{};
   LmState* d_state = nullptr;
-  LmState* h_state = nullptr;   // pinned
+  LmState* h_state = nullptr;       // pinned: [0] final state, [1], [2] pipelined polls
+  int* h_err = nullptr;             // pinned: exchange error flag
+  char* h_trace = nullptr;          // pinned staging of the trace block
   Trace trace{};
+  char* d_trace = nullptr;          // [4][capacity] doubles | [capacity] ints
   int trace_capacity = 0;
-  // owned device buffers
-  std::vector<void*> owned;
-  double2* d_obs_in = nullptr;   // staging: reference layout [V][K]
+  bool x_in_set1 = false;           // host-side knowledge of LmState::cur after the last run
+  // device memory
+  Arena arena;
+  std::vector<void*> extra;         // later allocations (forced Schur form, bigger trace)
+  double2* d_obs_in = nullptr;      // staging: reference layout [V][K]
   double2* d_obsT = nullptr;
   double* d_scale_e = nullptr;
   double* d_scale_c = nullptr;
@@ -122,70 +217,60 @@ struct tscm_solver {
   double* d_rpart = nullptr;
   double* d_Sr = nullptr;
   double* d_yc = nullptr;
-  double* d_mom = nullptr;       // [ntiles][188][32] moments of the evaluation in flight (k_eval5 -> k_view_blocks)
-  double* d_fcg = nullptr;       // [ntiles][27][32] frame constants of the evaluation in flight
+  double* d_mom = nullptr;          // [ntiles][188][32] moments of the evaluation in flight (k_eval5 -> k_view_blocks)
+  double* d_fcg = nullptr;          // [ntiles][27][32] frame constants of the evaluation in flight
   double* d_bs_part = nullptr;
   double* d_gmax_part = nullptr;
   double* d_xn2_part = nullptr;
   unsigned int* d_ticket = nullptr;
   double* d_comm_stage = nullptr;   // NCCL fallback: staged evaluation record (+ gmax)
-  double* d_dbg_lhs = nullptr;
-  double* d_dbg_rhs = nullptr;
+  char* d_blob = nullptr;
+  // Schur elimination
   SchurArgs schur{};
   Schur2Args schur2{};
   SchurSplitArgs split{};
-  bool split_ok = false;
-  size_t split_smem = 0;
-  bool split_frames8 = false;    // dense rows produced by k_pair_frames + k_pair_blocks
-  bool pairs_ok = false;         // sparse visibility: per-camera-pair Schur update (tscm_schur_pairs.cuh)
   PairArgs pairs{};
-  bool schur2_ok = false;
+  int schur_form = kSchurAuto;      // the form in use (never kSchurAuto after creation)
+  size_t split_smem = 0, schur2_smem = 0;
   int schur2_nt = 0;
-  size_t schur2_smem = 0;
-  int schur_nblk = 0, schur_nt = 256, schur_ept = 20;
-  size_t schur_smem = 0, solve_smem = 0, eval3_smem = 0, eval4_smem = 0, eval5_smem = 0;
-  int eval_variant = 5;
-  int want_err = 0;   // accumulate sum sqrt(s) (reprojection read-out only)
-  int prof = 0;
+  int schur_nblk = 0, schur_nt = 256, schur_ept = 1;
+  SolveDims solve{};
+  size_t eval5_smem = 0;
+  int want_err = 0;                 // accumulate sum sqrt(s) (reprojection read-out only)
   int bs_nblk = 0, fg_nblk = 0;
-  // graph of one LM iteration
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t graph_exec = nullptr;
+  // graph of one LM iteration (and of kGroupIters iterations, group shards only)
+  cudaGraphExec_t graph_exec = nullptr, graph_exec_n = nullptr;
   bool graph_dirty = true;
+  int launches_per_iter = 0;
+  cudaEvent_t poll_ev[2] = {nullptr, nullptr};
   // comm
   NcclApi::Comm comm = nullptr;
   int rank = 0, num_ranks = 1;
-  // NVLink peer-memory exchange (tscm_p2p.cuh): mailbox of this rank, IPC mappings of the peers
+  // NVLink peer-memory exchange (tscm_p2p.cuh): mailbox of this rank, mappings of the peers
   bool p2p_on = false;
-  double* d_mailbox = nullptr;
+  double* d_mailbox = nullptr;      // own cudaMalloc: its IPC handle is exported
   unsigned long long* d_p2p_seq = nullptr;
   unsigned int* d_p2p_ticket = nullptr;
   int* d_p2p_err = nullptr;
-  void* p2p_peer[kP2PMaxRanks] = {};
+  void* p2p_ipc[kP2PMaxRanks] = {};
   P2PArgs p2p{};
   int64_t launches = 0;
-  // host copies needed later
+  // host copies
   int C = 0, F = 0, K = 0, V = 0;
-
-  template <typename T>
-  int alloc(T** p, size_t n) {
-    CUDA_TRY(cudaMalloc((void**)p, std::max<size_t>(1, n) * sizeof(T)));
-    CUDA_TRY(cudaMemsetAsync(*p, 0, std::max<size_t>(1, n) * sizeof(T), stream));
-    owned.push_back(*p);
-    return TSCM_OK;
-  }
-  template <typename T>
-  int put(const T** p, const std::vector<T>& v) {
-    T* d = nullptr;
-    int rc = upload(&d, v);
-    if (rc) return rc;
-    owned.push_back(d);
-    *p = d;
-    return TSCM_OK;
-  }
+  std::vector<int> h_view_camera, h_view_frame, h_frame_ptr, h_frame_views, h_live_off;
+  std::vector<double> h_board;
+  int fixed_camera = 0;
+  std::vector<double> obs_count;    // [C] observations per camera: local (ranks) or global (group shards)
+  // group (num_gpus > 1): this object is a facade, the shards do the work
+  std::vector<tscm_solver*> kids;
+  std::vector<int> kid_frame;       // [n + 1] frame range of every shard
+  std::vector<std::vector<ObsSegment>> kid_seg;
+  bool is_kid = false;
 };
 
 namespace {
+
+constexpr int kGroupIters = 4;      // LM iterations per graph launch of a group shard
 
 void fill_lm_options(const tscm_options& o, LmOptions& lm) {
   lm.max_num_iterations = o.max_num_iterations;
@@ -205,15 +290,35 @@ void fill_lm_options(const tscm_options& o, LmOptions& lm) {
   lm.ptol_needs_success = o.parameter_tolerance_needs_successful_step;
   lm.disable_tolerances = o.disable_tolerances;
 }
+bool lm_equal(const LmOptions& a, const LmOptions& b) {
+  return a.max_num_iterations == b.max_num_iterations && a.function_tolerance == b.function_tolerance &&
+         a.gradient_tolerance == b.gradient_tolerance && a.parameter_tolerance == b.parameter_tolerance &&
+         a.initial_radius == b.initial_radius && a.max_radius == b.max_radius && a.min_radius == b.min_radius &&
+         a.min_relative_decrease == b.min_relative_decrease && a.min_lm_diagonal == b.min_lm_diagonal &&
+         a.max_lm_diagonal == b.max_lm_diagonal &&
+         a.max_num_consecutive_invalid_steps == b.max_num_consecutive_invalid_steps &&
+         a.jacobi_scaling == b.jacobi_scaling && a.loss_type == b.loss_type && a.loss_scale == b.loss_scale &&
+         a.ptol_needs_success == b.ptol_needs_success && a.disable_tolerances == b.disable_tolerances;
+}
 
-int validate_problem(const tscm_problem* p) {
+int validate_options(const tscm_options* o) {
+  if (o->max_num_iterations < 0 || !(o->initial_trust_region_radius > 0.0) ||
+      (o->loss_type != TSCM_LOSS_NONE && !(o->loss_scale > 0.0)) || o->loss_type < 0 ||
+      o->loss_type > TSCM_LOSS_CAUCHY || o->num_gpus < 0 || o->num_gpus > kP2PMaxRanks) {
+    set_error("invalid options");
+    return TSCM_ERR_INVALID_ARGUMENT;
+  }
+  return TSCM_OK;
+}
+
+int validate_problem(const tscm_problem* p, bool need_obs) {
   if (!p) { set_error("problem is NULL"); return TSCM_ERR_INVALID_ARGUMENT; }
   if (p->num_cameras <= 0 || p->num_frames <= 0 || p->corners_per_board <= 0 || p->num_views <= 0) {
     set_error("empty problem: C=%d F=%d K=%d views=%d", p->num_cameras, p->num_frames,
               p->corners_per_board, p->num_views);
     return TSCM_ERR_INVALID_ARGUMENT;
   }
-  if (!p->board_xy || !p->view_camera || !p->view_frame || !p->obs_xy) {
+  if (!p->board_xy || !p->view_camera || !p->view_frame || (need_obs && !p->obs_xy)) {
     set_error("problem has NULL arrays");
     return TSCM_ERR_INVALID_ARGUMENT;
   }
@@ -245,34 +350,31 @@ int validate_problem(const tscm_problem* p) {
   return TSCM_OK;
 }
 
-// The residual + Jacobian + normal-equation kernel: k_eval4 (moment form, default) or
-// k_eval3 (rank-1 sweeps of full Jacobian rows; TSCM_EVAL_VARIANT=3, kept for A/B timing).
+// ---------------------------------------------------------------------------
+// kernel launches of one shard
+// ---------------------------------------------------------------------------
+// The residual + Jacobian + normal-equation pass: k_eval5 (moments of every view) followed by
+// k_view_blocks (per-view blocks from the moments).
 // part: 0 = the whole pass, 1 = k_eval5 only, 2 = k_view_blocks only (stage timing).
 void launch_eval_kernel(tscm_solver* s, int which, int part = 0) {
   const DeviceProblem& P = s->P;
-  if (s->eval_variant == 5) {
-    const int ntiles = (P.V + 31) / 32;
-    if (part != 2)
-      k_eval5<<<std::min(ntiles, s->sm_count), kE5Threads, s->eval5_smem, s->stream>>>(
-          P, s->ps[0], s->ps[1], s->d_state, which, s->lm, s->want_err, s->d_mom, s->d_fcg);
-    if (part != 1)
-      k_view_blocks<<<ntiles, kVbThreads, vb_smem_bytes(), s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which,
-                                                                        s->d_mom, s->d_fcg);
-    if (part == 0) s->launches += 1;
-  } else if (part == 2) {
-    return;
-  } else if (s->eval_variant == 3)
-    k_eval3<<<(P.V + 31) / 32, kE3Threads, s->eval3_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state,
-                                                                      which, s->lm, s->prof);
-  else
-    k_eval4<<<(P.V + 31) / 32, kE3Threads, s->eval4_smem, s->stream>>>(P, s->ps[0], s->ps[1], s->d_state,
-                                                                      which, s->lm, s->want_err);
+  const int ntiles = (P.V + 31) / 32;
+  if (part != 2) {
+    k_eval5<<<std::min(ntiles, s->sm_count), kE5Threads, s->eval5_smem, s->stream>>>(
+        P, s->ps[0], s->ps[1], s->d_state, which, s->lm, s->want_err, s->d_mom, s->d_fcg);
+    s->launches += 1;
+  }
+  if (part != 1) {
+    k_view_blocks<<<ntiles, kVbThreads, vb_smem_bytes(), s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which,
+                                                                      s->d_mom, s->d_fcg);
+    s->launches += 1;
+  }
 }
 
 // which: 0 = current, 1 = candidate (relative to st->cur); 2/3 = absolute set 0/1.
-// prep: run k_prep_cams first (the iteration graph does not: k_solve already wrote the
-// candidate's constants).  decide: fold the accept/reject decision into the tail block
-// (single GPU; with several GPUs the records are all-reduced first and k_decide follows).
+// prep: run k_prep_cams first (the iteration graph does not: k_backsub's extra block already
+// wrote the candidate's constants).  decide: fold the accept/reject decision into the tail block
+// (single GPU; with several GPUs the records are exchanged first and the decision follows).
 void launch_evaluation(tscm_solver* s, int which, int initial, bool prep = true, bool decide = false) {
   const DeviceProblem& P = s->P;
   cudaStream_t st = s->stream;
@@ -287,12 +389,11 @@ void launch_evaluation(tscm_solver* s, int which, int initial, bool prep = true,
   a.ticket = s->d_ticket; a.initial = initial; a.decide = decide ? 1 : 0;
   k_post_eval<<<P.C + s->fg_nblk, kPostThreads, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which,
                                                             s->lm, s->trace, a);
-  s->launches += 2;
+  s->launches += 1;
 }
 
-// Global sums of the evaluation record.  The record lives in ps[sel].comm; the
-// selection is only known on the device, so both candidates are reduced when
-// `which` is relative (they are tiny: C*107+4 doubles).
+// Global sums of the evaluation record.  The record lives in ps[sel].comm; the selection is
+// only known on the device.
 int launch_eval_allreduce(tscm_solver* s, int which, bool decide = false) {
   if (s->num_ranks <= 1) return TSCM_OK;
   if (s->p2p_on) {
@@ -322,92 +423,86 @@ int launch_eval_allreduce(tscm_solver* s, int which, bool decide = false) {
 void launch_schur(tscm_solver* s, double radius_override) {
   SchurArgs a = s->schur;
   a.radius_override = radius_override;
-  if (s->split_ok) {
+  if (s->schur_form == kSchurRows) {
     SchurSplitArgs b = s->split;
     b.a = a;
-    if (s->split_frames8) {
-      // per-frame chain with 8 lanes per frame, then the rows with one thread per column
-      k_pair_frames<<<(s->F + 31) / 32, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
-      k_pair_blocks<<<(s->V * 16 + 255) / 256, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, b);
-      s->launches += 1;
-    } else {
-      k_schur_frames<<<(s->F + 7) / 8, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
-    }
+    k_schur_frames<<<(s->F + 7) / 8, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
     if (s->schur_ept == 1)
       k_schur_update<1><<<s->schur_nblk, s->schur_nt, s->split_smem, s->stream>>>(s->P, s->d_state, b);
     else
       k_schur_update<2><<<s->schur_nblk, s->schur_nt, s->split_smem, s->stream>>>(s->P, s->d_state, b);
-    s->launches += 1;
-  } else if (s->pairs_ok) {
+    s->launches += 2;
+  } else if (s->schur_form == kSchurPairs) {
     SchurSplitArgs b = s->split;
     b.a = a;
     k_pair_frames<<<(s->F + 31) / 32, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
     k_pair_blocks<<<(s->V * 16 + 255) / 256, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, b);
     k_schur_pairs2<<<s->sm_count, kPairWarps * 32, kPair2Smem, s->stream>>>(s->d_state, s->pairs);
     k_reduce_pairs<<<s->pairs.npairs, kPairReduceGroups * kPairPart, 0, s->stream>>>(s->P, s->d_state, s->pairs);
-    s->launches += 3;
-  } else if (s->schur2_ok) {
+    s->launches += 4;
+  } else {
     Schur2Args b = s->schur2;
     b.a = a;
     k_schur2<<<s->schur_nblk, s->schur2_nt, s->schur2_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
                                                                         s->d_state, s->lm, b);
-  } else if (s->schur_ept == 1)
-    k_schur<1, 512><<<s->schur_nblk, s->schur_nt, s->schur_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
-                                                                             s->d_state, s->lm, a);
-  else
-    k_schur<2, 768><<<s->schur_nblk, s->schur_nt, s->schur_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
-                                                                             s->d_state, s->lm, a);
+    s->launches += 1;
+  }
   const int n = s->P.Q + s->P.NL;
-  const int nparts = s->pairs_ok ? 1 : s->schur_nblk;   // k_reduce_pairs leaves one complete partial
+  const int nparts = s->schur_form == kSchurPairs ? 1 : s->schur_nblk;   // k_reduce_pairs leaves one complete partial
+  AssembleArgs g;
+  g.scale_c = s->d_scale_c; g.radius_override = radius_override; g.nbk = s->solve.nbk;
+  g.add_cam = (s->num_ranks > 1 && !s->p2p_on) ? 0 : 1;                  // NCCL: after the all-reduce
   if (s->p2p_on && s->num_ranks > 1)
-    k_reduce_s_p2p<<<(n + 31) / 32, kReduceThreads, 0, s->stream>>>(s->P, s->d_state, s->d_Spart, s->d_rpart,
-                                                                    nparts, s->d_Sr, s->p2p);
+    k_reduce_s_p2p<<<(n + 31) / 32, kReduceThreads, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm,
+                                                                    s->d_Spart, s->d_rpart, nparts, s->d_Sr, g, s->p2p);
   else
-    k_reduce_s<<<(n + 31) / 32, kReduceThreads, 0, s->stream>>>(s->P, s->d_state, s->d_Spart, s->d_rpart,
-                                                                nparts, s->d_Sr);
-  s->launches += 2;
+    k_reduce_s<<<(n + 31) / 32, kReduceThreads, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm,
+                                                                s->d_Spart, s->d_rpart, nparts, s->d_Sr, g);
+  s->launches += 1;
 }
 
-int launch_schur_allreduce(tscm_solver* s) {
+int launch_schur_allreduce(tscm_solver* s, double radius_override) {
   if (s->num_ranks <= 1 || s->p2p_on) return TSCM_OK;   // P2P: exchanged inside k_reduce_s_p2p
   NcclApi& n = nccl();
-  int rc = n.AllReduce(s->d_Sr, s->d_Sr, (size_t)s->P.Q + s->P.NL, kNcclFloat64, kNcclSum, s->comm, s->stream);
+  int rc = n.AllReduce(s->d_Sr, s->d_Sr, (size_t)s->solve.ntile * 16, kNcclFloat64, kNcclSum, s->comm, s->stream);
   if (rc) { set_error("ncclAllReduce(S) failed: %d", rc); return TSCM_ERR_COMM; }
+  AssembleArgs g;
+  g.scale_c = s->d_scale_c; g.radius_override = radius_override; g.nbk = s->solve.nbk; g.add_cam = 1;
+  const int cnt = s->P.Q + s->P.NL;
+  k_add_cam_terms<<<(cnt + 255) / 256, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, s->d_Sr, g);
+  s->launches += 1;
   return TSCM_OK;
 }
 
-void launch_solve(tscm_solver* s, double radius_override, bool debug) {
-  double* dl = debug ? s->d_dbg_lhs : nullptr;
-  double* dr = debug ? s->d_dbg_rhs : nullptr;
-  const int bmax = (s->P.NL + 1 + 31) / 32;
-#define TSCM_SOLVE(B)                                                                          \
-  k_solve<B><<<1, kSolveThreads, s->solve_smem, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, \
-      s->lm, s->d_Sr, s->d_scale_c, s->d_yc, radius_override, dl, dr, s->prof)
-  if (bmax <= 2) TSCM_SOLVE(2);
-  else if (bmax <= 4) TSCM_SOLVE(4);
-  else TSCM_SOLVE(7);
-#undef TSCM_SOLVE
+void launch_solve(tscm_solver* s) {
+  const SolveDims& d = s->solve;
+  const int prof = (g_debug & 2) ? 1 : 0;
+  if (d.T == 1)
+    k_solve<1, 4><<<1, d.NT, d.smem, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->d_Sr, s->d_scale_c,
+                                                   s->d_yc, prof);
+  else
+    k_solve<4, 7><<<1, d.NT, d.smem, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->d_Sr, s->d_scale_c,
+                                                   s->d_yc, prof);
   s->launches += 1;
 }
 
 void launch_backsub(tscm_solver* s) {
-  k_backsub<<<s->bs_nblk, kBacksubThreads, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state,
-                                                          s->schur, s->d_yc, s->d_bs_part, s->bs_nblk,
-                                                          s->split_ok ? s->split.Wg : nullptr);
+  // one extra block prepares the derived constants of the candidate cameras
+  k_backsub<<<s->bs_nblk + 1, kBacksubThreads, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state,
+                                                              s->schur, s->d_yc, s->d_bs_part, s->bs_nblk,
+                                                              s->schur_form == kSchurRows ? s->split.Wg : nullptr);
   s->launches += 1;
 }
 
 int launch_iteration(tscm_solver* s) {
   launch_schur(s, 0.0);
-  int rc = launch_schur_allreduce(s);
-  if (rc) return rc;
-  launch_solve(s, 0.0, false);
+  RC_TRY(launch_schur_allreduce(s, 0.0));
+  launch_solve(s);
   launch_backsub(s);
   const bool single = s->num_ranks <= 1;
   launch_evaluation(s, 1, 0, /*prep=*/false, /*decide=*/single);
   if (!single) {
-    rc = launch_eval_allreduce(s, 1, /*decide=*/true);
-    if (rc) return rc;
+    RC_TRY(launch_eval_allreduce(s, 1, /*decide=*/true));
     if (!s->p2p_on) {
       k_decide<<<1, 32, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, s->trace);
       s->launches += 1;
@@ -416,32 +511,39 @@ int launch_iteration(tscm_solver* s) {
   return TSCM_OK;
 }
 
-int launches_per_iteration(const tscm_solver* s) {
-  return (s->num_ranks <= 1 ? 6 : (s->p2p_on ? 7 : 9)) + (s->split_ok ? (s->split_frames8 ? 2 : 1) : (s->pairs_ok ? 3 : 0)) + (s->eval_variant == 5 ? 1 : 0);
+int capture_iterations(tscm_solver* s, int iters, cudaGraphExec_t* out) {
+  cudaGraph_t graph = nullptr;
+  const int64_t before = s->launches;
+  CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = TSCM_OK;
+  for (int k = 0; k < iters && !rc; ++k) rc = launch_iteration(s);
+  const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+  s->launches_per_iter = (int)((s->launches - before) / std::max(1, iters));
+  s->launches = before;
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return TSCM_ERR_CUDA; }
+  const cudaError_t ei = cudaGraphInstantiate(out, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ei != cudaSuccess) { set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); return TSCM_ERR_CUDA; }
+  return TSCM_OK;
 }
 
 int ensure_graph(tscm_solver* s) {
   if (!s->graph_dirty && s->graph_exec) return TSCM_OK;
   if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
-  if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
-  const int64_t before = s->launches;
-  CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-  int rc = launch_iteration(s);
-  cudaError_t e = cudaStreamEndCapture(s->stream, &s->graph);
-  s->launches = before;
-  if (rc) return rc;
-  if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return TSCM_ERR_CUDA; }
-  CUDA_TRY(cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
+  if (s->graph_exec_n) { cudaGraphExecDestroy(s->graph_exec_n); s->graph_exec_n = nullptr; }
+  RC_TRY(capture_iterations(s, 1, &s->graph_exec));
+  if (s->is_kid) RC_TRY(capture_iterations(s, kGroupIters, &s->graph_exec_n));
   s->graph_dirty = false;
   return TSCM_OK;
 }
 
-// Iteration zero: evaluate the initial point held in parameter set 0.
+// Iteration zero: evaluate the initial point held in parameter set 0.  Asynchronous.
 int run_initial(tscm_solver* s) {
   CUDA_TRY(cudaMemsetAsync(s->d_state, 0, sizeof(LmState), s->stream));
+  CUDA_TRY(cudaMemsetAsync(s->d_p2p_err, 0, sizeof(int), s->stream));
   launch_evaluation(s, 2, 1);
-  int rc = launch_eval_allreduce(s, 2);
-  if (rc) return rc;
+  RC_TRY(launch_eval_allreduce(s, 2));
   const int n = s->P.F * 6 + s->P.C * 13;
   k_jacobi_scale<<<(n + 255) / 256, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm,
                                                         s->d_scale_e, s->d_scale_c);
@@ -457,16 +559,37 @@ int fetch_state(tscm_solver* s) {
   return TSCM_OK;
 }
 
-int ensure_trace(tscm_solver* s, int capacity) {
-  if (capacity <= s->trace_capacity) return TSCM_OK;
-  int rc;
-  if ((rc = s->alloc(&s->trace.cost, capacity))) return rc;
-  if ((rc = s->alloc(&s->trace.radius, capacity))) return rc;
-  if ((rc = s->alloc(&s->trace.gmax, capacity))) return rc;
-  if ((rc = s->alloc(&s->trace.step_norm, capacity))) return rc;
-  if ((rc = s->alloc(&s->trace.flags, capacity))) return rc;
+// x always starts a run / a timed stage in parameter set 0
+int move_x_to_set0(tscm_solver* k) {
+  if (!k->x_in_set1) return TSCM_OK;
+  CUDA_TRY(cudaMemcpyAsync(k->ps[0].intr, k->ps[1].intr, (size_t)k->C * 9 * sizeof(double), cudaMemcpyDeviceToDevice, k->stream));
+  CUDA_TRY(cudaMemcpyAsync(k->ps[0].cam_rt, k->ps[1].cam_rt, (size_t)k->C * 6 * sizeof(double), cudaMemcpyDeviceToDevice, k->stream));
+  CUDA_TRY(cudaMemcpyAsync(k->ps[0].board_rt, k->ps[1].board_rt, (size_t)k->F * 6 * sizeof(double), cudaMemcpyDeviceToDevice, k->stream));
+  k->x_in_set1 = false;
+  return TSCM_OK;
+}
+
+size_t trace_bytes(int capacity) { return (size_t)capacity * (4 * sizeof(double) + sizeof(int)); }
+void wire_trace(tscm_solver* s, int capacity) {
+  double* d = reinterpret_cast<double*>(s->d_trace);
+  s->trace.cost = d; s->trace.radius = d + capacity; s->trace.gmax = d + 2 * (size_t)capacity;
+  s->trace.step_norm = d + 3 * (size_t)capacity;
+  s->trace.flags = reinterpret_cast<int*>(d + 4 * (size_t)capacity);
   s->trace.capacity = capacity;
   s->trace_capacity = capacity;
+}
+int ensure_trace(tscm_solver* s, int capacity) {
+  if (capacity <= s->trace_capacity) return TSCM_OK;
+  capacity = std::max(capacity, 128);
+  char* d = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d, trace_bytes(capacity)));
+  CUDA_TRY(cudaMemsetAsync(d, 0, trace_bytes(capacity), s->stream));
+  s->extra.push_back(d);
+  s->d_trace = d;
+  if (s->h_trace) cudaFreeHost(s->h_trace);
+  s->h_trace = nullptr;
+  CUDA_TRY(cudaMallocHost((void**)&s->h_trace, trace_bytes(capacity)));
+  wire_trace(s, capacity);
   s->graph_dirty = true;
   return TSCM_OK;
 }
@@ -475,12 +598,571 @@ const char* termination_name(int t) {
   return t == TSCM_CONVERGENCE ? "CONVERGENCE" : t == TSCM_NO_CONVERGENCE ? "NO_CONVERGENCE" : "FAILURE";
 }
 
+// ---------------------------------------------------------------------------
+// Schur-elimination form: tables and buffers
+// ---------------------------------------------------------------------------
+double visibility_fill(const tscm_solver* s) {
+  // live columns of the views over F x NL
+  double cols = 0.0;
+  for (int v = 0; v < s->V; ++v) {
+    const int m = s->h_view_camera[v];
+    cols += s->h_live_off[m + 1] - s->h_live_off[m];
+  }
+  return cols / ((double)s->F * s->P.NL);
+}
+
+int choose_schur_form(const tscm_solver* s) {
+  const int NLp = s->schur.NLp, ntiles = s->schur.ntiles;
+  const size_t split_smem = (size_t)(2 * (2 * kSchurFB * 6 * NLp + kSchurFB * 6)) * sizeof(double);
+  if (visibility_fill(s) >= 0.4 && split_smem <= s->smem_optin) return kSchurRows;
+  const int schur2_nt = kSchurFB * 32 + (ntiles + 31) / 32 * 32;
+  const size_t schur2_smem = (size_t)(2 * (2 * kSchurFB * 6 * NLp + kSchurFB * 6) + kSchurFB * 64) * sizeof(double);
+  if (schur2_nt <= 640 && schur2_smem <= s->smem_optin) return kSchurFused;
+  return kSchurPairs;
+}
+
+// Registers the tables (blob) and buffers (arena) of `form`; pointers are valid after
+// arena.commit() + blob.upload().
+int plan_schur(tscm_solver* s, int form, Arena& arena, Blob& blob) {
+  const int F = s->F, V = s->V, C = s->C, NL = s->P.NL, NLp = s->schur.NLp, ntiles = s->schur.ntiles;
+  if (V >= (1 << 27)) { set_error("too many views"); return TSCM_ERR_UNSUPPORTED; }
+  if (form == kSchurRows || form == kSchurFused) {
+    // per-frame column descriptors: live columns of the frame's views, camera order
+    std::vector<int> col_ptr(F + 1, 0);
+    for (int f = 0; f < F; ++f) {
+      int n = 0;
+      for (int q = s->h_frame_ptr[f]; q < s->h_frame_ptr[f + 1]; ++q) {
+        const int m = s->h_view_camera[s->h_frame_views[q]];
+        n += s->h_live_off[m + 1] - s->h_live_off[m];
+      }
+      col_ptr[f + 1] = col_ptr[f] + n;
+    }
+    const size_t ncol = (size_t)col_ptr[F];
+    std::vector<int> col_src(ncol);
+    std::vector<short> col_g(ncol), col_sidx(ncol);
+    for (int f = 0; f < F; ++f) {
+      size_t o = (size_t)col_ptr[f];
+      for (int q = s->h_frame_ptr[f]; q < s->h_frame_ptr[f + 1]; ++q) {
+        const int v = s->h_frame_views[q], m = s->h_view_camera[v];
+        const int n = s->h_live_off[m + 1] - s->h_live_off[m];
+        for (int k = 0; k < n; ++k, ++o) {
+          const int kk = n == 13 ? k : k + 6;
+          col_src[o] = v * 16 + kk;
+          col_g[o] = (short)(s->h_live_off[m] + k);
+          col_sidx[o] = (short)(m * 13 + kk);
+        }
+      }
+    }
+    blob.add(&s->schur2.col_ptr, col_ptr);
+    blob.add(&s->schur2.col_src, col_src);
+    blob.add(&s->schur2.col_g, col_g);
+    blob.add(&s->split.col_sidx, col_sidx);
+  }
+  if (form == kSchurRows) {
+    s->split_smem = (size_t)(2 * (2 * kSchurFB * 6 * NLp + kSchurFB * 6)) * sizeof(double);
+    if (s->split_smem > s->smem_optin) { set_error("dense-row Schur form needs %zu bytes of shared memory", s->split_smem); return TSCM_ERR_UNSUPPORTED; }
+    arena.want(&s->split.Wg, (size_t)F * 6 * NLp);
+    arena.want(&s->split.Yg, (size_t)F * 6 * NLp);
+    arena.want(&s->split.zg, ((size_t)F + 8) * 6);
+    arena.want(&s->split.fact, (size_t)F * 32);
+  } else if (form == kSchurFused) {
+    s->schur2_nt = kSchurFB * 32 + (ntiles + 31) / 32 * 32;
+    s->schur2_smem = (size_t)(2 * (2 * kSchurFB * 6 * NLp + kSchurFB * 6) + kSchurFB * 64) * sizeof(double);
+    if (s->schur2_nt > 640 || s->schur2_smem > s->smem_optin) {
+      set_error("fused Schur form cannot hold a reduced system of %d live parameters", NL);
+      return TSCM_ERR_UNSUPPORTED;
+    }
+  } else if (form == kSchurPairs) {
+    static_assert(sizeof(PairEntry) == sizeof(int2) && sizeof(PairRange) == sizeof(int2), "int2 layout");
+    if (kPair2Smem > s->smem_optin) { set_error("pair Schur form needs %zu bytes of shared memory", (size_t)kPair2Smem); return TSCM_ERR_UNSUPPORTED; }
+    const PairLists lists = build_pair_lists(C, F, V, s->h_view_camera.data(), s->h_view_frame.data(), kPairChunk);
+    std::vector<short> loff(C + 1);
+    for (int m = 0; m <= C; ++m) loff[m] = (short)s->h_live_off[m];
+    s->pairs.nitems = (int)lists.item_range.size();
+    s->pairs.npairs = (int)lists.pair_a.size();
+    blob.add(reinterpret_cast<const PairEntry**>(&s->pairs.ent), lists.ent);
+    blob.add(reinterpret_cast<const PairRange**>(&s->pairs.item_range), lists.item_range);
+    blob.add(&s->pairs.pair_item, lists.pair_item);
+    blob.add(&s->pairs.pair_items, lists.pair_items);
+    blob.add(&s->pairs.pair_a, lists.pair_a);
+    blob.add(&s->pairs.pair_b, lists.pair_b);
+    blob.add(&s->pairs.live_off, loff);
+    arena.want(&s->pairs.part, (size_t)std::max(1, s->pairs.nitems) * kPairPart);
+    arena.want(&s->split.Wv, (size_t)V * 96);
+    arena.want(&s->split.Yv, (size_t)V * 96);
+    arena.want(&s->split.fact, (size_t)F * 32);
+  } else {
+    set_error("unknown Schur form %d", form);
+    return TSCM_ERR_INVALID_ARGUMENT;
+  }
+  return TSCM_OK;
+}
+
+int set_smem_attr(const void* fn, size_t bytes) {
+  if (bytes > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return TSCM_OK;
+}
+
+// after commit + upload
+int wire_schur(tscm_solver* s, int form) {
+  s->split.col_ptr = s->schur2.col_ptr; s->split.col_src = s->schur2.col_src; s->split.col_g = s->schur2.col_g;
+  if (form == kSchurRows) {
+    s->split.Wv = nullptr; s->split.Yv = nullptr;
+    RC_TRY(set_smem_attr((const void*)k_schur_update<1>, s->split_smem));
+    RC_TRY(set_smem_attr((const void*)k_schur_update<2>, s->split_smem));
+  } else if (form == kSchurFused) {
+    RC_TRY(set_smem_attr((const void*)k_schur2, s->schur2_smem));
+  } else {
+    s->pairs.Wv = s->split.Wv; s->pairs.Yv = s->split.Yv;
+    s->pairs.Sout = s->d_Spart; s->pairs.rout = s->d_rpart;
+    RC_TRY(set_smem_attr((const void*)k_schur_pairs2, kPair2Smem));
+  }
+  s->schur_form = form;
+  s->graph_dirty = true;
+  return TSCM_OK;
+}
+
+void free_shard(tscm_solver* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  if (s->graph_exec_n) cudaGraphExecDestroy(s->graph_exec_n);
+  if (s->comm && nccl().ok) nccl().CommDestroy(s->comm);
+  for (int r = 0; r < kP2PMaxRanks; ++r)
+    if (s->p2p_ipc[r]) cudaIpcCloseMemHandle(s->p2p_ipc[r]);
+  for (int k = 0; k < 2; ++k)
+    if (s->poll_ev[k]) cudaEventDestroy(s->poll_ev[k]);
+  if (s->arena.base) cudaFree(s->arena.base);
+  for (void* p : s->extra) cudaFree(p);
+  if (s->d_mailbox) cudaFree(s->d_mailbox);
+  if (s->h_state) cudaFreeHost(s->h_state);
+  if (s->h_err) cudaFreeHost(s->h_err);
+  if (s->h_trace) cudaFreeHost(s->h_trace);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int upload_observations(tscm_solver* s, const double* obs_xy, const std::vector<ObsSegment>* segs) {
+  CUDA_TRY(cudaSetDevice(s->device));
+  const size_t view_bytes = (size_t)s->K * sizeof(double2);
+  if (!segs) {
+    CUDA_TRY(cudaMemcpyAsync(s->d_obs_in, obs_xy, (size_t)s->V * view_bytes, cudaMemcpyHostToDevice, s->stream));
+  } else {
+    for (const ObsSegment& g : *segs)
+      CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(s->d_obs_in) + (size_t)g.dst_view * view_bytes,
+                               reinterpret_cast<const char*>(obs_xy) + (size_t)g.src_view * view_bytes,
+                               (size_t)g.count * view_bytes, cudaMemcpyHostToDevice, s->stream));
+  }
+  dim3 grid((s->V + 31) / 32, (s->K + 31) / 32), block(32, 8);
+  k_transpose_obs<<<grid, block, 0, s->stream>>>(s->d_obs_in, s->d_obsT, s->V, s->K, s->P.Vpad);
+  s->launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return TSCM_OK;
+}
+
+// One shard on one device.  p->obs_xy may be NULL (uploaded later).
+int create_shard(const tscm_problem* p, const tscm_options* o, int device, bool is_kid, tscm_solver** out) {
+  *out = nullptr;
+  const auto t0 = Clock::now();
+  auto lap = [&](const char* what) {
+    if (g_debug & 1) std::fprintf(stderr, "[tscm create] %-28s %8.2f ms\n", what, ms_since(t0));
+  };
+  DeviceInfo info;
+  RC_TRY(device_info(device, &info));
+  if (info.major < 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, info.major, info.minor);
+    return TSCM_ERR_NO_DEVICE;
+  }
+  CUDA_TRY(cudaSetDevice(device));
+  tscm_solver* s = new tscm_solver();
+  s->device = device;
+  s->sm_count = info.sm_count;
+  s->smem_optin = info.smem_optin;
+  s->is_kid = is_kid;
+  s->options = *o;
+  fill_lm_options(*o, s->lm);
+#define TRY_S(x) do { const int rc_ = (x); if (rc_) { free_shard(s); return rc_; } } while (0)
+#define CUDA_S(x) do { const cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); free_shard(s); return TSCM_ERR_CUDA; } } while (0)
+  CUDA_S(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  const int C = p->num_cameras, F = p->num_frames, K = p->corners_per_board, V = p->num_views;
+  s->C = C; s->F = F; s->K = K; s->V = V; s->fixed_camera = p->fixed_camera;
+  DeviceProblem& P = s->P;
+  P.C = C; P.F = F; P.K = K; P.V = V; P.fixed_camera = p->fixed_camera;
+  P.Vpad = (V + 31) / 32 * 32;
+
+  // ---- index tables (host) -------------------------------------------------------------
+  s->h_view_camera.assign(p->view_camera, p->view_camera + V);
+  s->h_view_frame.assign(p->view_frame, p->view_frame + V);
+  s->h_board.assign(p->board_xy, p->board_xy + 2 * (size_t)K);
+  std::vector<int>& live_off = s->h_live_off;
+  live_off.assign(C + 1, 0);
+  for (int c = 0; c < C; ++c) live_off[c + 1] = live_off[c] + (c == p->fixed_camera ? 7 : 13);
+  const int NL = live_off[C];
+  P.NL = NL; P.Q = NL * (NL + 1) / 2;
+  if (NL > 216) {
+    set_error("reduced system of %d live parameters exceeds this build's limit (216, i.e. 17 cameras)", NL);
+    free_shard(s); return TSCM_ERR_UNSUPPORTED;
+  }
+  std::vector<short> live_cam(NL), live_kk(NL);
+  for (int c = 0; c < C; ++c)
+    for (int k = 0; k < live_off[c + 1] - live_off[c]; ++k) {
+      live_cam[live_off[c] + k] = (short)c;
+      live_kk[live_off[c] + k] = (short)(c == p->fixed_camera ? k + 6 : k);
+    }
+  std::vector<int>& frame_ptr = s->h_frame_ptr;
+  std::vector<int>& frame_views = s->h_frame_views;
+  frame_ptr.assign(F + 1, 0);
+  frame_views.assign(V, 0);
+  std::vector<int> cam_view_begin(C + 1, 0);
+  for (int v = 0; v < V; ++v) { frame_ptr[p->view_frame[v] + 1]++; cam_view_begin[p->view_camera[v] + 1]++; }
+  for (int i = 0; i < F; ++i) frame_ptr[i + 1] += frame_ptr[i];
+  for (int c = 0; c < C; ++c) cam_view_begin[c + 1] += cam_view_begin[c];
+  {
+    std::vector<int> fill(frame_ptr.begin(), frame_ptr.end() - 1);
+    for (int v = 0; v < V; ++v) frame_views[fill[p->view_frame[v]]++] = v;   // camera order kept
+  }
+  s->obs_count.assign(C, 0.0);
+  for (int c = 0; c < C; ++c) s->obs_count[c] = (double)(cam_view_begin[c + 1] - cam_view_begin[c]) * K;
+  // camera-partial slots: one per (evaluation tile of 32 views, distinct camera in it)
+  const int nblk_eval = (V + 31) / 32;
+  std::vector<int> blk_slot(nblk_eval + 1, 0), cam_slot_begin(C + 1, 0);
+  {
+    int nslot = 0, prev_cam = -1;
+    for (int b = 0; b < nblk_eval; ++b) {
+      blk_slot[b] = nslot;
+      int last = -1;
+      for (int v = 32 * b; v < std::min(V, 32 * b + 32); ++v)
+        if (p->view_camera[v] != last) {
+          last = p->view_camera[v];
+          if (last < prev_cam) { set_error("internal: slot table"); free_shard(s); return TSCM_ERR_INVALID_ARGUMENT; }
+          prev_cam = last;
+          cam_slot_begin[last + 1]++;
+          ++nslot;
+        }
+    }
+    blk_slot[nblk_eval] = nslot;
+    P.nslot = nslot;
+    for (int c = 0; c < C; ++c) cam_slot_begin[c + 1] += cam_slot_begin[c];
+  }
+  // 4x4 tiles of the upper block triangle, row-major (k_schur_update / k_schur2)
+  const int nb = (NL + 3) / 4;
+  std::vector<short> tile_bi, tile_bj;
+  for (int bi = 0; bi < nb; ++bi) for (int bj = bi; bj < nb; ++bj) { tile_bi.push_back((short)bi); tile_bj.push_back((short)bj); }
+  const int ntiles = (int)tile_bi.size();
+  s->schur.ntiles = ntiles;
+  s->schur.NLp = nb * 4;
+  s->schur_ept = ntiles <= 512 ? 1 : 2;
+  s->schur_nt = std::max(256, ((ntiles + s->schur_ept - 1) / s->schur_ept + 31) / 32 * 32);
+  s->schur_nblk = std::max(1, std::min(s->sm_count, (F + kSchurFB - 1) / kSchurFB));
+  int fpb = (F + s->schur_nblk - 1) / s->schur_nblk;
+  fpb = (fpb + kSchurFB - 1) / kSchurFB * kSchurFB;
+  s->schur_nblk = (F + fpb - 1) / fpb;
+  s->schur.frames_per_block = fpb;
+  s->schur.Fpad = (F + 31) / 32 * 32;
+  s->solve = solve_dims(NL, C);
+  s->eval5_smem = e5_smem_bytes(K, C);
+  if (s->eval5_smem > s->smem_optin || s->solve.smem > s->smem_optin) {
+    set_error("problem (%d corners, %d cameras) needs %zu / %zu bytes of shared memory per CTA (limit %zu)", K, C,
+              s->eval5_smem, s->solve.smem, s->smem_optin);
+    free_shard(s); return TSCM_ERR_UNSUPPORTED;
+  }
+  lap("index tables (host)");
+
+  Blob blob;
+  Arena& A = s->arena;
+  blob.add(&P.board_xy, s->h_board);
+  blob.add(&P.view_camera, s->h_view_camera);
+  blob.add(&P.view_frame, s->h_view_frame);
+  blob.add(&P.frame_ptr, frame_ptr);
+  blob.add(&P.frame_views, frame_views);
+  blob.add(&P.cam_view_begin, cam_view_begin);
+  blob.add(&P.live_off, live_off);
+  blob.add(&P.live_cam, live_cam);
+  blob.add(&P.live_kk, live_kk);
+  {
+    std::vector<short> q_i(P.Q), q_j(P.Q);
+    int q = 0;
+    for (int i = 0; i < NL; ++i) for (int j = i; j < NL; ++j) { q_i[q] = (short)i; q_j[q] = (short)j; ++q; }
+    blob.add(&P.q_i, q_i);
+    blob.add(&P.q_j, q_j);
+  }
+  blob.add(&P.blk_slot, blk_slot);
+  blob.add(&P.cam_slot_begin, cam_slot_begin);
+  blob.add(&s->schur.tile_bi, tile_bi);
+  blob.add(&s->schur.tile_bj, tile_bj);
+  const int form = choose_schur_form(s);
+  TRY_S(plan_schur(s, form, A, blob));
+  lap("Schur tables (host)");
+
+  // ---- buffers ----------------------------------------------------------------------------
+  A.want(&s->d_obs_in, (size_t)V * K);
+  A.want(&s->d_obsT, (size_t)P.Vpad * K);
+  for (int k = 0; k < 2; ++k) {
+    A.want(&s->ps[k].intr, (size_t)C * 9);
+    A.want(&s->ps[k].cam_rt, (size_t)C * 6);
+    A.want(&s->ps[k].board_rt, (size_t)F * 6);
+    A.want(&s->ps[k].cam, (size_t)C);
+    A.want(&s->ps[k].G, (size_t)V * kViewStride);
+    A.want(&s->ps[k].cam_part, (size_t)P.nslot * kCamRec);
+    A.want(&s->ps[k].comm, (size_t)C * kCamRec + kCommExtra);
+    A.want(&s->ps[k].gmax, 1);
+  }
+  A.want(&s->d_state, 1);
+  A.want(&s->d_scale_e, (size_t)F * 6);
+  A.want(&s->d_scale_c, (size_t)C * 13);
+  A.want(&s->schur.frame_rec, (size_t)kFrameRec * s->schur.Fpad);
+  A.want(&s->d_Spart, (size_t)s->schur_nblk * P.Q);
+  A.want(&s->d_rpart, (size_t)s->schur_nblk * NL);
+  A.want(&s->d_Sr, (size_t)s->solve.ntile * 16);
+  A.want(&s->d_yc, (size_t)NL);
+  s->bs_nblk = (F + kBacksubThreads / 32 - 1) / (kBacksubThreads / 32);
+  s->fg_nblk = (F * 6 + kPostThreads - 1) / kPostThreads;
+  A.want(&s->d_ticket, 1);
+  A.want(&s->d_p2p_seq, 2);
+  A.want(&s->d_p2p_ticket, 1);
+  A.want(&s->d_p2p_err, 1);
+  A.want(&s->d_comm_stage, (size_t)C * kCamRec + kCommExtra + 8);
+  A.want(&s->d_bs_part, (size_t)4 * s->bs_nblk);
+  A.want(&s->d_gmax_part, (size_t)s->fg_nblk);
+  A.want(&s->d_xn2_part, (size_t)s->fg_nblk);
+  {
+    const size_t ntile_e = ((size_t)V + 31) / 32;
+    A.want(&s->d_mom, ntile_e * kE5MomEntries * 32);
+    A.want(&s->d_fcg, ntile_e * kFcElems * 32);
+  }
+  const int cap = std::max(128, std::min(s->options.max_num_iterations, 1 << 16) + 2);
+  A.want(&s->d_trace, trace_bytes(cap));
+  A.want(&s->d_blob, blob.bytes.size());
+  TRY_S(A.commit(s->stream));
+  blob.d_base = s->d_blob;
+  TRY_S(blob.upload(s->stream));
+  lap("arena + table upload");
+  P.obsT = s->d_obsT;
+  s->schur.Spart = s->d_Spart; s->schur.rpart = s->d_rpart;
+  s->schur.scale_e = s->d_scale_e; s->schur.scale_c = s->d_scale_c;
+  wire_trace(s, cap);
+  CUDA_S(cudaMallocHost((void**)&s->h_state, 3 * sizeof(LmState)));
+  CUDA_S(cudaMallocHost((void**)&s->h_err, sizeof(int)));
+  *s->h_err = 0;
+  CUDA_S(cudaMallocHost((void**)&s->h_trace, trace_bytes(cap)));
+  CUDA_S(cudaEventCreateWithFlags(&s->poll_ev[0], cudaEventDisableTiming));
+  CUDA_S(cudaEventCreateWithFlags(&s->poll_ev[1], cudaEventDisableTiming));
+  {
+    // mailbox of the peer-memory exchange (tiny; its own allocation so that its IPC handle can
+    // be exported right after creation)
+    const int nwords = P.Q + NL;
+    s->p2p.nA = (nwords + 31) / 32 * 32;
+    s->p2p.nctaA = (nwords + 31) / 32;
+    s->p2p.nB = (C * kCamRec + kCommExtra + 1 + 31) / 32 * 32;
+    const size_t words = p2p_mailbox_words(s->p2p.nA, s->p2p.nctaA, s->p2p.nB);
+    CUDA_S(cudaMalloc((void**)&s->d_mailbox, words * sizeof(double)));
+    CUDA_S(cudaMemsetAsync(s->d_mailbox, 0, words * sizeof(double), s->stream));
+    s->p2p.seq = s->d_p2p_seq; s->p2p.ticket = s->d_p2p_ticket; s->p2p.err = s->d_p2p_err;
+    s->p2p.timeout_ns = 10ull * 1000000000ull;
+  }
+  TRY_S(wire_schur(s, form));
+  TRY_S(set_smem_attr((const void*)k_solve<1, 4>, s->solve.smem));
+  TRY_S(set_smem_attr((const void*)k_solve<4, 7>, s->solve.smem));
+  TRY_S(set_smem_attr((const void*)k_eval5, s->eval5_smem));
+  TRY_S(set_smem_attr((const void*)k_view_blocks, vb_smem_bytes()));
+  lap("kernel attributes");
+  if (p->obs_xy) {
+    TRY_S(upload_observations(s, p->obs_xy, nullptr));
+    CUDA_S(cudaStreamSynchronize(s->stream));
+    lap("observations H2D + transpose");
+  }
+#undef TRY_S
+#undef CUDA_S
+  *out = s;
+  return TSCM_OK;
+}
+
+// ---------------------------------------------------------------------------
+// group = one shard per device of this process
+// ---------------------------------------------------------------------------
+struct ShardPlan {
+  std::vector<int> frame;                         // [n + 1]
+  std::vector<std::vector<int>> vcam, vfrm;       // per shard
+  std::vector<std::vector<ObsSegment>> seg;       // per shard
+};
+
+// Contiguous frame ranges balanced by view count; a shard's views keep the camera-major order.
+ShardPlan plan_shards(const tscm_problem* p, int n) {
+  ShardPlan sp;
+  const int F = p->num_frames, V = p->num_views, C = p->num_cameras;
+  std::vector<int> per_frame(F, 0), cvb(C + 1, 0);
+  for (int v = 0; v < V; ++v) { per_frame[p->view_frame[v]]++; cvb[p->view_camera[v] + 1]++; }
+  for (int c = 0; c < C; ++c) cvb[c + 1] += cvb[c];
+  sp.frame.assign(n + 1, 0);
+  {
+    long long acc = 0;
+    int r = 1;
+    for (int f = 0; f < F && r < n; ++f) {
+      acc += per_frame[f];
+      // close shard r - 1 once it holds its share, or when every later shard needs the frames left
+      if (acc * n >= (long long)V * r || F - (f + 1) <= n - r) sp.frame[r++] = f + 1;
+    }
+    for (; r <= n; ++r) sp.frame[r] = F;
+  }
+  sp.vcam.resize(n); sp.vfrm.resize(n); sp.seg.resize(n);
+  for (int r = 0; r < n; ++r) {
+    const int f0 = sp.frame[r], f1 = sp.frame[r + 1];
+    for (int m = 0; m < C; ++m) {
+      const int* fb = p->view_frame + cvb[m];
+      const int* fe = p->view_frame + cvb[m + 1];
+      const int a = (int)(std::lower_bound(fb, fe, f0) - p->view_frame);
+      const int b = (int)(std::lower_bound(fb, fe, f1) - p->view_frame);
+      if (b > a) sp.seg[r].push_back(ObsSegment{(int)sp.vcam[r].size(), a, b - a});
+      for (int v = a; v < b; ++v) { sp.vcam[r].push_back(m); sp.vfrm[r].push_back(p->view_frame[v] - f0); }
+    }
+  }
+  return sp;
+}
+
+void destroy_solver(tscm_solver* s) {
+  if (!s) return;
+  if (!s->kids.empty() || (!s->stream && !s->arena.base)) {   // group facade (owns no device state itself)
+    for (tscm_solver* k : s->kids) free_shard(k);
+    delete s;
+    return;
+  }
+  free_shard(s);
+}
+
+int create_group(const tscm_problem* p, const tscm_options* o, int device, int n, tscm_solver** out) {
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device + n > ndev) {
+    set_error("num_gpus = %d from device %d, but only %d device(s) are visible", n, device, ndev);
+    return TSCM_ERR_NO_DEVICE;
+  }
+  if (p->num_frames < n) { set_error("%d frames cannot be sharded over %d GPUs", p->num_frames, n); return TSCM_ERR_INVALID_ARGUMENT; }
+  tscm_solver* g = new tscm_solver();
+  g->device = device;
+  g->options = *o;
+  g->C = p->num_cameras; g->F = p->num_frames; g->K = p->corners_per_board; g->V = p->num_views;
+  g->fixed_camera = p->fixed_camera;
+  g->h_view_camera.assign(p->view_camera, p->view_camera + p->num_views);
+  g->h_view_frame.assign(p->view_frame, p->view_frame + p->num_views);
+  g->h_board.assign(p->board_xy, p->board_xy + 2 * (size_t)p->corners_per_board);
+  g->obs_count.assign(g->C, 0.0);
+  for (int v = 0; v < g->V; ++v) g->obs_count[p->view_camera[v]] += g->K;
+  ShardPlan sp = plan_shards(p, n);
+  g->kid_frame = sp.frame;
+  g->kid_seg = sp.seg;
+  for (int r = 0; r < n; ++r) {
+    tscm_problem q = *p;
+    q.num_frames = sp.frame[r + 1] - sp.frame[r];
+    q.num_views = (int)sp.vcam[r].size();
+    q.view_camera = sp.vcam[r].data();
+    q.view_frame = sp.vfrm[r].data();
+    q.obs_xy = nullptr;
+    tscm_solver* k = nullptr;
+    const int rc = create_shard(&q, o, device + r, true, &k);
+    if (rc) { destroy_solver(g); return rc; }
+    k->obs_count = g->obs_count;      // global counts: the read-out divides global sums
+    g->kids.push_back(k);
+  }
+  // peer access + direct mailbox pointers
+  for (int i = 0; i < n; ++i) {
+    cudaSetDevice(device + i);
+    for (int j = 0; j < n; ++j) {
+      if (i == j) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, device + i, device + j);
+      if (!can) { set_error("device %d cannot access device %d: num_gpus needs peer access", device + i, device + j); destroy_solver(g); return TSCM_ERR_UNSUPPORTED; }
+      const cudaError_t e = cudaDeviceEnablePeerAccess(device + j, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else if (e != cudaSuccess) { set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", device + i, device + j, cudaGetErrorString(e)); destroy_solver(g); return TSCM_ERR_CUDA; }
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    tscm_solver* k = g->kids[i];
+    cudaSetDevice(k->device);
+    cudaStreamSynchronize(k->stream);     // mailbox zeroed before any peer writes to it
+  }
+  for (int i = 0; i < n; ++i) {
+    tscm_solver* k = g->kids[i];
+    for (int j = 0; j < n; ++j) k->p2p.mb[j] = g->kids[j]->d_mailbox;
+    k->p2p.rank = i; k->p2p.world = n;
+    k->rank = i; k->num_ranks = n;
+    k->p2p_on = true;
+    k->graph_dirty = true;
+  }
+  if (p->obs_xy) {
+    for (int i = 0; i < n; ++i) {
+      const int rc = upload_observations(g->kids[i], p->obs_xy, &g->kid_seg[i]);
+      if (rc) { destroy_solver(g); return rc; }
+    }
+    for (tscm_solver* k : g->kids) { cudaSetDevice(k->device); cudaStreamSynchronize(k->stream); }
+  }
+  *out = g;
+  return TSCM_OK;
+}
+
+// every shard (or the solver itself)
+template <typename Fn>
+int for_shards(tscm_solver* s, Fn fn) {
+  if (s->kids.empty()) return fn(s, 0);
+  for (size_t i = 0; i < s->kids.size(); ++i) {
+    const int rc = fn(s->kids[i], (int)i);
+    if (rc) return rc;
+  }
+  return TSCM_OK;
+}
+int sync_shards(tscm_solver* s) {
+  return for_shards(s, [](tscm_solver* k, int) -> int {
+    CUDA_TRY(cudaSetDevice(k->device));
+    CUDA_TRY(cudaStreamSynchronize(k->stream));
+    return TSCM_OK;
+  });
+}
+tscm_solver* lead(tscm_solver* s) { return s->kids.empty() ? s : s->kids[0]; }
+
+// ---------------------------------------------------------------------------
+// solver cache of tscm_solve()
+// ---------------------------------------------------------------------------
+struct CacheEntry {
+  tscm_solver* solver = nullptr;
+  int device = 0, num_gpus = 1;
+  uint64_t stamp = 0;
+};
+std::mutex g_cache_mu;
+std::vector<CacheEntry> g_cache;
+int g_cache_max = 1;
+uint64_t g_cache_clock = 0;
+
+bool same_structure(const tscm_solver* s, const tscm_problem* p) {
+  if (s->C != p->num_cameras || s->F != p->num_frames || s->K != p->corners_per_board || s->V != p->num_views ||
+      s->fixed_camera != p->fixed_camera)
+    return false;
+  return std::memcmp(s->h_view_camera.data(), p->view_camera, (size_t)s->V * sizeof(int)) == 0 &&
+         std::memcmp(s->h_view_frame.data(), p->view_frame, (size_t)s->V * sizeof(int)) == 0 &&
+         std::memcmp(s->h_board.data(), p->board_xy, (size_t)s->K * 2 * sizeof(double)) == 0;
+}
+
+void cache_evict_oldest_locked() {
+  size_t old = 0;
+  for (size_t i = 1; i < g_cache.size(); ++i) if (g_cache[i].stamp < g_cache[old].stamp) old = i;
+  destroy_solver(g_cache[old].solver);
+  g_cache.erase(g_cache.begin() + old);
+}
+
+int upload_all_observations(tscm_solver* s, const double* obs_xy) {
+  return for_shards(s, [&](tscm_solver* k, int i) -> int {
+    return upload_observations(k, obs_xy, s->kids.empty() ? nullptr : &s->kid_seg[i]);
+  });
+}
+
 }  // namespace
 
 extern "C" {
 
 const char* tscm_last_error(void) { return g_last_error.c_str(); }
-const char* tscm_version(void) { return "tscm-b200 0.1.0 (sm_100a, fp64)"; }
+const char* tscm_version(void) { return "tscm-b200 0.2.0 (sm_100a, fp64)"; }
+void tscm_set_debug(int32_t flags) { g_debug = flags; }
 
 void tscm_options_init(tscm_options* o) {
   if (!o) return;
@@ -499,423 +1181,166 @@ void tscm_options_init(tscm_options* o) {
   o->jacobi_scaling = 1;
   o->loss_type = TSCM_LOSS_NONE;
   o->loss_scale = 1.0;
+  o->num_gpus = 1;
 }
+
+void* tscm_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, std::max<size_t>(1, bytes)) != cudaSuccess) {
+    set_error("cudaMallocHost(%zu) failed", bytes);
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void tscm_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int tscm_solver_set_options(tscm_solver* s, const tscm_options* o) {
   if (!s || !o) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
-  if (o->max_num_iterations < 0 || !(o->initial_trust_region_radius > 0.0) ||
-      (o->loss_type != TSCM_LOSS_NONE && !(o->loss_scale > 0.0)) || o->loss_type < 0 ||
-      o->loss_type > TSCM_LOSS_CAUCHY) {
-    set_error("invalid options");
-    return TSCM_ERR_INVALID_ARGUMENT;
-  }
+  RC_TRY(validate_options(o));
   s->options = *o;
-  fill_lm_options(*o, s->lm);
-  s->graph_dirty = true;
-  return TSCM_OK;
+  return for_shards(s, [&](tscm_solver* k, int) -> int {
+    LmOptions lm{};
+    fill_lm_options(*o, lm);
+    // the options are kernel arguments baked into the iteration graph
+    if (!lm_equal(lm, k->lm)) k->graph_dirty = true;
+    k->lm = lm;
+    k->options = *o;
+    return TSCM_OK;
+  });
 }
 
-int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
-                       tscm_solver** out) {
+int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device, tscm_solver** out) {
   if (!out) { set_error("out is NULL"); return TSCM_ERR_INVALID_ARGUMENT; }
   *out = nullptr;
-  const auto t_create0 = std::chrono::steady_clock::now();
-  auto lap = [&](const char* what) {
-    if (!getenv("TSCM_PROF")) return;
-    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_create0).count();
-    std::fprintf(stderr, "[tscm create] %-28s %8.2f ms\n", what, ms);
-  };
-  int rc = validate_problem(p);
-  if (rc) return rc;
+  const auto t0 = Clock::now();
+  RC_TRY(validate_problem(p, false));
+  tscm_options defaults;
+  tscm_options_init(&defaults);
+  if (!o) o = &defaults;
+  RC_TRY(validate_options(o));
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
     set_error("no CUDA device: the calibration solve has no CPU fallback");
     return TSCM_ERR_NO_DEVICE;
   }
   if (device < 0) CUDA_TRY(cudaGetDevice(&device));
-  CUDA_TRY(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-  if (prop.major < 10) {
-    set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-    return TSCM_ERR_NO_DEVICE;
-  }
-  lap("validate + device query");
-  tscm_solver* s = new tscm_solver();
-  s->device = device;
-  s->sm_count = prop.multiProcessorCount;
-  tscm_options defaults;
-  tscm_options_init(&defaults);
-  if ((rc = tscm_solver_set_options(s, o ? o : &defaults))) { delete s; return rc; }
-  if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
-    set_error("cudaStreamCreate failed"); delete s; return TSCM_ERR_CUDA;
-  }
-  const int C = p->num_cameras, F = p->num_frames, K = p->corners_per_board, V = p->num_views;
-  s->C = C; s->F = F; s->K = K; s->V = V;
-  DeviceProblem& P = s->P;
-  P.C = C; P.F = F; P.K = K; P.V = V; P.fixed_camera = p->fixed_camera;
-  P.Vpad = (V + 31) / 32 * 32;
-
-  // ---- index tables -------------------------------------------------------
-  std::vector<int> live_off(C + 1, 0);
-  for (int c = 0; c < C; ++c) live_off[c + 1] = live_off[c] + (c == p->fixed_camera ? 7 : 13);
-  const int NL = live_off[C];
-  P.NL = NL; P.Q = NL * (NL + 1) / 2;
-  std::vector<short> live_cam(NL), live_kk(NL);
-  for (int c = 0; c < C; ++c)
-    for (int k = 0; k < live_off[c + 1] - live_off[c]; ++k) {
-      live_cam[live_off[c] + k] = (short)c;
-      live_kk[live_off[c] + k] = (short)(c == p->fixed_camera ? k + 6 : k);
-    }
-  std::vector<short> q_i(P.Q), q_j(P.Q);
-  {
-    int q = 0;
-    for (int i = 0; i < NL; ++i) for (int j = i; j < NL; ++j) { q_i[q] = (short)i; q_j[q] = (short)j; ++q; }
-  }
-  std::vector<int> frame_ptr(F + 1, 0), frame_views(V), cam_view_begin(C + 1, 0);
-  for (int v = 0; v < V; ++v) { frame_ptr[p->view_frame[v] + 1]++; cam_view_begin[p->view_camera[v] + 1]++; }
-  for (int i = 0; i < F; ++i) frame_ptr[i + 1] += frame_ptr[i];
-  for (int c = 0; c < C; ++c) cam_view_begin[c + 1] += cam_view_begin[c];
-  {
-    std::vector<int> fill(frame_ptr.begin(), frame_ptr.end() - 1);
-    for (int v = 0; v < V; ++v) frame_views[fill[p->view_frame[v]]++] = v;   // camera order kept
-  }
-  // camera-partial slots: one per (evaluation CTA of 32 views, distinct camera in it)
-  const int nblk_eval = (V + 31) / 32;
-  std::vector<int> blk_slot(nblk_eval + 1, 0), cam_slot_begin(C + 1, 0);
-  {
-    std::vector<int> slot_cam;
-    for (int b = 0; b < nblk_eval; ++b) {
-      blk_slot[b] = (int)slot_cam.size();
-      int last = -1;
-      for (int v = 32 * b; v < std::min(V, 32 * b + 32); ++v)
-        if (p->view_camera[v] != last) { last = p->view_camera[v]; slot_cam.push_back(last); }
-    }
-    blk_slot[nblk_eval] = (int)slot_cam.size();
-    P.nslot = (int)slot_cam.size();
-    for (int c : slot_cam) cam_slot_begin[c + 1]++;
-    for (int c = 0; c < C; ++c) cam_slot_begin[c + 1] += cam_slot_begin[c];
-    // camera-major views => slots are camera-major too (checked, not assumed)
-    for (size_t i = 1; i < slot_cam.size(); ++i)
-      if (slot_cam[i] < slot_cam[i - 1]) { set_error("internal: slot table"); delete s; return TSCM_ERR_INVALID_ARGUMENT; }
-  }
-
-  if (NL > 216) {
-    set_error("reduced system of %d live parameters exceeds this build's limit (216, i.e. 17 cameras)", NL);
-    delete s; return TSCM_ERR_UNSUPPORTED;
-  }
-  // 4x4 tiles of the upper block triangle, row-major
-  const int nb = (NL + 3) / 4;
-  std::vector<short> tile_bi, tile_bj;
-  for (int bi = 0; bi < nb; ++bi) for (int bj = bi; bj < nb; ++bj) { tile_bi.push_back((short)bi); tile_bj.push_back((short)bj); }
-  const int ntiles = (int)tile_bi.size();
-  lap("index tables (host)");
-#define TRY_RC(x) do { rc = (x); if (rc) { tscm_solver_destroy(s); return rc; } } while (0)
-  std::vector<double> board(p->board_xy, p->board_xy + 2 * (size_t)K);
-  std::vector<int> vcam(p->view_camera, p->view_camera + V), vfrm(p->view_frame, p->view_frame + V);
-  TRY_RC(s->put(&P.board_xy, board));
-  TRY_RC(s->put(&P.view_camera, vcam));
-  TRY_RC(s->put(&P.view_frame, vfrm));
-  TRY_RC(s->put(&P.frame_ptr, frame_ptr));
-  TRY_RC(s->put(&P.frame_views, frame_views));
-  TRY_RC(s->put(&P.cam_view_begin, cam_view_begin));
-  TRY_RC(s->put(&P.live_off, live_off));
-  TRY_RC(s->put(&P.live_cam, live_cam));
-  TRY_RC(s->put(&P.live_kk, live_kk));
-  TRY_RC(s->put(&P.q_i, q_i));
-  TRY_RC(s->put(&P.q_j, q_j));
-  TRY_RC(s->put(&P.blk_slot, blk_slot));
-  TRY_RC(s->put(&P.cam_slot_begin, cam_slot_begin));
-
-  lap("table upload");
-  // ---- buffers --------------------------------------------------------------
-  TRY_RC(s->alloc(&s->d_obs_in, (size_t)V * K));
-  TRY_RC(s->alloc(&s->d_obsT, (size_t)P.Vpad * K));
-  P.obsT = s->d_obsT;
-  for (int k = 0; k < 2; ++k) {
-    TRY_RC(s->alloc(&s->ps[k].intr, (size_t)C * 9));
-    TRY_RC(s->alloc(&s->ps[k].cam_rt, (size_t)C * 6));
-    TRY_RC(s->alloc(&s->ps[k].board_rt, (size_t)F * 6));
-    TRY_RC(s->alloc(&s->ps[k].cam, (size_t)C));
-    TRY_RC(s->alloc(&s->ps[k].G, (size_t)V * kViewStride));
-    TRY_RC(s->alloc(&s->ps[k].cam_part, (size_t)P.nslot * kCamRec));
-    TRY_RC(s->alloc(&s->ps[k].comm, (size_t)C * kCamRec + kCommExtra));
-    TRY_RC(s->alloc(&s->ps[k].gmax, 1));
-  }
-  TRY_RC(s->alloc(&s->d_state, 1));
-  if (cudaMallocHost((void**)&s->h_state, sizeof(LmState)) != cudaSuccess) {
-    set_error("cudaMallocHost failed"); tscm_solver_destroy(s); return TSCM_ERR_CUDA;
-  }
-  TRY_RC(s->alloc(&s->d_scale_e, (size_t)F * 6));
-  TRY_RC(s->alloc(&s->d_scale_c, (size_t)C * 13));
-  // Schur configuration: one 4x4 tile per thread up to 512 tiles, two beyond
-  s->schur_ept = ntiles <= 512 ? 1 : 2;
-  s->schur_nt = std::max(256, ((ntiles + s->schur_ept - 1) / s->schur_ept + 31) / 32 * 32);
-  s->schur.ntiles = ntiles;
-  s->schur.NLp = nb * 4;
-  TRY_RC(s->put(&s->schur.tile_bi, tile_bi));
-  TRY_RC(s->put(&s->schur.tile_bj, tile_bj));
-  s->schur_nblk = std::max(1, std::min(s->sm_count, (F + kSchurFB - 1) / kSchurFB));
-  int fpb = (F + s->schur_nblk - 1) / s->schur_nblk;
-  fpb = (fpb + kSchurFB - 1) / kSchurFB * kSchurFB;
-  s->schur_nblk = (F + fpb - 1) / fpb;
-  s->schur.frames_per_block = fpb;
-  s->schur.Fpad = (F + 31) / 32 * 32;
-  s->schur_smem = (size_t)(2 * kSchurFB * 6 * s->schur.NLp + kSchurFB * 6 + kSchurFB * 64) * sizeof(double) +
-                  kSchurFB * 32 * sizeof(int);
-  s->solve_smem = (size_t)((NL + 1) * (NL + 2) / 2 + 4 * NL + 4 + 4 * (NL + 1) + 2 * kSolveThreads + 8 +
-                           C * kCamRec) * sizeof(double) +
-                  (size_t)2 * NL * sizeof(short) + 16;
-  if (const char* pv = getenv("TSCM_PROF")) s->prof = atoi(pv) >= 2 ? 1 : 0;   // 2: in-kernel cycle printf
-  s->eval3_smem = (size_t)(2 * kE3Group * kE2Elems * 32 + 2 * K) * sizeof(double) +
-                  (size_t)C * sizeof(CamConst);
-  {
-    const size_t main_d = (size_t)2 * kE3Group * kE4Elems * 32;
-    const size_t epi_d = (size_t)kE4Mom * 33 + 32 * 108 + 32 * kViewStride + (size_t)kCamRec * 33;
-    const size_t kpad = ((size_t)K + kE3Group - 1) / kE3Group * kE3Group;
-    s->eval4_smem = (std::max(main_d, epi_d) + kFcElems * 32 + 5 * kpad + (kpad & 1)) * sizeof(double) +
-                    (size_t)C * sizeof(CamConst);
-  }
-  // k_eval5 (persistent, mbarrier-pipelined) is the default; it needs ~214 KB of shared
-  // memory plus the camera table, so very large rigs fall back to k_eval4.
-  s->eval5_smem = e5_smem_bytes(K, C);
-  if (const char* ev = getenv("TSCM_EVAL_VARIANT")) {
-    const int v = atoi(ev);
-    s->eval_variant = v == 3 ? 3 : (v == 4 ? 4 : 5);
-  }
-  if (s->eval_variant == 5 && s->eval5_smem > (size_t)prop.sharedMemPerBlockOptin) s->eval_variant = 4;
-  TRY_RC(s->alloc(&s->schur.frame_rec, (size_t)kFrameRec * s->schur.Fpad));
-  TRY_RC(s->alloc(&s->d_Spart, (size_t)s->schur_nblk * P.Q));
-  TRY_RC(s->alloc(&s->d_rpart, (size_t)s->schur_nblk * NL));
-  s->schur.Spart = s->d_Spart; s->schur.rpart = s->d_rpart;
-  s->schur.scale_e = s->d_scale_e; s->schur.scale_c = s->d_scale_c;
-  TRY_RC(s->alloc(&s->d_Sr, (size_t)P.Q + NL));
-  {
-    // per-frame column descriptors for the pipelined Schur kernel
-    std::vector<int> col_ptr(F + 1, 0), col_src;
-    std::vector<short> col_g, col_sidx;
-    for (int f = 0; f < F; ++f) {
-      for (int q = frame_ptr[f]; q < frame_ptr[f + 1]; ++q) {
-        const int v = frame_views[q], m = p->view_camera[v];
-        const int n = live_off[m + 1] - live_off[m];
-        for (int k = 0; k < n; ++k) {
-          col_src.push_back(v * 16 + (n == 13 ? k : k + 6));
-          col_g.push_back((short)(live_off[m] + k));
-          col_sidx.push_back((short)(m * 13 + (n == 13 ? k : k + 6)));
-        }
-      }
-      col_ptr[f + 1] = (int)col_src.size();
-    }
-    TRY_RC(s->put(&s->schur2.col_ptr, col_ptr));
-    TRY_RC(s->put(&s->schur2.col_src, col_src));
-    TRY_RC(s->put(&s->schur2.col_g, col_g));
-    TRY_RC(s->put(&s->split.col_sidx, col_sidx));
-    const int cons = (ntiles + 31) / 32 * 32;
-    s->schur2_nt = kSchurFB * 32 + cons;
-    s->schur2_smem = (size_t)(2 * (2 * kSchurFB * 6 * s->schur.NLp + kSchurFB * 6) + kSchurFB * 64) * sizeof(double);
-    // split form: materialise W_s, Y, z per frame (dense rows) when the rig's visibility is
-    // dense enough for that to be cheaper than staging inside one CTA
-    s->split.col_ptr = s->schur2.col_ptr; s->split.col_src = s->schur2.col_src; s->split.col_g = s->schur2.col_g;
-    s->split_smem = (size_t)(2 * (2 * kSchurFB * 6 * s->schur.NLp + kSchurFB * 6)) * sizeof(double);
-    const double fill = (double)col_src.size() / ((double)F * NL);
-    s->split_ok = fill >= 0.4 && s->split_smem <= (size_t)prop.sharedMemPerBlockOptin && V < (1 << 27) &&
-                  !getenv("TSCM_SCHUR_FUSED");
-    if (s->split_ok) {
-      TRY_RC(s->alloc(&s->split.Wg, (size_t)F * 6 * s->schur.NLp));
-      TRY_RC(s->alloc(&s->split.Yg, (size_t)F * 6 * s->schur.NLp));
-      TRY_RC(s->alloc(&s->split.zg, ((size_t)F + 8) * 6));
-      TRY_RC(s->alloc(&s->split.fact, (size_t)F * 32));
-      const char* f8 = getenv("TSCM_SPLIT_FRAMES8");
-      s->split_frames8 = f8 ? atoi(f8) != 0 : false;   // measured on config 3: -6 us of kernel time, +1 launch: no net gain
-    }
-    s->schur2_ok = s->schur2_nt <= 640 && s->schur2_smem <= (size_t)prop.sharedMemPerBlockOptin &&
-                   V < (1 << 27) && !getenv("TSCM_SCHUR_V1");
-    // Sparse visibility with a reduced system too wide for the fused kernel (BASELINE config 4):
-    // per-camera-pair update on per-view blocks.  TSCM_SCHUR_PAIRS=1 forces it (parity tests),
-    // =0 disables it.
-    const char* pe = getenv("TSCM_SCHUR_PAIRS");
-    const bool want_pairs = pe ? atoi(pe) != 0 : (!s->split_ok && !s->schur2_ok);
-    if (want_pairs && V < (1 << 27) && kPair2Smem <= (size_t)prop.sharedMemPerBlockOptin) {
-      static_assert(sizeof(PairEntry) == sizeof(int2) && sizeof(PairRange) == sizeof(int2), "int2 layout");
-      const PairLists lists = build_pair_lists(C, F, V, p->view_camera, p->view_frame, kPairChunk);
-      std::vector<short> loff(C + 1);
-      for (int m = 0; m <= C; ++m) loff[m] = (short)live_off[m];
-      const int nitems = (int)lists.item_range.size();
-      s->pairs.nitems = nitems;
-      s->pairs.npairs = (int)lists.pair_a.size();
-      TRY_RC(s->put(reinterpret_cast<const PairEntry**>(&s->pairs.ent), lists.ent));
-      TRY_RC(s->put(reinterpret_cast<const PairRange**>(&s->pairs.item_range), lists.item_range));
-      TRY_RC(s->put(&s->pairs.pair_item, lists.pair_item));
-      TRY_RC(s->put(&s->pairs.pair_items, lists.pair_items));
-      TRY_RC(s->put(&s->pairs.pair_a, lists.pair_a));
-      TRY_RC(s->put(&s->pairs.pair_b, lists.pair_b));
-      TRY_RC(s->put(&s->pairs.live_off, loff));
-      TRY_RC(s->alloc(&s->pairs.part, (size_t)std::max(1, nitems) * kPairPart));
-      TRY_RC(s->alloc(&s->split.Wv, (size_t)V * 96));
-      TRY_RC(s->alloc(&s->split.Yv, (size_t)V * 96));
-      TRY_RC(s->alloc(&s->split.fact, (size_t)F * 32));
-      s->pairs.Wv = s->split.Wv; s->pairs.Yv = s->split.Yv;
-      s->pairs.Sout = s->d_Spart; s->pairs.rout = s->d_rpart;
-      s->split_ok = false; s->schur2_ok = false;
-      s->pairs_ok = true;
-    }
-  }
-  TRY_RC(s->alloc(&s->d_yc, (size_t)NL));
-  s->bs_nblk = (F + kBacksubThreads / 32 - 1) / (kBacksubThreads / 32);
-  s->fg_nblk = (F * 6 + kPostThreads - 1) / kPostThreads;
-  TRY_RC(s->alloc(&s->d_ticket, 1));
-  {
-    // mailbox of the peer-memory exchange (tiny; allocated always so that its IPC handle can
-    // be exported right after creation)
-    const int nwords = P.Q + NL;
-    s->p2p.nA = (nwords + 31) / 32 * 32;
-    s->p2p.nctaA = (nwords + 31) / 32;
-    s->p2p.nB = (C * kCamRec + kCommExtra + 1 + 31) / 32 * 32;
-    TRY_RC(s->alloc(&s->d_mailbox, p2p_mailbox_words(s->p2p.nA, s->p2p.nctaA, s->p2p.nB)));
-    TRY_RC(s->alloc(&s->d_p2p_seq, 2));
-    TRY_RC(s->alloc(&s->d_p2p_ticket, 1));
-    TRY_RC(s->alloc(&s->d_p2p_err, 1));
-    s->p2p.seq = s->d_p2p_seq; s->p2p.ticket = s->d_p2p_ticket; s->p2p.err = s->d_p2p_err;
-  }
-  TRY_RC(s->alloc(&s->d_comm_stage, (size_t)C * kCamRec + kCommExtra + 8));
-  TRY_RC(s->alloc(&s->d_bs_part, (size_t)4 * s->bs_nblk));
-  TRY_RC(s->alloc(&s->d_gmax_part, (size_t)s->fg_nblk));
-  TRY_RC(s->alloc(&s->d_xn2_part, (size_t)s->fg_nblk));
-  TRY_RC(s->alloc(&s->d_dbg_lhs, (size_t)NL * NL));
-  TRY_RC(s->alloc(&s->d_dbg_rhs, (size_t)NL));
-  TRY_RC(ensure_trace(s, std::min(s->options.max_num_iterations, 1 << 16) + 2));
-
-  lap("buffers");
-  auto set_smem = [&](const void* fn, size_t bytes) -> int {
-    if (bytes > 48 * 1024)
-      CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return TSCM_OK;
-  };
-  if (s->schur_smem > (size_t)prop.sharedMemPerBlockOptin || s->solve_smem > (size_t)prop.sharedMemPerBlockOptin) {
-    set_error("problem needs %zu / %zu bytes of shared memory per CTA (limit %zu)", s->schur_smem,
-              s->solve_smem, (size_t)prop.sharedMemPerBlockOptin);
-    tscm_solver_destroy(s); return TSCM_ERR_UNSUPPORTED;
-  }
-  if (s->schur2_ok) TRY_RC(set_smem((const void*)k_schur2, s->schur2_smem));
-  if (s->pairs_ok) TRY_RC(set_smem((const void*)k_schur_pairs2, kPair2Smem));
-  if (s->split_ok) {
-    TRY_RC(set_smem((const void*)k_schur_update<1>, s->split_smem));
-    TRY_RC(set_smem((const void*)k_schur_update<2>, s->split_smem));
-  }
-  TRY_RC(set_smem((const void*)k_schur<1, 512>, s->schur_smem));
-  TRY_RC(set_smem((const void*)k_schur<2, 768>, s->schur_smem));
-  TRY_RC(set_smem((const void*)k_solve<2>, s->solve_smem));
-  TRY_RC(set_smem((const void*)k_solve<4>, s->solve_smem));
-  TRY_RC(set_smem((const void*)k_solve<7>, s->solve_smem));
-  TRY_RC(set_smem((const void*)k_eval3, s->eval3_smem));
-  TRY_RC(set_smem((const void*)k_eval4, s->eval4_smem));
-  if (s->eval_variant == 5) {
-    TRY_RC(set_smem((const void*)k_eval5, s->eval5_smem));
-    TRY_RC(set_smem((const void*)k_view_blocks, vb_smem_bytes()));
-    const size_t ntiles = ((size_t)V + 31) / 32;
-    TRY_RC(s->alloc(&s->d_mom, ntiles * kE5MomEntries * 32));
-    TRY_RC(s->alloc(&s->d_fcg, ntiles * kFcElems * 32));
-  }
-
-  lap("kernel attributes");
-  TRY_RC(tscm_solver_set_observations(s, p->obs_xy));
-  lap("observations H2D + transpose");
-#undef TRY_RC
-  *out = s;
-  return TSCM_OK;
+  if (device >= ndev) { set_error("device %d does not exist (%d visible)", device, ndev); return TSCM_ERR_NO_DEVICE; }
+  if (g_debug & 1) std::fprintf(stderr, "[tscm create] %-28s %8.2f ms\n", "validate", ms_since(t0));
+  const int n = std::max(1, o->num_gpus);
+  if (n > 1) return create_group(p, o, device, n, out);
+  return create_shard(p, o, device, false, out);
 }
 
-void tscm_solver_destroy(tscm_solver* s) {
-  if (!s) return;
-  cudaSetDevice(s->device);
-  if (s->stream) cudaStreamSynchronize(s->stream);
-  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
-  if (s->graph) cudaGraphDestroy(s->graph);
-  if (s->comm && nccl().ok) nccl().CommDestroy(s->comm);
-  for (int r = 0; r < kP2PMaxRanks; ++r)
-    if (s->p2p_peer[r]) cudaIpcCloseMemHandle(s->p2p_peer[r]);
-  for (void* p : s->owned) cudaFree(p);
-  if (s->h_state) cudaFreeHost(s->h_state);
-  if (s->stream) cudaStreamDestroy(s->stream);
-  delete s;
-}
+void tscm_solver_destroy(tscm_solver* s) { destroy_solver(s); }
 
 int tscm_solver_set_observations(tscm_solver* s, const double* obs_xy) {
   if (!s || !obs_xy) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
-  CUDA_TRY(cudaSetDevice(s->device));
-  CUDA_TRY(cudaMemcpyAsync(s->d_obs_in, obs_xy, (size_t)s->V * s->K * sizeof(double2),
-                           cudaMemcpyHostToDevice, s->stream));
-  dim3 grid((s->V + 31) / 32, (s->K + 31) / 32), block(32, 8);
-  k_transpose_obs<<<grid, block, 0, s->stream>>>(s->d_obs_in, s->d_obsT, s->V, s->K, s->P.Vpad);
-  s->launches += 1;
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaStreamSynchronize(s->stream));
-  return TSCM_OK;
+  RC_TRY(upload_all_observations(s, obs_xy));
+  return sync_shards(s);     // the caller may reuse obs_xy
 }
 
 int tscm_solver_set_parameters(tscm_solver* s, const double* intr, const double* cam_rt,
                                const double* board_rt) {
   if (!s || !intr || !cam_rt || !board_rt) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
-  CUDA_TRY(cudaSetDevice(s->device));
-  // The initial point always goes to parameter set 0; run() resets cur = 0.
-  CUDA_TRY(cudaMemcpyAsync(s->ps[0].intr, intr, (size_t)s->C * 9 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-  CUDA_TRY(cudaMemcpyAsync(s->ps[0].cam_rt, cam_rt, (size_t)s->C * 6 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-  CUDA_TRY(cudaMemcpyAsync(s->ps[0].board_rt, board_rt, (size_t)s->F * 6 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-  // the constant block and the b, c intrinsics must also exist in set 1
-  CUDA_TRY(cudaMemcpyAsync(s->ps[1].intr, intr, (size_t)s->C * 9 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-  CUDA_TRY(cudaMemcpyAsync(s->ps[1].cam_rt, cam_rt, (size_t)s->C * 6 * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-  CUDA_TRY(cudaMemsetAsync(s->d_state, 0, sizeof(LmState), s->stream));
-  CUDA_TRY(cudaStreamSynchronize(s->stream));
-  return TSCM_OK;
+  RC_TRY(for_shards(s, [&](tscm_solver* k, int i) -> int {
+    CUDA_TRY(cudaSetDevice(k->device));
+    const double* brt = s->kids.empty() ? board_rt : board_rt + (size_t)s->kid_frame[i] * 6;
+    // The initial point always goes to parameter set 0; run() starts with cur = 0.
+    CUDA_TRY(cudaMemcpyAsync(k->ps[0].intr, intr, (size_t)k->C * 9 * sizeof(double), cudaMemcpyHostToDevice, k->stream));
+    CUDA_TRY(cudaMemcpyAsync(k->ps[0].cam_rt, cam_rt, (size_t)k->C * 6 * sizeof(double), cudaMemcpyHostToDevice, k->stream));
+    CUDA_TRY(cudaMemcpyAsync(k->ps[0].board_rt, brt, (size_t)k->F * 6 * sizeof(double), cudaMemcpyHostToDevice, k->stream));
+    // the constant block and the b, c intrinsics must also exist in set 1
+    CUDA_TRY(cudaMemcpyAsync(k->ps[1].intr, intr, (size_t)k->C * 9 * sizeof(double), cudaMemcpyHostToDevice, k->stream));
+    CUDA_TRY(cudaMemcpyAsync(k->ps[1].cam_rt, cam_rt, (size_t)k->C * 6 * sizeof(double), cudaMemcpyHostToDevice, k->stream));
+    CUDA_TRY(cudaMemsetAsync(k->d_state, 0, sizeof(LmState), k->stream));
+    k->x_in_set1 = false;
+    return TSCM_OK;
+  }));
+  return sync_shards(s);
 }
 
 int tscm_solver_get_parameters(tscm_solver* s, double* intr, double* cam_rt, double* board_rt) {
   if (!s) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
-  CUDA_TRY(cudaSetDevice(s->device));
-  int rc = fetch_state(s);
-  if (rc) return rc;
-  const ParamSet& ps = s->ps[s->h_state->cur & 1];
-  if (intr) CUDA_TRY(cudaMemcpyAsync(intr, ps.intr, (size_t)s->C * 9 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-  if (cam_rt) CUDA_TRY(cudaMemcpyAsync(cam_rt, ps.cam_rt, (size_t)s->C * 6 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-  if (board_rt) CUDA_TRY(cudaMemcpyAsync(board_rt, ps.board_rt, (size_t)s->F * 6 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-  CUDA_TRY(cudaStreamSynchronize(s->stream));
-  return TSCM_OK;
+  RC_TRY(for_shards(s, [&](tscm_solver* k, int i) -> int {
+    CUDA_TRY(cudaSetDevice(k->device));
+    const ParamSet& ps = k->ps[k->x_in_set1 ? 1 : 0];
+    double* brt = board_rt ? (s->kids.empty() ? board_rt : board_rt + (size_t)s->kid_frame[i] * 6) : nullptr;
+    if (i == 0 && intr) CUDA_TRY(cudaMemcpyAsync(intr, ps.intr, (size_t)k->C * 9 * sizeof(double), cudaMemcpyDeviceToHost, k->stream));
+    if (i == 0 && cam_rt) CUDA_TRY(cudaMemcpyAsync(cam_rt, ps.cam_rt, (size_t)k->C * 6 * sizeof(double), cudaMemcpyDeviceToHost, k->stream));
+    if (brt) CUDA_TRY(cudaMemcpyAsync(brt, ps.board_rt, (size_t)k->F * 6 * sizeof(double), cudaMemcpyDeviceToHost, k->stream));
+    return TSCM_OK;
+  }));
+  return sync_shards(s);
 }
 
 int tscm_solver_run(tscm_solver* s, tscm_summary* summary) {
   if (!s) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
-  CUDA_TRY(cudaSetDevice(s->device));
-  int rc = ensure_trace(s, std::min(s->options.max_num_iterations, 1 << 16) + 2);
-  if (rc) return rc;
-  // If a previous run left x in set 1, move it to set 0 (the initial point).
-  if ((rc = fetch_state(s))) return rc;
-  if (s->h_state->cur & 1) {
-    CUDA_TRY(cudaMemcpyAsync(s->ps[0].intr, s->ps[1].intr, (size_t)s->C * 9 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(s->ps[0].cam_rt, s->ps[1].cam_rt, (size_t)s->C * 6 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
-    CUDA_TRY(cudaMemcpyAsync(s->ps[0].board_rt, s->ps[1].board_rt, (size_t)s->F * 6 * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
-  }
-  if ((rc = ensure_graph(s))) return rc;
-  if ((rc = run_initial(s))) return rc;
-  // Replay the iteration graph; poll the device-side `done` flag every few
-  // iterations (kernels of a finished solve are no-ops).
+  const int max_it = s->options.max_num_iterations;
+  // ---- prepare every shard (no exchange kernels yet) -----------------------------------------
+  RC_TRY(for_shards(s, [&](tscm_solver* k, int) -> int {
+    CUDA_TRY(cudaSetDevice(k->device));
+    RC_TRY(ensure_trace(k, std::min(max_it, 1 << 16) + 2));
+    RC_TRY(move_x_to_set0(k));
+    return ensure_graph(k);
+  }));
+  // ---- iteration zero on every shard, then batches of iterations ------------------------------
+  RC_TRY(for_shards(s, [&](tscm_solver* k, int) -> int {
+    CUDA_TRY(cudaSetDevice(k->device));
+    return run_initial(k);
+  }));
+  // Replay the iteration graph in batches; the device-side `done` flag of the batch BEFORE the
+  // one just enqueued is polled, so the GPU never waits for the host (kernels of a finished
+  // solve are no-ops).
+  tscm_solver* L = lead(s);
+  const bool group = !s->kids.empty();
   const int batch = 8;
-  int launched = 0;
-  while (launched < s->options.max_num_iterations) {
-    const int n = std::min(batch, s->options.max_num_iterations - launched);
-    for (int k = 0; k < n; ++k) CUDA_TRY(cudaGraphLaunch(s->graph_exec, s->stream));
-    s->launches += (int64_t)n * launches_per_iteration(s);
+  int launched = 0, nbatch = 0;
+  bool done = false;
+  while (launched < max_it && !done) {
+    const int n = std::min(batch, max_it - launched);
+    RC_TRY(for_shards(s, [&](tscm_solver* k, int) -> int {
+      CUDA_TRY(cudaSetDevice(k->device));
+      int left = n;
+      if (group)
+        for (; left >= kGroupIters; left -= kGroupIters) CUDA_TRY(cudaGraphLaunch(k->graph_exec_n, k->stream));
+      for (; left > 0; --left) CUDA_TRY(cudaGraphLaunch(k->graph_exec, k->stream));
+      k->launches += (int64_t)n * k->launches_per_iter;
+      return TSCM_OK;
+    }));
     launched += n;
-    if ((rc = fetch_state(s))) return rc;
-    if (s->h_state->done) break;
+    CUDA_TRY(cudaSetDevice(L->device));
+    CUDA_TRY(cudaMemcpyAsync(L->h_state + 1 + (nbatch & 1), L->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, L->stream));
+    CUDA_TRY(cudaEventRecord(L->poll_ev[nbatch & 1], L->stream));
+    if (nbatch > 0) {
+      CUDA_TRY(cudaEventSynchronize(L->poll_ev[(nbatch - 1) & 1]));
+      done = L->h_state[1 + ((nbatch - 1) & 1)].done != 0;
+    }
+    ++nbatch;
   }
-  if ((rc = fetch_state(s))) return rc;
-  CUDA_TRY(cudaGetLastError());
-  if (s->p2p_on) {
-    int perr = 0;
-    CUDA_TRY(cudaMemcpy(&perr, s->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (perr) { set_error("peer-memory exchange timed out waiting for another rank"); return TSCM_ERR_COMM; }
+  // ---- results ----------------------------------------------------------------------------------
+  RC_TRY(for_shards(s, [&](tscm_solver* k, int) -> int {
+    CUDA_TRY(cudaSetDevice(k->device));
+    CUDA_TRY(cudaMemcpyAsync(k->h_state, k->d_state, sizeof(LmState), cudaMemcpyDeviceToHost, k->stream));
+    if (k->p2p_on) CUDA_TRY(cudaMemcpyAsync(k->h_err, k->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost, k->stream));
+    return TSCM_OK;
+  }));
+  const int want_trace = summary ? std::min(std::max(0, (int)summary->trace_capacity), L->trace.capacity) : 0;
+  if (want_trace > 0) {
+    CUDA_TRY(cudaSetDevice(L->device));
+    CUDA_TRY(cudaMemcpyAsync(L->h_trace, L->d_trace, trace_bytes(L->trace.capacity), cudaMemcpyDeviceToHost, L->stream));
   }
-  const LmState& st = *s->h_state;
+  RC_TRY(sync_shards(s));
+  int comm_err = 0;
+  RC_TRY(for_shards(s, [&](tscm_solver* k, int) -> int {
+    CUDA_TRY(cudaSetDevice(k->device));
+    CUDA_TRY(cudaGetLastError());
+    k->x_in_set1 = (k->h_state->cur & 1) != 0;
+    if (k->p2p_on && *k->h_err) comm_err = 1;
+    return TSCM_OK;
+  }));
+  const LmState& st = *L->h_state;
   if (summary) {
     summary->termination_type = st.done ? st.termination : TSCM_NO_CONVERGENCE;
     summary->num_iterations = st.recorded;
@@ -924,16 +1349,19 @@ int tscm_solver_run(tscm_solver* s, tscm_summary* summary) {
     summary->initial_cost = st.initial_cost;
     summary->final_cost = st.final_cost;
     summary->final_radius = st.radius;
-    const int n = std::min({st.recorded, summary->trace_capacity, s->trace.capacity});
+    const int n = std::min(st.recorded, want_trace);
     if (n > 0) {
-      if (summary->trace_cost) CUDA_TRY(cudaMemcpy(summary->trace_cost, s->trace.cost, n * sizeof(double), cudaMemcpyDeviceToHost));
-      if (summary->trace_radius) CUDA_TRY(cudaMemcpy(summary->trace_radius, s->trace.radius, n * sizeof(double), cudaMemcpyDeviceToHost));
-      if (summary->trace_gradient_max_norm) CUDA_TRY(cudaMemcpy(summary->trace_gradient_max_norm, s->trace.gmax, n * sizeof(double), cudaMemcpyDeviceToHost));
-      if (summary->trace_step_norm) CUDA_TRY(cudaMemcpy(summary->trace_step_norm, s->trace.step_norm, n * sizeof(double), cudaMemcpyDeviceToHost));
-      if (summary->trace_step_flags) CUDA_TRY(cudaMemcpy(summary->trace_step_flags, s->trace.flags, n * sizeof(int), cudaMemcpyDeviceToHost));
+      const size_t cap = (size_t)L->trace.capacity;
+      const double* h = reinterpret_cast<const double*>(L->h_trace);
+      if (summary->trace_cost) std::memcpy(summary->trace_cost, h, n * sizeof(double));
+      if (summary->trace_radius) std::memcpy(summary->trace_radius, h + cap, n * sizeof(double));
+      if (summary->trace_gradient_max_norm) std::memcpy(summary->trace_gradient_max_norm, h + 2 * cap, n * sizeof(double));
+      if (summary->trace_step_norm) std::memcpy(summary->trace_step_norm, h + 3 * cap, n * sizeof(double));
+      if (summary->trace_step_flags) std::memcpy(summary->trace_step_flags, h + 4 * cap, n * sizeof(int));
     }
   }
-  if (s->options.verbose && s->rank == 0) {
+  if (comm_err) { set_error("peer-memory exchange timed out waiting for another rank"); return TSCM_ERR_COMM; }
+  if (s->options.verbose && L->rank == 0) {
     // summary.BriefReport() of TS.cpp:280 / multi_calib.cpp:218
     std::printf("Ceres Solver Report: Iterations: %d, Initial cost: %e, Final cost: %e, Termination: %s\n",
                 st.num_successful + st.num_unsuccessful, st.initial_cost, st.final_cost,
@@ -942,28 +1370,82 @@ int tscm_solver_run(tscm_solver* s, tscm_summary* summary) {
   return TSCM_OK;
 }
 
+void tscm_cache_configure(int32_t max_solvers) {
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  g_cache_max = std::max(0, (int)max_solvers);
+  while ((int)g_cache.size() > g_cache_max) cache_evict_oldest_locked();
+}
+void tscm_cache_release(void) {
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  for (CacheEntry& e : g_cache) destroy_solver(e.solver);
+  g_cache.clear();
+}
+
 int tscm_solve(const tscm_problem* problem, const tscm_options* options, double* intrinsics,
                double* cam_rt, double* board_rt, tscm_summary* summary, int device) {
-  const bool prof = getenv("TSCM_PROF") != nullptr;
-  auto now = []() { return std::chrono::steady_clock::now(); };
-  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-    return std::chrono::duration<double, std::milli>(b - a).count();
-  };
-  const auto t0 = now();
+  const auto t0 = Clock::now();
+  RC_TRY(validate_problem(problem, true));
+  if (!intrinsics || !cam_rt || !board_rt) { set_error("NULL parameter arrays"); return TSCM_ERR_INVALID_ARGUMENT; }
+  tscm_options defaults;
+  tscm_options_init(&defaults);
+  if (!options) options = &defaults;
+  RC_TRY(validate_options(options));
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device: the calibration solve has no CPU fallback");
+    return TSCM_ERR_NO_DEVICE;
+  }
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  const int ngpu = std::max(1, options->num_gpus);
+  // ---- solver: cached for this structure, or new ---------------------------------------------
   tscm_solver* s = nullptr;
-  int rc = tscm_solver_create(problem, options, device, &s);
-  if (rc) return rc;
-  const auto t1 = now();
-  rc = tscm_solver_set_parameters(s, intrinsics, cam_rt, board_rt);
-  const auto t2 = now();
+  bool hit = false;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    for (size_t i = 0; i < g_cache.size(); ++i) {
+      CacheEntry& e = g_cache[i];
+      if (e.device == device && e.num_gpus == ngpu && same_structure(e.solver, problem)) {
+        s = e.solver;
+        g_cache.erase(g_cache.begin() + i);     // checked out: nobody else may use it meanwhile
+        hit = true;
+        break;
+      }
+    }
+  }
+  const double ms_lookup = ms_since(t0);
+  int rc = TSCM_OK;
+  if (hit) {
+    rc = tscm_solver_set_options(s, options);
+  } else {
+    tscm_problem q = *problem;
+    q.obs_xy = nullptr;                        // uploaded below, without a sync of its own
+    rc = tscm_solver_create(&q, options, device, &s);
+  }
+  if (!rc) rc = upload_all_observations(s, problem->obs_xy);
+  const double ms_create = ms_since(t0);
+  // the parameters ride behind the observations on the same streams (one sync for both)
+  if (!rc) rc = tscm_solver_set_parameters(s, intrinsics, cam_rt, board_rt);
+  const double ms_set = ms_since(t0);
   if (!rc) rc = tscm_solver_run(s, summary);
-  const auto t3 = now();
+  const double ms_run = ms_since(t0);
   if (!rc) rc = tscm_solver_get_parameters(s, intrinsics, cam_rt, board_rt);
-  const auto t4 = now();
-  tscm_solver_destroy(s);
-  if (prof)
-    std::fprintf(stderr, "[tscm_solve] create %.2f  set %.2f  run %.2f  get %.2f  destroy %.2f ms\n",
-                 ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), ms(t4, now()));
+  const double ms_get = ms_since(t0);
+  if (s) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    if (rc == TSCM_OK && g_cache_max > 0) {
+      while ((int)g_cache.size() >= g_cache_max) cache_evict_oldest_locked();
+      CacheEntry e;
+      e.solver = s; e.device = device; e.num_gpus = ngpu; e.stamp = ++g_cache_clock;
+      g_cache.push_back(e);
+    } else {
+      destroy_solver(s);
+    }
+  }
+  if (g_debug & 1)
+    std::fprintf(stderr, "[tscm_solve] %s: lookup %.2f  create/upload %.2f  set %.2f  run %.2f  get %.2f  total %.2f ms\n",
+                 hit ? "cached solver" : "new solver", ms_lookup, ms_create - ms_lookup, ms_set - ms_create,
+                 ms_run - ms_set, ms_get - ms_run, ms_since(t0));
   return rc;
 }
 
@@ -977,8 +1459,17 @@ int tscm_comm_unique_id(void* unique_id_128) {
   return TSCM_OK;
 }
 
+#define NO_GROUP(s, what)                                                                           \
+  do {                                                                                              \
+    if (!(s)->kids.empty()) {                                                                       \
+      set_error(what " works on single-device solvers (num_gpus <= 1)");                            \
+      return TSCM_ERR_UNSUPPORTED;                                                                  \
+    }                                                                                               \
+  } while (0)
+
 int tscm_solver_attach_comm(tscm_solver* s, int rank, int num_ranks, const void* unique_id_128) {
   if (!s || !unique_id_128 || rank < 0 || rank >= num_ranks) { set_error("bad comm arguments"); return TSCM_ERR_INVALID_ARGUMENT; }
+  NO_GROUP(s, "tscm_solver_attach_comm");
   NcclApi& n = nccl();
   if (!n.ok) { set_error("libnccl.so.2 could not be loaded"); return TSCM_ERR_COMM; }
   CUDA_TRY(cudaSetDevice(s->device));
@@ -993,6 +1484,7 @@ int tscm_solver_attach_comm(tscm_solver* s, int rank, int num_ranks, const void*
 
 int tscm_solver_p2p_export(tscm_solver* s, void* handle_64) {
   if (!s || !handle_64) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
+  NO_GROUP(s, "tscm_solver_p2p_export");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   CUDA_TRY(cudaSetDevice(s->device));
   CUDA_TRY(cudaStreamSynchronize(s->stream));      // the mailbox is zeroed before anyone maps it
@@ -1004,6 +1496,7 @@ int tscm_solver_p2p_export(tscm_solver* s, void* handle_64) {
 
 int tscm_solver_p2p_attach(tscm_solver* s, int rank, int num_ranks, const void* handles) {
   if (!s || !handles || rank < 0 || rank >= num_ranks) { set_error("bad p2p arguments"); return TSCM_ERR_INVALID_ARGUMENT; }
+  NO_GROUP(s, "tscm_solver_p2p_attach");
   if (num_ranks > kP2PMaxRanks) { set_error("peer-memory exchange supports at most %d ranks", kP2PMaxRanks); return TSCM_ERR_INVALID_ARGUMENT; }
   CUDA_TRY(cudaSetDevice(s->device));
   for (int r = 0; r < num_ranks; ++r) {
@@ -1016,7 +1509,7 @@ int tscm_solver_p2p_attach(tscm_solver* s, int rank, int num_ranks, const void* 
       set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(e));
       return TSCM_ERR_COMM;
     }
-    s->p2p_peer[r] = ptr;
+    s->p2p_ipc[r] = ptr;
     s->p2p.mb[r] = static_cast<double*>(ptr);
   }
   s->p2p.rank = rank; s->p2p.world = num_ranks;
@@ -1026,12 +1519,40 @@ int tscm_solver_p2p_attach(tscm_solver* s, int rank, int num_ranks, const void* 
   return TSCM_OK;
 }
 
+int tscm_solver_set_exchange_timeout(tscm_solver* s, double seconds) {
+  if (!s || !(seconds > 0.0)) { set_error("bad arguments"); return TSCM_ERR_INVALID_ARGUMENT; }
+  return for_shards(s, [&](tscm_solver* k, int) -> int {
+    k->p2p.timeout_ns = (unsigned long long)(seconds * 1e9);
+    k->graph_dirty = true;
+    return TSCM_OK;
+  });
+}
+
+int tscm_solver_set_schur_form(tscm_solver* s, int form) {
+  if (!s) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
+  return for_shards(s, [&](tscm_solver* k, int) -> int {
+    CUDA_TRY(cudaSetDevice(k->device));
+    const int f = form == kSchurAuto ? choose_schur_form(k) : form;
+    if (f == k->schur_form) return TSCM_OK;
+    CUDA_TRY(cudaStreamSynchronize(k->stream));
+    Arena a;
+    Blob b;
+    RC_TRY(plan_schur(k, f, a, b));
+    char* d_blob = nullptr;
+    a.want(&d_blob, b.bytes.size());
+    RC_TRY(a.commit(k->stream));
+    k->extra.push_back(a.base);
+    b.d_base = d_blob;
+    RC_TRY(b.upload(k->stream));
+    return wire_schur(k, f);
+  });
+}
+
 int tscm_solver_eval_jacobian(tscm_solver* s, double* residuals, double* jacobian, double* cost) {
   if (!s) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
+  NO_GROUP(s, "tscm_solver_eval_jacobian");
   CUDA_TRY(cudaSetDevice(s->device));
-  int rc = fetch_state(s);
-  if (rc) return rc;
-  const int cur = s->h_state->cur & 1;
+  const int cur = s->x_in_set1 ? 1 : 0;
   const size_t N = (size_t)s->V * s->K;
   double *d_r = nullptr, *d_J = nullptr;
   if (residuals) CUDA_TRY(cudaMalloc((void**)&d_r, N * 2 * sizeof(double)));
@@ -1041,8 +1562,7 @@ int tscm_solver_eval_jacobian(tscm_solver* s, double* residuals, double* jacobia
   s->launches += 2;
   if (cost) {
     launch_evaluation(s, 2 + cur, 1);
-    rc = launch_eval_allreduce(s, 2 + cur);
-    if (rc) return rc;
+    RC_TRY(launch_eval_allreduce(s, 2 + cur));
   }
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   CUDA_TRY(cudaGetLastError());
@@ -1058,63 +1578,88 @@ int tscm_solver_eval_jacobian(tscm_solver* s, double* residuals, double* jacobia
   return TSCM_OK;
 }
 
-int tscm_solver_reduced_size(const tscm_solver* s) { return s ? s->P.NL : -1; }
+int tscm_solver_reduced_size(const tscm_solver* s) {
+  if (!s) return -1;
+  return s->kids.empty() ? s->P.NL : s->kids[0]->P.NL;
+}
 
 int tscm_solver_reduced_system(tscm_solver* s, double radius, double* lhs, double* rhs) {
   if (!s || !(radius > 0.0)) { set_error("bad arguments"); return TSCM_ERR_INVALID_ARGUMENT; }
+  NO_GROUP(s, "tscm_solver_reduced_system");
   CUDA_TRY(cudaSetDevice(s->device));
   // Evaluate the point in set `cur`, compute Jacobi scaling there (as iteration 0 does).
-  int rc = fetch_state(s);
-  if (rc) return rc;
-  const int cur = s->h_state->cur & 1;
-  CUDA_TRY(cudaMemsetAsync(s->d_state, 0, sizeof(LmState), s->stream));
-  if (cur) {
-    LmState tmp{}; tmp.cur = 1;
-    CUDA_TRY(cudaMemcpyAsync(s->d_state, &tmp, sizeof(LmState), cudaMemcpyHostToDevice, s->stream));
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-  }
+  const int cur = s->x_in_set1 ? 1 : 0;
+  LmState* tmp = s->h_state + 1;
+  std::memset(tmp, 0, sizeof(LmState));
+  tmp->cur = cur;
+  CUDA_TRY(cudaMemcpyAsync(s->d_state, tmp, sizeof(LmState), cudaMemcpyHostToDevice, s->stream));
   launch_evaluation(s, 2 + cur, 1);
-  if ((rc = launch_eval_allreduce(s, 2 + cur))) return rc;
+  RC_TRY(launch_eval_allreduce(s, 2 + cur));
   const int n = s->P.F * 6 + s->P.C * 13;
   k_jacobi_scale<<<(n + 255) / 256, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm,
                                                         s->d_scale_e, s->d_scale_c);
+  s->launches += 1;
   launch_schur(s, radius);
-  if ((rc = launch_schur_allreduce(s))) return rc;
-  launch_solve(s, radius, true);
+  RC_TRY(launch_schur_allreduce(s, radius));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   CUDA_TRY(cudaGetLastError());
-  const int NL = s->P.NL;
-  if (lhs) CUDA_TRY(cudaMemcpy(lhs, s->d_dbg_lhs, (size_t)NL * NL * sizeof(double), cudaMemcpyDeviceToHost));
-  if (rhs) CUDA_TRY(cudaMemcpy(rhs, s->d_dbg_rhs, (size_t)NL * sizeof(double), cudaMemcpyDeviceToHost));
+  // the assembled system as k_solve receives it (4x4 tiles of the lower block triangle)
+  const int NL = s->P.NL, nbk = s->solve.nbk;
+  std::vector<double> tiles((size_t)s->solve.ntile * 16);
+  CUDA_TRY(cudaMemcpy(tiles.data(), s->d_Sr, tiles.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  auto at = [&](int r, int c) { return tiles[(size_t)solve_tile_id(r >> 2, c >> 2, nbk) * 16 + (r & 3) * 4 + (c & 3)]; };
+  for (int r = 0; r < NL; ++r)
+    for (int c = 0; c <= r; ++c) {
+      if (lhs) { lhs[(size_t)r * NL + c] = at(r, c); lhs[(size_t)c * NL + r] = at(r, c); }
+    }
+  if (rhs) for (int c = 0; c < NL; ++c) rhs[c] = at(NL, c);
   return TSCM_OK;
 }
 
+// Mean Euclidean reprojection error per camera and overall (multi_calib.cpp:235-283).  On a
+// sharded solve (ranks or a num_gpus group) the sums are global, and so must the counts be: a
+// group knows them; the ranks of a multi-process solve exchange them like an evaluation record.
 int tscm_solver_reprojection_error(tscm_solver* s, double* per_camera, double* overall, double* rms) {
   if (!s) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
-  CUDA_TRY(cudaSetDevice(s->device));
-  int rc = fetch_state(s);
-  if (rc) return rc;
-  const int cur = s->h_state->cur & 1;
+  const int C = s->C;
   // Read-out uses the plain (loss-free) residuals, like multi_calib.cpp:235-283.
-  LmOptions saved = s->lm;
-  s->lm.loss_type = 0;
-  s->want_err = 1;
-  launch_evaluation(s, 2 + cur, 1);
-  rc = launch_eval_allreduce(s, 2 + cur);
-  s->lm = saved;
-  s->want_err = 0;
-  if (rc) return rc;
-  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  auto evaluate = [&](bool plain) -> int {
+    RC_TRY(for_shards(s, [&](tscm_solver* k, int) -> int {
+      CUDA_TRY(cudaSetDevice(k->device));
+      const int cur = k->x_in_set1 ? 1 : 0;
+      const LmOptions saved = k->lm;
+      if (plain) { k->lm.loss_type = 0; k->want_err = 1; }
+      launch_evaluation(k, 2 + cur, 1);
+      const int rc = launch_eval_allreduce(k, 2 + cur);
+      k->lm = saved;
+      k->want_err = 0;
+      return rc;
+    }));
+    return sync_shards(s);
+  };
+  RC_TRY(evaluate(true));
+  tscm_solver* L = lead(s);
+  const int cur = L->x_in_set1 ? 1 : 0;
+  CUDA_TRY(cudaSetDevice(L->device));
   CUDA_TRY(cudaGetLastError());
-  std::vector<double> comm((size_t)s->C * kCamRec);
-  CUDA_TRY(cudaMemcpy(comm.data(), s->ps[cur].comm, comm.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  // per-camera observation counts (global when sharded: counts are summed like the records)
-  std::vector<int> cvb(s->C + 1);
-  CUDA_TRY(cudaMemcpy(cvb.data(), s->P.cam_view_begin, cvb.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  std::vector<double> comm((size_t)C * kCamRec);
+  CUDA_TRY(cudaMemcpy(comm.data(), L->ps[cur].comm, comm.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  std::vector<double> count = L->obs_count;
+  const bool multi_process = s->kids.empty() && s->num_ranks > 1;
+  if (multi_process) {
+    // exchange the local counts through the record's err slot
+    std::vector<double> rec((size_t)C * kCamRec + kCommExtra, 0.0);
+    for (int m = 0; m < C; ++m) rec[(size_t)m * kCamRec + kCamErr] = L->obs_count[m];
+    CUDA_TRY(cudaMemcpyAsync(L->ps[cur].comm, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice, L->stream));
+    RC_TRY(launch_eval_allreduce(L, 2 + cur));
+    CUDA_TRY(cudaStreamSynchronize(L->stream));
+    CUDA_TRY(cudaMemcpy(rec.data(), L->ps[cur].comm, rec.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int m = 0; m < C; ++m) count[m] = rec[(size_t)m * kCamRec + kCamErr];
+  }
   double sum = 0.0, cost = 0.0, total = 0.0;
-  for (int m = 0; m < s->C; ++m) {
+  for (int m = 0; m < C; ++m) {
     const double e = comm[(size_t)m * kCamRec + kCamErr];
-    const double n = (double)(cvb[m + 1] - cvb[m]) * s->K;
+    const double n = count[m];
     if (per_camera) per_camera[m] = n > 0 ? e / n : 0.0;
     sum += e; total += n;
     cost += comm[(size_t)m * kCamRec + kCamCost];
@@ -1122,15 +1667,20 @@ int tscm_solver_reprojection_error(tscm_solver* s, double* per_camera, double* o
   if (overall) *overall = total > 0 ? sum / total : 0.0;
   if (rms) *rms = total > 0 ? std::sqrt(2.0 * cost / total) : 0.0;
   // restore the records of the configured loss for a subsequent run()
-  if (saved.loss_type) { launch_evaluation(s, 2 + cur, 1); CUDA_TRY(cudaStreamSynchronize(s->stream)); }
+  if (L->lm.loss_type || multi_process) RC_TRY(evaluate(false));
   return TSCM_OK;
 }
 
 int tscm_solver_time_stage(tscm_solver* s, int stage, int repeats, double* ms_per_launch) {
   if (!s || repeats <= 0 || !ms_per_launch) { set_error("bad arguments"); return TSCM_ERR_INVALID_ARGUMENT; }
-  CUDA_TRY(cudaSetDevice(s->device));
-  int rc;
-  if ((rc = ensure_graph(s))) return rc;
+  if (stage != 4) NO_GROUP(s, "tscm_solver_time_stage (stages other than 4)");
+  RC_TRY(for_shards(s, [&](tscm_solver* k, int) -> int {
+    CUDA_TRY(cudaSetDevice(k->device));
+    RC_TRY(move_x_to_set0(k));
+    return ensure_graph(k);
+  }));
+  tscm_solver* L = lead(s);
+  CUDA_TRY(cudaSetDevice(L->device));
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
   CUDA_TRY(cudaEventCreate(&e1));
@@ -1138,22 +1688,21 @@ int tscm_solver_time_stage(tscm_solver* s, int stage, int repeats, double* ms_pe
     // make the device state valid and not `done`
     LmOptions saved = s->lm;
     s->lm.disable_tolerances = 1; s->lm.max_num_iterations = 1 << 30;
-    rc = run_initial(s);
-    if (!rc) { launch_schur(s, 0.0); rc = launch_schur_allreduce(s); }
-    if (!rc) { launch_solve(s, 0.0, false); launch_backsub(s); launch_evaluation(s, 3, 0); }
+    int rc = run_initial(s);
+    if (!rc) { launch_schur(s, 0.0); rc = launch_schur_allreduce(s, 0.0); }
+    if (!rc) { launch_solve(s); launch_backsub(s); launch_evaluation(s, 3, 0); }
     if (rc) { s->lm = saved; return rc; }
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     CUDA_TRY(cudaEventRecord(e0, s->stream));
-    const DeviceProblem& P = s->P;
     for (int r = 0; r < repeats; ++r) {
       switch (stage) {
-        case 0: launch_eval_kernel(s, 3); s->launches += 1; break;
+        case 0: launch_eval_kernel(s, 3); break;
         case 1: launch_schur(s, 0.0); break;
-        case 2: launch_solve(s, 0.0, false); break;
+        case 2: launch_solve(s); break;
         case 3: launch_backsub(s); break;
         case 5: launch_evaluation(s, 3, 0); break;
-        case 6: launch_eval_kernel(s, 3, 1); s->launches += 1; break;
-        case 7: launch_eval_kernel(s, 3, 2); s->launches += 1; break;
+        case 6: launch_eval_kernel(s, 3, 1); break;
+        case 7: launch_eval_kernel(s, 3, 2); break;
         default: s->lm = saved; set_error("unknown stage %d", stage); return TSCM_ERR_INVALID_ARGUMENT;
       }
     }
@@ -1163,30 +1712,57 @@ int tscm_solver_time_stage(tscm_solver* s, int stage, int repeats, double* ms_pe
     // whole LM iterations: iteration zero, then replay the graph.  The options
     // baked into the graph are the solver's (use disable_tolerances = 1 and
     // max_num_iterations >= repeats for a fixed-iteration measurement).
-    if ((rc = run_initial(s))) return rc;
-    CUDA_TRY(cudaStreamSynchronize(s->stream));
-    CUDA_TRY(cudaEventRecord(e0, s->stream));
-    for (int r = 0; r < repeats; ++r) CUDA_TRY(cudaGraphLaunch(s->graph_exec, s->stream));
-    s->launches += (int64_t)repeats * launches_per_iteration(s);
-    CUDA_TRY(cudaEventRecord(e1, s->stream));
+    RC_TRY(for_shards(s, [&](tscm_solver* k, int) -> int {
+      CUDA_TRY(cudaSetDevice(k->device));
+      return run_initial(k);
+    }));
+    RC_TRY(sync_shards(s));
+    CUDA_TRY(cudaSetDevice(L->device));
+    CUDA_TRY(cudaEventRecord(e0, L->stream));
+    const bool group = !s->kids.empty();
+    int left = repeats;
+    while (left > 0) {
+      const int n = group && left >= kGroupIters ? kGroupIters : 1;
+      RC_TRY(for_shards(s, [&](tscm_solver* k, int) -> int {
+        CUDA_TRY(cudaSetDevice(k->device));
+        CUDA_TRY(cudaGraphLaunch(n == 1 ? k->graph_exec : k->graph_exec_n, k->stream));
+        k->launches += (int64_t)n * k->launches_per_iter;
+        return TSCM_OK;
+      }));
+      left -= n;
+    }
+    CUDA_TRY(cudaSetDevice(L->device));
+    CUDA_TRY(cudaEventRecord(e1, L->stream));
   }
   CUDA_TRY(cudaEventSynchronize(e1));
+  RC_TRY(sync_shards(s));
+  CUDA_TRY(cudaSetDevice(L->device));
   CUDA_TRY(cudaGetLastError());
   float ms = 0.f;
   CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   *ms_per_launch = (double)ms / repeats;
+  // where x ended up (the timed stages evaluate set 1 explicitly and never flip `cur`)
+  RC_TRY(fetch_state(L));
+  const bool in1 = (L->h_state->cur & 1) != 0;
+  for_shards(s, [&](tscm_solver* k, int) -> int { k->x_in_set1 = in1; return TSCM_OK; });
   if (stage == 4) {
     // a solve that terminated early turns the remaining launches into no-ops:
     // such a measurement is not a measurement
-    if ((rc = fetch_state(s))) return rc;
-    if (s->h_state->done || s->h_state->iteration != repeats) {
+    if (L->h_state->done || L->h_state->iteration != repeats) {
       set_error("LM loop stopped after %d of %d timed iterations (termination %d)",
-                s->h_state->iteration, repeats, s->h_state->termination);
+                L->h_state->iteration, repeats, L->h_state->termination);
       return TSCM_ERR_UNSUPPORTED;
     }
   }
   return TSCM_OK;
+}
+
+int64_t tscm_solver_launch_count(const tscm_solver* s) {
+  if (!s) return 0;
+  int64_t n = s->launches;
+  for (const tscm_solver* k : s->kids) n += k->launches;
+  return n;
 }
 
 // Remap tables: TS.cpp:284-330, rectify.cpp:86-199 as one batched kernel.
@@ -1230,8 +1806,8 @@ int tscm_remap_tables(const tscm_remap_job* jobs, int32_t num_jobs, int32_t map_
   if (device >= 0) CUDA_TRY(cudaSetDevice(device));
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  DeviceInfo prop;
+  RC_TRY(device_info(dev, &prop));
   if (prop.major < 10) {
     set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
     return TSCM_ERR_NO_DEVICE;
@@ -1262,7 +1838,7 @@ int tscm_remap_tables(const tscm_remap_job* jobs, int32_t num_jobs, int32_t map_
   REMAP_TRY(cudaEventCreate(&e1));
   // one wave of resident CTAs (8 x 256 threads per SM), grid-stride over the pixels
   const int64_t want = (total + 255) / 256;
-  const int grid = (int)std::min<int64_t>(want, (int64_t)prop.multiProcessorCount * 8);
+  const int grid = (int)std::min<int64_t>(want, (int64_t)prop.sm_count * 8);
   REMAP_TRY(cudaEventRecord(e0, 0));
   k_remap_tables<<<grid, 256>>>(d_batch, d_x, d_y);
   REMAP_TRY(cudaEventRecord(e1, 0));
@@ -1284,17 +1860,15 @@ int tscm_remap_tables(const tscm_remap_job* jobs, int32_t num_jobs, int32_t map_
   return rc;
 }
 
-int64_t tscm_solver_launch_count(const tscm_solver* s) { return s ? s->launches : 0; }
-
 int tscm_device_fp64_peak(int device, double* tflops) {
   if (!tflops) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
   if (device >= 0) CUDA_TRY(cudaSetDevice(device));
-  cudaDeviceProp prop;
+  DeviceInfo prop;
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
-  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  RC_TRY(device_info(dev, &prop));
   double* d_out = nullptr;
-  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  const int blocks = prop.sm_count * 8, threads = 256, iters = 4096;
   CUDA_TRY(cudaMalloc((void**)&d_out, (size_t)blocks * threads * sizeof(double)));
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));

@@ -73,9 +73,6 @@ __host__ __device__ inline size_t e5_smem_bytes(int K, int C) {
   d += 5 * kpad + (kpad & 1);                           // board moments table
   return d * sizeof(double) + (size_t)C * sizeof(CamConst);
 }
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // all lanes have finished their shared-memory accesses -> one elected arrival
 __device__ __forceinline__ void warp_arrive(unsigned long long* bar, int lane) {
   __syncwarp();

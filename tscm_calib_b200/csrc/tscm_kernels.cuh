@@ -1,12 +1,15 @@
 // tscm_kernels.cuh — sm_100a FP64 kernels of the calibration solve.
 //
 // Stage map (reference stage each replaces):
-//   k_prep_cams, k_eval3       K1+K2  Jet evaluation of multi_calib.h:146-195 for every
+//   k_prep_cams, k_eval5,
+//   k_view_blocks (tscm_eval5.cuh)  K1+K2  Jet evaluation of multi_calib.h:146-195 for every
 //                                     residual block + SchurEliminator's E^T E / E^T F /
 //                                     F^T F / E^T b / F^T b products (multi_calib.cpp:162-207)
 //   k_post_eval                K2     per-camera F^T F, F^T b, cost; gradient max-norm
-//   k_schur2 (k_schur), k_reduce_s  K3  SchurEliminator::Eliminate chunk loop
-//   k_solve                    K4     DenseSchurComplementSolver (Eigen LLT) on the reduced
+//   k_schur_frames + k_schur_update,
+//   k_schur2, k_pair_* (+ tscm_schur_pairs.cuh),
+//   k_reduce_s                 K3     SchurEliminator::Eliminate chunk loop
+//   k_solve (tscm_solve.cuh)   K4     DenseSchurComplementSolver (Eigen LLT) on the reduced
 //                                     camera system
 //   k_backsub                  K4     SchurEliminator::BackSubstitute + candidate point
 //   k_init, k_decide (or the
@@ -118,525 +121,17 @@ __global__ void k_prep_cams(DeviceProblem P, ParamSet ps0, ParamSet ps1, const L
 }
 
 // ---------------------------------------------------------------------------
-// K1+K2: residual + analytic Jacobian + normal-equation blocks, warp-specialised.  A CTA owns 32 views (lane =
-// view) and runs 4 CONSUMER warps (one Gram slice each, accumulators in
-// registers) plus 8 PRODUCER warps.  Per group of 8 corners, producer p
-// evaluates corner j0 + p of every lane's view (projection, residual, analytic
-// Jacobian, loss) and publishes the 42-double row to a double-buffered staging
-// area [buffer][corner][element][lane]; the consumers fold the previous group
-// at the same time.  One __syncthreads per group.  The producers' long
-// dependent FP64 chains (3 sqrt + reciprocals, ~25-cycle FP64 latency) are
-// hidden behind the consumers' independent FMAs on the same SM sub-partition
-// (warps 0-3 = consumers, one per sub-partition; two producers on each).
-// A consumer folds a corner as two rank-1 sweeps (u row, then v row) so that
-// consecutive FMAs on one accumulator are a full sweep apart, and loads the
-// operands of the next sweep-but-one while the current sweep runs.
+// K1+K2: residual + analytic Jacobian + normal-equation blocks live in tscm_eval5.cuh
+// (k_eval5 + k_view_blocks).  Shared here: the structural-zero pattern of the intrinsic
+// block and the size of the per-view frame-constant record.
 // ---------------------------------------------------------------------------
-constexpr int kE2Elems = 42;     // doubles per published row: Ju[20] | Jv[20] | 1/2 rho | sqrt(s)
-constexpr int kE3Group = 8;
-constexpr int kE3Consumers = 4;
-constexpr int kE3Threads = 32 * (kE3Consumers + kE3Group);   // 384
-
-// operand vector of one residual row for a consumer role; `row` points at element 0
-// of that row (Ju: rows, Jv: rows + 20 * 32)
-template <int ROLE>
-__device__ __forceinline__ void e3_load(const double* __restrict__ row, int lane, double* x) {
-  if (ROLE == 0) {
-#pragma unroll
-    for (int k = 0; k < 12; ++k) x[k] = row[k * 32 + lane];
-  } else {
-    constexpr int base = ROLE == 1 ? 0 : 6;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) x[k] = row[(base + k) * 32 + lane];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) x[6 + k] = row[(12 + k) * 32 + lane];
-    // roles 2 and 3 also own one row of BC each (load balance): they need B4 / B5
-    if (ROLE == 2) x[14] = row[4 * 32 + lane];
-    if (ROLE == 3) x[14] = row[5 * 32 + lane];
-  }
-}
-
-// One rank-1 sweep acc += x x^T restricted to the role's slice.  ROW selects the residual
-// row (0 = u, 1 = v): the intrinsic block of a row has structural zeros (u does not depend
-// on fy, cy; v not on fx, cx — TS.h:124-125), which also survive the loss scaling, so those
-// products are skipped; fma(x, 0, acc) == acc, the result is bit-identical.
+// The intrinsic block of a residual row has structural zeros (u does not depend on fy, cy;
+// v not on fx, cx — TS.h:124-125), which also survive the loss scaling.
 __device__ __forceinline__ constexpr bool e3_live(int row, int icol) {
   // icol: 0 fx, 1 fy, 2 cx, 3 cy, 4 xi, 5 lambda, 6 alpha, 7 residual
   return row == 0 ? !(icol == 1 || icol == 3) : !(icol == 0 || icol == 2);
 }
-
-template <int ROLE, int ROW>
-__device__ __forceinline__ void e3_sweep(const double* x, double* __restrict__ acc) {
-  // slices (FMAs per sweep): role 0 = BB + BC rows 0-3 (45), role 1 = BI (36 live),
-  // role 2 = CC + II + BC row 4 (48 live), role 3 = CI + BC row 5 (42 live)
-  if (ROLE == 0) {
-#pragma unroll
-    for (int a = 0; a < 6; ++a) {
-#pragma unroll
-      for (int b = a; b < 6; ++b) acc[tri6(a, b)] = fma(x[a], x[b], acc[tri6(a, b)]);
-      if (a < 4) {
-#pragma unroll
-        for (int b = 0; b < 6; ++b) acc[21 + a * 6 + b] = fma(x[a], x[6 + b], acc[21 + a * 6 + b]);
-      }
-    }
-  } else if (ROLE == 2) {
-#pragma unroll
-    for (int a = 0; a < 6; ++a)
-#pragma unroll
-      for (int b = a; b < 6; ++b) acc[tri6(a, b)] = fma(x[a], x[b], acc[tri6(a, b)]);
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int b = a; b < 8; ++b)
-        if (e3_live(ROW, a) && e3_live(ROW, b))
-          acc[21 + tri8(a, b)] = fma(x[6 + a], x[6 + b], acc[21 + tri8(a, b)]);
-#pragma unroll
-    for (int b = 0; b < 6; ++b) acc[59 + b] = fma(x[14], x[b], acc[59 + b]);      // BC row 4
-  } else {
-#pragma unroll
-    for (int a = 0; a < 6; ++a)
-#pragma unroll
-      for (int b = 0; b < 8; ++b)
-        if (e3_live(ROW, b)) acc[a * 8 + b] = fma(x[a], x[6 + b], acc[a * 8 + b]);
-    if (ROLE == 3) {
-#pragma unroll
-      for (int b = 0; b < 6; ++b) acc[48 + b] = fma(x[14], x[b], acc[48 + b]);    // BC row 5
-    }
-  }
-}
-
-template <int ROLE>
-__device__ __forceinline__ void e3_consume_group(const double* __restrict__ buf, int lane,
-                                                 double* __restrict__ acc) {
-  constexpr int kRow = kE2Elems * 32;
-  double xu[15], xv[15];
-  e3_load<ROLE>(buf, lane, xu);
-  e3_load<ROLE>(buf + 20 * 32, lane, xv);
-#pragma unroll 1
-  for (int o = 0; o < kE3Group; ++o) {
-    const double* nxt = buf + (o + 1 < kE3Group ? o + 1 : o) * kRow;
-    e3_sweep<ROLE, 0>(xu, acc);
-    if (ROLE == 2) { acc[57] += buf[o * kRow + 40 * 32 + lane]; acc[58] += buf[o * kRow + 41 * 32 + lane]; }
-    e3_load<ROLE>(nxt, lane, xu);              // next corner's u row, hidden behind the v sweep
-    e3_sweep<ROLE, 1>(xv, acc);
-    e3_load<ROLE>(nxt + 20 * 32, lane, xv);    // next corner's v row, hidden behind the next u sweep
-  }
-}
-
-__global__ void __launch_bounds__(kE3Threads, 1)
-k_eval3(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which, LmOptions opt,
-        int prof) {
-  if (which < 2 && st->done) return;
-  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
-  const ParamSet& ps = sel ? ps1 : ps0;
-  extern __shared__ __align__(16) double s_mem[];
-  double* s_rows = s_mem;                                             // [2][8][42][32]
-  double* s_board = s_rows + 2 * kE3Group * kE2Elems * 32;            // [K][2]
-  CamConst* s_cam = reinterpret_cast<CamConst*>(s_board + 2 * P.K);   // [C]
-  for (int i = threadIdx.x; i < 2 * P.K; i += blockDim.x) s_board[i] = P.board_xy[i];
-  {
-    const int n = P.C * (int)(sizeof(CamConst) / sizeof(double));
-    const double* src = reinterpret_cast<const double*>(ps.cam);
-    double* dst = reinterpret_cast<double*>(s_cam);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int v0 = blockIdx.x * 32 + lane;
-  const bool valid = v0 < P.V;
-  const int v = valid ? v0 : P.V - 1;
-  __syncthreads();
-  const int ngroups = (P.K + kE3Group - 1) / kE3Group;
-  constexpr int kBuf = kE3Group * kE2Elems * 32;
-
-  // Register re-partition between the warpgroups (sm_90a+/sm_100a setmaxnreg): the
-  // kernel launches with 168 registers per thread (384 threads); the two producer
-  // warpgroups release 24 each, the consumer warpgroup takes 48 more so that its 59
-  // FP64 accumulators and two operand sets live in registers without spilling.
-  if (warp >= kE3Consumers) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 144;");
-    // ------------------------------ producer ------------------------------------
-    const int p = warp - kE3Consumers;
-    const CamConst& cc = s_cam[P.view_camera[v]];
-    const double2* obs = P.obsT + v;
-    FrameConst fc;
-    make_frame_const(ps.board_rt + 6 * P.view_frame[v], fc);
-    for (int g = 0; g <= ngroups; ++g) {
-      if (g < ngroups) {
-        const int j = g * kE3Group + p;
-        double* mine = s_rows + (g & 1) * kBuf + p * (kE2Elems * 32);
-        if (j < P.K && valid) {
-          const double2 uv = obs[(size_t)j * P.Vpad];
-          ObsRow o;
-          obs_jacobian<true, true, true>(cc, fc, s_board[2 * j], s_board[2 * j + 1], uv.x, uv.y, o);
-          double err;
-          const double half_rho = obs_apply_loss<0, 19>(opt.loss_type, opt.loss_scale, o, &err);
-#pragma unroll
-          for (int k = 0; k < 20; ++k) { mine[k * 32 + lane] = o.Ju[k]; mine[(20 + k) * 32 + lane] = o.Jv[k]; }
-          mine[40 * 32 + lane] = half_rho;
-          mine[41 * 32 + lane] = err;
-        } else {
-#pragma unroll
-          for (int k = 0; k < kE2Elems; ++k) mine[k * 32 + lane] = 0.0;
-        }
-      }
-      __syncthreads();
-    }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    // ------------------------------ consumer ------------------------------------
-    double acc[65];
-#pragma unroll
-    for (int i = 0; i < 65; ++i) acc[i] = 0.0;
-    for (int g = 0; g <= ngroups; ++g) {
-      if (g > 0) {
-        const double* buf = s_rows + ((g - 1) & 1) * kBuf;
-        if (warp == 0) e3_consume_group<0>(buf, lane, acc);
-        else if (warp == 1) e3_consume_group<1>(buf, lane, acc);
-        else if (warp == 2) e3_consume_group<2>(buf, lane, acc);
-        else e3_consume_group<3>(buf, lane, acc);
-      }
-      __syncthreads();
-    }
-    // View part (BB | BC | BI) -> per-view record staged in shared memory (the row buffers
-    // are free now); camera part (CC | CI | II | cost | err) -> summed over the lanes that
-    // share a camera with a fixed-order butterfly and written as one partial per
-    // (CTA, camera).  Views are camera-major, so a CTA normally sees a single camera.
-    if (warp < 2) {
-      double* rec = s_rows + lane * kViewStride;
-      if (warp == 0) {
-#pragma unroll
-        for (int i = 0; i < 45; ++i) rec[kOffBB + i] = acc[i];     // BB, BC rows 0-3
-      } else {
-#pragma unroll
-        for (int i = 0; i < 48; ++i) rec[kOffBI + i] = acc[i];
-        rec[kViewStride - 1] = 0.0;
-      }
-    } else {
-      // camera part: staged [entry][33] (conflict free both ways); summed over lanes below
-      double* cs = s_rows + 32 * kViewStride;
-      double* rec = s_rows + lane * kViewStride;
-#pragma unroll
-      for (int b = 0; b < 6; ++b) {       // the BC rows these roles own
-        if (warp == 2) rec[kOffBC + 4 * 6 + b] = acc[59 + b];
-        else rec[kOffBC + 5 * 6 + b] = acc[48 + b];
-      }
-      if (warp == 2) {
-#pragma unroll
-        for (int i = 0; i < 21; ++i) cs[(kCamCC + i) * 33 + lane] = acc[i];
-#pragma unroll
-        for (int i = 0; i < 36; ++i) cs[(kCamII + i) * 33 + lane] = acc[21 + i];
-        cs[kCamCost * 33 + lane] = acc[57];
-        cs[kCamErr * 33 + lane] = acc[58];
-      } else {
-#pragma unroll
-        for (int i = 0; i < 48; ++i) cs[(kCamCI + i) * 33 + lane] = acc[i];
-      }
-    }
-  }
-  __syncthreads();
-  // Camera partials: one record per (CTA, camera).  Views are camera-major, so the lanes of
-  // one camera are contiguous; thread e sums entry e over each camera's lane range in lane
-  // order (fixed order => deterministic).
-  if (threadIdx.x < kCamRec) {
-    const double* cs = s_rows + 32 * kViewStride + threadIdx.x * 33;
-    const int nv = min(32, P.V - blockIdx.x * 32);
-    const int* vc = P.view_camera + blockIdx.x * 32;
-    int slot = P.blk_slot[blockIdx.x];
-    int l = 0;
-    while (l < nv) {
-      const int c = vc[l];
-      double s0 = 0.0, s1 = 0.0;
-      int k = l;
-      for (; k + 1 < nv && vc[k + 1] == c; k += 2) { s0 += cs[k]; s1 += cs[k + 1]; }
-      if (k < nv && vc[k] == c) { s0 += cs[k]; ++k; }
-      ps.cam_part[(size_t)slot * kCamRec + threadIdx.x] = s0 + s1;
-      ++slot;
-      l = k;
-    }
-  }
-  // coalesced copy-out: the 32 view records of this CTA are contiguous in G
-  {
-    const int nv = min(32, P.V - blockIdx.x * 32);
-    double* dst = ps.G + (size_t)blockIdx.x * 32 * kViewStride;
-    const int n = nv * kViewStride;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = s_rows[i];
-  }
-}
-
-// ---------------------------------------------------------------------------
-// K1+K2, moment form (default).  Same warp-specialised skeleton as k_eval3 — a CTA owns 32
-// views (lane = view), 8 producer warps, 4 consumer warps, double-buffered rows, one barrier
-// per group of 8 corners — but built on the moment formulation of tscm_math.cuh:
-//  * a producer evaluates only the projection, At = -d(u,v)/dP (2x3), the intrinsic rows and
-//    the residual of its corner (24 doubles published instead of 42; no 2x12 extrinsic chain);
-//  * consumer 0 accumulates the 36 second moments M[m][n] of At^T At, consumers 1..3 the 24
-//    entries of N[m] = sum mu_m At^T [J_I | r] for m = X, Y, 1 plus a third of II each;
-//  * once per view, all 384 threads rebuild the 12x12 / 12x8 extrinsic blocks from the
-//    moments (thread = (view, column), view_blocks_column) and write the per-view record and
-//    the per-(CTA, camera) partial record exactly as k_eval3 does.
-// ~48 % fewer FP64 instructions per corner than k_eval3 on the busiest sub-partition.
-// ---------------------------------------------------------------------------
-constexpr int kE4Elems = 24;     // au[3] av[3] ju[8] jv[8] 1/2rho sqrt(s)
-constexpr int kE4Mom = 108;      // M 36 | N 72
-constexpr int kFcElems = 27;
-
-// live intrinsic columns of a residual row (see e3_live)
-template <int ROLE>
-__device__ __forceinline__ void e4_consume(const double* __restrict__ row, int lane,
-                                           const double* __restrict__ mu, double* __restrict__ acc) {
-  // row elements: au 0..2, av 3..5, ju 6..13, jv 14..21, cost 22, err 23
-  double au[3], av[3];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { au[k] = row[k * 32 + lane]; av[k] = row[(3 + k) * 32 + lane]; }
-  if (ROLE == 0) {
-    double q[6];
-    q[0] = fma(av[0], av[0], au[0] * au[0]); q[1] = fma(av[0], av[1], au[0] * au[1]);
-    q[2] = fma(av[0], av[2], au[0] * au[2]); q[3] = fma(av[1], av[1], au[1] * au[1]);
-    q[4] = fma(av[1], av[2], au[1] * au[2]); q[5] = fma(av[2], av[2], au[2] * au[2]);
-    // pairs 00 01 02 11 12 22 <-> weights X^2, XY, X, Y^2, Y, 1   (mu = X, Y, X^2, XY, Y^2)
-    const double w[5] = {mu[2], mu[3], mu[0], mu[4], mu[1]};
-#pragma unroll
-    for (int pr = 0; pr < 5; ++pr)
-#pragma unroll
-      for (int e = 0; e < 6; ++e) acc[pr * 6 + e] = fma(w[pr], q[e], acc[pr * 6 + e]);
-#pragma unroll
-    for (int e = 0; e < 6; ++e) acc[30 + e] += q[e];
-    acc[36] += row[22 * 32 + lane];
-    acc[37] += row[23 * 32 + lane];
-  } else {
-    double ju[8], jv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { ju[i] = row[(6 + i) * 32 + lane]; jv[i] = row[(14 + i) * 32 + lane]; }
-    if (ROLE < 3) {
-      const double m = mu[ROLE - 1];      // X or Y
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { au[k] *= m; av[k] *= m; }
-    }
-    // two passes (u terms, then v terms): consecutive FMAs on one accumulator are a whole
-    // pass apart, so the ~24-cycle FP64 latency never stalls the warp
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (e3_live(0, i)) acc[k * 8 + i] = fma(au[k], ju[i], acc[k * 8 + i]);
-    constexpr int lo = 12 * (ROLE - 1);   // this role's third of II: tri8 entries lo .. lo + 11
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int b = a; b < 8; ++b) {
-        const int e = tri8(a, b);
-        if (e >= lo && e < lo + 12 && e3_live(0, a) && e3_live(0, b))
-          acc[24 + e - lo] = fma(ju[a], ju[b], acc[24 + e - lo]);
-      }
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (e3_live(1, i)) acc[k * 8 + i] = fma(av[k], jv[i], acc[k * 8 + i]);
-#pragma unroll
-    for (int a = 0; a < 8; ++a)
-#pragma unroll
-      for (int b = a; b < 8; ++b) {
-        const int e = tri8(a, b);
-        if (e >= lo && e < lo + 12 && e3_live(1, a) && e3_live(1, b))
-          acc[24 + e - lo] = fma(jv[a], jv[b], acc[24 + e - lo]);
-      }
-  }
-}
-
-__global__ void __launch_bounds__(kE3Threads, 1)
-k_eval4(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which, LmOptions opt,
-        int want_err) {
-  if (which < 2 && st->done) return;
-  const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
-  const ParamSet& ps = sel ? ps1 : ps0;
-  extern __shared__ __align__(16) double s_mem[];
-  constexpr int kBuf = kE3Group * kE4Elems * 32;
-  // main-loop layout: rows [2][8][24][32]; epilogue layout (re-uses the rows region):
-  // moments [108][33] | colvecs [32][108] | view records [32][106] | camera staging [107][33]
-  constexpr int kMainDoubles = 2 * kBuf;
-  constexpr int kEpiDoubles = kE4Mom * 33 + 32 * 108 + 32 * kViewStride + kCamRec * 33;
-  constexpr int kRegion = kMainDoubles > kEpiDoubles ? kMainDoubles : kEpiDoubles;
-  double* s_rows = s_mem;
-  double* s_fc = s_mem + kRegion;                                     // [27][32]
-  double* s_mu = s_fc + kFcElems * 32;                                // [Kpad][5], Kpad = K rounded up to 8
-  const int Kpad = (P.K + kE3Group - 1) / kE3Group * kE3Group;
-  CamConst* s_cam = reinterpret_cast<CamConst*>(s_mu + 5 * Kpad + (Kpad & 1));   // [C]
-  for (int j = threadIdx.x; j < Kpad; j += blockDim.x) {
-    const double X = j < P.K ? P.board_xy[2 * j] : 0.0, Y = j < P.K ? P.board_xy[2 * j + 1] : 0.0;
-    s_mu[5 * j] = X; s_mu[5 * j + 1] = Y; s_mu[5 * j + 2] = X * X; s_mu[5 * j + 3] = X * Y; s_mu[5 * j + 4] = Y * Y;
-  }
-  {
-    const int n = P.C * (int)(sizeof(CamConst) / sizeof(double));
-    const double* src = reinterpret_cast<const double*>(ps.cam);
-    double* dst = reinterpret_cast<double*>(s_cam);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int v0 = blockIdx.x * 32 + lane;
-  const bool valid = v0 < P.V;
-  const int v = valid ? v0 : P.V - 1;
-  if (warp == kE3Consumers) {
-    FrameConst fc;
-    make_frame_const(ps.board_rt + 6 * P.view_frame[v], fc);
-    const double* fp = reinterpret_cast<const double*>(&fc);
-#pragma unroll
-    for (int e = 0; e < kFcElems; ++e) s_fc[e * 32 + lane] = fp[e];
-  }
-  __syncthreads();
-  const int ngroups = (P.K + kE3Group - 1) / kE3Group;
-
-  if (warp >= kE3Consumers) {
-    // ------------------------------ producer ------------------------------------
-    const int p = warp - kE3Consumers;
-    const CamConst& cc = s_cam[P.view_camera[v]];
-    const double2* obs = P.obsT + v;
-    ViewConst vc;
-    {
-      FrameConst fc;
-      double* fp = reinterpret_cast<double*>(&fc);
-#pragma unroll
-      for (int e = 0; e < kFcElems; ++e) fp[e] = s_fc[e * 32 + lane];
-      make_view_const(cc, fc, vc);
-    }
-    // the observation of the NEXT group is requested before the current corner is evaluated,
-    // so its ~700-cycle global-load latency hides behind the projection's FP64 chain
-    double2 uv_next = make_double2(0.0, 0.0);
-    if (p < P.K && valid) uv_next = obs[(size_t)p * P.Vpad];
-    for (int g = 0; g <= ngroups; ++g) {
-      if (g < ngroups) {
-        const int j = g * kE3Group + p;
-        double* mine = s_rows + (g & 1) * kBuf + p * (kE4Elems * 32);
-        const double2 uv = uv_next;
-        if (j + kE3Group < P.K && valid) uv_next = obs[(size_t)(j + kE3Group) * P.Vpad];
-        if (j < P.K && valid) {
-          ObsCompact o;
-          obs_compact(cc, vc, s_mu[5 * j], s_mu[5 * j + 1], uv.x, uv.y, o);
-          double err;
-          const double half_rho = obs_compact_loss(opt.loss_type, opt.loss_scale, o, &err, (want_err & 1) != 0);
-#pragma unroll
-          for (int k = 0; k < 3; ++k) { mine[k * 32 + lane] = o.au[k]; mine[(3 + k) * 32 + lane] = o.av[k]; }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) { mine[(6 + k) * 32 + lane] = o.ju[k]; mine[(14 + k) * 32 + lane] = o.jv[k]; }
-          mine[22 * 32 + lane] = half_rho;
-          mine[23 * 32 + lane] = err;
-        } else {
-#pragma unroll
-          for (int k = 0; k < kE4Elems; ++k) mine[k * 32 + lane] = 0.0;
-        }
-      }
-      __syncthreads();
-    }
-  } else {
-    // ------------------------------ consumer ------------------------------------
-    double acc[38];
-#pragma unroll
-    for (int i = 0; i < 38; ++i) acc[i] = 0.0;
-    for (int g = 0; g <= ngroups; ++g) {
-      if (g > 0) {
-        const double* buf = s_rows + ((g - 1) & 1) * kBuf;
-        const double* mu = s_mu + 5 * (g - 1) * kE3Group;
-        if (warp == 0) {
-#pragma unroll 2
-          for (int o = 0; o < kE3Group; ++o) e4_consume<0>(buf + o * (kE4Elems * 32), lane, mu + 5 * o, acc);
-        } else if (warp == 1) {
-#pragma unroll 2
-          for (int o = 0; o < kE3Group; ++o) e4_consume<1>(buf + o * (kE4Elems * 32), lane, mu + 5 * o, acc);
-        } else if (warp == 2) {
-#pragma unroll 2
-          for (int o = 0; o < kE3Group; ++o) e4_consume<2>(buf + o * (kE4Elems * 32), lane, mu + 5 * o, acc);
-        } else {
-#pragma unroll 2
-          for (int o = 0; o < kE3Group; ++o) e4_consume<3>(buf + o * (kE4Elems * 32), lane, mu + 5 * o, acc);
-        }
-      }
-      __syncthreads();
-    }
-    // moments -> shared [entry][33]; II, cost, err straight to the camera staging area
-    double* mom = s_rows;
-    double* cs = s_rows + kE4Mom * 33 + 32 * 108 + 32 * kViewStride;
-    if (warp == 0) {
-#pragma unroll
-      for (int i = 0; i < 36; ++i) mom[i * 33 + lane] = acc[i];
-      cs[kCamCost * 33 + lane] = acc[36];
-      cs[kCamErr * 33 + lane] = acc[37];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 24; ++i) mom[(36 + (warp - 1) * 24 + i) * 33 + lane] = acc[i];
-#pragma unroll
-      for (int i = 0; i < 12; ++i) cs[(kCamII + 12 * (warp - 1) + i) * 33 + lane] = acc[24 + i];
-    }
-  }
-  // (the staging writes above touch the rows region: every warp is past the last barrier of
-  // the main loop, and the last group consumed lives in buffer (ngroups-1)&1 — the moments
-  // area overlaps it, so synchronise before anyone reads and after everyone consumed)
-  __syncthreads();
-  double* mom = s_rows;
-  double* colv = s_rows + kE4Mom * 33;                 // [32][12][9]
-  double* recs = colv + 32 * 108;                      // [32][106]
-  double* cs = recs + 32 * kViewStride;                // [107][33]
-  {
-    // column vectors: thread (view, column)
-    const int vw = threadIdx.x / 12, b = threadIdx.x % 12;
-    if (vw < 32) {
-      const int gv = min(blockIdx.x * 32 + vw, P.V - 1);
-      FrameConst fc;
-      double* fp = reinterpret_cast<double*>(&fc);
-#pragma unroll
-      for (int e = 0; e < kFcElems; ++e) fp[e] = s_fc[e * 32 + vw];
-      view_column_vectors(s_cam[P.view_camera[gv]], fc, b, colv + (vw * 12 + b) * 9);
-    }
-  }
-  __syncthreads();
-  {
-    const int vw = threadIdx.x / 12, b = threadIdx.x % 12;
-    if (vw < 32) {
-      double oe[12], ox[8];
-      const double* mv = mom + vw;
-      view_blocks_column(colv + vw * 108, 9, b, [mv](int k) { return mv[k * 33]; }, oe, ox);
-      double* rec = recs + vw * kViewStride;
-      if (b < 6) {
-#pragma unroll
-        for (int a = 0; a < 6; ++a) if (a <= b) rec[kOffBB + tri6(a, b)] = oe[a];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rec[kOffBI + b * 8 + i] = ox[i];
-        if (b == 0) rec[kViewStride - 1] = 0.0;
-      } else {
-        const int c = b - 6;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) rec[kOffBC + a * 6 + c] = oe[a];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) if (a <= c) cs[(kCamCC + tri6(a, c)) * 33 + vw] = oe[6 + a];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cs[(kCamCI + c * 8 + i) * 33 + vw] = ox[i];
-      }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < kCamRec) {
-    const double* c1 = cs + threadIdx.x * 33;
-    const int nv = min(32, P.V - blockIdx.x * 32);
-    const int* vc = P.view_camera + blockIdx.x * 32;
-    int slot = P.blk_slot[blockIdx.x];
-    int l = 0;
-    while (l < nv) {
-      const int c = vc[l];
-      double s0 = 0.0, s1 = 0.0;
-      int k = l;
-      for (; k + 1 < nv && vc[k + 1] == c; k += 2) { s0 += c1[k]; s1 += c1[k + 1]; }
-      if (k < nv && vc[k] == c) { s0 += c1[k]; ++k; }
-      ps.cam_part[(size_t)slot * kCamRec + threadIdx.x] = s0 + s1;
-      ++slot;
-      l = k;
-    }
-  }
-  {
-    const int nv = min(32, P.V - blockIdx.x * 32);
-    double* dst = ps.G + (size_t)blockIdx.x * 32 * kViewStride;
-    const int n = nv * kViewStride;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = recs[i];
-  }
-}
+constexpr int kFcElems = 27;     // doubles of a FrameConst
 
 // Inspection kernel: one thread per observation, full residual + Jacobian rows
 // in the reference's column order (camera_rt 6, chessboard_rt 6, intrinsic 9).
@@ -760,172 +255,6 @@ struct SchurArgs {
   int ntiles;
   int NLp;                 // NL rounded up to a multiple of 4
 };
-
-template <int T, int MAXNT>
-__global__ void __launch_bounds__(MAXNT)
-k_schur(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
-        SchurArgs A) {
-  if (st->done) return;
-  const ParamSet& ps = st->cur ? ps1 : ps0;
-  const double radius = A.radius_override > 0.0 ? A.radius_override : st->radius;
-  extern __shared__ __align__(32) double s_mem[];
-  const int NL = P.NL, NLp = A.NLp, NT = blockDim.x;
-  double* Ws = s_mem;                               // [FB*6][NLp]
-  double* Ys = Ws + kSchurFB * 6 * NLp;             // [FB*6][NLp]
-  double* zs = Ys + kSchurFB * 6 * NLp;             // [FB*6]
-  double* scr = zs + kSchurFB * 6;                  // [FB][64] per-warp scratch
-  int* colbase = reinterpret_cast<int*>(scr + kSchurFB * 64);  // [FB][32]
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int tbi[T], tbj[T];
-  double acc[T][16];
-#pragma unroll
-  for (int k = 0; k < T; ++k) {
-    const int t = tid + k * NT;
-    tbi[k] = t < A.ntiles ? A.tile_bi[t] : -1;
-    tbj[k] = t < A.ntiles ? A.tile_bj[t] : 0;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) acc[k][e] = 0.0;
-  }
-  double racc = 0.0;
-
-  const int f_begin = blockIdx.x * A.frames_per_block;
-  const int f_end = min(P.F, f_begin + A.frames_per_block);
-  for (int fb = f_begin; fb < f_end; fb += kSchurFB) {
-    for (int i = tid; i < 2 * kSchurFB * 6 * NLp + kSchurFB * 6; i += NT) s_mem[i] = 0.0;
-    __syncthreads();
-    const int f = fb + warp;
-    if (warp < kSchurFB && f < f_end) {
-      double* my = scr + warp * 64;
-      int* cb = colbase + warp * 32;
-      const int p0 = P.frame_ptr[f], nv = P.frame_ptr[f + 1] - p0;
-      if (lane < 27) {
-        const int e = lane < 21 ? kOffBB + lane : kOffBI + (lane - 21) * 8 + 7;
-        double s = 0.0;
-        for (int p = 0; p < nv; ++p) s += ps.G[(size_t)P.frame_views[p0 + p] * kViewStride + e];
-        my[lane] = s;
-      }
-      if (lane == 0) {
-        int c0 = 0;
-        for (int p = 0; p < nv; ++p) {
-          cb[p] = c0;
-          const int m = P.view_camera[P.frame_views[p0 + p]];
-          c0 += P.live_off[m + 1] - P.live_off[m];
-        }
-        cb[nv] = c0;
-      }
-      __syncwarp();
-      // every lane builds the damped, scaled 6x6 system redundantly
-      double se[6], M[36], gs[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) se[i] = A.scale_e[f * 6 + i];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int j = i; j < 6; ++j) {
-          const double v = se[i] * se[j] * my[tri6(i, j)];
-          M[i * 6 + j] = v;
-          M[j * 6 + i] = v;
-        }
-        gs[i] = se[i] * my[21 + i];
-      }
-      __syncwarp();
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-#pragma unroll
-          for (int j = i; j < 6; ++j) my[27 + tri6(i, j)] = M[i * 6 + j];
-          my[48 + i] = gs[i];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const double d = fmin(fmax(M[i * 6 + i], opt.min_lm_diagonal), opt.max_lm_diagonal);
-        const double D = sqrt(d / radius);
-        M[i * 6 + i] += D * D;
-      }
-      chol6(M);   // a failed pivot yields NaNs that k_decide turns into an invalid step
-      double z[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) z[i] = gs[i];
-      chol6_solve(M, z);
-      if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-#pragma unroll
-          for (int j = 0; j <= i; ++j) my[(i * (i + 1)) / 2 + j] = M[i * 6 + j];
-          my[21 + i] = z[i];
-          zs[warp * 6 + i] = z[i];
-        }
-      }
-      __syncwarp();
-      for (int i = lane; i < kFrameRec; i += 32) A.frame_rec[(size_t)i * A.Fpad + f] = my[i];
-      // columns of W_s and Y = (V + D^2)^-1 W_s
-      const int ncols = cb[nv];
-      for (int col = lane; col < ncols; col += 32) {
-        int vi = 0;
-        while (col >= cb[vi + 1]) ++vi;
-        const int v = P.frame_views[p0 + vi];
-        const int m = P.view_camera[v];
-        const int k = col - cb[vi];
-        const int kk = (P.live_off[m + 1] - P.live_off[m] == 13) ? k : k + 6;
-        const double sc = A.scale_c[m * 13 + kk];
-        const double* Gv = ps.G + (size_t)v * kViewStride;
-        double w[6];
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          const double raw = kk < 6 ? Gv[kOffBC + r * 6 + kk] : Gv[kOffBI + r * 8 + (kk - 6)];
-          w[r] = se[r] * raw * sc;
-        }
-        const int gcol = P.live_off[m] + k;
-#pragma unroll
-        for (int r = 0; r < 6; ++r) Ws[(warp * 6 + r) * NLp + gcol] = w[r];
-        chol6_solve(M, w);
-#pragma unroll
-        for (int r = 0; r < 6; ++r) Ys[(warp * 6 + r) * NLp + gcol] = w[r];
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < T; ++k) {
-      if (tbi[k] >= 0) {
-        const double* wp = Ws + 4 * tbi[k];
-        const double* yp = Ys + 4 * tbj[k];
-#pragma unroll 4
-        for (int r = 0; r < kSchurFB * 6; ++r) {
-          const double4 w4 = *reinterpret_cast<const double4*>(wp + r * NLp);
-          const double4 y4 = *reinterpret_cast<const double4*>(yp + r * NLp);
-          const double w[4] = {w4.x, w4.y, w4.z, w4.w};
-          const double y[4] = {y4.x, y4.y, y4.z, y4.w};
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[k][a * 4 + b] = fma(-w[a], y[b], acc[k][a * 4 + b]);
-        }
-      }
-    }
-    if (tid < NL) {
-      double a = racc;
-      for (int r = 0; r < kSchurFB * 6; ++r) a = fma(-Ws[r * NLp + tid], zs[r], a);
-      racc = a;
-    }
-    __syncthreads();
-  }
-  double* Sp = A.Spart + (size_t)blockIdx.x * P.Q;
-#pragma unroll
-  for (int k = 0; k < T; ++k) {
-    if (tbi[k] < 0) continue;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int i = 4 * tbi[k] + a, j = 4 * tbj[k] + b;
-        if (i <= j && j < NL) Sp[i * NL - (i * (i - 1)) / 2 + (j - i)] = acc[k][a * 4 + b];
-      }
-    }
-  }
-  if (tid < NL) A.rpart[(size_t)blockIdx.x * NL + tid] = racc;
-}
 
 // ---------------------------------------------------------------------------
 // K3, pipelined form (used when two staging buffers fit in shared memory):
@@ -1103,6 +432,9 @@ k_schur2(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptio
           }
         }
       }
+      // the lane-divergent column loops above must have reconverged before the aligned
+      // CTA barrier (compute-sanitizer synccheck, profiles/r02_sanitizer_*)
+      __syncwarp();
       __syncthreads();
     }
     return;
@@ -1410,7 +742,6 @@ k_pair_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, Lm
   if (active) {
     for (int i = g; i < kFrameRec; i += 8) A.frame_rec[(size_t)i * A.Fpad + f] = rec[i];
     for (int i = g; i < 27; i += 8) B.fact[(size_t)f * 32 + i] = rec[i];
-    if (B.Wv == nullptr && g < 6) B.zg[(size_t)f * 6 + g] = rec[21 + g];   // dense-row form
   }
 }
 
@@ -1443,23 +774,6 @@ k_pair_blocks(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, Sc
       w[q] = se[q] * raw * csc;
     }
   }
-  if (B.Wv == nullptr) {
-    // dense-row form (k_schur_update): rows [F][6][NLp], columns permuted (schur_perm); columns
-    // of cameras that do not see the frame were zeroed at allocation and are never written
-    if (!live) return;
-    const int col = schur_perm(P.live_off[m] + (free_rt ? c : c - 6), B.a.NLp);
-    double* Wr = B.Wg + (size_t)f * 6 * B.a.NLp + col;
-    double* Yr = B.Yg + (size_t)f * 6 * B.a.NLp + col;
-#pragma unroll
-    for (int q = 0; q < 6; ++q) Wr[q * B.a.NLp] = w[q];
-    double L[21];
-#pragma unroll
-    for (int i = 0; i < 21; ++i) L[i] = Lp[i];
-    chol6_solve_packed(L, w);
-#pragma unroll
-    for (int q = 0; q < 6; ++q) Yr[q * B.a.NLp] = w[q];
-    return;
-  }
   double* Wb = B.Wv + (size_t)v * 96 + c;
 #pragma unroll
   for (int q = 0; q < 6; ++q) Wb[q * 16] = w[q];
@@ -1485,6 +799,9 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) {
 }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
@@ -1614,19 +931,82 @@ k_schur_update(DeviceProblem P, const LmState* st, SchurSplitArgs B) {
   if (tid < NL) A.rpart[(size_t)blockIdx.x * NL + tid] = racc;
 }
 
-// Sum the per-CTA partials: out = [S packed upper (Q) | rhs (NL)].  A CTA owns 32 consecutive
-// entries; its 8 warps each sum every 8th partial (4 loads in flight per thread, 256-byte
-// coalesced rows) and the 8 warp sums are added in a fixed order: ~5 dependent L2 round
-// trips instead of the 37 of a one-thread-per-entry sum.
+// U(i, j) of camera record `U` for in-camera indices a <= b (0..12 over [rt 6 | intr 7]).
+__device__ __forceinline__ double cam_block(const double* U, int a, int b) {
+  if (b < 6) return U[kCamCC + tri6(a, b)];
+  if (a < 6) return U[kCamCI + a * 8 + (b - 6)];
+  return U[kCamII + tri8(a - 6, b - 6)];
+}
+__device__ __forceinline__ double cam_grad(const double* U, int a) {
+  return a < 6 ? U[kCamCI + a * 8 + 7] : U[kCamII + tri8(a - 6, 7)];
+}
+
+// ---------------------------------------------------------------------------
+// The reduced camera system handed to k_solve: the AUGMENTED matrix [[lhs, rhs], [rhs^T, .]]
+//   lhs = sum_f(-W^T V^-1 W) [Schur partials] + U_s + D_c^2,   rhs = sum_f(-W^T z) + g_s
+// as 4x4 tiles of the lower block triangle, tile (bi, bj) at tile_id(bi, bj) * 16, entry
+// (a, b) of a tile at a * 4 + b — exactly the 16 registers a k_solve thread owns, so that its
+// load is eight 16-byte loads from one 128-byte line.  Entries outside the system (identity
+// padding, the upper part of diagonal tiles) are never written and stay zero; k_solve
+// overrides them.  The assembly (camera blocks U_s, the LM diagonal D_c^2 = clamp(diag) /
+// radius, the gradient) happens HERE, in the thread that finishes an entry, because this
+// kernel has 155 mostly idle CTAs while k_solve is one latency-bound CTA.
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int solve_tile_id(int bi, int bj, int nbk) {   // bi >= bj, column-major
+  return bj * nbk - (bj * (bj - 1)) / 2 + (bi - bj);
+}
+struct AssembleArgs {
+  const double* scale_c;     // [C][13]
+  double radius_override;    // > 0: use instead of st->radius (inspection)
+  int nbk;                   // ceil((NL + 1) / 4)
+  int add_cam;               // 0: raw sums only (NCCL fallback: the camera terms follow the all-reduce)
+};
+// position of linear entry i (< Q: packed upper S, then rhs) in the tile-major system
+__device__ __forceinline__ int assemble_position(const DeviceProblem& P, const AssembleArgs& A, int i, int* row,
+                                                 int* col) {
+  int r, c;
+  if (i < P.Q) { c = P.q_i[i]; r = P.q_j[i]; } else { c = i - P.Q; r = P.NL; }
+  *row = r; *col = c;
+  return solve_tile_id(r >> 2, c >> 2, A.nbk) * 16 + (r & 3) * 4 + (c & 3);
+}
+// U_s + D_c^2 (or the scaled gradient for the rhs row) of entry (r, c), c <= r
+__device__ __forceinline__ double assemble_cam_term(const DeviceProblem& P, const ParamSet& ps, const LmOptions& opt,
+                                                    const AssembleArgs& A, double radius, int r, int c) {
+  const int cc = P.live_cam[c], kc = P.live_kk[c];
+  const double* U = ps.comm + cc * kCamRec;
+  const double sc_c = A.scale_c[cc * 13 + kc];
+  if (r == P.NL) return sc_c * cam_grad(U, kc);
+  if (P.live_cam[r] != cc) return 0.0;
+  const int kr = P.live_kk[r];
+  const double us = sc_c * A.scale_c[cc * 13 + kr] * cam_block(U, kc, kr);
+  if (r != c) return us;
+  const double d = fmin(fmax(us, opt.min_lm_diagonal), opt.max_lm_diagonal);
+  const double D = sqrt(d / radius);
+  return us + D * D;
+}
+
+// Sum the per-CTA partials.  A CTA owns 32 consecutive entries; its 8 warps each sum every 8th
+// partial (4 loads in flight per thread, 256-byte coalesced rows) and the 8 warp sums are added
+// in a fixed order: ~5 dependent L2 round trips instead of the 37 of a one-thread-per-entry sum.
 constexpr int kReduceThreads = 256;
 __global__ void __launch_bounds__(kReduceThreads)
-k_reduce_s(DeviceProblem P, const LmState* st, const double* __restrict__ Spart,
-           const double* __restrict__ rpart, int nblk, double* __restrict__ out) {
+k_reduce_s(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
+           const double* __restrict__ Spart, const double* __restrict__ rpart, int nblk,
+           double* __restrict__ out, AssembleArgs A) {
   if (st->done) return;
   __shared__ double s_part[8][33];
   const int e = threadIdx.x & 31, part = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + e;
   const bool ok = i < P.Q + P.NL;
+  // the finishing thread's camera term is requested first: its loads overlap the partial sums
+  int pos = 0;
+  double cam = 0.0;
+  if (part == 0 && ok) {
+    int r, c;
+    pos = assemble_position(P, A, i, &r, &c);
+    if (A.add_cam)
+      cam = assemble_cam_term(P, st->cur ? ps1 : ps0, opt, A, A.radius_override > 0.0 ? A.radius_override : st->radius, r, c);
+  }
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   if (ok) {
     const double* src = i < P.Q ? Spart + i : rpart + (i - P.Q);
@@ -1646,37 +1026,19 @@ k_reduce_s(DeviceProblem P, const LmState* st, const double* __restrict__ Spart,
     double t = s_part[0][e];
 #pragma unroll
     for (int q = 1; q < 8; ++q) t += s_part[q][e];
-    out[i] = t;
+    out[pos] = t + cam;
   }
 }
 
-// ---------------------------------------------------------------------------
-// K4: reduced camera system — assemble, factor, solve (single CTA, 512 threads).
-//   lhs = sum_f(-W^T V^-1 W) [all-reduced] + U_s + D_c^2
-// Square-root-free blocked Cholesky (L D L^T, 4 columns per step) of the
-// AUGMENTED matrix [[lhs, rhs], [rhs^T, .]] held column-major packed in shared
-// memory: the extra row carries the forward substitution through the
-// factorisation for free.  Per step: (1) every thread factors the 4x4 pivot
-// block redundantly (Newton reciprocals, no divisions), one thread per row
-// eliminates the 4 panel columns of its row; (2) rank-4 update of the trailing
-// triangle, lanes along rows (contiguous, conflict-free) and warps along
-// columns, 4 FMAs per shared-memory load/store pair.  Two barriers per 4
-// columns.  A warp then back-substitutes.  Same pivots and the same
-// positive-definiteness test (d_j > 0) as the Eigen LLT Ceres uses here.
-// ---------------------------------------------------------------------------
-constexpr int kSolveThreads = 512;
-constexpr int kSolveNB = 4;
-
-__device__ __forceinline__ int idxL(int r, int c) { return (r * (r + 1)) / 2 + c; }  // r >= c
-
-// U(i, j) of camera record `U` for in-camera indices a <= b (0..12 over [rt 6 | intr 7]).
-__device__ __forceinline__ double cam_block(const double* U, int a, int b) {
-  if (b < 6) return U[kCamCC + tri6(a, b)];
-  if (a < 6) return U[kCamCI + a * 8 + (b - 6)];
-  return U[kCamII + tri8(a - 6, b - 6)];
-}
-__device__ __forceinline__ double cam_grad(const double* U, int a) {
-  return a < 6 ? U[kCamCI + a * 8 + 7] : U[kCamII + tri8(a - 6, 7)];
+// NCCL fallback: the camera terms are added once, after the all-reduce of the raw sums.
+__global__ void k_add_cam_terms(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
+                                double* __restrict__ out, AssembleArgs A) {
+  if (st->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.Q + P.NL) return;
+  int r, c;
+  const int pos = assemble_position(P, A, i, &r, &c);
+  out[pos] += assemble_cam_term(P, st->cur ? ps1 : ps0, opt, A, A.radius_override > 0.0 ? A.radius_override : st->radius, r, c);
 }
 
 // 1/d to ~1 ulp: hardware seed + two Newton steps (no IEEE division sequence on
@@ -1687,298 +1049,6 @@ __device__ __forceinline__ double fast_rcp(double d) {
   x = fma(x, fma(-d, x, 1.0), x);
   x = fma(x, fma(-d, x, 1.0), x);
   return x;
-}
-
-template <int AMAX>   // ceil((NL + 1) / 32): 32-row blocks a lane may own
-__global__ void __launch_bounds__(kSolveThreads)
-k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
-        const double* __restrict__ Sr /*[Q + NL]*/, const double* __restrict__ scale_c,
-        double* __restrict__ y_c /*[NL]*/, double radius_override,
-        double* __restrict__ dbg_lhs, double* __restrict__ dbg_rhs, int prof) {
-  if (st->done) return;
-  long long tk0 = clock64(), tk1 = 0, tk2 = 0, tk3 = 0;
-  const int sel = st->cur;
-  const ParamSet& ps = sel ? ps1 : ps0;     // current x
-  const ParamSet& pc = sel ? ps0 : ps1;     // candidate
-  const double radius = radius_override > 0.0 ? radius_override : st->radius;
-  extern __shared__ double s_mem[];
-  const int NL = P.NL, n1 = NL + 1, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int kWarps = kSolveThreads / 32;
-  // column-major packed lower triangle of the n1 x n1 augmented matrix:
-  // element (i, k), i >= k, at colptr(k) + i - k, colptr(k) = k n1 - k (k - 1) / 2
-  double* L = s_mem;
-  double* x = L + (n1 * (n1 + 1)) / 2;     // [NL] solution y
-  double* gsv = x + NL;                    // [NL] scaled gradient
-  double* sc = gsv + NL;                   // [NL] scale
-  double* dinv = sc + NL;                  // [NL + 4] 1 / d_j
-  double* Pb = dinv + NL + 4;              // [4][n1] panel P[c][i]
-  double* dummy = Pb + 4 * n1;             // [kSolveThreads] sink for masked lanes
-  double* s_red = dummy + kSolveThreads;   // [kSolveThreads]
-  double* s_comm = s_red + kSolveThreads;  // [C][kCamRec] camera records of the current point
-  short* s_cam = reinterpret_cast<short*>(s_comm + P.C * kCamRec);   // [NL]
-  short* s_kk = s_cam + NL;                                         // [NL]
-  __shared__ int s_ok;
-#define COLPTR(k) ((k) * n1 - ((k) * ((k) - 1)) / 2)
-  if (tid == 0) s_ok = 1;
-  for (int i = tid; i < NL; i += kSolveThreads) {
-    const int c = P.live_cam[i], kk = P.live_kk[i];
-    s_cam[i] = (short)c; s_kk[i] = (short)kk;
-    sc[i] = scale_c[c * 13 + kk];
-  }
-  for (int i = tid; i < P.C * kCamRec; i += kSolveThreads) s_comm[i] = ps.comm[i];
-  __syncthreads();
-  // assemble: one thread per packed entry q = (k, i), k <= i, four global loads in flight
-  // per thread (Sr and the index tables are L2-resident; the camera records sit in shared
-  // memory), instead of a warp walking a column with two dependent global loads per step
-  for (int q0 = tid; q0 < P.Q; q0 += 4 * kSolveThreads) {
-    double v[4];
-    int kk_[4], ii_[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int q = q0 + u * kSolveThreads;
-      const bool ok = q < P.Q;
-      v[u] = ok ? Sr[q] : 0.0;
-      kk_[u] = ok ? P.q_i[q] : -1;
-      ii_[u] = ok ? P.q_j[q] : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (kk_[u] < 0) continue;
-      const int k = kk_[u], i = ii_[u];
-      const int ck = s_cam[k];
-      double val = v[u];
-      if (s_cam[i] == ck) {
-        const double us = sc[k] * sc[i] * cam_block(s_comm + ck * kCamRec, s_kk[k], s_kk[i]);
-        val += us;
-        if (i == k) {
-          const double d = fmin(fmax(us, opt.min_lm_diagonal), opt.max_lm_diagonal);
-          const double D = sqrt(d / radius);
-          val += D * D;
-        }
-      }
-      L[COLPTR(k) - k + i] = val;
-    }
-  }
-  for (int k = tid; k < NL; k += kSolveThreads) {
-    const double g = sc[k] * cam_grad(s_comm + s_cam[k] * kCamRec, s_kk[k]);
-    gsv[k] = g;
-    L[COLPTR(k) - k + NL] = Sr[P.Q + k] + g;          // augmented row = rhs
-  }
-  __syncthreads();
-  if (dbg_lhs) {
-    for (int idx = tid; idx < NL * NL; idx += kSolveThreads) {
-      const int r = idx / NL, c = idx % NL;
-      dbg_lhs[idx] = r >= c ? L[COLPTR(c) + r - c] : L[COLPTR(r) + c - r];
-    }
-    for (int i = tid; i < NL; i += kSolveThreads) dbg_rhs[i] = L[COLPTR(i) + NL - i];
-    __syncthreads();
-  }
-  tk1 = clock64();
-  long long tp0 = 0, tp1 = 0, tp2 = 0;
-  for (int j = 0; j < NL; j += kSolveNB) {
-    const long long ta = clock64();
-    const int nb = min(kSolveNB, NL - j);
-    // ---- pivot block (every thread, redundantly) -------------------------------
-    const int c0 = COLPTR(j), c1 = COLPTR(j + 1), c2 = COLPTR(j + 2), c3 = COLPTR(j + 3);
-    const double t00 = L[c0];
-    const double t10 = nb > 1 ? L[c0 + 1] : 0.0, t11 = nb > 1 ? L[c1] : 1.0;
-    const double t20 = nb > 2 ? L[c0 + 2] : 0.0, t21 = nb > 2 ? L[c1 + 1] : 0.0, t22 = nb > 2 ? L[c2] : 1.0;
-    const double t30 = nb > 3 ? L[c0 + 3] : 0.0, t31 = nb > 3 ? L[c1 + 2] : 0.0,
-                 t32 = nb > 3 ? L[c2 + 1] : 0.0, t33 = nb > 3 ? L[c3] : 1.0;
-    const double d0 = t00, i0 = fast_rcp(d0);
-    const double l10 = t10 * i0;
-    const double d1 = fma(-t10, l10, t11), i1 = fast_rcp(d1);
-    const double l20 = t20 * i0;
-    const double w21 = fma(-t20, l10, t21), l21 = w21 * i1;
-    const double d2 = fma(-w21, l21, fma(-t20, l20, t22)), i2 = fast_rcp(d2);
-    const double l30 = t30 * i0;
-    const double w31 = fma(-t30, l10, t31), l31 = w31 * i1;
-    const double w32 = fma(-w31, l21, fma(-t30, l20, t32)), l32 = w32 * i2;
-    const double d3 = fma(-w32, l32, fma(-w31, l31, fma(-t30, l30, t33))), i3 = fast_rcp(d3);
-    const double g0 = i0, g1 = nb > 1 ? i1 : 0.0, g2 = nb > 2 ? i2 : 0.0, g3 = nb > 3 ? i3 : 0.0;
-    __syncthreads();   // everyone has read the pivot block before it is rewritten
-    const long long tb = clock64();
-    if (tid == 0) {
-      dinv[j] = i0;
-      bool ok = d0 > 0.0;
-      if (nb > 1) { dinv[j + 1] = i1; ok = ok && d1 > 0.0; }
-      if (nb > 2) { dinv[j + 2] = i2; L[c1 + 1] = w21; ok = ok && d2 > 0.0; }
-      if (nb > 3) { dinv[j + 3] = i3; L[c1 + 2] = w31; L[c2 + 1] = w32; ok = ok && d3 > 0.0; }
-      if (!ok) s_ok = 0;
-    }
-    // ---- panel: one thread per row below the pivot block ------------------------
-    for (int i = j + nb + tid; i <= NL; i += kSolveThreads) {
-      const double p0 = L[c0 + i - j];
-      double p1 = 0.0, p2 = 0.0, p3 = 0.0;
-      if (nb > 1) { p1 = fma(-p0, l10, L[c1 + i - j - 1]); L[c1 + i - j - 1] = p1; }
-      if (nb > 2) { p2 = fma(-p1, l21, fma(-p0, l20, L[c2 + i - j - 2])); L[c2 + i - j - 2] = p2; }
-      if (nb > 3) { p3 = fma(-p2, l32, fma(-p1, l31, fma(-p0, l30, L[c3 + i - j - 3]))); L[c3 + i - j - 3] = p3; }
-      Pb[i] = p0; Pb[n1 + i] = p1; Pb[2 * n1 + i] = p2; Pb[3 * n1 + i] = p3;
-    }
-    __syncthreads();
-    const long long tc = clock64();
-    tp0 += tb - ta; tp1 += tc - tb;
-    // ---- rank-4 update of the trailing triangle ---------------------------------
-    const int base = j + nb;
-    if (base < NL) {
-      double f[AMAX][4];
-#pragma unroll
-      for (int a = 0; a < AMAX; ++a) {
-        const int i = base + lane + 32 * a;
-        const bool ok = i <= NL;
-        f[a][0] = ok ? Pb[i] : 0.0;
-        f[a][1] = ok ? Pb[n1 + i] : 0.0;
-        f[a][2] = ok ? Pb[2 * n1 + i] : 0.0;
-        f[a][3] = ok ? Pb[3 * n1 + i] : 0.0;
-      }
-      // two columns per pass; all loads of a pass are issued before the first
-      // store so the 2 * AMAX FMA chains overlap (the compiler cannot hoist them
-      // itself: the stores alias).
-      for (int k = base + warp; k < NL; k += 2 * kWarps) {
-        const int k2 = k + kWarps;
-        const bool has2 = k2 < NL;
-        const int kk2 = has2 ? k2 : k;
-        const double q0 = Pb[k] * g0, q1 = Pb[n1 + k] * g1, q2 = Pb[2 * n1 + k] * g2,
-                     q3 = Pb[3 * n1 + k] * g3;
-        const double r0 = Pb[kk2] * g0, r1 = Pb[n1 + kk2] * g1, r2 = Pb[2 * n1 + kk2] * g2,
-                     r3 = Pb[3 * n1 + kk2] * g3;
-        const int cp = COLPTR(k) - k, cp2 = COLPTR(kk2) - kk2;
-        double* pa[AMAX];
-        double* pb[AMAX];
-        double va[AMAX], vb[AMAX];
-#pragma unroll
-        for (int a = 0; a < AMAX; ++a) {
-          const int i = base + lane + 32 * a;
-          pa[a] = (i >= k && i <= NL) ? &L[cp + i] : &dummy[tid];
-          pb[a] = (has2 && i >= k2 && i <= NL) ? &L[cp2 + i] : &dummy[tid];
-          va[a] = *pa[a];
-          vb[a] = *pb[a];
-        }
-#pragma unroll
-        for (int a = 0; a < AMAX; ++a) {
-          va[a] = fma(-f[a][0], q0, va[a]); vb[a] = fma(-f[a][0], r0, vb[a]);
-        }
-#pragma unroll
-        for (int a = 0; a < AMAX; ++a) {
-          va[a] = fma(-f[a][1], q1, va[a]); vb[a] = fma(-f[a][1], r1, vb[a]);
-        }
-#pragma unroll
-        for (int a = 0; a < AMAX; ++a) {
-          va[a] = fma(-f[a][2], q2, va[a]); vb[a] = fma(-f[a][2], r2, vb[a]);
-        }
-#pragma unroll
-        for (int a = 0; a < AMAX; ++a) {
-          va[a] = fma(-f[a][3], q3, va[a]); vb[a] = fma(-f[a][3], r3, vb[a]);
-        }
-#pragma unroll
-        for (int a = 0; a < AMAX; ++a) {
-          *pa[a] = va[a];
-          *pb[a] = vb[a];
-        }
-      }
-    }
-    __syncthreads();
-    tp2 += clock64() - tc;
-  }
-  tk2 = clock64();
-  // Back-substitution, row-owner form: thread i keeps r_i = rhs'_i - sum_{j solved} A'[j][i] x_j
-  // in a register.  Per block of 4 columns (right to left): the owners publish their r_j,
-  // one thread solves the 4x4 unit-triangular tail (x_j = (r_j - ...) / d_j), then every row
-  // above the block folds the 4 new x_j in with 4 FMAs on 4 consecutive entries of its own
-  // column.  Two barriers and ~15 dependent FP64 operations per 4 columns (the previous
-  // warp-0 form reduced four dot products through shuffles per block: 3x the latency).
-  {
-    const bool own = tid < NL;
-    double r = own ? L[COLPTR(tid) - tid + NL] : 0.0;
-    for (int jb = ((NL - 1) >> 2) << 2; jb >= 0; jb -= 4) {
-      const int nb = min(4, NL - jb);
-      if (own && tid >= jb && tid < jb + nb) x[tid] = r;
-      __syncthreads();
-      if (tid == 0) {
-        double xs[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-        for (int c = 3; c >= 0; --c) {
-          if (c < nb) {
-            const int j = jb + c;
-            const int cp = COLPTR(j) - j;
-            double t = x[j];
-#pragma unroll
-            for (int d = 3; d > 0; --d)
-              if (d > c && d < nb) t = fma(-L[cp + jb + d], xs[d], t);
-            xs[c] = t * dinv[j];
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) if (c < nb) x[jb + c] = xs[c];
-      }
-      __syncthreads();
-      if (own && tid < jb) {
-        const double* col = L + COLPTR(tid) - tid + jb;     // A'[jb + c][tid], c = 0..3
-        double acc = r;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) if (c < nb) acc = fma(-col[c], x[jb + c], acc);
-        r = acc;
-      }
-    }
-  }
-  __syncthreads();
-#undef COLPTR
-  tk3 = clock64();
-  // y_c, candidate camera parameters, camera-side partial sums.
-  double lin = 0.0, dn2 = 0.0, quad = 0.0;
-  for (int i = tid; i < NL; i += kSolveThreads) {
-    const double y = x[i];
-    y_c[i] = y;
-    lin += y * gsv[i];
-    const double delta = -y * sc[i];
-    dn2 += delta * delta;
-    // quad: y^T U_s y restricted to this row (both triangles)
-    const int ci = s_cam[i];
-    const double* U = s_comm + ci * kCamRec;
-    const int o0 = P.live_off[ci], n = P.live_off[ci + 1] - o0;
-    const int ki = s_kk[i];
-    double row = 0.0;
-    for (int t = 0; t < n; ++t) {
-      const int jj = o0 + t, kj = s_kk[jj];
-      const double u = ki <= kj ? cam_block(U, ki, kj) : cam_block(U, kj, ki);
-      row += sc[i] * sc[jj] * u * x[jj];
-    }
-    quad += y * row;
-  }
-  // candidate camera parameters (b, c intrinsics are carried unchanged)
-  double xn2 = 0.0;
-  for (int idx = tid; idx < P.C * 15; idx += kSolveThreads) {
-    const int c = idx / 15, k = idx % 15;   // k < 6: rt, else intrinsic k - 6
-    const bool free_rt = (c != P.fixed_camera);
-    const double xv = k < 6 ? ps.cam_rt[c * 6 + k] : ps.intr[c * 9 + (k - 6)];
-    double xn = xv;
-    if (k < 6) {
-      if (free_rt) xn = xv + (-x[P.live_off[c] + k] * sc[P.live_off[c] + k]);
-    } else if (k - 6 < 7) {
-      const int li = P.live_off[c] + (free_rt ? 6 : 0) + (k - 6);
-      xn = xv + (-x[li] * sc[li]);
-    }
-    if (k < 6) pc.cam_rt[c * 6 + k] = xn; else pc.intr[c * 9 + (k - 6)] = xn;
-    if (k >= 6 || free_rt) xn2 += xn * xn;
-  }
-  __syncthreads();   // candidate parameters are complete
-  if (tid < P.C) {
-    // per-camera constants of the candidate (what k_prep_cams would do)
-    CamConst cc;
-    make_cam_const(pc.cam_rt + 6 * tid, pc.intr + 9 * tid, tid != P.fixed_camera, cc);
-    pc.cam[tid] = cc;
-  }
-  const double t_lin = block_sum(lin, s_red);
-  const double t_quad = block_sum(quad, s_red);
-  const double t_dn2 = block_sum(dn2, s_red);
-  const double t_xn2 = block_sum(xn2, s_red);
-  if (tid == 0) {
-    st->cam_lin = t_lin; st->cam_quad = t_quad; st->cam_dn2 = t_dn2; st->cam_xn2 = t_xn2;
-    st->solve_ok = s_ok;
-    if (prof)
-      printf("k_solve cycles: assemble %lld  ldlt %lld (pivot %lld panel %lld trailing %lld)  backsub %lld  tail %lld\n",
-             tk1 - tk0, tk2 - tk1, tp0, tp1, tp2, tk3 - tk2, clock64() - tk3);
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1994,6 +1064,18 @@ k_backsub(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, SchurA
   __shared__ double s_red[kBacksubThreads];
   __shared__ double s_yp[224];
   if (st->done) return;
+  if ((int)blockIdx.x == nblk) {
+    // extra block: derived constants of the candidate cameras, whose parameters k_solve has
+    // just written (what k_prep_cams does for an explicitly uploaded point)
+    const ParamSet& pcand = st->cur ? ps0 : ps1;
+    const int c = threadIdx.x;
+    if (c < P.C) {
+      CamConst cc;
+      make_cam_const(pcand.cam_rt + 6 * c, pcand.intr + 9 * c, c != P.fixed_camera, cc);
+      pcand.cam[c] = cc;
+    }
+    return;
+  }
   if (Wg) {
     for (int i = threadIdx.x; i < A.NLp; i += kBacksubThreads) s_yp[i] = 0.0;
     __syncthreads();
@@ -2203,13 +1285,15 @@ __device__ inline void decide_step(const DeviceProblem& P, const ParamSet& ps0, 
   const double step_norm = sqrt(dn2);
   st->step_norm = step_norm;
   if (!opt.disable_tolerances) {
-    // ParameterToleranceReached
+    // Ceres <= 2.0 tests both tolerances on every valid step; >= 2.1 only once a step has been
+    // successful (tscm_options.parameter_tolerance_needs_successful_step)
     const bool armed = !opt.ptol_needs_success || st->atleast_one_successful_step;
+    // ParameterToleranceReached
     if (armed && step_norm <= opt.parameter_tolerance * (st->x_norm + opt.parameter_tolerance)) {
       st->termination = 0; st->done = 1; return;
     }
     // FunctionToleranceReached
-    if (fabs(st->x_cost - candidate_cost) <= opt.function_tolerance * st->x_cost) {
+    if (armed && fabs(st->x_cost - candidate_cost) <= opt.function_tolerance * st->x_cost) {
       st->termination = 0; st->done = 1; return;
     }
   }
@@ -2245,7 +1329,7 @@ __global__ void k_decide(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* s
 
 // ---------------------------------------------------------------------------
 // Post-evaluation kernel.  Blocks [0, C): camera c sums its partial slots (written by
-// k_eval3, one per (CTA, camera)) in a fixed order into the comm record.  Blocks
+// k_view_blocks, one per (tile, camera)) in a fixed order into the comm record.  Blocks
 // [C, C + fg_nblk): frame gradient max-norm |x - (x - g)|_inf and |x_f|^2 partials.  The LAST
 // block to finish (threadfence + ticket) folds the frame partials and the step scalars into
 // the record and — on a single GPU — runs the accept/reject decision itself.  Which block

@@ -20,8 +20,9 @@
 //                   spread over 155 CTAs
 //   k_xchg_eval     exchange of the evaluation record (C*107 + 4 sums and one max), followed
 //                   by the accept/reject decision (replaces ncclAllReduce x2 + k_decide)
-// A wait that does not complete within ~4 s sets *err and falls through (the host reports
-// TSCM_ERR_COMM); nothing spins forever.
+// A wait that does not complete within P2PArgs::timeout_ns (wall clock, %globaltimer) sets
+// *err; k_xchg_eval then ends the solve with FAILURE instead of deciding on stale sums and the
+// host reports TSCM_ERR_COMM.  Nothing spins forever; the flag is cleared at the start of a run.
 #pragma once
 
 #include "tscm_kernels.cuh"
@@ -39,6 +40,7 @@ struct P2PArgs {
   int nA;                       // doubles per Schur slot
   int nctaA;                    // CTAs of k_reduce_s_p2p (one flag each)
   int nB;                       // doubles per evaluation slot (C*kCamRec + kCommExtra + 1)
+  unsigned long long timeout_ns;   // a wait gives up after this long (tscm_solver_set_exchange_timeout)
 };
 // mailbox layout (8-byte words), W = kP2PMaxRanks source ranks:
 //   A[2][W][nA] | flagA[2][W][nctaA] | B[2][W][nB] | flagB[2][W]
@@ -63,19 +65,36 @@ __device__ __forceinline__ unsigned long long* p2p_flagB(const P2PArgs& x, int r
 __device__ __forceinline__ void p2p_post(unsigned long long* flag, unsigned long long s) {
   *reinterpret_cast<volatile unsigned long long*>(flag) = s;
 }
-__device__ __forceinline__ bool p2p_wait(const unsigned long long* flag, unsigned long long s, int* err) {
+__device__ __forceinline__ unsigned long long p2p_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Spin on a LOCAL flag until a peer has posted `s`.  Gives up after x.timeout_ns of wall time
+// (a peer that never entered the solve): sets *x.err, which k_xchg_eval turns into a FAILURE
+// termination instead of a decision on stale data, and which the host reports as TSCM_ERR_COMM.
+__device__ __forceinline__ bool p2p_wait(const unsigned long long* flag, unsigned long long s, const P2PArgs& x) {
   const volatile unsigned long long* f = flag;
-  for (int i = 0; i < (1 << 24); ++i) {
+  unsigned long long t0 = 0;
+  for (unsigned i = 0;; ++i) {
     if (*f >= s) { __threadfence_system(); return true; }
-    if (i > 64) __nanosleep(100);
+    if (i > 64) {
+      __nanosleep(100);
+      if ((i & 1023u) == 0) {
+        const unsigned long long now = p2p_now_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > x.timeout_ns) break;
+      }
+    }
   }
-  *err = 1;
+  *x.err = 1;
   return false;
 }
 
 __global__ void __launch_bounds__(kReduceThreads)
-k_reduce_s_p2p(DeviceProblem P, const LmState* st, const double* __restrict__ Spart,
-               const double* __restrict__ rpart, int nblk, double* __restrict__ out, P2PArgs x) {
+k_reduce_s_p2p(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
+               const double* __restrict__ Spart, const double* __restrict__ rpart, int nblk,
+               double* __restrict__ out, AssembleArgs A, P2PArgs x) {
   if (st->done) return;
   __shared__ double s_part[8][33];
   __shared__ double s_mine[32];
@@ -84,6 +103,14 @@ k_reduce_s_p2p(DeviceProblem P, const LmState* st, const double* __restrict__ Sp
   const bool ok = i < P.Q + P.NL;
   const unsigned long long s = x.seq[0] + 1;
   const int par = (int)(s & 1ull);
+  // camera term of the finishing thread (added once, after the cross-rank sum)
+  int pos = 0;
+  double cam = 0.0;
+  if (part == 0 && ok) {
+    int r, c;
+    pos = assemble_position(P, A, i, &r, &c);
+    cam = assemble_cam_term(P, st->cur ? ps1 : ps0, opt, A, A.radius_override > 0.0 ? A.radius_override : st->radius, r, c);
+  }
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   if (ok) {
     const double* src = i < P.Q ? Spart + i : rpart + (i - P.Q);
@@ -115,7 +142,7 @@ k_reduce_s_p2p(DeviceProblem P, const LmState* st, const double* __restrict__ Sp
       __syncwarp();
       if (e == 0) {
         p2p_post(p2p_flagA(x, part, par, x.rank) + blockIdx.x, s);
-        p2p_wait(p2p_flagA(x, x.rank, par, part) + blockIdx.x, s, x.err);
+        p2p_wait(p2p_flagA(x, x.rank, par, part) + blockIdx.x, s, x);
       }
       __syncwarp();
       v = *reinterpret_cast<const volatile double*>(p2p_A(x, x.rank, par, part) + blockIdx.x * 32 + e);
@@ -128,7 +155,7 @@ k_reduce_s_p2p(DeviceProblem P, const LmState* st, const double* __restrict__ Sp
   if (part == 0 && ok) {
     double t = s_part[0][e];
     for (int q = 1; q < x.world; ++q) t += s_part[q][e];
-    out[i] = t;
+    out[pos] = t + cam;
   }
   // the last CTA to finish closes the exchange (every CTA has read seq by then)
   if (threadIdx.x == 0) {
@@ -161,7 +188,7 @@ k_xchg_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, int which,
   if (tid < x.world) {
     if (tid != x.rank) p2p_post(p2p_flagB(x, tid, par, x.rank), s);
   }
-  if (tid < x.world && tid != x.rank) p2p_wait(p2p_flagB(x, x.rank, par, tid), s, x.err);
+  if (tid < x.world && tid != x.rank) p2p_wait(p2p_flagB(x, x.rank, par, tid), s, x);
   __syncthreads();
   for (int i = tid; i <= n; i += kXchgThreads) {
     double acc = *reinterpret_cast<const volatile double*>(p2p_B(x, x.rank, par, 0) + i);
@@ -175,7 +202,12 @@ k_xchg_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, int which,
   __syncthreads();
   if (tid == 0) {
     x.seq[1] = s;
-    if (decide) decide_step(P, ps0, ps1, st, opt, tr);
+    if (*reinterpret_cast<volatile int*>(x.err)) {
+      // a peer did not show up in this or the preceding Schur exchange: the sums are not global
+      st->termination = 2; st->done = 1;
+    } else if (decide) {
+      decide_step(P, ps0, ps1, st, opt, tr);
+    }
   }
 }
 
