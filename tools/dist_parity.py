@@ -25,19 +25,25 @@ for cfg, frames in CASES:
     s.set_parameters(sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt[fr])
     res = s.run()
     intr, cam_rt, board_rt = s.get_parameters()
+    per_cam, overall, rms = s.reprojection_error()      # global sums / global counts on every rank
     s.close()
     if rank == 0:
         a, b, c, ref = capi.solve(sp.problem, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt, opt, device=local)
+        one = capi.Solver(sp.problem, opt, device=local)
+        one.set_parameters(a, b, c)
+        per1, overall1, rms1 = one.reprojection_error()
+        one.close()
+        readout = max(float(np.max(np.abs(per_cam - per1))), abs(overall - overall1), abs(rms - rms1))
         same_iters = res.num_iterations == ref.num_iterations and res.termination == ref.termination
         n = min(len(res.cost), len(ref.cost))
         cost_rel = float(np.max(np.abs(res.cost[:n] - ref.cost[:n]) / ref.cost[:n]))
         p_rel = max(float(np.max(np.abs(intr - a) / (np.abs(a) + 1e-9))),
                     float(np.max(np.abs(cam_rt - b) / (np.abs(b) + 1e-9))),
                     float(np.max(np.abs(board_rt - c[fr]) / (np.abs(c[fr]) + 1e-9))))
-        good = same_iters and cost_rel < 1e-9 and p_rel < 1e-7
+        good = same_iters and cost_rel < 1e-9 and p_rel < 1e-7 and readout < 1e-9
         ok = ok and good
         print(f"cfg{cfg} world={world}: iters {res.num_iterations}/{ref.num_iterations} {res.termination} "
-              f"cost_rel {cost_rel:.2e} param_rel {p_rel:.2e} -> {'OK' if good else 'MISMATCH'}", flush=True)
+              f"cost_rel {cost_rel:.2e} param_rel {p_rel:.2e} read-out diff {readout:.1e} px -> {'OK' if good else 'MISMATCH'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:

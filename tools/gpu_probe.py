@@ -44,3 +44,33 @@ if "cfg4_create" in what:
         r = s.run(); t3 = time.perf_counter()
         s.close(); t4 = time.perf_counter()
         print(f"cfg4 rep {rep}: create {1e3*(t1-t):.1f} set {1e3*(t2-t1):.1f} run(5 it) {1e3*(t3-t2):.1f} destroy {1e3*(t4-t3):.1f} ms", flush=True)
+if "group" in what:
+    import torch
+    n = min(int(os.environ.get("GROUP_GPUS", "2")), torch.cuda.device_count())
+    capi.cache_release()
+    sp = synth.config(3)
+    obs = capi.pinned_array(sp.problem.obs_xy.shape)
+    obs[...] = sp.problem.obs_xy
+    hp = capi.ProblemArrays(sp.problem.board_xy, sp.problem.view_camera, sp.problem.view_frame, obs,
+                            sp.problem.num_cameras, sp.problem.num_frames, sp.problem.fixed_camera)
+    init = (sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt)
+    for ng in (1, n):
+        opt = capi.default_options(max_num_iterations=20, disable_tolerances=1, num_gpus=ng)
+        capi.set_debug(1)
+        for rep in range(3):
+            t = time.perf_counter()
+            capi.solve(hp, *init, opt)
+            print(f"num_gpus={ng} one-shot rep {rep}: {(time.perf_counter()-t)*1e3:.2f} ms", flush=True)
+        capi.set_debug(0)
+        s = capi.Solver(hp, capi.default_options(max_num_iterations=200, disable_tolerances=1, num_gpus=ng))
+        s.set_parameters(*init)
+        s.time_stage(4, 8)
+        s.set_parameters(*init)
+        print(f"num_gpus={ng}: graph replay {s.time_stage(4, 40)*1e3:.1f} us per LM iteration", flush=True)
+        for k in range(3):
+            t = time.perf_counter(); s.set_observations(obs); t1 = time.perf_counter()
+            s.set_parameters(*init); t2 = time.perf_counter(); r = s.run(); t3 = time.perf_counter()
+            s.get_parameters(); t4 = time.perf_counter()
+            print(f"   resident: obs {1e3*(t1-t):.2f} set {1e3*(t2-t1):.2f} run(200) {1e3*(t3-t2):.2f} get {1e3*(t4-t3):.2f} ms", flush=True)
+        s.close()
+        capi.cache_release()

@@ -1102,6 +1102,14 @@ int create_group(const tscm_problem* p, const tscm_options* o, int device, int n
   return TSCM_OK;
 }
 
+// The library switches devices (shards of a group, an explicit `device` argument); the caller's
+// current device is restored on the way out of every entry point.
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // every shard (or the solver itself)
 template <typename Fn>
 int for_shards(tscm_solver* s, Fn fn) {
@@ -1211,6 +1219,7 @@ int tscm_solver_set_options(tscm_solver* s, const tscm_options* o) {
 }
 
 int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device, tscm_solver** out) {
+  DeviceGuard device_guard_;
   if (!out) { set_error("out is NULL"); return TSCM_ERR_INVALID_ARGUMENT; }
   *out = nullptr;
   const auto t0 = Clock::now();
@@ -1233,9 +1242,13 @@ int tscm_solver_create(const tscm_problem* p, const tscm_options* o, int device,
   return create_shard(p, o, device, false, out);
 }
 
-void tscm_solver_destroy(tscm_solver* s) { destroy_solver(s); }
+void tscm_solver_destroy(tscm_solver* s) {
+  DeviceGuard device_guard_;
+  destroy_solver(s);
+}
 
 int tscm_solver_set_observations(tscm_solver* s, const double* obs_xy) {
+  DeviceGuard device_guard_;
   if (!s || !obs_xy) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
   RC_TRY(upload_all_observations(s, obs_xy));
   return sync_shards(s);     // the caller may reuse obs_xy
@@ -1243,6 +1256,7 @@ int tscm_solver_set_observations(tscm_solver* s, const double* obs_xy) {
 
 int tscm_solver_set_parameters(tscm_solver* s, const double* intr, const double* cam_rt,
                                const double* board_rt) {
+  DeviceGuard device_guard_;
   if (!s || !intr || !cam_rt || !board_rt) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
   RC_TRY(for_shards(s, [&](tscm_solver* k, int i) -> int {
     CUDA_TRY(cudaSetDevice(k->device));
@@ -1262,6 +1276,7 @@ int tscm_solver_set_parameters(tscm_solver* s, const double* intr, const double*
 }
 
 int tscm_solver_get_parameters(tscm_solver* s, double* intr, double* cam_rt, double* board_rt) {
+  DeviceGuard device_guard_;
   if (!s) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
   RC_TRY(for_shards(s, [&](tscm_solver* k, int i) -> int {
     CUDA_TRY(cudaSetDevice(k->device));
@@ -1276,6 +1291,7 @@ int tscm_solver_get_parameters(tscm_solver* s, double* intr, double* cam_rt, dou
 }
 
 int tscm_solver_run(tscm_solver* s, tscm_summary* summary) {
+  DeviceGuard device_guard_;
   if (!s) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
   const int max_it = s->options.max_num_iterations;
   // ---- prepare every shard (no exchange kernels yet) -----------------------------------------
@@ -1371,11 +1387,13 @@ int tscm_solver_run(tscm_solver* s, tscm_summary* summary) {
 }
 
 void tscm_cache_configure(int32_t max_solvers) {
+  DeviceGuard device_guard_;
   std::lock_guard<std::mutex> lock(g_cache_mu);
   g_cache_max = std::max(0, (int)max_solvers);
   while ((int)g_cache.size() > g_cache_max) cache_evict_oldest_locked();
 }
 void tscm_cache_release(void) {
+  DeviceGuard device_guard_;
   std::lock_guard<std::mutex> lock(g_cache_mu);
   for (CacheEntry& e : g_cache) destroy_solver(e.solver);
   g_cache.clear();
@@ -1383,6 +1401,7 @@ void tscm_cache_release(void) {
 
 int tscm_solve(const tscm_problem* problem, const tscm_options* options, double* intrinsics,
                double* cam_rt, double* board_rt, tscm_summary* summary, int device) {
+  DeviceGuard device_guard_;
   const auto t0 = Clock::now();
   RC_TRY(validate_problem(problem, true));
   if (!intrinsics || !cam_rt || !board_rt) { set_error("NULL parameter arrays"); return TSCM_ERR_INVALID_ARGUMENT; }
@@ -1468,6 +1487,7 @@ int tscm_comm_unique_id(void* unique_id_128) {
   } while (0)
 
 int tscm_solver_attach_comm(tscm_solver* s, int rank, int num_ranks, const void* unique_id_128) {
+  DeviceGuard device_guard_;
   if (!s || !unique_id_128 || rank < 0 || rank >= num_ranks) { set_error("bad comm arguments"); return TSCM_ERR_INVALID_ARGUMENT; }
   NO_GROUP(s, "tscm_solver_attach_comm");
   NcclApi& n = nccl();
@@ -1483,6 +1503,7 @@ int tscm_solver_attach_comm(tscm_solver* s, int rank, int num_ranks, const void*
 }
 
 int tscm_solver_p2p_export(tscm_solver* s, void* handle_64) {
+  DeviceGuard device_guard_;
   if (!s || !handle_64) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
   NO_GROUP(s, "tscm_solver_p2p_export");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -1495,6 +1516,7 @@ int tscm_solver_p2p_export(tscm_solver* s, void* handle_64) {
 }
 
 int tscm_solver_p2p_attach(tscm_solver* s, int rank, int num_ranks, const void* handles) {
+  DeviceGuard device_guard_;
   if (!s || !handles || rank < 0 || rank >= num_ranks) { set_error("bad p2p arguments"); return TSCM_ERR_INVALID_ARGUMENT; }
   NO_GROUP(s, "tscm_solver_p2p_attach");
   if (num_ranks > kP2PMaxRanks) { set_error("peer-memory exchange supports at most %d ranks", kP2PMaxRanks); return TSCM_ERR_INVALID_ARGUMENT; }
@@ -1529,6 +1551,7 @@ int tscm_solver_set_exchange_timeout(tscm_solver* s, double seconds) {
 }
 
 int tscm_solver_set_schur_form(tscm_solver* s, int form) {
+  DeviceGuard device_guard_;
   if (!s) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
   return for_shards(s, [&](tscm_solver* k, int) -> int {
     CUDA_TRY(cudaSetDevice(k->device));
@@ -1549,6 +1572,7 @@ int tscm_solver_set_schur_form(tscm_solver* s, int form) {
 }
 
 int tscm_solver_eval_jacobian(tscm_solver* s, double* residuals, double* jacobian, double* cost) {
+  DeviceGuard device_guard_;
   if (!s) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
   NO_GROUP(s, "tscm_solver_eval_jacobian");
   CUDA_TRY(cudaSetDevice(s->device));
@@ -1584,6 +1608,7 @@ int tscm_solver_reduced_size(const tscm_solver* s) {
 }
 
 int tscm_solver_reduced_system(tscm_solver* s, double radius, double* lhs, double* rhs) {
+  DeviceGuard device_guard_;
   if (!s || !(radius > 0.0)) { set_error("bad arguments"); return TSCM_ERR_INVALID_ARGUMENT; }
   NO_GROUP(s, "tscm_solver_reduced_system");
   CUDA_TRY(cudaSetDevice(s->device));
@@ -1620,6 +1645,7 @@ int tscm_solver_reduced_system(tscm_solver* s, double radius, double* lhs, doubl
 // sharded solve (ranks or a num_gpus group) the sums are global, and so must the counts be: a
 // group knows them; the ranks of a multi-process solve exchange them like an evaluation record.
 int tscm_solver_reprojection_error(tscm_solver* s, double* per_camera, double* overall, double* rms) {
+  DeviceGuard device_guard_;
   if (!s) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
   const int C = s->C;
   // Read-out uses the plain (loss-free) residuals, like multi_calib.cpp:235-283.
@@ -1672,6 +1698,7 @@ int tscm_solver_reprojection_error(tscm_solver* s, double* per_camera, double* o
 }
 
 int tscm_solver_time_stage(tscm_solver* s, int stage, int repeats, double* ms_per_launch) {
+  DeviceGuard device_guard_;
   if (!s || repeats <= 0 || !ms_per_launch) { set_error("bad arguments"); return TSCM_ERR_INVALID_ARGUMENT; }
   if (stage != 4) NO_GROUP(s, "tscm_solver_time_stage (stages other than 4)");
   RC_TRY(for_shards(s, [&](tscm_solver* k, int) -> int {
@@ -1768,6 +1795,7 @@ int64_t tscm_solver_launch_count(const tscm_solver* s) {
 // Remap tables: TS.cpp:284-330, rectify.cpp:86-199 as one batched kernel.
 int tscm_remap_tables(const tscm_remap_job* jobs, int32_t num_jobs, int32_t map_width,
                       int32_t map_height, float* mapx, float* mapy, int device, double* kernel_ms) {
+  DeviceGuard device_guard_;
   if (!jobs || !mapx || !mapy || num_jobs <= 0 || map_width <= 0 || map_height <= 0) {
     set_error("bad remap arguments"); return TSCM_ERR_INVALID_ARGUMENT;
   }
@@ -1861,6 +1889,7 @@ int tscm_remap_tables(const tscm_remap_job* jobs, int32_t num_jobs, int32_t map_
 }
 
 int tscm_device_fp64_peak(int device, double* tflops) {
+  DeviceGuard device_guard_;
   if (!tflops) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
   if (device >= 0) CUDA_TRY(cudaSetDevice(device));
   DeviceInfo prop;

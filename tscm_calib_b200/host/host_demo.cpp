@@ -17,7 +17,7 @@
 static bool read_all(FILE* f, void* p, size_t n) { return std::fread(p, 1, n, f) == n; }
 
 int main(int argc, char** argv) {
-  if (argc < 4) { std::fprintf(stderr, "usage: host_demo problem.bin result.bin calib.yaml [--yaml-only]\n"); return 2; }
+  if (argc < 4) { std::fprintf(stderr, "usage: host_demo problem.bin result.bin calib.yaml [--yaml-only] [--gpus N]\n"); return 2; }
   FILE* f = std::fopen(argv[1], "rb");
   if (!f) return 2;
   int32_t C, F, K;
@@ -62,7 +62,12 @@ int main(int argc, char** argv) {
     boards.push_back(b);
   }
   MultiCalib calib(cams, boards, worlds);
-  const bool yaml_only = argc > 4 && std::string(argv[4]) == "--yaml-only";   // no GPU needed
+  bool yaml_only = false;                                                       // no GPU needed
+  for (int k = 4; k < argc; ++k) {
+    if (std::string(argv[k]) == "--yaml-only") yaml_only = true;
+    // frames sharded over N GPUs of this process (tscm_options.num_gpus)
+    if (std::string(argv[k]) == "--gpus" && k + 1 < argc) calib.options().num_gpus = std::atoi(argv[++k]);
+  }
   if (!yaml_only) calib.calibrate();
   if (!calib.write_yaml(argv[3])) return 3;
 

@@ -170,7 +170,6 @@ void MultiCalib::calibrate() {
   // with no view are not part of the problem.
   std::vector<int> frame_id(B, -1);
   std::vector<int32_t> view_camera, view_frame;
-  std::vector<double> obs;
   std::vector<char> used(B, 0);
   for (int m = 0; m < C; ++m) {
     const auto& px = cameras_[m].pixels_ref();
@@ -185,12 +184,27 @@ void MultiCalib::calibrate() {
       if (!chessboards_[i].is_initial() || (int)px[i].size() != K) continue;
       view_camera.push_back(m);
       view_frame.push_back(frame_id[i]);
-      const size_t o = obs.size();
-      obs.resize(o + 2 * (size_t)K);
-      std::memcpy(&obs[o], px[i].data(), sizeof(double) * 2 * K);   // cv::Point2d = {x, y}
     }
   }
   if (F == 0 || view_camera.empty()) { std::cout << "[tscm] nothing to calibrate" << std::endl; return; }
+  // the detections are packed into page-locked staging memory (tscm_host_alloc), so that the
+  // upload inside tscm_solve() runs at the full PCIe rate; pageable memory if that fails
+  const size_t obs_doubles = view_camera.size() * 2 * (size_t)K;
+  double* pinned = static_cast<double*>(tscm_host_alloc(obs_doubles * sizeof(double)));
+  std::vector<double> pageable;
+  if (!pinned) pageable.resize(obs_doubles);
+  double* obs = pinned ? pinned : pageable.data();
+  {
+    size_t o = 0;
+    for (int m = 0; m < C; ++m) {
+      const auto& px = cameras_[m].pixels_ref();
+      for (int i = 0; i < B; ++i) {
+        if (!chessboards_[i].is_initial() || (int)px[i].size() != K) continue;
+        std::memcpy(obs + o, px[i].data(), sizeof(double) * 2 * K);   // cv::Point2d = {x, y}
+        o += 2 * (size_t)K;
+      }
+    }
+  }
   std::vector<double> intr(9 * (size_t)C), cam_rt(6 * (size_t)C), board_rt(6 * (size_t)F);
   for (int m = 0; m < C; ++m) {
     std::memcpy(&intr[9 * m], cameras_[m].intrinsic_.data(), sizeof(double) * 9);
@@ -202,12 +216,13 @@ void MultiCalib::calibrate() {
   tscm_problem p;
   p.num_cameras = C; p.num_frames = F; p.corners_per_board = K; p.num_views = (int)view_camera.size();
   p.board_xy = board_xy.data(); p.view_camera = view_camera.data(); p.view_frame = view_frame.data();
-  p.obs_xy = obs.data();
+  p.obs_xy = obs;
   p.fixed_camera = 0;                     // SetParameterBlockConstant(cameras_[0].rt_), multi_calib.cpp:186
   std::memset(&summary_, 0, sizeof(summary_));
   tscm_options opt = options_;
   if (quiet) opt.verbose = 0;
   const int rc = tscm_solve(&p, &opt, intr.data(), cam_rt.data(), board_rt.data(), &summary_, device);
+  tscm_host_free(pinned);
   if (rc != TSCM_OK) { std::cout << "[tscm] calibrate failed: " << tscm_last_error() << std::endl; return; }
   for (int m = 0; m < C; ++m) {
     std::memcpy(cameras_[m].intrinsic_.data(), &intr[9 * m], sizeof(double) * 9);
