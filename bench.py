@@ -233,6 +233,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         cpu_group = dist.new_group(backend="gloo")   # host-side waits that keep the other GPUs idle
     capi.load_library()
+    if args.debug_flags:
+        capi.set_debug(args.debug_flags)
 
     def barrier():
         torch.cuda.synchronize()
@@ -488,6 +490,7 @@ def main():
     ap.add_argument("--parity-frames", type=int, default=1000, help="N = 1 parity_check sample size (frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling side figure at N > 1")
+    ap.add_argument("--debug-flags", type=int, default=0, help="tscm_set_debug() flags (4 = no programmatic dependent launch)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

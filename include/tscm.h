@@ -229,7 +229,9 @@ int tscm_solver_time_stage(tscm_solver* solver, int stage, int repeats, double* 
  * producer/consumer CTA (k_schur2), 3 = per-camera-pair (k_pair_* + k_schur_pairs2).  Returns
  * TSCM_ERR_UNSUPPORTED when the form cannot hold this problem. */
 int tscm_solver_set_schur_form(tscm_solver* solver, int form);
-/* bit 0: creation / solve phase timings on stderr; bit 1: in-kernel cycle counts of k_solve. */
+/* bit 0: creation / solve phase timings on stderr; bit 1: in-kernel cycle counts of k_solve;
+ * bit 2: solvers created from now on chain their kernels WITHOUT programmatic dependent launch
+ * (A/B timing). */
 void tscm_set_debug(int32_t flags);
 /* Number of kernels launched by this solver since creation. */
 int64_t tscm_solver_launch_count(const tscm_solver* solver);

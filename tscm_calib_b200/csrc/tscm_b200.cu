@@ -237,11 +237,14 @@ struct tscm_solver {
   SolveDims solve{};
   size_t eval5_smem = 0;
   int want_err = 0;                 // accumulate sum sqrt(s) (reprojection read-out only)
-  int bs_nblk = 0, fg_nblk = 0;
+  int bs_nblk = 0, fg_nblk = 0, post_lpf = 8;
+  double* d_cam_sum_part = nullptr;
   // graph of one LM iteration (and of kGroupIters iterations, group shards only)
   cudaGraphExec_t graph_exec = nullptr, graph_exec_n = nullptr;
   bool graph_dirty = true;
   int launches_per_iter = 0;
+  bool use_pdl = true;              // tscm_set_debug bit 2 turns it off (A/B timing)
+  bool pdl = false;                 // launches carry the programmatic-dependent-launch attribute (graph capture)
   cudaEvent_t poll_ev[2] = {nullptr, nullptr};
   // comm
   NcclApi::Comm comm = nullptr;
@@ -353,6 +356,21 @@ int validate_problem(const tscm_problem* p, bool need_obs) {
 // ---------------------------------------------------------------------------
 // kernel launches of one shard
 // ---------------------------------------------------------------------------
+// Every launch goes through here.  While the iteration graph is captured (s->pdl) the kernels
+// are chained with programmatic dependent launch: see pdl_entry() in tscm_kernels.cuh.
+template <typename... KArgs, typename... Args>
+void launch_k(tscm_solver* s, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = s->pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+  s->launches += 1;
+}
+
 // The residual + Jacobian + normal-equation pass: k_eval5 (moments of every view) followed by
 // k_view_blocks (per-view blocks from the moments).
 // part: 0 = the whole pass, 1 = k_eval5 only, 2 = k_view_blocks only (stage timing).
@@ -360,14 +378,12 @@ void launch_eval_kernel(tscm_solver* s, int which, int part = 0) {
   const DeviceProblem& P = s->P;
   const int ntiles = (P.V + 31) / 32;
   if (part != 2) {
-    k_eval5<<<std::min(ntiles, s->sm_count), kE5Threads, s->eval5_smem, s->stream>>>(
+    launch_k(s, k_eval5, dim3(std::min(ntiles, s->sm_count)), dim3(kE5Threads), (size_t)(s->eval5_smem), 
         P, s->ps[0], s->ps[1], s->d_state, which, s->lm, s->want_err, s->d_mom, s->d_fcg);
-    s->launches += 1;
   }
   if (part != 1) {
-    k_view_blocks<<<ntiles, kVbThreads, vb_smem_bytes(), s->stream>>>(P, s->ps[0], s->ps[1], s->d_state, which,
+    launch_k(s, k_view_blocks, dim3(ntiles), dim3(kVbThreads), (size_t)(vb_smem_bytes()), P, s->ps[0], s->ps[1], s->d_state, which,
                                                                       s->d_mom, s->d_fcg);
-    s->launches += 1;
   }
 }
 
@@ -379,17 +395,16 @@ void launch_evaluation(tscm_solver* s, int which, int initial, bool prep = true,
   const DeviceProblem& P = s->P;
   cudaStream_t st = s->stream;
   if (prep) {
-    k_prep_cams<<<(P.C + 31) / 32, 32, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which);
-    s->launches += 1;
+    launch_k(s, k_prep_cams, dim3((P.C + 31) / 32), dim3(32), (size_t)(0), P, s->ps[0], s->ps[1], s->d_state, which);
   }
   launch_eval_kernel(s, which);
   PostArgs a;
   a.gmax_part = s->d_gmax_part; a.xn2_part = s->d_xn2_part;
   a.bs_part = s->d_bs_part; a.bs_nblk = s->bs_nblk; a.fg_nblk = s->fg_nblk;
+  a.cam_sum_part = s->d_cam_sum_part; a.lanes_per_frame = s->post_lpf;
   a.ticket = s->d_ticket; a.initial = initial; a.decide = decide ? 1 : 0;
-  k_post_eval<<<P.C + s->fg_nblk, kPostThreads, 0, st>>>(P, s->ps[0], s->ps[1], s->d_state, which,
+  launch_k(s, k_post_eval, dim3(P.C * kPostSplit + s->fg_nblk), dim3(kPostThreads), (size_t)(0), P, s->ps[0], s->ps[1], s->d_state, which,
                                                             s->lm, s->trace, a);
-  s->launches += 1;
 }
 
 // Global sums of the evaluation record.  The record lives in ps[sel].comm; the selection is
@@ -397,9 +412,8 @@ void launch_evaluation(tscm_solver* s, int which, int initial, bool prep = true,
 int launch_eval_allreduce(tscm_solver* s, int which, bool decide = false) {
   if (s->num_ranks <= 1) return TSCM_OK;
   if (s->p2p_on) {
-    k_xchg_eval<<<1, kXchgThreads, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, which, s->lm,
+    launch_k(s, k_xchg_eval, dim3(1), dim3(kXchgThreads), (size_t)(0), s->P, s->ps[0], s->ps[1], s->d_state, which, s->lm,
                                                     s->trace, s->p2p, decide ? 1 : 0);
-    s->launches += 1;
     return TSCM_OK;
   }
   // The record of the set the device selects is staged through a fixed buffer: only that
@@ -407,7 +421,7 @@ int launch_eval_allreduce(tscm_solver* s, int which, bool decide = false) {
   NcclApi& n = nccl();
   const int cnt = s->P.C * kCamRec + kCommExtra;
   const int blocks = (cnt + 1 + 255) / 256;
-  k_comm_stage<<<blocks, 256, 0, s->stream>>>(s->ps[0], s->ps[1], s->d_state, which, cnt, s->d_comm_stage, 0);
+  launch_k(s, k_comm_stage, dim3(blocks), dim3(256), (size_t)(0), s->ps[0], s->ps[1], s->d_state, which, cnt, s->d_comm_stage, 0);
   n.GroupStart();
   int rc = n.AllReduce(s->d_comm_stage, s->d_comm_stage, (size_t)cnt, kNcclFloat64, kNcclSum, s->comm, s->stream);
   if (rc) { set_error("ncclAllReduce(sum) failed: %d", rc); n.GroupEnd(); return TSCM_ERR_COMM; }
@@ -415,8 +429,7 @@ int launch_eval_allreduce(tscm_solver* s, int which, bool decide = false) {
   if (rc) { set_error("ncclAllReduce(max) failed: %d", rc); n.GroupEnd(); return TSCM_ERR_COMM; }
   rc = n.GroupEnd();
   if (rc) { set_error("ncclGroupEnd failed: %d", rc); return TSCM_ERR_COMM; }
-  k_comm_stage<<<blocks, 256, 0, s->stream>>>(s->ps[0], s->ps[1], s->d_state, which, cnt, s->d_comm_stage, 1);
-  s->launches += 2;
+  launch_k(s, k_comm_stage, dim3(blocks), dim3(256), (size_t)(0), s->ps[0], s->ps[1], s->d_state, which, cnt, s->d_comm_stage, 1);
   return TSCM_OK;
 }
 
@@ -426,26 +439,23 @@ void launch_schur(tscm_solver* s, double radius_override) {
   if (s->schur_form == kSchurRows) {
     SchurSplitArgs b = s->split;
     b.a = a;
-    k_schur_frames<<<(s->F + 7) / 8, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
+    launch_k(s, k_schur_frames, dim3((s->F + 7) / 8), dim3(256), (size_t)(0), s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
     if (s->schur_ept == 1)
-      k_schur_update<1><<<s->schur_nblk, s->schur_nt, s->split_smem, s->stream>>>(s->P, s->d_state, b);
+      launch_k(s, k_schur_update<1>, dim3(s->schur_nblk), dim3(s->schur_nt), (size_t)(s->split_smem), s->P, s->d_state, b);
     else
-      k_schur_update<2><<<s->schur_nblk, s->schur_nt, s->split_smem, s->stream>>>(s->P, s->d_state, b);
-    s->launches += 2;
+      launch_k(s, k_schur_update<2>, dim3(s->schur_nblk), dim3(s->schur_nt), (size_t)(s->split_smem), s->P, s->d_state, b);
   } else if (s->schur_form == kSchurPairs) {
     SchurSplitArgs b = s->split;
     b.a = a;
-    k_pair_frames<<<(s->F + 31) / 32, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
-    k_pair_blocks<<<(s->V * 16 + 255) / 256, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, b);
-    k_schur_pairs2<<<s->sm_count, kPairWarps * 32, kPair2Smem, s->stream>>>(s->d_state, s->pairs);
-    k_reduce_pairs<<<s->pairs.npairs, kPairReduceGroups * kPairPart, 0, s->stream>>>(s->P, s->d_state, s->pairs);
-    s->launches += 4;
+    launch_k(s, k_pair_frames, dim3((s->F + 31) / 32), dim3(256), (size_t)(0), s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
+    launch_k(s, k_pair_blocks, dim3((s->V * 16 + 255) / 256), dim3(256), (size_t)(0), s->P, s->ps[0], s->ps[1], s->d_state, b);
+    launch_k(s, k_schur_pairs2, dim3(s->sm_count), dim3(kPairWarps * 32), (size_t)(kPair2Smem), s->d_state, s->pairs);
+    launch_k(s, k_reduce_pairs, dim3(s->pairs.npairs), dim3(kPairReduceGroups * kPairPart), (size_t)(0), s->P, s->d_state, s->pairs);
   } else {
     Schur2Args b = s->schur2;
     b.a = a;
-    k_schur2<<<s->schur_nblk, s->schur2_nt, s->schur2_smem, s->stream>>>(s->P, s->ps[0], s->ps[1],
+    launch_k(s, k_schur2, dim3(s->schur_nblk), dim3(s->schur2_nt), (size_t)(s->schur2_smem), s->P, s->ps[0], s->ps[1],
                                                                         s->d_state, s->lm, b);
-    s->launches += 1;
   }
   const int n = s->P.Q + s->P.NL;
   const int nparts = s->schur_form == kSchurPairs ? 1 : s->schur_nblk;   // k_reduce_pairs leaves one complete partial
@@ -453,12 +463,11 @@ void launch_schur(tscm_solver* s, double radius_override) {
   g.scale_c = s->d_scale_c; g.radius_override = radius_override; g.nbk = s->solve.nbk;
   g.add_cam = (s->num_ranks > 1 && !s->p2p_on) ? 0 : 1;                  // NCCL: after the all-reduce
   if (s->p2p_on && s->num_ranks > 1)
-    k_reduce_s_p2p<<<(n + 31) / 32, kReduceThreads, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm,
+    launch_k(s, k_reduce_s_p2p, dim3((n + 31) / 32), dim3(kReduceThreads), (size_t)(0), s->P, s->ps[0], s->ps[1], s->d_state, s->lm,
                                                                     s->d_Spart, s->d_rpart, nparts, s->d_Sr, g, s->p2p);
   else
-    k_reduce_s<<<(n + 31) / 32, kReduceThreads, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm,
+    launch_k(s, k_reduce_s, dim3((n + 31) / 32), dim3(kReduceThreads), (size_t)(0), s->P, s->ps[0], s->ps[1], s->d_state, s->lm,
                                                                 s->d_Spart, s->d_rpart, nparts, s->d_Sr, g);
-  s->launches += 1;
 }
 
 int launch_schur_allreduce(tscm_solver* s, double radius_override) {
@@ -469,8 +478,7 @@ int launch_schur_allreduce(tscm_solver* s, double radius_override) {
   AssembleArgs g;
   g.scale_c = s->d_scale_c; g.radius_override = radius_override; g.nbk = s->solve.nbk; g.add_cam = 1;
   const int cnt = s->P.Q + s->P.NL;
-  k_add_cam_terms<<<(cnt + 255) / 256, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, s->d_Sr, g);
-  s->launches += 1;
+  launch_k(s, k_add_cam_terms, dim3((cnt + 255) / 256), dim3(256), (size_t)(0), s->P, s->ps[0], s->ps[1], s->d_state, s->lm, s->d_Sr, g);
   return TSCM_OK;
 }
 
@@ -478,20 +486,18 @@ void launch_solve(tscm_solver* s) {
   const SolveDims& d = s->solve;
   const int prof = (g_debug & 2) ? 1 : 0;
   if (d.T == 1)
-    k_solve<1, 4><<<1, d.NT, d.smem, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->d_Sr, s->d_scale_c,
+    launch_k(s, k_solve<1, 4>, dim3(1), dim3(d.NT), (size_t)(d.smem), s->P, s->ps[0], s->ps[1], s->d_state, s->d_Sr, s->d_scale_c,
                                                    s->d_yc, prof);
   else
-    k_solve<4, 7><<<1, d.NT, d.smem, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->d_Sr, s->d_scale_c,
+    launch_k(s, k_solve<4, 7>, dim3(1), dim3(d.NT), (size_t)(d.smem), s->P, s->ps[0], s->ps[1], s->d_state, s->d_Sr, s->d_scale_c,
                                                    s->d_yc, prof);
-  s->launches += 1;
 }
 
 void launch_backsub(tscm_solver* s) {
   // one extra block prepares the derived constants of the candidate cameras
-  k_backsub<<<s->bs_nblk + 1, kBacksubThreads, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state,
+  launch_k(s, k_backsub, dim3(s->bs_nblk + 1), dim3(kBacksubThreads), (size_t)(0), s->P, s->ps[0], s->ps[1], s->d_state,
                                                               s->schur, s->d_yc, s->d_bs_part, s->bs_nblk,
                                                               s->schur_form == kSchurRows ? s->split.Wg : nullptr);
-  s->launches += 1;
 }
 
 int launch_iteration(tscm_solver* s) {
@@ -504,8 +510,7 @@ int launch_iteration(tscm_solver* s) {
   if (!single) {
     RC_TRY(launch_eval_allreduce(s, 1, /*decide=*/true));
     if (!s->p2p_on) {
-      k_decide<<<1, 32, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, s->trace);
-      s->launches += 1;
+      launch_k(s, k_decide, dim3(1), dim3(kDecideThreads), (size_t)(0), s->P, s->ps[0], s->ps[1], s->d_state, s->lm, s->trace);
     }
   }
   return TSCM_OK;
@@ -516,7 +521,9 @@ int capture_iterations(tscm_solver* s, int iters, cudaGraphExec_t* out) {
   const int64_t before = s->launches;
   CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
   int rc = TSCM_OK;
+  s->pdl = s->use_pdl;
   for (int k = 0; k < iters && !rc; ++k) rc = launch_iteration(s);
+  s->pdl = false;
   const cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
   s->launches_per_iter = (int)((s->launches - before) / std::max(1, iters));
   s->launches = before;
@@ -547,7 +554,7 @@ int run_initial(tscm_solver* s) {
   const int n = s->P.F * 6 + s->P.C * 13;
   k_jacobi_scale<<<(n + 255) / 256, 256, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm,
                                                         s->d_scale_e, s->d_scale_c);
-  k_init<<<1, 32, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, s->trace);
+  k_init<<<1, kDecideThreads, 0, s->stream>>>(s->P, s->ps[0], s->ps[1], s->d_state, s->lm, s->trace);
   s->launches += 2;
   CUDA_TRY(cudaGetLastError());
   return TSCM_OK;
@@ -781,6 +788,7 @@ int create_shard(const tscm_problem* p, const tscm_options* o, int device, bool 
   s->sm_count = info.sm_count;
   s->smem_optin = info.smem_optin;
   s->is_kid = is_kid;
+  s->use_pdl = (g_debug & 4) == 0;
   s->options = *o;
   fill_lm_options(*o, s->lm);
 #define TRY_S(x) do { const int rc_ = (x); if (rc_) { free_shard(s); return rc_; } } while (0)
@@ -917,8 +925,15 @@ int create_shard(const tscm_problem* p, const tscm_options* o, int device, bool 
   A.want(&s->d_rpart, (size_t)s->schur_nblk * NL);
   A.want(&s->d_Sr, (size_t)s->solve.ntile * 16);
   A.want(&s->d_yc, (size_t)NL);
-  s->bs_nblk = (F + kBacksubThreads / 32 - 1) / (kBacksubThreads / 32);
-  s->fg_nblk = (F * 6 + kPostThreads - 1) / kPostThreads;
+  s->bs_nblk = (F + kBacksubFrames - 1) / kBacksubFrames;
+  {
+    int maxv = 1;
+    for (int f = 0; f < F; ++f) maxv = std::max(maxv, frame_ptr[f + 1] - frame_ptr[f]);
+    s->post_lpf = maxv <= 8 ? 8 : (maxv <= 16 ? 16 : 32);     // <= 17 cameras
+    const int fpc = kPostThreads / s->post_lpf;
+    s->fg_nblk = (F + fpc - 1) / fpc;
+  }
+  A.want(&s->d_cam_sum_part, (size_t)C * kPostSplit * kCamRec);
   A.want(&s->d_ticket, 1);
   A.want(&s->d_p2p_seq, 2);
   A.want(&s->d_p2p_ticket, 1);

@@ -310,6 +310,7 @@ __device__ __forceinline__ void e5_consumer(const double* __restrict__ s_ring,
 __global__ void __launch_bounds__(kE5Threads, 1)
 k_eval5(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which, LmOptions opt,
         int want_err, double* __restrict__ mom_g, double* __restrict__ fc_g) {
+  pdl_entry();
   if (which < 2 && st->done) return;
   const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
   const ParamSet& ps = sel ? ps1 : ps0;
@@ -547,6 +548,7 @@ __device__ __forceinline__ double vb_dot(const double* __restrict__ ca, const do
 __global__ void __launch_bounds__(kVbThreads, 2)
 k_view_blocks(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which,
               const double* __restrict__ mom_g, const double* __restrict__ fc_g) {
+  pdl_entry();
   if (which < 2 && st->done) return;
   const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
   const ParamSet& ps = sel ? ps1 : ps0;

@@ -68,6 +68,15 @@ struct Trace {
   int capacity;
 };
 
+// Programmatic dependent launch (CUDA graphs keep the edges): every kernel of the LM-iteration
+// graph lets its successor's CTAs become resident as soon as all of its own have started, and
+// waits for its predecessor's memory before it reads anything an earlier kernel produced.  The
+// semantics are those of plain stream order; what overlaps is launch latency and drain.
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // Static problem description on the device.
 struct DeviceProblem {
   int C, F, K, V, Vpad, fixed_camera;
@@ -278,6 +287,7 @@ constexpr int kS2ColsPerLane = 4;   // raw W columns a lane keeps in registers p
 __global__ void __launch_bounds__(640)
 k_schur2(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
          Schur2Args B) {
+  pdl_entry();
   if (st->done) return;
   const SchurArgs& A = B.a;
   const ParamSet& ps = st->cur ? ps1 : ps0;
@@ -532,6 +542,7 @@ __host__ __device__ __forceinline__ int pair_pos(int c) { return c + (c >= 7 ? 1
 __global__ void __launch_bounds__(256, TSCM_SF_MINB)
 k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
                SchurSplitArgs B) {
+  pdl_entry();
   if (st->done) return;
   __shared__ double s_scr[8][64];
   const SchurArgs& A = B.a;
@@ -663,6 +674,7 @@ k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, L
 __global__ void __launch_bounds__(256, 2)
 k_pair_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
               SchurSplitArgs B) {
+  pdl_entry();
   if (st->done) return;
   __shared__ double s_rec[32][kFrameRec + 2];
   const SchurArgs& A = B.a;
@@ -752,6 +764,7 @@ k_pair_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, Lm
 // completely (full 128-byte rows, padding included).
 __global__ void __launch_bounds__(256)
 k_pair_blocks(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, SchurSplitArgs B) {
+  pdl_entry();
   if (st->done) return;
   const ParamSet& ps = st->cur ? ps1 : ps0;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -831,6 +844,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigne
 template <int T>   // 4x4 tiles per thread
 __global__ void __launch_bounds__(T == 1 ? 512 : 768)
 k_schur_update(DeviceProblem P, const LmState* st, SchurSplitArgs B) {
+  pdl_entry();
   if (st->done) return;
   const SchurArgs& A = B.a;
   extern __shared__ __align__(128) double s_mem[];
@@ -993,6 +1007,7 @@ __global__ void __launch_bounds__(kReduceThreads)
 k_reduce_s(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
            const double* __restrict__ Spart, const double* __restrict__ rpart, int nblk,
            double* __restrict__ out, AssembleArgs A) {
+  pdl_entry();
   if (st->done) return;
   __shared__ double s_part[8][33];
   const int e = threadIdx.x & 31, part = threadIdx.x >> 5;
@@ -1033,6 +1048,7 @@ k_reduce_s(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOpt
 // NCCL fallback: the camera terms are added once, after the all-reduce of the raw sums.
 __global__ void k_add_cam_terms(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
                                 double* __restrict__ out, AssembleArgs A) {
+  pdl_entry();
   if (st->done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.Q + P.NL) return;
@@ -1056,13 +1072,20 @@ __device__ __forceinline__ double fast_rcp(double d) {
 // and the frame-side sums of the model cost change.  One warp per frame.
 // ---------------------------------------------------------------------------
 constexpr int kBacksubThreads = 256;
+constexpr int kBacksubFrames = 32;      // frames per CTA: 8 lanes per frame, then lane = frame
 
+// Round 1 ran one warp per frame and left the 6x6 solve, the 54 strided loads of the frame record
+// and the model-cost sums to lane 0 (20 us at 5,000 frames, FP64 pipe 12 % busy).  Now a CTA owns
+// 32 frames: (1) eight lanes per frame form w = W_s y_c (all loads of a frame in flight at once),
+// (2) warp 0 takes over with lane = frame — coalesced frame records, 32 solves side by side,
+// shuffle sums — and writes one partial per CTA (157 instead of 625 for k_post_eval to add).
 __global__ void __launch_bounds__(kBacksubThreads)
 k_backsub(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, SchurArgs A,
           const double* __restrict__ y_c, double* __restrict__ part /*[4][nblk]*/, int nblk,
           const double* __restrict__ Wg /* materialised, permuted W_s rows or nullptr */) {
-  __shared__ double s_red[kBacksubThreads];
   __shared__ double s_yp[224];
+  __shared__ double s_w[kBacksubFrames][7];
+  pdl_entry();
   if (st->done) return;
   if ((int)blockIdx.x == nblk) {
     // extra block: derived constants of the candidate cameras, whose parameters k_solve has
@@ -1085,85 +1108,103 @@ k_backsub(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, SchurA
   const int sel = st->cur;
   const ParamSet& ps = sel ? ps1 : ps0;
   const ParamSet& pc = sel ? ps0 : ps1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.x * (kBacksubThreads / 32) + warp;
-  double lin = 0.0, quad = 0.0, dn2 = 0.0, xn2 = 0.0;
-  if (f < P.F) {
-    double se[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) se[i] = A.scale_e[f * 6 + i];
-    // w = W_s y_c : lanes stride over the frame's live columns
+  {
+    // ---- w = W_s y_c, eight lanes per frame ---------------------------------------------------
+    const int grp = threadIdx.x >> 3, g = threadIdx.x & 7;
+    const int f = blockIdx.x * kBacksubFrames + grp;
     double w[6] = {0, 0, 0, 0, 0, 0};
-    const int p0 = P.frame_ptr[f], nv = Wg ? 0 : P.frame_ptr[f + 1] - p0;
-    if (Wg) {
-      const double* Wf = Wg + (size_t)f * 6 * A.NLp;
-      for (int c = lane; c < A.NLp; c += 32) {
-        const double yv = s_yp[c];
+    if (f < P.F) {
+      if (Wg) {
+        const double* Wf = Wg + (size_t)f * 6 * A.NLp;
+#pragma unroll 4
+        for (int c = g; c < A.NLp; c += 8) {
+          const double yv = s_yp[c];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) w[r] = fma(Wf[r * A.NLp + c], yv, w[r]);
-      }
-    }
-    for (int p = 0; p < nv; ++p) {
-      const int v = P.frame_views[p0 + p];
-      const int m = P.view_camera[v];
-      const int o0 = P.live_off[m], n = P.live_off[m + 1] - o0;
-      const double* Gv = ps.G + (size_t)v * kViewStride;
-      for (int k = lane; k < n; k += 32) {
-        const int kk = n == 13 ? k : k + 6;
-        const double f_sc = A.scale_c[m * 13 + kk] * y_c[o0 + k];
+          for (int r = 0; r < 6; ++r) w[r] = fma(Wf[r * A.NLp + c], yv, w[r]);
+        }
+      } else {
+        const int p0 = P.frame_ptr[f], nv = P.frame_ptr[f + 1] - p0;
+        for (int p = 0; p < nv; ++p) {
+          const int v = P.frame_views[p0 + p];
+          const int m = P.view_camera[v];
+          const int o0 = P.live_off[m], n = P.live_off[m + 1] - o0;
+          const double* Gv = ps.G + (size_t)v * kViewStride;
+          for (int k = g; k < n; k += 8) {
+            const int kk = n == 13 ? k : k + 6;
+            const double f_sc = A.scale_c[m * 13 + kk] * y_c[o0 + k];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          const double raw = kk < 6 ? Gv[kOffBC + r * 6 + kk] : Gv[kOffBI + r * 8 + (kk - 6)];
-          w[r] += raw * f_sc;
+            for (int r = 0; r < 6; ++r) {
+              const double raw = kk < 6 ? Gv[kOffBC + r * 6 + kk] : Gv[kOffBI + r * 8 + (kk - 6)];
+              w[r] += raw * f_sc;
+            }
+          }
         }
       }
     }
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
 #pragma unroll
-      for (int s = 16; s > 0; s >>= 1) w[r] += __shfl_xor_sync(0xffffffffu, w[r], s);
-      if (!Wg) w[r] *= se[r];     // the materialised rows are already scaled
+      for (int o = 4; o > 0; o >>= 1) w[r] += __shfl_xor_sync(0xffffffffu, w[r], o);
     }
-    if (lane == 0) {
-      double Lm[36], z[6], Vs[21], gs[6];
+    if (g == 0) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int j = 0; j <= i; ++j) Lm[i * 6 + j] = A.frame_rec[(size_t)((i * (i + 1)) / 2 + j) * A.Fpad + f];
-        z[i] = A.frame_rec[(size_t)(21 + i) * A.Fpad + f];
-        gs[i] = A.frame_rec[(size_t)(48 + i) * A.Fpad + f];
-      }
-#pragma unroll
-      for (int i = 0; i < 21; ++i) Vs[i] = A.frame_rec[(size_t)(27 + i) * A.Fpad + f];
-      double t[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) t[i] = w[i];
-      chol6_solve(Lm, t);
-      double y[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) y[i] = z[i] - t[i];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        lin += y[i] * gs[i];
-        double row = 0.0;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) row += (i <= j ? Vs[tri6(i, j)] : Vs[tri6(j, i)]) * y[j];
-        quad += y[i] * (row + 2.0 * w[i]);
-        const double delta = -y[i] * se[i];
-        const double xn = ps.board_rt[f * 6 + i] + delta;
-        pc.board_rt[f * 6 + i] = xn;
-        dn2 += delta * delta;
-        xn2 += xn * xn;
-      }
+      for (int r = 0; r < 6; ++r) s_w[grp][r] = w[r];
     }
   }
-  const double t0 = block_sum(lin, s_red);
-  const double t1 = block_sum(quad, s_red);
-  const double t2 = block_sum(dn2, s_red);
-  const double t3 = block_sum(xn2, s_red);
-  if (threadIdx.x == 0) {
-    part[blockIdx.x] = t0; part[nblk + blockIdx.x] = t1;
-    part[2 * nblk + blockIdx.x] = t2; part[3 * nblk + blockIdx.x] = t3;
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
+  // ---- y_e = z - (V + D^2)^-1 w, candidate pose, model-cost sums: lane = frame ------------------
+  const int lane = threadIdx.x;
+  const int f = blockIdx.x * kBacksubFrames + lane;
+  double lin = 0.0, quad = 0.0, dn2 = 0.0, xn2 = 0.0;
+  if (f < P.F) {
+    double se[6], w[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      se[i] = A.scale_e[f * 6 + i];
+      w[i] = Wg ? s_w[lane][i] : s_w[lane][i] * se[i];     // the materialised rows are already scaled
+    }
+    double Lm[36], z[6], Vs[21], gs[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) Lm[i * 6 + j] = A.frame_rec[(size_t)((i * (i + 1)) / 2 + j) * A.Fpad + f];
+      z[i] = A.frame_rec[(size_t)(21 + i) * A.Fpad + f];
+      gs[i] = A.frame_rec[(size_t)(48 + i) * A.Fpad + f];
+    }
+#pragma unroll
+    for (int i = 0; i < 21; ++i) Vs[i] = A.frame_rec[(size_t)(27 + i) * A.Fpad + f];
+    double t[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) t[i] = w[i];
+    chol6_solve(Lm, t);
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = z[i] - t[i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      lin += y[i] * gs[i];
+      double row = 0.0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) row += (i <= j ? Vs[tri6(i, j)] : Vs[tri6(j, i)]) * y[j];
+      quad += y[i] * (row + 2.0 * w[i]);
+      const double delta = -y[i] * se[i];
+      const double xn = ps.board_rt[f * 6 + i] + delta;
+      pc.board_rt[f * 6 + i] = xn;
+      dn2 += delta * delta;
+      xn2 += xn * xn;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lin += __shfl_xor_sync(0xffffffffu, lin, o);
+    quad += __shfl_xor_sync(0xffffffffu, quad, o);
+    dn2 += __shfl_xor_sync(0xffffffffu, dn2, o);
+    xn2 += __shfl_xor_sync(0xffffffffu, xn2, o);
+  }
+  if (lane == 0) {
+    part[blockIdx.x] = lin; part[nblk + blockIdx.x] = quad;
+    part[2 * nblk + blockIdx.x] = dn2; part[3 * nblk + blockIdx.x] = xn2;
   }
 }
 
@@ -1175,171 +1216,178 @@ k_backsub(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, SchurA
 // ---------------------------------------------------------------------------
 // Camera part of |x - (x - g)|_inf and |x_c|^2 for a parameter set whose comm
 // record is globally summed.
-__device__ inline void camera_grad_norms(const DeviceProblem& P, const ParamSet& ps, double* gmax,
-                                         double* xn2) {
-  double gm = 0.0, s = 0.0;
-  for (int c = 0; c < P.C; ++c) {
-    const double* U = ps.comm + c * kCamRec;
-    const bool free_rt = c != P.fixed_camera;
-    for (int k = 0; k < 15; ++k) {
-      if (k < 6 && !free_rt) continue;
-      const double x = k < 6 ? ps.cam_rt[c * 6 + k] : ps.intr[c * 9 + (k - 6)];
-      double g = 0.0;
-      if (k < 6) g = cam_grad(U, k); else if (k - 6 < 7) g = cam_grad(U, k);
-      const double projected = x + (-g);
-      gm = fmax(gm, fabs(x - projected));
-      s += x * x;
-    }
+// Camera-side inputs of the bookkeeping for a parameter set whose comm record is globally summed:
+// total cost, camera part of |x - (x - g)|_inf and |x_c|^2.  Block-wide (every thread of the CTA
+// calls it; s_red holds >= 33 doubles): the serial loops over global memory that one thread ran
+// here in round 1 were most of k_post_eval's 20 us.
+struct CameraSummary { double cost, gmax, xn2; };
+__device__ inline CameraSummary camera_summary(const DeviceProblem& P, const ParamSet& ps, double* s_red) {
+  double c = 0.0, gm = 0.0, s = 0.0;
+  for (int idx = threadIdx.x; idx < P.C * 15; idx += blockDim.x) {
+    const int cam = idx / 15, k = idx % 15;
+    const double* U = ps.comm + cam * kCamRec;
+    if (k == 0) c += U[kCamCost];
+    if (k < 6 && cam == P.fixed_camera) continue;
+    const double x = k < 6 ? ps.cam_rt[cam * 6 + k] : ps.intr[cam * 9 + (k - 6)];
+    const double g = k < 13 ? cam_grad(U, k) : 0.0;
+    const double projected = x + (-g);
+    gm = fmax(gm, fabs(x - projected));
+    s += x * x;
   }
-  *gmax = gm; *xn2 = s;
+  CameraSummary r;
+  r.cost = block_sum(c, s_red);
+  r.gmax = block_max(gm, s_red);
+  r.xn2 = block_sum(s, s_red);
+  return r;
 }
 
-__device__ inline double total_cost(const DeviceProblem& P, const ParamSet& ps) {
-  double c = 0.0;
-  for (int m = 0; m < P.C; ++m) c += ps.comm[m * kCamRec + kCamCost];
-  return c;
-}
-
-__device__ inline void trace_push(Trace tr, LmState* st, double cost, double gmax,
+__device__ inline void trace_push(Trace tr, LmState& st, double cost, double gmax,
                                   double step_norm, int flags) {
-  const int k = st->recorded;
+  const int k = st.recorded;
   if (k < tr.capacity) {
-    tr.cost[k] = cost; tr.radius[k] = st->radius; tr.gmax[k] = gmax;
+    tr.cost[k] = cost; tr.radius[k] = st.radius; tr.gmax[k] = gmax;
     tr.step_norm[k] = step_norm; tr.flags[k] = flags;
   }
-  st->final_cost = k == 0 ? cost : fmin(st->final_cost, cost);
-  st->recorded = k + 1;
+  st.final_cost = k == 0 ? cost : fmin(st.final_cost, cost);
+  st.recorded = k + 1;
 }
 
 // FinalizeIterationAndCheckIfMinimizerCanContinue
-__device__ inline void finalize_iteration(LmState* st, const LmOptions& opt, Trace tr,
+__device__ inline void finalize_iteration(LmState& st, const LmOptions& opt, Trace tr,
                                           int iteration, bool valid, bool successful,
                                           double cost, double step_norm) {
   if (successful) {
-    st->num_successful++;
-    if (st->x_cost < st->minimum_cost) st->minimum_cost = st->x_cost;
+    st.num_successful++;
+    if (st.x_cost < st.minimum_cost) st.minimum_cost = st.x_cost;
   } else {
-    st->num_unsuccessful++;
+    st.num_unsuccessful++;
   }
-  trace_push(tr, st, cost, st->gmax, step_norm, (valid ? 1 : 0) | (successful ? 2 : 0));
-  st->iteration = iteration;
-  if (iteration >= opt.max_num_iterations) { st->termination = 1; st->done = 1; return; }
+  trace_push(tr, st, cost, st.gmax, step_norm, (valid ? 1 : 0) | (successful ? 2 : 0));
+  st.iteration = iteration;
+  if (iteration >= opt.max_num_iterations) { st.termination = 1; st.done = 1; return; }
   if (!opt.disable_tolerances) {
-    if (successful && st->gmax <= opt.gradient_tolerance) { st->termination = 0; st->done = 1; return; }
-    if (!(st->radius > opt.min_radius)) { st->termination = 0; st->done = 1; return; }
+    if (successful && st.gmax <= opt.gradient_tolerance) { st.termination = 0; st.done = 1; return; }
+    if (!(st.radius > opt.min_radius)) { st.termination = 0; st.done = 1; return; }
   }
 }
 
-// IterationZero: consumes the evaluation of the initial point (set `cur`).
-__global__ void k_init(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
+// IterationZero: consumes the evaluation of the initial point (set `cur`).  One CTA.
+__global__ void k_init(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* stg, LmOptions opt,
                        Trace tr) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  const ParamSet& ps = st->cur ? ps1 : ps0;
-  double cgm, cxn2;
-  camera_grad_norms(P, ps, &cgm, &cxn2);
-  st->x_cost = total_cost(P, ps);
-  st->initial_cost = st->x_cost;
-  st->x_norm = sqrt(cxn2 + ps.comm[P.C * kCamRec + 3]);
-  st->gmax = fmax(cgm, ps.gmax[0]);
-  st->radius = opt.initial_radius;
-  st->decrease_factor = 2.0;
-  st->minimum_cost = DBL_MAX;
-  st->num_successful = st->num_unsuccessful = st->num_consecutive_invalid = 0;
-  st->atleast_one_successful_step = 0;
-  st->recorded = 0;
-  st->done = 0;
-  st->termination = 1;
-  st->solve_ok = 1;
-  finalize_iteration(st, opt, tr, 0, true, true, st->x_cost, 0.0);
+  __shared__ double s_red[40];
+  const ParamSet& ps = stg->cur ? ps1 : ps0;
+  const CameraSummary cs = camera_summary(P, ps, s_red);
+  if (threadIdx.x != 0) return;
+  LmState st = *stg;                      // the state lives in registers while it is worked on
+  st.x_cost = cs.cost;
+  st.initial_cost = st.x_cost;
+  st.x_norm = sqrt(cs.xn2 + ps.comm[P.C * kCamRec + 3]);
+  st.gmax = fmax(cs.gmax, ps.gmax[0]);
+  st.radius = opt.initial_radius;
+  st.decrease_factor = 2.0;
+  st.minimum_cost = DBL_MAX;
+  st.num_successful = st.num_unsuccessful = st.num_consecutive_invalid = 0;
+  st.atleast_one_successful_step = 0;
+  st.recorded = 0;
+  st.done = 0;
+  st.termination = 1;
+  st.solve_ok = 1;
+  finalize_iteration(st, opt, tr, 0, true, true, st.x_cost, 0.0);
+  *stg = st;
 }
 
-// TrustRegionMinimizer step bookkeeping for the candidate just evaluated (one thread).
+// TrustRegionMinimizer step bookkeeping for the candidate just evaluated (one thread; `cs` is the
+// block-wide camera_summary of the candidate set).
 __device__ inline void decide_step(const DeviceProblem& P, const ParamSet& ps0, const ParamSet& ps1,
-                                   LmState* st, const LmOptions& opt, Trace tr) {
-  if (st->done) return;
-  const ParamSet& pc = st->cur ? ps0 : ps1;   // candidate
+                                   LmState* stg, const LmOptions& opt, Trace tr, const CameraSummary& cs) {
+  LmState st = *stg;                      // one vector load instead of ~40 dependent global accesses
+  if (st.done) return;
+  const ParamSet& pc = st.cur ? ps0 : ps1;   // candidate
   const double* extra = pc.comm + P.C * kCamRec;
-  const double lin = st->cam_lin + extra[0];
-  const double quad = st->cam_quad + extra[1];
-  const double dn2 = st->cam_dn2 + extra[2];
-  const double xn2c = st->cam_xn2 + extra[3];
+  const double lin = st.cam_lin + extra[0];
+  const double quad = st.cam_quad + extra[1];
+  const double dn2 = st.cam_dn2 + extra[2];
+  const double xn2c = st.cam_xn2 + extra[3];
+  const double frame_gmax = pc.gmax[0];
   const double model_cost_change = lin - 0.5 * quad;
-  st->model_cost_change = model_cost_change;
-  const int iteration = st->iteration + 1;
-  const bool solver_ok = st->solve_ok && isfinite(dn2) && isfinite(model_cost_change);
+  st.model_cost_change = model_cost_change;
+  const int iteration = st.iteration + 1;
+  const bool solver_ok = st.solve_ok && isfinite(dn2) && isfinite(model_cost_change);
   const bool valid = solver_ok && model_cost_change > 0.0;
   if (!valid) {
     // HandleInvalidStep
-    if (++st->num_consecutive_invalid >= opt.max_num_consecutive_invalid_steps) {
-      st->termination = 2; st->done = 1; return;
+    if (++st.num_consecutive_invalid >= opt.max_num_consecutive_invalid_steps) {
+      st.termination = 2; st.done = 1; *stg = st; return;
     }
-    st->radius = st->radius / st->decrease_factor;
-    st->decrease_factor *= 2.0;
-    finalize_iteration(st, opt, tr, iteration, false, false, st->x_cost, 0.0);
+    st.radius = st.radius / st.decrease_factor;
+    st.decrease_factor *= 2.0;
+    finalize_iteration(st, opt, tr, iteration, false, false, st.x_cost, 0.0);
+    *stg = st;
     return;
   }
-  st->num_consecutive_invalid = 0;
-  double candidate_cost = total_cost(P, pc);
+  st.num_consecutive_invalid = 0;
+  double candidate_cost = cs.cost;
   if (!isfinite(candidate_cost)) candidate_cost = DBL_MAX;
-  st->candidate_cost = candidate_cost;
+  st.candidate_cost = candidate_cost;
   const double step_norm = sqrt(dn2);
-  st->step_norm = step_norm;
+  st.step_norm = step_norm;
   if (!opt.disable_tolerances) {
     // Ceres <= 2.0 tests both tolerances on every valid step; >= 2.1 only once a step has been
     // successful (tscm_options.parameter_tolerance_needs_successful_step)
-    const bool armed = !opt.ptol_needs_success || st->atleast_one_successful_step;
+    const bool armed = !opt.ptol_needs_success || st.atleast_one_successful_step;
     // ParameterToleranceReached
-    if (armed && step_norm <= opt.parameter_tolerance * (st->x_norm + opt.parameter_tolerance)) {
-      st->termination = 0; st->done = 1; return;
+    if (armed && step_norm <= opt.parameter_tolerance * (st.x_norm + opt.parameter_tolerance)) {
+      st.termination = 0; st.done = 1; *stg = st; return;
     }
     // FunctionToleranceReached
-    if (armed && fabs(st->x_cost - candidate_cost) <= opt.function_tolerance * st->x_cost) {
-      st->termination = 0; st->done = 1; return;
+    if (armed && fabs(st.x_cost - candidate_cost) <= opt.function_tolerance * st.x_cost) {
+      st.termination = 0; st.done = 1; *stg = st; return;
     }
   }
   // IsStepSuccessful (monotonic TrustRegionStepEvaluator)
   const double relative_decrease =
-      candidate_cost >= DBL_MAX ? -DBL_MAX : (st->x_cost - candidate_cost) / model_cost_change;
+      candidate_cost >= DBL_MAX ? -DBL_MAX : (st.x_cost - candidate_cost) / model_cost_change;
   if (relative_decrease > opt.min_relative_decrease) {
     // HandleSuccessfulStep: x = candidate, gradient/Jacobian are already there
-    st->cur ^= 1;
-    st->x_cost = candidate_cost;
-    st->x_norm = sqrt(xn2c);
-    double cgm, cxn2;
-    camera_grad_norms(P, pc, &cgm, &cxn2);
-    st->gmax = fmax(cgm, pc.gmax[0]);
+    st.cur ^= 1;
+    st.x_cost = candidate_cost;
+    st.x_norm = sqrt(xn2c);
+    st.gmax = fmax(cs.gmax, frame_gmax);
     const double t = 2.0 * relative_decrease - 1.0;
-    st->radius = st->radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
-    st->radius = fmin(opt.max_radius, st->radius);
-    st->decrease_factor = 2.0;
-    st->atleast_one_successful_step = 1;
-    finalize_iteration(st, opt, tr, iteration, true, true, st->x_cost, step_norm);
+    st.radius = st.radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
+    st.radius = fmin(opt.max_radius, st.radius);
+    st.decrease_factor = 2.0;
+    st.atleast_one_successful_step = 1;
+    finalize_iteration(st, opt, tr, iteration, true, true, st.x_cost, step_norm);
   } else {
-    st->radius = st->radius / st->decrease_factor;
-    st->decrease_factor *= 2.0;
+    st.radius = st.radius / st.decrease_factor;
+    st.decrease_factor *= 2.0;
     finalize_iteration(st, opt, tr, iteration, true, false, candidate_cost, step_norm);
   }
+  *stg = st;
 }
 
-__global__ void k_decide(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt,
-                         Trace tr) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  decide_step(P, ps0, ps1, st, opt, tr);
+constexpr int kDecideThreads = 128;
+__global__ void __launch_bounds__(kDecideThreads)
+k_decide(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, LmOptions opt, Trace tr) {
+  __shared__ double s_red[40];
+  pdl_entry();
+  if (st->done) return;
+  const CameraSummary cs = camera_summary(P, st->cur ? ps0 : ps1, s_red);
+  if (threadIdx.x == 0) decide_step(P, ps0, ps1, st, opt, tr, cs);
 }
 
 // ---------------------------------------------------------------------------
-// Post-evaluation kernel.  Blocks [0, C): camera c sums its partial slots (written by
-// k_view_blocks, one per (tile, camera)) in a fixed order into the comm record.  Blocks
-// [C, C + fg_nblk): frame gradient max-norm |x - (x - g)|_inf and |x_f|^2 partials.  The LAST
-// block to finish (threadfence + ticket) folds the frame partials and the step scalars into
-// the record and — on a single GPU — runs the accept/reject decision itself.  Which block
-// runs the tail varies; the arithmetic it performs does not, so results stay deterministic.
+// Post-evaluation kernel.
 // ---------------------------------------------------------------------------
+constexpr int kPostSplit = 4;      // blocks per camera
 struct PostArgs {
   double* gmax_part;       // [fg_nblk]
   double* xn2_part;        // [fg_nblk]
   const double* bs_part;   // [4][bs_nblk]
+  double* cam_sum_part;    // [C][kPostSplit][kCamRec]
   int bs_nblk, fg_nblk;
+  int lanes_per_frame;     // 8 / 16 / 32 >= the largest number of views of a frame
   unsigned int* ticket;
   int initial;             // evaluation of the initial point (no step quantities)
   int decide;              // 1: single GPU, run decide_step in the tail
@@ -1347,23 +1395,36 @@ struct PostArgs {
 
 constexpr int kPostThreads = 512;
 
+// Blocks [0, kPostSplit C): camera c's partial slots (written by k_view_blocks, one per (tile,
+// camera)), a quarter of them per block, summed in a fixed order.  Blocks behind them: frame
+// gradient max-norm |x - (x - g)|_inf and |x_f|^2 — a group of lanes per frame fetches the
+// gradient entries of all its views at once (round 1 walked the views one dependent load after
+// the other: most of that kernel's 24 us).  The LAST block to finish (threadfence + ticket) adds
+// the camera quarters into the comm record, folds the frame partials and the step scalars in
+// and — on a single GPU — runs the accept/reject decision itself.  Which block runs the tail
+// varies; the arithmetic it performs does not, so results stay deterministic.
 __global__ void __launch_bounds__(kPostThreads)
 k_post_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, int which, LmOptions opt,
             Trace tr, PostArgs A) {
   __shared__ double s_red[kPostThreads];
   __shared__ int s_last;
+  pdl_entry();
   if (which < 2 && st->done) return;
   const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
   const ParamSet& ps = sel ? ps1 : ps0;
   const int t = threadIdx.x;
-  if ((int)blockIdx.x < P.C) {
-    // 4 thread groups of 128 take every 4th slot; 4 loads in flight per thread
-    const int c = blockIdx.x, e = t & 127, grp = t >> 7;
+  const int ncam_blk = P.C * kPostSplit;
+  if ((int)blockIdx.x < ncam_blk) {
+    // 4 thread groups of 128 take every 4th slot of this block's quarter; 4 loads in flight
+    const int c = blockIdx.x / kPostSplit, quarter = blockIdx.x % kPostSplit;
+    const int e = t & 127, grp = t >> 7;
+    const int b0 = P.cam_slot_begin[c], b1 = P.cam_slot_begin[c + 1];
+    const int chunk = (b1 - b0 + kPostSplit - 1) / kPostSplit;
+    const int se = min(b1, b0 + (quarter + 1) * chunk);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (e < kCamRec) {
       const double* part = ps.cam_part + e;
-      int sl = P.cam_slot_begin[c] + grp;
-      const int se = P.cam_slot_begin[c + 1];
+      int sl = b0 + quarter * chunk + grp;
       for (; sl + 12 < se; sl += 16) {
         s0 += part[(size_t)sl * kCamRec];
         s1 += part[(size_t)(sl + 4) * kCamRec];
@@ -1375,18 +1436,29 @@ k_post_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, int which,
     s_red[t] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (t < kCamRec)
-      ps.comm[c * kCamRec + t] = (s_red[t] + s_red[t + 128]) + (s_red[t + 256] + s_red[t + 384]);
+      A.cam_sum_part[(size_t)blockIdx.x * kCamRec + t] = (s_red[t] + s_red[t + 128]) + (s_red[t + 256] + s_red[t + 384]);
   } else {
-    const int fb = blockIdx.x - P.C;
-    const int idx = fb * kPostThreads + t;
+    const int fb = blockIdx.x - ncam_blk;
+    const int lpf = A.lanes_per_frame, fpc = kPostThreads / lpf;
+    const int f = fb * fpc + t / lpf, j = t % lpf;
+    double g[6] = {0, 0, 0, 0, 0, 0};
+    if (f < P.F) {
+      const int p0 = P.frame_ptr[f], nv = P.frame_ptr[f + 1] - p0;
+      if (j < nv) {
+        const double* Gv = ps.G + (size_t)P.frame_views[p0 + j] * kViewStride + kOffBI + 7;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) g[b] = Gv[b * 8];
+      }
+    }
+    for (int o = lpf >> 1; o > 0; o >>= 1) {
+#pragma unroll
+      for (int b = 0; b < 6; ++b) g[b] += __shfl_xor_sync(0xffffffffu, g[b], o);
+    }
     double gm = 0.0, xn2 = 0.0;
-    if (idx < P.F * 6) {
-      const int f = idx / 6, b = idx % 6;
-      double g = 0.0;
-      for (int p = P.frame_ptr[f]; p < P.frame_ptr[f + 1]; ++p)
-        g += ps.G[(size_t)P.frame_views[p] * kViewStride + kOffBI + b * 8 + 7];
-      const double x = ps.board_rt[idx];
-      const double projected = x + (-g);
+    if (f < P.F && j < 6) {
+      const double gb = j == 0 ? g[0] : (j == 1 ? g[1] : (j == 2 ? g[2] : (j == 3 ? g[3] : (j == 4 ? g[4] : g[5]))));
+      const double x = ps.board_rt[f * 6 + j];
+      const double projected = x + (-gb);
       gm = fabs(x - projected);
       xn2 = x * x;
     }
@@ -1404,6 +1476,11 @@ k_post_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, int which,
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  for (int i = t; i < P.C * kCamRec; i += kPostThreads) {
+    const int c = i / kCamRec, e = i % kCamRec;
+    const volatile double* q = A.cam_sum_part + (size_t)c * kPostSplit * kCamRec + e;
+    ps.comm[i] = (q[0] + q[kCamRec]) + (q[2 * kCamRec] + q[3 * kCamRec]);
+  }
   double* extra = ps.comm + P.C * kCamRec;
   for (int k = 0; k < 4; ++k) {
     double s = 0.0;
@@ -1424,9 +1501,11 @@ k_post_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, int which,
     if (t == 0) ps.gmax[0] = tot;
   }
   __syncthreads();
-  if (t == 0) {
-    *A.ticket = 0u;
-    if (A.decide) { __threadfence(); decide_step(P, ps0, ps1, st, opt, tr); }
+  if (t == 0) *A.ticket = 0u;
+  if (A.decide && !st->done) {
+    // the candidate's comm record is complete (written above by this block)
+    const CameraSummary cs = camera_summary(P, ps, s_red);
+    if (t == 0) decide_step(P, ps0, ps1, st, opt, tr, cs);
   }
 }
 
@@ -1437,6 +1516,7 @@ k_post_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, int which,
 // dir 0: ps[sel].comm, gmax -> stage[0..n), stage[n]; dir 1: back.
 __global__ void k_comm_stage(ParamSet ps0, ParamSet ps1, const LmState* st, int which, int n,
                              double* __restrict__ stage, int dir) {
+  pdl_entry();
   const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
   const ParamSet& ps = sel ? ps1 : ps0;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(kReduceThreads)
 k_reduce_s_p2p(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
                const double* __restrict__ Spart, const double* __restrict__ rpart, int nblk,
                double* __restrict__ out, AssembleArgs A, P2PArgs x) {
+  pdl_entry();
   if (st->done) return;
   __shared__ double s_part[8][33];
   __shared__ double s_mine[32];
@@ -169,6 +170,7 @@ constexpr int kXchgThreads = 512;
 __global__ void __launch_bounds__(kXchgThreads)
 k_xchg_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, int which, LmOptions opt, Trace tr,
             P2PArgs x, int decide) {
+  pdl_entry();
   if (which < 2 && st->done) return;
   const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
   const ParamSet& ps = sel ? ps1 : ps0;
@@ -200,14 +202,15 @@ k_xchg_eval(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, int which,
   }
   __threadfence();
   __syncthreads();
-  if (tid == 0) {
-    x.seq[1] = s;
-    if (*reinterpret_cast<volatile int*>(x.err)) {
-      // a peer did not show up in this or the preceding Schur exchange: the sums are not global
-      st->termination = 2; st->done = 1;
-    } else if (decide) {
-      decide_step(P, ps0, ps1, st, opt, tr);
-    }
+  if (tid == 0) x.seq[1] = s;
+  const bool failed = *reinterpret_cast<volatile int*>(x.err) != 0;
+  if (failed) {
+    // a peer did not show up in this or the preceding Schur exchange: the sums are not global
+    if (tid == 0) { st->termination = 2; st->done = 1; }
+  } else if (decide && !st->done) {
+    __shared__ double s_red[40];
+    const CameraSummary cs = camera_summary(P, ps, s_red);     // ps: the candidate set (which = 1)
+    if (tid == 0) decide_step(P, ps0, ps1, st, opt, tr, cs);
   }
 }
 

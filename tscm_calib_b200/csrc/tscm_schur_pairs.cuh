@@ -71,6 +71,7 @@ constexpr size_t kPair2Smem = (size_t)kPairWarps * kPair2Stages * 384 * sizeof(d
 
 __global__ void __launch_bounds__(kPairWarps * 32, 1)
 k_schur_pairs2(const LmState* st, PairArgs A) {
+  pdl_entry();
   if (st->done) return;
   extern __shared__ __align__(128) double s_ring[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -162,6 +163,7 @@ constexpr int kPairReduceGroups = 4;
 
 __global__ void __launch_bounds__(kPairReduceGroups * kPairPart)
 k_reduce_pairs(DeviceProblem P, const LmState* st, PairArgs A) {
+  pdl_entry();
   if (st->done) return;
   __shared__ double s_sum[kPairReduceGroups][kPairPart];
   const int pr = blockIdx.x;

@@ -107,6 +107,7 @@ template <int T, int RMAX>   // tiles per thread; rows per lane of the back-subs
 __global__ void __launch_bounds__(T == 1 ? 512 : 384)
 k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, const double* __restrict__ M /*tiles*/,
         const double* __restrict__ scale_c, double* __restrict__ y_c /*[NL]*/, int prof) {
+  pdl_entry();
   if (st->done) return;
   long long tk0 = clock64(), tk1 = 0, tk2 = 0, tk3 = 0;
   const int sel = st->cur;
