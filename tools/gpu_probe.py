@@ -74,3 +74,22 @@ if "group" in what:
             print(f"   resident: obs {1e3*(t1-t):.2f} set {1e3*(t2-t1):.2f} run(200) {1e3*(t3-t2):.2f} get {1e3*(t4-t3):.2f} ms", flush=True)
         s.close()
         capi.cache_release()
+if "schur_forms" in what:
+    for frames in (625, 1250, 2500, 5000):
+        sp = synth.config(3, num_frames=frames)
+        for form in ("rows", "fused", "pairs"):
+            try:
+                s = capi.Solver(sp.problem, capi.default_options(max_num_iterations=100, disable_tolerances=1), schur_form=form)
+            except capi.TscmError as e:
+                print(frames, form, "unsupported"); continue
+            s.set_parameters(sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt)
+            s.time_stage(1, 3)
+            t1 = s.time_stage(1, 20)
+            s.set_parameters(sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt)
+            s.time_stage(4, 5)
+            s.set_parameters(sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt)
+            t4 = s.time_stage(4, 30)
+            st = {n: s.time_stage(i, 10) for i, n in ((6, "eval5"), (7, "vblocks"), (5, "evalpass"), (2, "solve"), (3, "backsub"))}
+            print(f"frames {frames:5d} {form:6s}: schur stage {t1*1e3:6.1f} us, iteration {t4*1e3:6.1f} us  " +
+                  " ".join(f"{k} {v*1e3:.1f}" for k, v in st.items()), flush=True)
+            s.close()

@@ -236,6 +236,7 @@ struct tscm_solver {
   int schur_nblk = 0, schur_nt = 256, schur_ept = 1;
   SolveDims solve{};
   size_t eval5_smem = 0;
+  E5Items e5items{};
   int want_err = 0;                 // accumulate sum sqrt(s) (reprojection read-out only)
   int bs_nblk = 0, fg_nblk = 0, post_lpf = 8;
   double* d_cam_sum_part = nullptr;
@@ -379,11 +380,11 @@ void launch_eval_kernel(tscm_solver* s, int which, int part = 0) {
   const int ntiles = (P.V + 31) / 32;
   if (part != 2) {
     launch_k(s, k_eval5, dim3(std::min(ntiles, s->sm_count)), dim3(kE5Threads), (size_t)(s->eval5_smem), 
-        P, s->ps[0], s->ps[1], s->d_state, which, s->lm, s->want_err, s->d_mom, s->d_fcg);
+        P, s->ps[0], s->ps[1], s->d_state, which, s->lm, s->want_err, s->d_mom, s->d_fcg, s->e5items);
   }
   if (part != 1) {
     launch_k(s, k_view_blocks, dim3(ntiles), dim3(kVbThreads), (size_t)(vb_smem_bytes()), P, s->ps[0], s->ps[1], s->d_state, which,
-                                                                      s->d_mom, s->d_fcg);
+                                                                      s->d_mom, s->d_fcg, s->e5items);
   }
 }
 
@@ -944,7 +945,8 @@ int create_shard(const tscm_problem* p, const tscm_options* o, int device, bool 
   A.want(&s->d_xn2_part, (size_t)s->fg_nblk);
   {
     const size_t ntile_e = ((size_t)V + 31) / 32;
-    A.want(&s->d_mom, ntile_e * kE5MomEntries * 32);
+    s->e5items = e5_items((int)ntile_e, std::min((int)ntile_e, s->sm_count), (K + kE5Producers - 1) / kE5Producers);
+    A.want(&s->d_mom, (size_t)s->e5items.nitems * kE5MomEntries * 32);
     A.want(&s->d_fcg, ntile_e * kFcElems * 32);
   }
   const int cap = std::max(128, std::min(s->options.max_num_iterations, 1 << 16) + 2);

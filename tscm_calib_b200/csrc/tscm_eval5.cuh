@@ -269,18 +269,55 @@ __device__ __forceinline__ double e5_loss(int loss_type, double loss_scale, ObsC
   return l.half_rho;
 }
 
+// Work items of k_eval5.  A tile of 32 views is one item — except the tiles of the LAST, partial
+// round of the persistent grid (1,250 tiles on 148 SMs: 8 full rounds + 66 tiles), which are cut
+// into `split` corner ranges so that the tail round costs 1 / split of a tile time; their partial
+// moments land in consecutive slots that k_view_blocks adds up.  item < n_whole: tile = item.
+struct E5Items {
+  int n_whole;    // tiles processed whole (a multiple of the grid size)
+  int split;      // parts per remaining tile (1, 2 or 4)
+  int nitems;     // n_whole + (ntiles - n_whole) * split; moment slot of an item = its index
+};
+inline E5Items e5_items(int ntiles, int grid, int ngroups) {
+  E5Items I;
+  I.n_whole = ntiles / grid * grid;
+  const int rem = ntiles - I.n_whole;
+  I.split = 1;
+  if (rem > 0) {
+    // rounds the remainder costs, in tile times: ceil(rem * split / grid) / split
+    double best = 1.0;
+    for (int sp = 2; sp <= 4 && sp <= ngroups; sp *= 2) {
+      const double cost = (double)((rem * sp + grid - 1) / grid) / sp;
+      if (cost < best - 1e-9) { best = cost; I.split = sp; }
+    }
+  }
+  I.nitems = I.n_whole + rem * I.split;
+  return I;
+}
+struct E5Item { int tile, g0, g1; };
+__device__ __forceinline__ E5Item e5_item(const E5Items& I, int item, int ngroups) {
+  E5Item it;
+  if (item < I.n_whole) { it.tile = item; it.g0 = 0; it.g1 = ngroups; return it; }
+  const int r = item - I.n_whole, p = r % I.split;
+  it.tile = I.n_whole + r / I.split;
+  it.g0 = p * ngroups / I.split;
+  it.g1 = (p + 1) * ngroups / I.split;
+  return it;
+}
+
 template <int W>
 __device__ __forceinline__ void e5_consumer(const double* __restrict__ s_ring,
                                             const double* __restrict__ s_mu, double* __restrict__ mom_g,
                                             unsigned long long* full, unsigned long long* empty,
-                                            int lane, int ntiles, int ngroups) {
+                                            int lane, E5Items items, int ngroups) {
   constexpr int NA = W < 2 ? 19 : 25;
   double acc[NA];
 #pragma unroll
   for (int i = 0; i < NA; ++i) acc[i] = 0.0;
   unsigned k = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    for (int g = 0; g < ngroups; ++g, ++k) {
+  for (int item = blockIdx.x; item < items.nitems; item += gridDim.x) {
+    const E5Item it = e5_item(items, item, ngroups);
+    for (int g = it.g0; g < it.g1; ++g, ++k) {
       const unsigned slot = k % kE5Depth, ph = (k / kE5Depth) & 1u;
       const double* mu = s_mu + 5 * g * kE5Producers;
       mbar_wait(full + slot, ph);            // all eight rows of the group are published
@@ -289,8 +326,8 @@ __device__ __forceinline__ void e5_consumer(const double* __restrict__ s_ring,
         e5_consume<W>(s_ring + (size_t)(o * kE5Depth + slot) * kE5Slot, lane, mu + 5 * o, acc);
       warp_arrive(empty + slot, lane);
     }
-    // the tile's sums go straight to the moment buffer (256-byte rows, lane = view)
-    double* dst = mom_g + (size_t)tile * (kE5MomEntries * 32) + lane;
+    // the item's sums go straight to its slot of the moment buffer (256-byte rows, lane = view)
+    double* dst = mom_g + (size_t)item * (kE5MomEntries * 32) + lane;
     if (W < 2) {
 #pragma unroll
       for (int i = 0; i < 18; ++i) { dst[(18 * W + i) * 32] = acc[i]; acc[i] = 0.0; }
@@ -309,7 +346,7 @@ __device__ __forceinline__ void e5_consumer(const double* __restrict__ s_ring,
 
 __global__ void __launch_bounds__(kE5Threads, 1)
 k_eval5(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which, LmOptions opt,
-        int want_err, double* __restrict__ mom_g, double* __restrict__ fc_g) {
+        int want_err, double* __restrict__ mom_g, double* __restrict__ fc_g, E5Items items) {
   pdl_entry();
   if (which < 2 && st->done) return;
   const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
@@ -351,7 +388,7 @@ k_eval5(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
   if (warp < kE5Consumers) {
     // ------------------------------ consumers -----------------------------------
     asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-#define TSCM_E5_CONSUMER(W) e5_consumer<W>(s_ring, s_mu, mom_g, full, empty, lane, ntiles, ngroups)
+#define TSCM_E5_CONSUMER(W) e5_consumer<W>(s_ring, s_mu, mom_g, full, empty, lane, items, ngroups)
     // sub-partition = warp % 4: one M slice or one row-u slice next to one row-v slice
     switch (warp) {
       case 0: TSCM_E5_CONSUMER(0); break;
@@ -382,7 +419,7 @@ k_eval5(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
                         fc_g + (size_t)tile * (kFcElems * 32), lane);
       warp_arrive(fc_full + buf, lane);
     };
-    if (p == 0 && (int)blockIdx.x < ntiles) publish_fc(blockIdx.x, 0, 0u);
+    if (p == 0 && (int)blockIdx.x < items.nitems) publish_fc(e5_item(items, blockIdx.x, ngroups).tile, 0, 0u);
     // Two corners (groups g, g+1) are evaluated together: the projection is one long
     // dependent FP64 chain (3 rsqrt + a reciprocal), two independent chains interleave in
     // one warp.  The observations of the NEXT pair (also across a tile boundary) are
@@ -408,8 +445,13 @@ k_eval5(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
 #pragma unroll
       for (int q = 0; q < 10; ++q) m2[q * 32] = pr[q];
     };
-    double2 uvA = fetch(blockIdx.x, p), uvB = fetch(blockIdx.x, p + kE5Producers);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    E5Item cur = e5_item(items, min((int)blockIdx.x, items.nitems - 1), ngroups);
+    double2 uvA = fetch(cur.tile, cur.g0 * kE5Producers + p), uvB = fetch(cur.tile, (cur.g0 + 1) * kE5Producers + p);
+    for (int item = blockIdx.x; item < items.nitems; item += gridDim.x, ++it) {
+      cur = e5_item(items, item, ngroups);
+      const int tile = cur.tile;
+      const bool has_next = item + (int)gridDim.x < items.nitems;
+      const E5Item nxt = e5_item(items, has_next ? item + (int)gridDim.x : item, ngroups);
       const int v0 = tile * 32 + lane;
       const bool valid = v0 < P.V;
       const int v = valid ? v0 : P.V - 1;
@@ -425,13 +467,16 @@ k_eval5(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
         make_view_const(cc, fc, vc);
         warp_arrive(fc_empty + (it & 1), lane);
       }
-      for (int g = 0; g < ngroups; g += 2) {
-        const bool two = g + 1 < ngroups;
+      for (int g = cur.g0; g < cur.g1; g += 2) {
+        const bool two = g + 1 < cur.g1;
         const int j0 = g * kE5Producers + p, j1 = j0 + kE5Producers;
-        const double2 uv0 = uvA, uv1 = uvB;
-        const int nt = tile + (int)gridDim.x;
-        uvA = g + 2 < ngroups ? fetch(tile, j0 + 2 * kE5Producers) : fetch(nt, p);
-        if (two) uvB = g + 3 < ngroups ? fetch(tile, j1 + 2 * kE5Producers) : fetch(nt, p + kE5Producers);
+        const double2 uv0 = uvA, uv1 = two ? uvB : make_double2(0.0, 0.0);
+        // the observations of the next pair — of this item or of the next one — are requested now
+        const int nt = has_next ? nxt.tile : ntiles;          // ntiles: fetch() returns zeros
+        const int nj = nxt.g0 * kE5Producers + p;
+        uvA = g + 2 < cur.g1 ? fetch(tile, j0 + 2 * kE5Producers) : fetch(nt, nj);
+        if (g + 2 < cur.g1) { if (g + 3 < cur.g1) uvB = fetch(tile, j1 + 2 * kE5Producers); }
+        else uvB = fetch(nt, nj + kE5Producers);
         const bool ok0 = j0 < P.K && valid, ok1 = two && j1 < P.K && valid;
         const int c0 = min(j0, P.K - 1), c1 = min(j1, P.K - 1);
         ObsCompact o[2];
@@ -462,7 +507,7 @@ k_eval5(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int whic
           warp_arrive(full + slot, lane);
           ++k;
         }
-        if (p == 0 && g == 0 && nt < ntiles) publish_fc(nt, (it + 1) & 1, (unsigned)(it + 1) >> 1);
+        if (p == 0 && g == cur.g0 && has_next) publish_fc(nxt.tile, (it + 1) & 1, (unsigned)(it + 1) >> 1);
       }
     }
   }
@@ -547,7 +592,7 @@ __device__ __forceinline__ double vb_dot(const double* __restrict__ ca, const do
 
 __global__ void __launch_bounds__(kVbThreads, 2)
 k_view_blocks(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, int which,
-              const double* __restrict__ mom_g, const double* __restrict__ fc_g) {
+              const double* __restrict__ mom_g, const double* __restrict__ fc_g, E5Items items) {
   pdl_entry();
   if (which < 2 && st->done) return;
   const int sel = which >= 2 ? which - 2 : (st->cur ^ which);
@@ -560,13 +605,17 @@ k_view_blocks(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, in
   double* s_colv = s_tail + kVbTail * 32;              // [108][32]
   double* s_fc = s_colv + 108 * 32;                    // [27][32]
   short* s_iisrc = reinterpret_cast<short*>(s_fc + kFcElems * 32);   // [36][2]
-  const int tile = blockIdx.x;
+  // the split tiles of the last k_eval5 round (a little more work: their parts are added below)
+  // go first, not into the tail of this grid
+  const int ntiles_all = (P.V + 31) / 32;
+  const int tile = ((int)blockIdx.x + items.n_whole) % ntiles_all;
   const int b = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const double* gm = mom_g + (size_t)tile * (kE5MomEntries * 32);
+    const int slot = tile < items.n_whole ? tile : items.n_whole + (tile - items.n_whole) * items.split;
+    const double* gm = mom_g + (size_t)slot * (kE5MomEntries * 32);
     mbar_expect_tx(bar, (unsigned)((kE5MomEntries + kFcElems) * 32 * sizeof(double)));
     tma_bulk_g2s(s_mn, gm, kVbMN * 32 * sizeof(double), bar);
     tma_bulk_g2s(s_tail, gm + kVbMN * 32, kVbTail * 32 * sizeof(double), bar);
@@ -595,6 +644,25 @@ k_view_blocks(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, in
   const int slot0 = P.blk_slot[tile];
   __syncthreads();          // barrier initialised before anyone polls it
   mbar_wait(bar, 0);
+  if (tile >= items.n_whole && items.split > 1) {
+    // a tile of the last round: its moments arrived as `split` partial sums over corner ranges
+    const double* gm = mom_g + (size_t)(items.n_whole + (tile - items.n_whole) * items.split) * (kE5MomEntries * 32);
+    constexpr int kN = kE5MomEntries * 32, kPer = (kN + kVbThreads - 1) / kVbThreads;
+    for (int q = 1; q < items.split; ++q) {
+      double v[kPer];                           // all loads of a part in flight at once
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const int i = threadIdx.x + u * kVbThreads;
+        v[u] = i < kN ? gm[(size_t)q * kN + i] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const int i = threadIdx.x + u * kVbThreads;
+        if (i < kN) s_mn[i] += v[u];
+      }
+    }
+    __syncthreads();
+  }
   double cb[9], h[9], ox[8];
   {
     // view_column_vectors(cam, fc, b) with the frame constants read from shared memory at

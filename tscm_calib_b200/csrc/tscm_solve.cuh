@@ -52,16 +52,16 @@ __host__ __device__ inline int solve_pan_off(int s, int nbk) {      // doubles
   return 16 * (s * (nbk - 1) - (s * (s - 1)) / 2);
 }
 // pivot record in shared memory: g = 1/d (4) | w10 w20 w21 w30 w31 w32 (unscaled in-block factor)
-// | N (10): upper-triangular inverse of the block's P^T, row-major
-constexpr int kPivRec = 20;
+// | N (10): upper-triangular inverse of the block's P^T, row-major | l10 l20 l21 l30 l31 l32
+constexpr int kPivRec = 26;
 __device__ __forceinline__ int piv_widx(int a, int b) { return 4 + (a * (a - 1)) / 2 + b; }   // a > b
 
 inline SolveDims solve_dims(int NL, int C) {
   SolveDims d;
   d.nbk = (NL + 1 + 3) / 4;
   d.ntile = d.nbk * (d.nbk + 1) / 2;
-  d.T = d.ntile <= 512 ? 1 : 4;
-  d.NT = std::max(128, ((d.ntile + d.T - 1) / d.T + 31) / 32 * 32);
+  d.T = d.ntile <= 480 ? 1 : 4;
+  d.NT = std::max(128, ((d.ntile + d.T - 1) / d.T + 31) / 32 * 32) + 32;    // + the pivot warp
   const size_t doubles = (size_t)solve_pan_off(d.nbk, d.nbk)     // panels
                          + (size_t)d.nbk * 10                    // published pivot tiles
                          + (size_t)d.nbk * kPivRec               // pivot records
@@ -104,7 +104,7 @@ __device__ __forceinline__ void ldlt4(const double* t, Piv4& f) {
 }
 
 template <int T, int RMAX>   // tiles per thread; rows per lane of the back-substitution warp
-__global__ void __launch_bounds__(T == 1 ? 512 : 384)
+__global__ void __launch_bounds__(T == 1 ? 512 : 448)
 k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, const double* __restrict__ M /*tiles*/,
         const double* __restrict__ scale_c, double* __restrict__ y_c /*[NL]*/, int prof) {
   pdl_entry();
@@ -135,8 +135,8 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, const double* 
   double acc[T][16];
 #pragma unroll
   for (int k = 0; k < T; ++k) {
-    const int id = tid + k * NT;
-    valid[k] = id < ntile;
+    const int id = tid + k * (NT - 32);
+    valid[k] = id < ntile && tid < NT - 32;
     bi[k] = bj[k] = -1;
     if (valid[k]) {
       const double2* src = reinterpret_cast<const double2*>(M + (size_t)id * 16);
@@ -167,9 +167,10 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, const double* 
       else if (r > NL) acc[k][e] = 0.0;
     }
   }
-  double pcp[10];                                    // private copy of the pivot block of my column
-#pragma unroll
-  for (int e = 0; e < 10; ++e) pcp[e] = 0.0;
+  // tiles are owned by threads [0, NTt); the last warp is the PIVOT warp: it owns no tile and
+  // factors the next 4x4 pivot block while the tile owners update
+  const int NTt = NT - 32;
+  const bool pivot_warp = tid >= NTt;
   if (tid == 0) {                                    // tile 0 = (0, 0)
     double* t = Pt;
     t[0] = acc[0][0];
@@ -178,54 +179,68 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, const double* 
     t[6] = acc[0][12]; t[7] = acc[0][13]; t[8] = acc[0][14]; t[9] = acc[0][15];
   }
   __syncthreads();
-  if (valid[0] && bj[0] == 0) {
+  // pivot record of block s: g = 1/d (4) | w10 w20 w21 w30 w31 w32 | N (10, filled after the loop)
+  // | l10 l20 l21 l30 l31 l32 (unit-lower factor for the panel solve)
+  auto factor_block = [&](int s, const double* t10) {
+    Piv4 f;
+    ldlt4(t10, f);
+    if (lane == 0) {
+      double* pr = piv + kPivRec * s;
+      pr[0] = f.i0; pr[1] = f.i1; pr[2] = f.i2; pr[3] = f.i3;
+      pr[4] = t10[1]; pr[5] = t10[3]; pr[6] = f.w21; pr[7] = t10[6]; pr[8] = f.w31; pr[9] = f.w32;
+      pr[20] = f.l10; pr[21] = f.l20; pr[22] = f.l21; pr[23] = f.l30; pr[24] = f.l31; pr[25] = f.l32;
+      const int j0 = 4 * s;
+      const bool ok = (j0 >= NL || f.d0 > 0.0) && (j0 + 1 >= NL || f.d1 > 0.0) &&
+                      (j0 + 2 >= NL || f.d2 > 0.0) && (j0 + 3 >= NL || f.d3 > 0.0);
+      if (!ok) s_ok = 0;
+    }
+  };
+  if (pivot_warp) {
+    double t10[10];
 #pragma unroll
-    for (int e = 0; e < 10; ++e) pcp[e] = Pt[e];
+    for (int e = 0; e < 10; ++e) t10[e] = Pt[e];
+    factor_block(0, t10);
   }
+  __syncthreads();
   tk1 = clock64();
-  // ---- blocked LDL^T: one barrier per block column --------------------------------------------
+  // ---- blocked LDL^T: two barriers per block column ---------------------------------------------
+  //   P(s): owners of tiles (i, s) eliminate their four panel rows with the factors of block s
+  //         -> panel s in shared memory; the owner of tile (s+1, s+1) publishes it
+  //   U(s): every tile (i, j), j > s: A -= P(i, s) D^-1 P(j, s)^T (64 FMAs on registers), WHILE
+  //         the pivot warp applies the same update to the published block and factors it
+  // The serial reciprocal chain of a step (~45 dependent instructions, ~450 cycles for a single
+  // warp) thus runs beside the updates instead of after them.
   // Element (row, col c) of panel s sits at c * nrows + (a >> 1) * (nrows / 2) + 2 * b + (a & 1),
   // row = 4 (s + 1 + b) + a: a warp's 16-byte loads of consecutive blocks are contiguous.
   for (int s = 0; s < nbk; ++s) {
     const int nrows = 4 * (nbk - 1 - s);
     double* pan = Lp + solve_pan_off(s, nbk);
-    // -- before the barrier: pivot record / panel of column s; publish the next pivot block --------
+    // -- P(s) --------------------------------------------------------------------------------------
 #pragma unroll
     for (int k = 0; k < T; ++k) {
       if (!valid[k]) continue;
-      if (bj[k] == s) {
-        Piv4 f;
-        ldlt4(pcp, f);
-        if (bi[k] == s) {
-          double* pr = piv + kPivRec * s;
-          pr[0] = f.i0; pr[1] = f.i1; pr[2] = f.i2; pr[3] = f.i3;
-          pr[4] = pcp[1]; pr[5] = pcp[3]; pr[6] = f.w21; pr[7] = pcp[6]; pr[8] = f.w31; pr[9] = f.w32;
-          const int j0 = 4 * s;
-          const bool ok = (j0 >= NL || f.d0 > 0.0) && (j0 + 1 >= NL || f.d1 > 0.0) &&
-                          (j0 + 2 >= NL || f.d2 > 0.0) && (j0 + 3 >= NL || f.d3 > 0.0);
-          if (!ok) s_ok = 0;
-        } else {
-          // eliminate the four panel columns of my four rows
-          const int b2 = 2 * (bi[k] - s - 1);
+      if (bj[k] == s && bi[k] > s) {
+        const double* pr = piv + kPivRec * s + 20;
+        const double l10 = pr[0], l20 = pr[1], l21 = pr[2], l30 = pr[3], l31 = pr[4], l32 = pr[5];
+        const int b2 = 2 * (bi[k] - s - 1);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            double p[2][4];
+        for (int h = 0; h < 2; ++h) {
+          double p[2][4];
 #pragma unroll
-            for (int a = 0; a < 2; ++a) {
-              const double* row = &acc[k][(2 * h + a) * 4];
-              const double p0 = row[0];
-              const double p1 = fma(-p0, f.l10, row[1]);
-              const double p2 = fma(-p1, f.l21, fma(-p0, f.l20, row[2]));
-              const double p3 = fma(-p2, f.l32, fma(-p1, f.l31, fma(-p0, f.l30, row[3])));
-              p[a][0] = p0; p[a][1] = p1; p[a][2] = p2; p[a][3] = p3;
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              *reinterpret_cast<double2*>(pan + c * nrows + h * (nrows >> 1) + b2) = make_double2(p[0][c], p[1][c]);
+          for (int a = 0; a < 2; ++a) {
+            const double* row = &acc[k][(2 * h + a) * 4];
+            const double p0 = row[0];
+            const double p1 = fma(-p0, l10, row[1]);
+            const double p2 = fma(-p1, l21, fma(-p0, l20, row[2]));
+            const double p3 = fma(-p2, l32, fma(-p1, l31, fma(-p0, l30, row[3])));
+            p[a][0] = p0; p[a][1] = p1; p[a][2] = p2; p[a][3] = p3;
           }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<double2*>(pan + c * nrows + h * (nrows >> 1) + b2) = make_double2(p[0][c], p[1][c]);
         }
       } else if (bj[k] == s + 1 && bi[k] == s + 1) {
-        // the next pivot block as it is BEFORE update s (its column owners apply update s themselves)
+        // the next pivot block as it is BEFORE update s (the pivot warp applies update s itself)
         double* t = Pt + 10 * (s + 1);
         t[0] = acc[k][0];
         t[1] = acc[k][4]; t[2] = acc[k][5];
@@ -235,43 +250,50 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, const double* 
     }
     __syncthreads();
     if (s + 1 == nbk) break;
-    // -- after the barrier: update s of my tiles; column s + 1 also updates its pivot copy (first:
-    //    that chain feeds the next ldlt4) ---------------------------------------------------------
+    // -- U(s) --------------------------------------------------------------------------------------
     const double g0 = piv[kPivRec * s], g1 = piv[kPivRec * s + 1], g2 = piv[kPivRec * s + 2],
                  g3 = piv[kPivRec * s + 3];
+    if (pivot_warp) {
+      double t10[10];
 #pragma unroll
-    for (int k = 0; k < T; ++k) {
-      if (!valid[k] || bj[k] <= s) continue;
-      const bool next = bj[k] == s + 1;
-      const double* pi = pan + 2 * (bi[k] - s - 1);
-      const double* pj = pan + 2 * (bj[k] - s - 1);
-      if (next) {
-#pragma unroll
-        for (int e = 0; e < 10; ++e) pcp[e] = Pt[10 * (s + 1) + e];
-      }
+      for (int e = 0; e < 10; ++e) t10[e] = Pt[10 * (s + 1) + e];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const double2 a01 = *reinterpret_cast<const double2*>(pi + c * nrows);
-        const double2 a23 = *reinterpret_cast<const double2*>(pi + c * nrows + (nrows >> 1));
-        const double2 b01 = *reinterpret_cast<const double2*>(pj + c * nrows);
-        const double2 b23 = *reinterpret_cast<const double2*>(pj + c * nrows + (nrows >> 1));
+        const double2 b01 = *reinterpret_cast<const double2*>(pan + c * nrows);               // block s + 1
+        const double2 b23 = *reinterpret_cast<const double2*>(pan + c * nrows + (nrows >> 1));
         const double g = c == 0 ? g0 : (c == 1 ? g1 : (c == 2 ? g2 : g3));
-        const double fa[4] = {a01.x, a01.y, a23.x, a23.y};
         const double fb[4] = {b01.x, b01.y, b23.x, b23.y};
         const double q[4] = {fb[0] * g, fb[1] * g, fb[2] * g, fb[3] * g};
-        if (next) {
-          pcp[0] = fma(-fb[0], q[0], pcp[0]);
-          pcp[1] = fma(-fb[1], q[0], pcp[1]); pcp[2] = fma(-fb[1], q[1], pcp[2]);
-          pcp[3] = fma(-fb[2], q[0], pcp[3]); pcp[4] = fma(-fb[2], q[1], pcp[4]); pcp[5] = fma(-fb[2], q[2], pcp[5]);
-          pcp[6] = fma(-fb[3], q[0], pcp[6]); pcp[7] = fma(-fb[3], q[1], pcp[7]); pcp[8] = fma(-fb[3], q[2], pcp[8]);
-          pcp[9] = fma(-fb[3], q[3], pcp[9]);
+        t10[0] = fma(-fb[0], q[0], t10[0]);
+        t10[1] = fma(-fb[1], q[0], t10[1]); t10[2] = fma(-fb[1], q[1], t10[2]);
+        t10[3] = fma(-fb[2], q[0], t10[3]); t10[4] = fma(-fb[2], q[1], t10[4]); t10[5] = fma(-fb[2], q[2], t10[5]);
+        t10[6] = fma(-fb[3], q[0], t10[6]); t10[7] = fma(-fb[3], q[1], t10[7]); t10[8] = fma(-fb[3], q[2], t10[8]);
+        t10[9] = fma(-fb[3], q[3], t10[9]);
+      }
+      factor_block(s + 1, t10);
+    } else {
+#pragma unroll
+      for (int k = 0; k < T; ++k) {
+        if (!valid[k] || bj[k] <= s) continue;
+        const double* pi = pan + 2 * (bi[k] - s - 1);
+        const double* pj = pan + 2 * (bj[k] - s - 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double2 a01 = *reinterpret_cast<const double2*>(pi + c * nrows);
+          const double2 a23 = *reinterpret_cast<const double2*>(pi + c * nrows + (nrows >> 1));
+          const double2 b01 = *reinterpret_cast<const double2*>(pj + c * nrows);
+          const double2 b23 = *reinterpret_cast<const double2*>(pj + c * nrows + (nrows >> 1));
+          const double g = c == 0 ? g0 : (c == 1 ? g1 : (c == 2 ? g2 : g3));
+          const double fa[4] = {a01.x, a01.y, a23.x, a23.y};
+          const double q[4] = {b01.x * g, b01.y * g, b23.x * g, b23.y * g};
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[k][a * 4 + b] = fma(-fa[a], q[b], acc[k][a * 4 + b]);
         }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) acc[k][a * 4 + b] = fma(-fa[a], q[b], acc[k][a * 4 + b]);
       }
     }
+    __syncthreads();
   }
   // explicit inverse N of every block's P^T (upper triangular) for the back-substitution: one
   // thread per block; columns that belong to the augmented row / padding are masked
@@ -298,14 +320,21 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, const double* 
     // ---- back-substitution: x_k = (y_k - sum_{j > k} P[j][k] x_j) / d_k, lane = row -------------
     const int bl = nbk - 1;                     // block of the augmented row NL
     double r[RMAX];
+    const double* colb[RMAX];   // column k of the panels, addressed by block row: colb + 2 jb (+ half)
+    int half[RMAX];
 #pragma unroll
     for (int m = 0; m < RMAX; ++m) {
       const int k = lane + 32 * m;
       r[m] = 0.0;
+      colb[m] = Lp;
+      half[m] = 0;
       if (k < NL) {
         const int s = k >> 2;
+        const int nr = 4 * (nbk - 1 - s);
+        colb[m] = Lp + solve_pan_off(s, nbk) + (k & 3) * nr - 2 * (s + 1);
+        half[m] = nr >> 1;
         if (s < bl) {
-          const int nr = 4 * (nbk - 1 - s), rr = NL - 4 * (s + 1);     // row NL inside panel s
+          const int rr = NL - 4 * (s + 1);     // row NL inside panel s
           r[m] = Lp[solve_pan_off(s, nbk) + (k & 3) * nr + ((rr >> 1) & 1) * (nr >> 1) + 2 * (rr >> 2) + (rr & 1)];
         }
         else r[m] = piv[kPivRec * bl + piv_widx(NL & 3, k & 3)];
@@ -321,11 +350,9 @@ k_solve(DeviceProblem P, ParamSet ps0, ParamSet ps1, LmState* st, const double* 
         const int k = lane + 32 * m;
         p01[m] = p23[m] = make_double2(0.0, 0.0);
         if (k < j0) {        // rows above the block (j0 <= NL - 1 < 32 RMAX)
-          const int s = k >> 2;
-          const int nr = 4 * (nbk - 1 - s);
-          const double* col = Lp + solve_pan_off(s, nbk) + (k & 3) * nr + 2 * (jb - s - 1);
+          const double* col = colb[m] + 2 * jb;
           p01[m] = *reinterpret_cast<const double2*>(col);
-          p23[m] = *reinterpret_cast<const double2*>(col + (nr >> 1));
+          p23[m] = *reinterpret_cast<const double2*>(col + half[m]);
         }
       }
       const double* nn = piv + kPivRec * jb + 10;
