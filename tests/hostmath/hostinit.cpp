@@ -97,6 +97,54 @@ int hostinit_calibrate(const double* px, const unsigned char* has, int F, int W,
   return ok ? 0 : 1;
 }
 
+// The plain-double projection family of the unchanged TS interface through the
+// adapter: project (TS.cpp:332-344), Reproject (TS.cpp:227-245), ReprojectError (TS.h:58-69 /
+// TS.cpp:205-225), get_unit_sphere_coordinate (TS.h:39-57).
+int hostinit_project(const double* intr9, const double* pts, int n, double* uv) {
+  TripleSphereCamera cam(intr9[0], intr9[1], intr9[2], intr9[3], intr9[4], intr9[5], intr9[6]);
+  for (int i = 0; i < n; ++i) {
+    cv::Mat P(3, 1);
+    for (int k = 0; k < 3; ++k) P.at<double>(k, 0) = pts[3 * i + k];
+    const cv::Point2d q = cam.project(P);
+    uv[2 * i] = q.x; uv[2 * i + 1] = q.y;
+  }
+  return 0;
+}
+int hostinit_reproject(const double* intr9, const double* Rt9, const double* worlds, int n, double* uv) {
+  TripleSphereCamera cam(intr9[0], intr9[1], intr9[2], intr9[3], intr9[4], intr9[5], intr9[6]);
+  cv::Mat M(3, 3);
+  for (int k = 0; k < 9; ++k) M.at<double>(k / 3, k % 3) = Rt9[k];
+  std::vector<cv::Point3d> w(n);
+  for (int i = 0; i < n; ++i) w[i] = cv::Point3d(worlds[3 * i], worlds[3 * i + 1], worlds[3 * i + 2]);
+  std::vector<cv::Point2d> px;
+  cam.Reproject(w, M, px);
+  if ((int)px.size() != n) return 1;
+  for (int i = 0; i < n; ++i) { uv[2 * i] = px[i].x; uv[2 * i + 1] = px[i].y; }
+  return 0;
+}
+double hostinit_reproject_error(const double* intr9, const double* pixels, const double* worlds, int n,
+                                const double* R9, const double* t3) {
+  TripleSphereCamera cam(intr9[0], intr9[1], intr9[2], intr9[3], intr9[4], intr9[5], intr9[6]);
+  cv::Mat R(3, 3), t(3, 1);
+  for (int k = 0; k < 9; ++k) R.at<double>(k / 3, k % 3) = R9[k];
+  for (int k = 0; k < 3; ++k) t.at<double>(k, 0) = t3[k];
+  std::vector<cv::Point3d> w(n);
+  std::vector<cv::Point2d> px(n);
+  for (int i = 0; i < n; ++i) {
+    w[i] = cv::Point3d(worlds[3 * i], worlds[3 * i + 1], worlds[3 * i + 2]);
+    px[i] = cv::Point2d(pixels[2 * i], pixels[2 * i + 1]);
+  }
+  return cam.ReprojectError(px, w, R, t);
+}
+int hostinit_unit_sphere(const double* intr9, const double* pixels, int n, double* xyz) {
+  TripleSphereCamera cam(intr9[0], intr9[1], intr9[2], intr9[3], intr9[4], intr9[5], intr9[6]);
+  for (int i = 0; i < n; ++i) {
+    const cv::Point3d p = cam.get_unit_sphere_coordinate(cv::Point2d(pixels[2 * i], pixels[2 * i + 1]));
+    xyz[3 * i] = p.x; xyz[3 * i + 1] = p.y; xyz[3 * i + 2] = p.z;
+  }
+  return 0;
+}
+
 // TS.cpp:284-306 and 308-326 through the adapter.
 int hostinit_undistort(const double* intr9, double fx, double fy, double cx, double cy, int w, int h,
                        float* mapx, float* mapy) {

@@ -51,3 +51,25 @@ def test_planar_pnp_matches_opencv_solvepnpransac(hostinit):
         np.testing.assert_allclose(t, tv0, rtol=5e-6, atol=5e-4)
         worse += cost > c0
     assert worse == 0
+
+
+def test_rodrigues_of_non_orthonormal_matrices_matches_opencv(hostinit):
+    """The reference hands cv::Rodrigues matrices that are not rotations (r3 = r1 x r2 from
+    float-truncated columns, chained pose-graph products: multi_calib.h:42-57, multi_calib.cpp:6-153).
+    OpenCV projects them onto SO(3) (SVD, U V^T) first; so does the shim.  Checked
+    against the cv2 wheel directly."""
+    cv2 = __import__("pytest").importorskip("cv2")
+    rng = np.random.default_rng(5)
+    for k in range(40):
+        v = rng.normal(size=3) * rng.uniform(0.05, 2.5)
+        R, _ = cv2.Rodrigues(v)
+        if k % 2 == 0:
+            M = R.astype(np.float32).astype(np.float64)            # float truncation, Rt_to_R_t style
+            M[:, 2] = np.cross(M[:, 0], M[:, 1])
+        else:
+            M = R + rng.normal(scale=1e-4, size=(3, 3))            # accumulated error of chained products
+        M = np.ascontiguousarray(M)
+        r0, _ = cv2.Rodrigues(M)
+        r = np.zeros(3)
+        hostinit.hostinit_rodrigues(_d(M), 1, _d(r))
+        np.testing.assert_allclose(r, r0.ravel(), atol=1e-12)

@@ -37,8 +37,11 @@ def test_residuals_and_jacobian_match_oracle(oracle, cfg):
     s.close()
 
 
-def test_jacobian_matches_mpmath_golden():
-    z = np.load("tests/golden/jacobian_mpmath.npz")
+@pytest.mark.parametrize("golden", ["jacobian_mpmath", "jacobian_sympy"])
+def test_jacobian_matches_mpmath_golden(golden):
+    """k_eval_rows against 50-digit central differences and against sympy's symbolic derivative
+    of the reference functor (tests/golden/make_golden_sympy.py)."""
+    z = np.load(f"tests/golden/{golden}.npz")
     for k in range(len(z["r"])):
         p = capi.ProblemArrays(z["board"][k][None, :], [0], [0], z["obs"][k][None, None, :], 1, 1,
                                fixed_camera=-1)

@@ -54,10 +54,13 @@ def test_oracle_jets_match_golden_autodiff(oracle, name):
     np.testing.assert_allclose(J[::stride], z["initial_jacobian_sample"], rtol=1e-10, atol=1e-10)
 
 
-def test_jets_and_analytic_jacobian_match_mpmath(oracle, hostmath):
-    """50-digit central differences pin both the Jet autodiff and the hand-derived
-    Jacobian, including the theta^2 <= eps Taylor branch of AngleAxisRotatePoint."""
-    z = np.load("tests/golden/jacobian_mpmath.npz")
+@pytest.mark.parametrize("golden", ["jacobian_mpmath", "jacobian_sympy"])
+def test_jets_and_analytic_jacobian_match_mpmath(oracle, hostmath, golden):
+    """50-digit central differences (mpmath) and sympy's SYMBOLIC derivative of the functor
+    multi_calib.h:146-195 (make_golden_sympy.py: nothing hand-derived) pin both the Jet autodiff
+    and the hand-derived Jacobian, including the theta^2 <= eps Taylor branch of
+    AngleAxisRotatePoint."""
+    z = np.load(f"tests/golden/{golden}.npz")
     n = len(z["r"])
     taylor = 0
     for k in range(n):

@@ -1,6 +1,6 @@
 """Small solves for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): every kernel of the LM
 iteration graph runs at least twice, on sizes a sanitizer finishes in a minute.
-  python tools/sanitize_case.py dense|pairs|mono|robust
+  python tools/sanitize_case.py dense|pairs|mono|robust|masks|group
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,6 +14,10 @@ elif case == "pairs":    # 16-camera ring, sparse visibility: k_pair_frames, k_p
     sp, opt = synth.config(4, num_frames=160), capi.default_options(max_num_iterations=4)
 elif case == "mono":
     sp, opt = synth.config(1), capi.default_options(max_num_iterations=4)
+elif case == "masks":    # 8-camera ring with visibility masks, fused Schur kernel (k_schur2), split tail tiles
+    sp, opt = synth.config(3, num_frames=150, dense=False, rig="ring"), capi.default_options(max_num_iterations=4)
+elif case == "group":    # tscm_options.num_gpus = 2: mailbox exchanges between two devices of one process
+    sp, opt = synth.config(3, num_frames=96), capi.default_options(max_num_iterations=4, num_gpus=2)
 else:                    # robust loss, ragged visibility (config 5)
     sp, opt = synth.config(5, num_frames=60), capi.default_options(max_num_iterations=4, loss_type="huber", loss_scale=1.0)
 a, b, c, s = capi.solve(sp.problem, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt, opt)

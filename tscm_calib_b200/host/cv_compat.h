@@ -124,9 +124,30 @@ inline void Rodrigues(const Mat& src, Mat& dst) {
                    c1 * x * z - s * y, c1 * y * z + s * x, c + c1 * z * z};
     for (int i = 0; i < 9; ++i) dst.at<double>(i / 3, i % 3) = R[i];
   } else {
-    // matrix -> vector through the quaternion (stable for every angle)
+    // matrix -> vector.  Like OpenCV (which takes the SVD and uses U V^T) the input is first
+    // replaced by the nearest rotation: the reference feeds matrices that are NOT orthonormal
+    // (r3 = r1 x r2 from float-truncated columns, chained pose-graph products).  The orthogonal
+    // polar factor — the same matrix as U V^T — comes from Newton's iteration X <- (X + X^-T) / 2.
+    // Then through the quaternion (stable for every angle).
+    assert(src.rows == 3 && src.cols == 3 && "cv::Rodrigues: 3x1, 1x3 or 3x3 input");
     double M[9];
     for (int i = 0; i < 9; ++i) M[i] = src.at<double>(i / 3, i % 3);
+    for (int it = 0; it < 12; ++it) {
+      const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+      const double det = M[0] * c00 + M[1] * c01 + M[2] * c02;
+      if (!(std::fabs(det) > 1e-300)) break;
+      // inverse transpose = cofactor matrix / det
+      const double T[9] = {c00, c01, c02,
+                           M[2] * M[7] - M[1] * M[8], M[0] * M[8] - M[2] * M[6], M[1] * M[6] - M[0] * M[7],
+                           M[1] * M[5] - M[2] * M[4], M[2] * M[3] - M[0] * M[5], M[0] * M[4] - M[1] * M[3]};
+      double change = 0.0;
+      for (int i = 0; i < 9; ++i) {
+        const double v = 0.5 * (M[i] + T[i] / det);
+        change = std::max(change, std::fabs(v - M[i]));
+        M[i] = v;
+      }
+      if (change < 1e-16) break;
+    }
     double q[4];
     const double tr = M[0] + M[4] + M[8];
     if (tr > 0) {

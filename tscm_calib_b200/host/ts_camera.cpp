@@ -190,7 +190,13 @@ void TripleSphereCamera::estimate_extrinsic(const std::vector<std::vector<cv::Po
       plane[i] = cv::Point2d(ray.x / ray.z, ray.y / ray.z);
     }
     cv::Mat rvec, tvec, pose;
-    cv::solvePnPRansac(worlds, plane, identity, cv::Mat::zeros(4, 0, cv::CV_64F), rvec, tvec);
+    const bool found = cv::solvePnPRansac(worlds, plane, identity, cv::Mat::zeros(4, 0, cv::CV_64F), rvec, tvec);
+    if (!found || rvec.empty() || tvec.empty()) {
+      // no pose (corners outside the model domain under the current guess give NaN rays): the
+      // frame does not take part in the refinement — where OpenCV would raise a cv::Exception
+      has_chessboard_[k] = false;
+      continue;
+    }
     cv::Rodrigues(rvec, pose);
     const cv::Mat back = facing.t();
     pose = back * pose;
