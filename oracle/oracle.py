@@ -21,7 +21,7 @@ _lib = None
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("tscm_oracle.cpp", "tscm_oracle.h", "remap_oracle.c",
+    src = [os.path.join(_HERE, f) for f in ("tscm_oracle.cpp", "tscm_oracle.h", "remap_oracle.c", "pose_graph_oracle.c",
                                             os.path.join("..", "include", "tscm.h"))]
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in src)):
@@ -62,6 +62,11 @@ def load():
     lib.tscm_oracle_remap_tables.argtypes = [P(TscmRemapJob), C.c_int32, C.c_int32, C.c_int32,
                                              P(C.c_float), P(C.c_float)]
     lib.tscm_oracle_remap_tables.restype = C.c_int
+    u8p, i32p = P(C.c_uint8), P(C.c_int32)
+    lib.tscm_oracle_pose_graph.argtypes = [C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, u8p,
+                                           c_double_p, c_double_p, c_double_p, c_double_p, u8p,
+                                           i32p, i32p, c_double_p, c_double_p]
+    lib.tscm_oracle_pose_graph.restype = C.c_int
     _lib = lib
     return lib
 
@@ -162,3 +167,38 @@ def remap_tables(jobs, map_size):
                                       mapy.ctypes.data_as(C.POINTER(C.c_float)))
     assert rc == 0
     return mapx, mapy
+
+
+class PoseGraph:
+    """Result of a pose-graph initialisation: poses as 12 doubles = R row-major | t."""
+
+    def __init__(self, C_, B):
+        self.rc = 0
+        self.camera_pose = np.zeros((C_, 12))
+        self.board_pose = np.zeros((B, 12))
+        self.board_init = np.zeros(B, dtype=np.uint8)
+        self.camera_choice = np.full(C_, -1, dtype=np.int32)
+        self.board_choice = np.full(B, -1, dtype=np.int32)
+        self.camera_candidate_error = np.full((C_, B), np.nan)
+        self.board_candidate_error = np.full((B, C_), np.nan)
+
+
+def pose_graph(worlds, intrinsics, has, mono_rt, pixels):
+    """CPU restatement of MultiCalib's constructor (multi_calib.cpp:6-153), pose_graph_oracle.c.
+    has [C][B], mono_rt [C][B][3][3], pixels [C][B][K][2], worlds [K][3]."""
+    lib = load()
+    has = np.ascontiguousarray(has, dtype=np.uint8)
+    C_, B = has.shape
+    worlds = np.ascontiguousarray(worlds, dtype=np.float64).reshape(-1, 3)
+    K = worlds.shape[0]
+    intr = np.ascontiguousarray(intrinsics, dtype=np.float64).reshape(C_, 9)
+    rt = np.ascontiguousarray(mono_rt, dtype=np.float64).reshape(C_, B, 9)
+    px = np.ascontiguousarray(pixels, dtype=np.float64).reshape(C_, B, K, 2)
+    r = PoseGraph(C_, B)
+    u8p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
+    r.rc = lib.tscm_oracle_pose_graph(C_, B, K, _dp(worlds), _dp(intr), has.ctypes.data_as(u8p), _dp(rt),
+                                      _dp(px), _dp(r.camera_pose), _dp(r.board_pose),
+                                      r.board_init.ctypes.data_as(u8p), r.camera_choice.ctypes.data_as(i32p),
+                                      r.board_choice.ctypes.data_as(i32p), _dp(r.camera_candidate_error),
+                                      _dp(r.board_candidate_error))
+    return r

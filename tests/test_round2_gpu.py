@@ -77,6 +77,29 @@ def test_both_ceres_tolerance_gatings_match_the_oracle(oracle, needs_success):
     assert s2.termination == s3.termination and s2.num_iterations == s3.num_iterations
 
 
+@pytest.mark.parametrize("form", ["auto", "rows", "pairs"])
+def test_masked_ring_sample_matches_the_oracle(oracle, form):
+    """8-camera outward ring with all-or-nothing visibility masks (config 3's named shape) at a
+    size the oracle solves in seconds; the default form here is the fused k_schur2.  The start is
+    hard enough for rejected steps, which the trace must reproduce too."""
+    sp = synth.config(3, num_frames=150, dense=False, rig="ring")
+    opt = capi.default_options(max_num_iterations=25)
+    init = (sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt)
+    a, b, c, s = capi.solve_resident(sp.problem, *init, opt, schur_form=form)
+    a0, b0, c0, s0 = oracle.solve(sp.problem, *init, opt, num_threads=4)
+    np.testing.assert_array_equal(s.step_flags, s0.step_flags)
+    rejected = (s.step_flags & 2) == 0
+    assert np.any(rejected)                         # at least one rejected step
+    # a rejected candidate lies far outside the basin (cost 1e12-1e13 against 1e7: points where
+    # the projection denominators nearly vanish), so its cost is conditioned 1e5 times worse
+    # than the accepted ones: 1e-5 there, the usual 1e-9 on every accepted iteration
+    np.testing.assert_allclose(s.cost[rejected], s0.cost[rejected], rtol=1e-5)
+    cost, cost0 = s.cost.copy(), s0.cost.copy()
+    cost[rejected] = cost0[rejected] = 0.0
+    s.cost, s0.cost = cost, cost0
+    assert_same(s, s0, (a, b, c), (a0, b0, c0))
+
+
 @pytest.mark.parametrize("rig,min_fill,other", [("array", 0.95, "pairs"), ("ring", 0.3, "rows")])
 def test_config3_with_visibility_masks_full_size(rig, min_fill, other):
     """BASELINE config 3 as named: 8 cameras, 5,000 frames, per-frame all-or-nothing visibility

@@ -20,6 +20,14 @@ elif case == "group":    # tscm_options.num_gpus = 2: mailbox exchanges between 
     sp, opt = synth.config(3, num_frames=96), capi.default_options(max_num_iterations=4, num_gpus=2)
 else:                    # robust loss, ragged visibility (config 5)
     sp, opt = synth.config(5, num_frames=60), capi.default_options(max_num_iterations=4, loss_type="huber", loss_scale=1.0)
-a, b, c, s = capi.solve(sp.problem, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt, opt)
+if case == "group":
+    # under a sanitizer kernels run 10-100x slower: give the exchanges time
+    h = capi.Solver(sp.problem, opt)
+    h.set_exchange_timeout(600.0)
+    h.set_parameters(sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt)
+    s = h.run()
+    h.close()
+else:
+    a, b, c, s = capi.solve(sp.problem, sp.init_intrinsics, sp.init_cam_rt, sp.init_board_rt, opt)
 print(case, s.termination, s.num_iterations, s.cost)
-assert np.all(np.isfinite(s.cost)) and s.cost[-1] < s.cost[0]
+assert np.all(np.isfinite(s.cost)) and s.final_cost < s.initial_cost     # (the trace also holds rejected candidates)

@@ -301,10 +301,21 @@ k_schur2(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptio
   const int f_end = min(P.F, f_begin + A.frames_per_block);
   const int nbatch = (f_end - f_begin + kSchurFB - 1) / kSchurFB;
 
-  if (warp < kSchurFB) {
-    // ------------------------------- producer -------------------------------------
-    double* my = scr + warp * 64;
-    for (int b = 0; b <= nbatch; ++b) {
+  // One loop, ONE barrier site for both roles (CUDA allows __syncthreads() in conditional code
+  // only if the whole block takes the same branch: compute-sanitizer synccheck flagged the two
+  // role-private loops of round 1, profiles/r02_sanitizer_synccheck_robust.log).
+  const bool producer = warp < kSchurFB;
+  double* my = scr + (producer ? warp : 0) * 64;
+  const int ct = tid - kSchurFB * 32;            // consumer thread index (negative: producer)
+  const int tbi = ct < A.ntiles ? A.tile_bi[ct] : -1;
+  const int tbj = ct < A.ntiles ? A.tile_bj[ct] : 0;
+  double acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+  double racc = 0.0;
+  for (int b = 0; b <= nbatch; ++b) {
+    if (producer) {
+      // ------------------------------- producer -------------------------------------
       if (b < nbatch) {
         double* Ws = s_mem + (b & 1) * buf_doubles;
         double* Ys = Ws + kSchurFB * 6 * NLp;
@@ -442,49 +453,38 @@ k_schur2(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptio
           }
         }
       }
-      // the lane-divergent column loops above must have reconverged before the aligned
-      // CTA barrier (compute-sanitizer synccheck, profiles/r02_sanitizer_*)
-      __syncwarp();
-      __syncthreads();
-    }
-    return;
-  }
-  // --------------------------------- consumer ---------------------------------------
-  const int ct = tid - kSchurFB * 32;            // consumer thread index
-  const int tbi = ct < A.ntiles ? A.tile_bi[ct] : -1;
-  const int tbj = ct < A.ntiles ? A.tile_bj[ct] : 0;
-  double acc[16];
-#pragma unroll
-  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
-  double racc = 0.0;
-  for (int b = 0; b <= nbatch; ++b) {
-    if (b > 0) {
-      const double* Ws = s_mem + ((b - 1) & 1) * buf_doubles;
-      const double* Ys = Ws + kSchurFB * 6 * NLp;
-      const double* zs = Ys + kSchurFB * 6 * NLp;
-      if (tbi >= 0) {
-        const double* wp = Ws + 4 * tbi;
-        const double* yp = Ys + 4 * tbj;
-#pragma unroll 4
-        for (int r = 0; r < kSchurFB * 6; ++r) {
-          const double4 w4 = *reinterpret_cast<const double4*>(wp + r * NLp);
-          const double4 y4 = *reinterpret_cast<const double4*>(yp + r * NLp);
-          const double w[4] = {w4.x, w4.y, w4.z, w4.w};
-          const double y[4] = {y4.x, y4.y, y4.z, y4.w};
-#pragma unroll
-          for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) acc[a * 4 + c] = fma(-w[a], y[c], acc[a * 4 + c]);
+    } else {
+      // ------------------------------- consumer -------------------------------------
+      if (b > 0) {
+        const double* Ws = s_mem + ((b - 1) & 1) * buf_doubles;
+        const double* Ys = Ws + kSchurFB * 6 * NLp;
+        const double* zs = Ys + kSchurFB * 6 * NLp;
+        if (tbi >= 0) {
+          const double* wp = Ws + 4 * tbi;
+          const double* yp = Ys + 4 * tbj;
+  #pragma unroll 4
+          for (int r = 0; r < kSchurFB * 6; ++r) {
+            const double4 w4 = *reinterpret_cast<const double4*>(wp + r * NLp);
+            const double4 y4 = *reinterpret_cast<const double4*>(yp + r * NLp);
+            const double w[4] = {w4.x, w4.y, w4.z, w4.w};
+            const double y[4] = {y4.x, y4.y, y4.z, y4.w};
+  #pragma unroll
+            for (int a = 0; a < 4; ++a)
+  #pragma unroll
+              for (int c = 0; c < 4; ++c) acc[a * 4 + c] = fma(-w[a], y[c], acc[a * 4 + c]);
+          }
+        }
+        if (ct < NL) {
+          double a = racc;
+          for (int r = 0; r < kSchurFB * 6; ++r) a = fma(-Ws[r * NLp + ct], zs[r], a);
+          racc = a;
         }
       }
-      if (ct < NL) {
-        double a = racc;
-        for (int r = 0; r < kSchurFB * 6; ++r) a = fma(-Ws[r * NLp + ct], zs[r], a);
-        racc = a;
-      }
     }
+    __syncwarp();          // lane-divergent column loops reconverge before the aligned CTA barrier
     __syncthreads();
   }
+  if (producer) return;
   double* Sp = A.Spart + (size_t)blockIdx.x * P.Q;
   if (tbi >= 0) {
 #pragma unroll
