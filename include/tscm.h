@@ -66,7 +66,8 @@ enum {
   TSCM_ERR_CUDA = 2,          /* CUDA runtime error; tscm_last_error() has the text */
   TSCM_ERR_NO_DEVICE = 3,     /* no sm_100 device: there is NO CPU fallback */
   TSCM_ERR_COMM = 4,          /* NCCL failure */
-  TSCM_ERR_UNSUPPORTED = 5
+  TSCM_ERR_UNSUPPORTED = 5,
+  TSCM_ERR_NO_CANDIDATE = 6   /* pose graph: no usable candidate (tscm_pose_graph_init) */
 };
 
 typedef struct tscm_problem {
@@ -267,6 +268,54 @@ typedef struct tscm_remap_job {
 int tscm_remap_tables(const tscm_remap_job* jobs, int32_t num_jobs, int32_t map_width,
                       int32_t map_height, float* mapx, float* mapy, int device,
                       double* kernel_ms);
+
+/* ---- pose-graph initialisation -------------------------------------
+ * MultiCalib's constructor, /root/reference/multi_calib.cpp:6-153, from the per-camera mono
+ * results: camera i is chained to camera i-1 through every board both detected
+ * (multi_calib.cpp:26-48); each of those n candidate poses is scored by the summed
+ * reprojection error (TS.h:58-69) of BOTH cameras over ALL n shared boards
+ * (multi_calib.cpp:50-88: n^2 x 2 x K TS projections — the hot loop, on the GPU here) and the
+ * smallest sum wins; board poses likewise over the cameras that see them
+ * (multi_calib.cpp:95-152).  The candidate errors are bit-identical to those loops evaluated
+ * in IEEE double without FMA contraction, so the same candidates win.
+ *   intrinsics  C x 9          {fx,fy,cx,cy,xi,lambda,alpha,b,c} of the mono calibrations
+ *   has_board   C x B bytes    TripleSphereCamera::has_chessboard(j)
+ *   mono_rt     C x B x 9      TripleSphereCamera::Rt(j), row-major 3x3 [r1 r2 t] (TS.cpp:195-201);
+ *                              r1, r2 are narrowed to float and r3 = r1 x r2 is a float product,
+ *                              as Rt_to_R_t does with cv::Vec3f (multi_calib.h:130-137)
+ *   pixels      C x B x K x 2  TripleSphereCamera::pixels()[j]; ignored where has_board = 0
+ *   worlds      K x 3
+ * Poses come back as 12 doubles: R row-major (9) | t (3) — MultiCalib_camera::R()/t(),
+ * MultiCalib_chessboard::R()/t().  Host pointers. */
+typedef struct tscm_pose_graph_problem {
+  int32_t num_cameras;        /* C */
+  int32_t num_boards;         /* B */
+  int32_t corners_per_board;  /* K */
+  const double* worlds;
+  const double* intrinsics;
+  const uint8_t* has_board;
+  const double* mono_rt;
+  const double* pixels;
+} tscm_pose_graph_problem;
+
+typedef struct tscm_pose_graph_result {
+  double* camera_pose;             /* C x 12, camera 0 = identity (multi_calib.cpp:18-23) */
+  double* board_pose;              /* B x 12, untouched where board_initialised = 0 */
+  uint8_t* board_initialised;      /* B: 0 for a board no camera saw (multi_calib.cpp:102) */
+  int32_t* camera_choice;          /* optional, C: board whose candidate won; -1 for camera 0 */
+  int32_t* board_choice;           /* optional, B: camera whose candidate won; -1 = uninitialised */
+  double* camera_candidate_error;  /* optional, C x B: summed error of the candidate built from
+                                      board j, NaN where the pair (i-1, i) does not share it */
+  double* board_candidate_error;   /* optional, B x C: NaN where camera j did not see board i or
+                                      the board has one candidate only (multi_calib.cpp:105-113) */
+  double kernel_ms;                /* out: device time of the scoring kernels (CUDA events) */
+  int64_t projections;             /* out: TS projections evaluated */
+} tscm_pose_graph_result;
+
+/* TSCM_ERR_NO_CANDIDATE: two adjacent cameras share no board (the reference indexes Rs[-1]
+ * there, multi_calib.cpp:51,86) or no candidate scored below the 1e10 start value. */
+int tscm_pose_graph_init(const tscm_pose_graph_problem* problem, int device,
+                         tscm_pose_graph_result* result);
 
 const char* tscm_last_error(void);
 const char* tscm_version(void);

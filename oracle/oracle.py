@@ -67,6 +67,9 @@ def load():
                                            c_double_p, c_double_p, c_double_p, c_double_p, u8p,
                                            i32p, i32p, c_double_p, c_double_p]
     lib.tscm_oracle_pose_graph.restype = C.c_int
+    lib.tscm_oracle_pose_pair_error.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, u8p,
+                                                c_double_p, c_double_p, c_double_p]
+    lib.tscm_oracle_pose_pair_error.restype = C.c_double
     _lib = lib
     return lib
 
@@ -202,3 +205,19 @@ def pose_graph(worlds, intrinsics, has, mono_rt, pixels):
                                       r.board_choice.ctypes.data_as(i32p), _dp(r.camera_candidate_error),
                                       _dp(r.board_candidate_error))
     return r
+
+
+def pose_pair_error(i, j, worlds, intrinsics, has, mono_rt, pixels, prev_camera_pose):
+    """Score of ONE chain candidate (camera i through board j) given the pose chosen for camera
+    i-1 (multi_calib.cpp:36-47, 53-81): spot checks of the scoring kernel at full size."""
+    lib = load()
+    has = np.ascontiguousarray(has, dtype=np.uint8)
+    C_, B = has.shape
+    worlds = np.ascontiguousarray(worlds, dtype=np.float64).reshape(-1, 3)
+    K = worlds.shape[0]
+    intr = np.ascontiguousarray(intrinsics, dtype=np.float64).reshape(C_, 9)
+    rt = np.ascontiguousarray(mono_rt, dtype=np.float64).reshape(C_, B, 9)
+    px = np.ascontiguousarray(pixels, dtype=np.float64).reshape(C_, B, K, 2)
+    pose = np.ascontiguousarray(prev_camera_pose, dtype=np.float64).reshape(12)
+    return lib.tscm_oracle_pose_pair_error(int(i), int(j), B, K, _dp(worlds), _dp(intr),
+                                           has.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(rt), _dp(px), _dp(pose))

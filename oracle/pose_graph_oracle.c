@@ -104,6 +104,61 @@ static double reproject_error(const double* in, const double* px, const double* 
   return error;
 }
 
+/* multi_calib.cpp:53-81: the score of one candidate pose (Rs | ts) of camera i — the summed
+ * reprojection error of camera i-1 and of camera i over every board both detected. */
+static double pair_candidate_error(int i, int B, int K, const double* worlds, const double* intr,
+                                   const uint8_t* has, const double* mono_rt, const double* pixels,
+                                   const double* camk, const double* cand) {
+  const size_t PK = (size_t)K * 2;
+  const double *Rk = camk, *tk = camk + 9, *Rs = cand, *ts = cand + 9;
+  const uint8_t *ha = has + (size_t)(i - 1) * B, *hb = has + (size_t)i * B;
+  double error = 0;
+  for (int k = 0; k < B; ++k) {
+    if (!ha[k] || !hb[k]) continue;
+    double Ri[9], ti[3], Rp[9], tp[3], R_ki[9], t_ki[3], R_ik[9], t_ik[3], R[9], t[3], v[3];
+    rt_to_R_t(mono_rt + ((size_t)i * B + k) * 9, Ri, ti);
+    mat33_bt(Rk, Rs, R_ki);
+    mat31(R_ki, ts, v);
+    for (int r = 0; r < 3; ++r) t_ki[r] = tk[r] - v[r];
+    mat33(R_ki, Ri, R);
+    mat31(R_ki, ti, v);
+    for (int r = 0; r < 3; ++r) t[r] = v[r] + t_ki[r];
+    error += reproject_error(intr + 9 * (i - 1), pixels + ((size_t)(i - 1) * B + k) * PK, worlds, K, R, t);
+    rt_to_R_t(mono_rt + ((size_t)(i - 1) * B + k) * 9, Rp, tp);
+    mat33_bt(Rs, Rk, R_ik);
+    mat31(R_ik, tk, v);
+    for (int r = 0; r < 3; ++r) t_ik[r] = ts[r] - v[r];
+    mat33(R_ik, Rp, R);
+    mat31(R_ik, tp, v);
+    for (int r = 0; r < 3; ++r) t[r] = v[r] + t_ik[r];
+    error += reproject_error(intr + 9 * i, pixels + ((size_t)i * B + k) * PK, worlds, K, R, t);
+  }
+  return error;
+}
+
+/* multi_calib.cpp:36-47: the candidate pose of camera i chained through board j */
+static void pair_candidate(int i, int j, int B, const double* mono_rt, const double* camk, double* cand) {
+  double Ri[9], ti[3], Rp[9], tp[3], R_ik[9], t_ik[3], v[3];
+  rt_to_R_t(mono_rt + ((size_t)i * B + j) * 9, Ri, ti);
+  rt_to_R_t(mono_rt + ((size_t)(i - 1) * B + j) * 9, Rp, tp);
+  mat33_bt(Ri, Rp, R_ik);
+  mat31(R_ik, tp, v);
+  for (int r = 0; r < 3; ++r) t_ik[r] = ti[r] - v[r];
+  mat33(R_ik, camk, cand);
+  mat31(R_ik, camk + 9, v);
+  for (int r = 0; r < 3; ++r) cand[9 + r] = v[r] + t_ik[r];
+}
+
+/* Score of the single candidate of camera i built from board j, given the pose (R | t) already
+ * chosen for camera i-1: for spot checks at sizes where the full n^2 loop takes minutes. */
+double tscm_oracle_pose_pair_error(int i, int j, int B, int K, const double* worlds, const double* intr,
+                                   const uint8_t* has, const double* mono_rt, const double* pixels,
+                                   const double* camk_pose) {
+  double cand[12];
+  pair_candidate(i, j, B, mono_rt, camk_pose, cand);
+  return pair_candidate_error(i, B, K, worlds, intr, has, mono_rt, pixels, camk_pose, cand);
+}
+
 /*
  * Returns 0, or 2 when two adjacent cameras share no board (the reference indexes Rs[-1] there,
  * multi_calib.cpp:51,86) or when no candidate scores below the 1e10 start value.
@@ -130,47 +185,17 @@ int tscm_oracle_pose_graph(int C, int B, int K, const double* worlds, const doub
       continue;
     }
     const double* Rk = camera_pose + 12 * (i - 1);
-    const double* tk = Rk + 9;
     const uint8_t *ha = has + (size_t)(i - 1) * B, *hb = has + (size_t)i * B;
     int n = 0;
     for (int j = 0; j < B; ++j) { /* multi_calib.cpp:29-48 */
       if (!ha[j] || !hb[j]) continue;
-      double Ri[9], ti[3], Rp[9], tp[3], R_ik[9], t_ik[3], v[3];
-      rt_to_R_t(mono_rt + ((size_t)i * B + j) * 9, Ri, ti);
-      rt_to_R_t(mono_rt + ((size_t)(i - 1) * B + j) * 9, Rp, tp);
-      mat33_bt(Ri, Rp, R_ik);
-      mat31(R_ik, tp, v);
-      for (int r = 0; r < 3; ++r) t_ik[r] = ti[r] - v[r];
-      mat33(R_ik, Rk, cand + 12 * n);
-      mat31(R_ik, tk, v);
-      for (int r = 0; r < 3; ++r) cand[12 * n + 9 + r] = v[r] + t_ik[r];
+      pair_candidate(i, j, B, mono_rt, Rk, cand + 12 * n);
       cand_board[n++] = j;
     }
     double min_error = 1e10;
     int min_id = -1;
     for (int c = 0; c < n; ++c) { /* multi_calib.cpp:50-88 */
-      const double *Rs = cand + 12 * c, *ts = Rs + 9;
-      double error = 0;
-      for (int k = 0; k < B; ++k) {
-        if (!ha[k] || !hb[k]) continue;
-        double Ri[9], ti[3], Rp[9], tp[3], R_ki[9], t_ki[3], R_ik[9], t_ik[3], R[9], t[3], v[3];
-        rt_to_R_t(mono_rt + ((size_t)i * B + k) * 9, Ri, ti);
-        mat33_bt(Rk, Rs, R_ki);
-        mat31(R_ki, ts, v);
-        for (int r = 0; r < 3; ++r) t_ki[r] = tk[r] - v[r];
-        mat33(R_ki, Ri, R);
-        mat31(R_ki, ti, v);
-        for (int r = 0; r < 3; ++r) t[r] = v[r] + t_ki[r];
-        error += reproject_error(intr + 9 * (i - 1), pixels + ((size_t)(i - 1) * B + k) * PK, worlds, K, R, t);
-        rt_to_R_t(mono_rt + ((size_t)(i - 1) * B + k) * 9, Rp, tp);
-        mat33_bt(Rs, Rk, R_ik);
-        mat31(R_ik, tk, v);
-        for (int r = 0; r < 3; ++r) t_ik[r] = ts[r] - v[r];
-        mat33(R_ik, Rp, R);
-        mat31(R_ik, tp, v);
-        for (int r = 0; r < 3; ++r) t[r] = v[r] + t_ik[r];
-        error += reproject_error(intr + 9 * i, pixels + ((size_t)i * B + k) * PK, worlds, K, R, t);
-      }
+      const double error = pair_candidate_error(i, B, K, worlds, intr, has, mono_rt, pixels, Rk, cand + 12 * c);
       if (cand_err) cand_err[(size_t)i * B + cand_board[c]] = error;
       if (error < min_error) {
         min_error = error;

@@ -50,15 +50,19 @@ def rt_to_R_t(Rt):
 def pose_graph(intr, Rt, has, pixels, worlds):
     C, F = has.shape
     cam_R, cam_t = np.zeros((C, 3, 3)), np.zeros((C, 3))
+    # candidate scores and the winners, for the scoring kernels' parity tests
+    cam_choice, cam_err = np.full(C, -1, dtype=np.int32), np.full((C, F), np.nan)
+    board_choice, board_err = np.full(F, -1, dtype=np.int32), np.full((F, C), np.nan)
     for i in range(C):
         if i == 0:
             cam_R[0], cam_t[0] = np.eye(3), 0.0
             continue
         Rk, tk = cam_R[i - 1], cam_t[i - 1]
-        Rs, ts = [], []
+        Rs, ts, src = [], [], []
         for j in range(F):
             if not (has[i - 1, j] and has[i, j]):
                 continue
+            src.append(j)
             Ri, ti = rt_to_R_t(Rt[i, j])
             Rp, tp = rt_to_R_t(Rt[i - 1, j])
             R_ik = Ri @ Rp.T
@@ -79,9 +83,11 @@ def pose_graph(intr, Rt, has, pixels, worlds):
                 R_ik = Rs[c] @ Rk.T
                 t_ik = ts[c] - R_ik @ tk
                 err += reproject_error(intr[i], pixels[i, k], worlds, R_ik @ Rp, R_ik @ tp + t_ik)
+            cam_err[i, src[c]] = err
             if err < best:
                 best, best_id = err, c
         cam_R[i], cam_t[i] = Rs[best_id], ts[best_id]
+        cam_choice[i] = src[best_id]
     board_R, board_t, board_init = np.zeros((F, 3, 3)), np.zeros((F, 3)), np.zeros(F, dtype=np.uint8)
     for i in range(F):
         ids = [j for j in range(C) if has[j, i]]
@@ -96,12 +102,16 @@ def pose_graph(intr, Rt, has, pixels, worlds):
         if len(ids) > 1:
             best = 1e10
             for c in range(len(Rs)):
-                err = sum(reproject_error(intr[j], pixels[j, i], worlds, cam_R[j] @ Rs[c], cam_R[j] @ ts[c] + cam_t[j])
-                          for j in ids)
+                err = 0.0
+                for j in ids:
+                    err += reproject_error(intr[j], pixels[j, i], worlds, cam_R[j] @ Rs[c], cam_R[j] @ ts[c] + cam_t[j])
+                board_err[i, ids[c]] = err
                 if err < best:
                     best, best_id = err, c
         board_R[i], board_t[i], board_init[i] = Rs[best_id], ts[best_id], 1
-    return cam_R, cam_t, board_R, board_t, board_init
+        board_choice[i] = ids[best_id]
+    return cam_R, cam_t, board_R, board_t, board_init, dict(cam_choice=cam_choice, cam_err=cam_err,
+                                                            board_choice=board_choice, board_err=board_err)
 
 
 def main():
@@ -123,12 +133,12 @@ def main():
             t = Rc[m] @ sp.gt_board_rt[i, 3:] + sp.gt_cam_rt[m, 3:] + rng.normal(0, 1.0, 3)
             Rt[m, i] = np.stack([R[:, 0], R[:, 1], t], axis=1)
     intr = sp.gt_intrinsics.copy()
-    cam_R, cam_t, board_R, board_t, board_init = pose_graph(intr, Rt, has, pixels, worlds)
+    cam_R, cam_t, board_R, board_t, board_init, scores = pose_graph(intr, Rt, has, pixels, worlds)
     err_t = np.abs(cam_t - sp.gt_cam_rt[:, 3:]).max()
     print("cameras: max |t - truth| =", err_t, "mm; boards initialised:", int(board_init.sum()), "of", F)
     np.savez_compressed(os.path.join(OUT, "pose_graph.npz"), board=np.array([11, 8]), square=45.0, has=has,
                         pixels=pixels, intrinsics=intr, Rt=Rt, cam_R=cam_R, cam_t=cam_t, board_R=board_R,
-                        board_t=board_t, board_init=board_init, gt_cam_rt=sp.gt_cam_rt, gt_board_rt=sp.gt_board_rt)
+                        board_t=board_t, board_init=board_init, gt_cam_rt=sp.gt_cam_rt, gt_board_rt=sp.gt_board_rt, **scores)
 
 
 if __name__ == "__main__":

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libtscm_b200.so")
 SOURCES = ["tscm_b200.cu"]
-HEADERS = ["tscm_kernels.cuh", "tscm_eval5.cuh", "tscm_solve.cuh", "tscm_math.cuh", "tscm_p2p.cuh", "tscm_remap.cuh", "tscm_schur_pairs.cuh", "tscm_pair_lists.h", os.path.join("..", "..", "include", "tscm.h")]
+HEADERS = ["tscm_kernels.cuh", "tscm_eval5.cuh", "tscm_solve.cuh", "tscm_math.cuh", "tscm_p2p.cuh", "tscm_remap.cuh", "tscm_posegraph.cuh", "tscm_schur_pairs.cuh", "tscm_pair_lists.h", os.path.join("..", "..", "include", "tscm.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

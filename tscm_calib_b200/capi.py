@@ -90,6 +90,26 @@ class TscmRemapJob(C.Structure):
     ]
 
 
+class TscmPoseGraphProblem(C.Structure):
+    """tscm_pose_graph_problem (include/tscm.h)."""
+    _fields_ = [
+        ("num_cameras", C.c_int32), ("num_boards", C.c_int32), ("corners_per_board", C.c_int32),
+        ("worlds", c_double_p), ("intrinsics", c_double_p), ("has_board", C.POINTER(C.c_uint8)),
+        ("mono_rt", c_double_p), ("pixels", c_double_p),
+    ]
+
+
+class TscmPoseGraphResult(C.Structure):
+    """tscm_pose_graph_result (include/tscm.h)."""
+    _fields_ = [
+        ("camera_pose", c_double_p), ("board_pose", c_double_p),
+        ("board_initialised", C.POINTER(C.c_uint8)),
+        ("camera_choice", c_int32_p), ("board_choice", c_int32_p),
+        ("camera_candidate_error", c_double_p), ("board_candidate_error", c_double_p),
+        ("kernel_ms", C.c_double), ("projections", C.c_int64),
+    ]
+
+
 def default_options(**overrides) -> TscmOptions:
     """ceres::Solver::Options defaults in force at TS.cpp:271-274 /
     multi_calib.cpp:209-212 (same values tscm_options_init() writes)."""
@@ -287,6 +307,8 @@ def load_library(path: str | None = None):
     lib.tscm_remap_tables.argtypes = [P(TscmRemapJob), C.c_int32, C.c_int32, C.c_int32,
                                       P(C.c_float), P(C.c_float), C.c_int, c_double_p]
     lib.tscm_remap_tables.restype = C.c_int
+    lib.tscm_pose_graph_init.argtypes = [P(TscmPoseGraphProblem), C.c_int, P(TscmPoseGraphResult)]
+    lib.tscm_pose_graph_init.restype = C.c_int
     lib.tscm_last_error.argtypes = []
     lib.tscm_last_error.restype = C.c_char_p
     lib.tscm_version.argtypes = []
@@ -306,7 +328,7 @@ EXPORTED_SYMBOLS = [
     "tscm_solver_launch_count", "tscm_device_fp64_peak", "tscm_remap_tables",
     "tscm_last_error", "tscm_version", "tscm_cache_configure", "tscm_cache_release",
     "tscm_host_alloc", "tscm_host_free", "tscm_solver_set_exchange_timeout",
-    "tscm_solver_set_schur_form", "tscm_set_debug",
+    "tscm_solver_set_schur_form", "tscm_set_debug", "tscm_pose_graph_init",
 ]
 
 SCHUR_FORM = {"auto": 0, "rows": 1, "fused": 2, "pairs": 3}
@@ -471,6 +493,43 @@ def remap_tables(jobs, map_size, device: int = -1, mapx=None, mapy=None):
     check(lib.tscm_remap_tables(arr, len(jobs), W, H, mapx.ctypes.data_as(C.POINTER(C.c_float)),
                                 mapy.ctypes.data_as(C.POINTER(C.c_float)), device, C.byref(ms)), lib)
     return mapx, mapy, ms.value
+
+
+class PoseGraphResult:
+    """Output of pose_graph_init(): poses as 12 doubles = R row-major | t."""
+
+    def __init__(self, C_, B):
+        self.camera_pose = np.zeros((C_, 12))
+        self.board_pose = np.zeros((B, 12))
+        self.board_init = np.zeros(B, dtype=np.uint8)
+        self.camera_choice = np.full(C_, -1, dtype=np.int32)
+        self.board_choice = np.full(B, -1, dtype=np.int32)
+        self.camera_candidate_error = np.full((C_, B), np.nan)
+        self.board_candidate_error = np.full((B, C_), np.nan)
+        self.kernel_ms = 0.0
+        self.projections = 0
+
+
+def pose_graph_init(worlds, intrinsics, has, mono_rt, pixels, device: int = -1) -> PoseGraphResult:
+    """tscm_pose_graph_init(): MultiCalib's constructor (multi_calib.cpp:6-153) with the candidate
+    scoring on the GPU.  has [C][B], mono_rt [C][B][3][3], pixels [C][B][K][2], worlds [K][3]."""
+    lib = load_library()
+    has = np.ascontiguousarray(has, dtype=np.uint8)
+    C_, B = has.shape
+    worlds = np.ascontiguousarray(worlds, dtype=np.float64).reshape(-1, 3)
+    K = worlds.shape[0]
+    intr = np.ascontiguousarray(intrinsics, dtype=np.float64).reshape(C_, 9)
+    rt = np.ascontiguousarray(mono_rt, dtype=np.float64).reshape(C_, B, 9)
+    px = np.ascontiguousarray(pixels, dtype=np.float64).reshape(C_, B, K, 2)
+    u8p = C.POINTER(C.c_uint8)
+    prob = TscmPoseGraphProblem(C_, B, K, _dp(worlds), _dp(intr), has.ctypes.data_as(u8p), _dp(rt), _dp(px))
+    r = PoseGraphResult(C_, B)
+    res = TscmPoseGraphResult(_dp(r.camera_pose), _dp(r.board_pose), r.board_init.ctypes.data_as(u8p),
+                              _ip(r.camera_choice), _ip(r.board_choice), _dp(r.camera_candidate_error),
+                              _dp(r.board_candidate_error), 0.0, 0)
+    check(lib.tscm_pose_graph_init(C.byref(prob), device, C.byref(res)), lib)
+    r.kernel_ms, r.projections = res.kernel_ms, res.projections
+    return r
 
 
 def comm_unique_id() -> bytes:

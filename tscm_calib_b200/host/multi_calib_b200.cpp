@@ -21,16 +21,6 @@ std::vector<double> pack_rt(const cv::Mat& R, const cv::Mat& t) {
           t.at<double>(0, 0), t.at<double>(1, 0), t.at<double>(2, 0)};
 }
 
-// [r1 r2 t] -> (R, t) with single-precision r1, r2 as multi_calib.h:130-137 (cv::Vec3f).
-void split_homography(const cv::Mat& Rt, cv::Mat& R, cv::Mat& t) {
-  const float r1[3] = {(float)Rt.at<double>(0, 0), (float)Rt.at<double>(1, 0), (float)Rt.at<double>(2, 0)};
-  const float r2[3] = {(float)Rt.at<double>(0, 1), (float)Rt.at<double>(1, 1), (float)Rt.at<double>(2, 1)};
-  const float r3[3] = {r1[1] * r2[2] - r1[2] * r2[1], r1[2] * r2[0] - r1[0] * r2[2], r1[0] * r2[1] - r1[1] * r2[0]};
-  R = cv::Mat(3, 3);
-  for (int k = 0; k < 3; ++k) { R.at<double>(k, 0) = r1[k]; R.at<double>(k, 1) = r2[k]; R.at<double>(k, 2) = r3[k]; }
-  t = vec3(Rt.at<double>(0, 2), Rt.at<double>(1, 2), Rt.at<double>(2, 2));
-}
-
 }  // namespace
 
 MultiCalib_camera::MultiCalib_camera(double cx, double cy, double fx, double fy, double xi, double lamda,
@@ -74,89 +64,72 @@ void MultiCalib::init_options() {
 }
 
 // Pose-graph initialisation (multi_calib.cpp:6-153): camera i is chained to camera i-1 through
-// every board both see, the candidate with the smallest summed reprojection error wins;
-// board poses likewise over the cameras that see them.
-MultiCalib::MultiCalib(std::vector<TripleSphereCamera> cameras, const std::vector<cv::Point3d>& worlds) {
+// every board both see, the candidate with the smallest summed reprojection error wins; board
+// poses likewise over the cameras that see them.  The exhaustive candidate scoring
+// (multi_calib.cpp:50-88, 128-149: n^2 x 2 x K projections per camera pair) runs on the GPU
+// through tscm_pose_graph_init(); there is no CPU path.
+MultiCalib::MultiCalib(std::vector<TripleSphereCamera> cameras, const std::vector<cv::Point3d>& worlds, int device_) {
   init_options();
+  device = device_;
   worlds_ = worlds;
   const int camera_num = (int)cameras.size();
-  const int board_num = (int)cameras[0].has_chessboard().size();
+  const int board_num = camera_num ? (int)cameras[0].has_chessboard().size() : 0;
+  const int K = (int)worlds.size();
   cameras_.resize(camera_num);
   chessboards_.resize(board_num);
-  for (int i = 0; i < camera_num; ++i) {
-    cv::Mat R, t;
-    if (i == 0) {
-      R = cv::Mat::eye(3, 3);            // camera 0 is the reference frame (multi_calib.cpp:21-22)
-      t = cv::Mat::zeros(3, 1);
-    } else {
-      if (!cameras_[i - 1].is_initial()) {
-        std::cout << "[tscm] cameras must be given in adjacent order" << std::endl;
+  if (camera_num == 0 || board_num == 0 || K == 0) return;
+  std::vector<double> w(3 * (size_t)K), intr(9 * (size_t)camera_num), rt(9 * (size_t)camera_num * board_num, 0.0),
+      px(2 * (size_t)camera_num * board_num * K, 0.0);
+  std::vector<uint8_t> has((size_t)camera_num * board_num, 0), board_ok(board_num, 0);
+  for (int j = 0; j < K; ++j) { w[3 * j] = worlds[j].x; w[3 * j + 1] = worlds[j].y; w[3 * j + 2] = worlds[j].z; }
+  for (int m = 0; m < camera_num; ++m) {
+    TripleSphereCamera& cam = cameras[m];
+    const double in[9] = {cam.fx(), cam.fy(), cam.cx(), cam.cy(), cam.xi(), cam.lamda(), cam.alpha(), cam.b(), cam.c()};
+    std::memcpy(intr.data() + 9 * (size_t)m, in, sizeof(in));
+    const auto pixels = cam.pixels();
+    for (int i = 0; i < board_num; ++i) {
+      const size_t v = (size_t)m * board_num + i;
+      if (!cam.has_chessboard(i)) continue;
+      if ((int)pixels[i].size() != K) {
+        std::cout << "[tscm] camera " << m << ", board " << i << ": " << pixels[i].size() << " corners, expected " << K << std::endl;
         return;
       }
-      std::vector<cv::Mat> Rs, ts;
-      cv::Mat Rk = cameras_[i - 1].R(), tk = cameras_[i - 1].t();
-      for (int j = 0; j < board_num; ++j) {
-        if (!cameras[i - 1].has_chessboard(j) || !cameras[i].has_chessboard(j)) continue;
-        cv::Mat Ri, ti, Rp, tp;
-        split_homography(cameras[i].Rt(j), Ri, ti);
-        split_homography(cameras[i - 1].Rt(j), Rp, tp);
-        cv::Mat R_ik = Ri * Rp.t();
-        cv::Mat t_ik = ti - R_ik * tp;
-        Rs.push_back(R_ik * Rk);
-        ts.push_back(R_ik * tk + t_ik);
-      }
-      if (Rs.empty()) {
-        std::cout << "[tscm] cameras " << i - 1 << " and " << i << " share no board" << std::endl;
-        return;                          // (the reference indexes Rs[-1] here: multi_calib.cpp:51,86)
-      }
-      double best = 1e10; int best_id = 0;
-      for (size_t c = 0; c < Rs.size(); ++c) {
-        double error = 0;
-        for (int k = 0; k < board_num; ++k) {
-          if (!cameras[i - 1].has_chessboard(k) || !cameras[i].has_chessboard(k)) continue;
-          cv::Mat Ri, ti, Rp, tp;
-          split_homography(cameras[i].Rt(k), Ri, ti);
-          cv::Mat R_ki = Rk * Rs[c].t();
-          cv::Mat t_ki = tk - R_ki * ts[c];
-          error += cameras[i - 1].ReprojectError(cameras[i - 1].pixels()[k], worlds, R_ki * Ri, R_ki * ti + t_ki);
-          split_homography(cameras[i - 1].Rt(k), Rp, tp);
-          cv::Mat R_ik = Rs[c] * Rk.t();
-          cv::Mat t_ik = ts[c] - R_ik * tk;
-          error += cameras[i].ReprojectError(cameras[i].pixels()[k], worlds, R_ik * Rp, R_ik * tp + t_ik);
-        }
-        if (error < best) { best = error; best_id = (int)c; }
-      }
-      R = Rs[best_id]; t = ts[best_id];
+      has[v] = 1;
+      const cv::Mat Rt = cam.Rt(i);
+      for (int k = 0; k < 9; ++k) rt[9 * v + k] = Rt.at<double>(k / 3, k % 3);
+      for (int j = 0; j < K; ++j) { px[(v * K + j) * 2] = pixels[i][j].x; px[(v * K + j) * 2 + 1] = pixels[i][j].y; }
     }
-    cameras_[i] = MultiCalib_camera(cameras[i].cx(), cameras[i].cy(), cameras[i].fx(), cameras[i].fy(),
-                                    cameras[i].xi(), cameras[i].lamda(), cameras[i].alpha(), cameras[i].b(),
-                                    cameras[i].c(), R, t, cameras[i].has_chessboard(), cameras[i].pixels());
+  }
+  std::vector<double> cam_pose(12 * (size_t)camera_num), board_pose(12 * (size_t)board_num, 0.0);
+  tscm_pose_graph_problem prob;
+  prob.num_cameras = camera_num; prob.num_boards = board_num; prob.corners_per_board = K;
+  prob.worlds = w.data(); prob.intrinsics = intr.data(); prob.has_board = has.data();
+  prob.mono_rt = rt.data(); prob.pixels = px.data();
+  tscm_pose_graph_result res;
+  std::memset(&res, 0, sizeof(res));
+  res.camera_pose = cam_pose.data(); res.board_pose = board_pose.data(); res.board_initialised = board_ok.data();
+  const int rc = tscm_pose_graph_init(&prob, device, &res);
+  if (rc != TSCM_OK) {
+    // the reference prints and returns (multi_calib.cpp:31-35) or indexes Rs[-1] (multi_calib.cpp:51,86)
+    std::cout << "[tscm] pose-graph initialisation failed: " << tscm_last_error() << std::endl;
+    return;
+  }
+  pose_graph_kernel_ms = res.kernel_ms;
+  auto mat = [](const double* p, int rows, int cols) {
+    cv::Mat M(rows, cols);
+    for (int r = 0; r < rows; ++r) for (int c = 0; c < cols; ++c) M.at<double>(r, c) = p[r * cols + c];
+    return M;
+  };
+  for (int m = 0; m < camera_num; ++m) {
+    TripleSphereCamera& cam = cameras[m];
+    const double* p = cam_pose.data() + 12 * (size_t)m;
+    cameras_[m] = MultiCalib_camera(cam.cx(), cam.cy(), cam.fx(), cam.fy(), cam.xi(), cam.lamda(), cam.alpha(), cam.b(),
+                                    cam.c(), mat(p, 3, 3), mat(p + 9, 3, 1), cam.has_chessboard(), cam.pixels());
   }
   for (int i = 0; i < board_num; ++i) {
-    std::vector<int> ids;
-    for (int j = 0; j < camera_num; ++j) if (cameras[j].has_chessboard(i)) ids.push_back(j);
-    if (ids.empty()) continue;           // multi_calib.cpp:102
-    std::vector<cv::Mat> Rs, ts;
-    for (int id : ids) {
-      cv::Mat Rb, tb;
-      split_homography(cameras[id].Rt(i), Rb, tb);
-      cv::Mat Rc = cameras_[id].R(), tc = cameras_[id].t();
-      Rs.push_back(Rc.t() * Rb);
-      ts.push_back(Rc.t() * (tb - tc));
-    }
-    int best_id = 0;
-    if (ids.size() > 1) {
-      double best = 1e10;
-      for (size_t c = 0; c < Rs.size(); ++c) {
-        double error = 0;
-        for (int id : ids) {
-          cv::Mat Rc = cameras_[id].R(), tc = cameras_[id].t();
-          error += cameras[id].ReprojectError(cameras[id].pixels()[i], worlds, Rc * Rs[c], Rc * ts[c] + tc);
-        }
-        if (error < best) { best = error; best_id = (int)c; }
-      }
-    }
-    chessboards_[i] = MultiCalib_chessboard(Rs[best_id], ts[best_id]);
+    if (!board_ok[i]) continue;                       // multi_calib.cpp:102
+    const double* p = board_pose.data() + 12 * (size_t)i;
+    chessboards_[i] = MultiCalib_chessboard(mat(p, 3, 3), mat(p + 9, 3, 1));
   }
 }
 

@@ -65,8 +65,9 @@ class MultiCalib_chessboard {
 
 class MultiCalib {
  public:
-  // Pose-graph initialisation of multi_calib.cpp:6-153 from per-camera mono calibrations.
-  MultiCalib(std::vector<TripleSphereCamera> cameras, const std::vector<cv::Point3d>& worlds);
+  // Pose-graph initialisation of multi_calib.cpp:6-153 from per-camera mono calibrations; the
+  // candidate scoring runs on CUDA device `device` (-1 = current), tscm_pose_graph_init().
+  MultiCalib(std::vector<TripleSphereCamera> cameras, const std::vector<cv::Point3d>& worlds, int device = -1);
   // Already-initialised rig (the members are public in the reference as well).
   MultiCalib(std::vector<MultiCalib_camera> cameras, std::vector<MultiCalib_chessboard> chessboards,
              const std::vector<cv::Point3d>& worlds)
@@ -86,6 +87,7 @@ class MultiCalib {
   double average_reprojection_error = 0.0;
   int device = -1;
   bool quiet = false;
+  double pose_graph_kernel_ms = 0.0;   // device time of the constructor's scoring kernels
 
  private:
   void init_options();

@@ -427,3 +427,24 @@ def config_batched(idx: int, num_frames: int, batch: int = 10000, processes: int
     else:
         parts = [_unpack_batch(_config_batch(j)) for j in jobs]
     return parts[0] if len(parts) == 1 else concat_frames(parts)
+
+
+def mono_results(sp: SyntheticProblem, seed: int = 42, rot_sigma: float = 2e-3, t_sigma: float = 1.0):
+    """Per-camera mono calibration results as MultiCalib's constructor consumes them
+    (multi_calib.cpp:6-153): for every (camera, frame) with a detection the 3x3 [r1 r2 t] board
+    pose in the camera frame = ground truth plus a small error, so that the pose-graph candidates
+    differ and the selection matters.  Returns (worlds [K][3], intrinsics [C][9], has [C][F] uint8,
+    Rt [C][F][3][3], pixels [C][F][K][2])."""
+    p = sp.problem
+    C, F, K = p.num_cameras, p.num_frames, p.corners_per_board
+    has = sp.visible.astype(np.uint8)
+    pixels = np.zeros((C, F, K, 2))
+    pixels[p.view_camera, p.view_frame] = p.obs_xy
+    worlds = np.concatenate([p.board_xy, np.zeros((K, 1))], axis=1)
+    rng = np.random.default_rng(seed)
+    Rc, Rb = rodrigues(sp.gt_cam_rt[:, :3]), rodrigues(sp.gt_board_rt[:, :3])
+    dR = rodrigues(rng.normal(0, rot_sigma, (C, F, 3)))
+    R = dR @ (Rc[:, None] @ Rb[None, :])
+    t = np.einsum("cij,fj->cfi", Rc, sp.gt_board_rt[:, 3:]) + sp.gt_cam_rt[:, None, 3:] + rng.normal(0, t_sigma, (C, F, 3))
+    Rt = np.stack([R[..., 0], R[..., 1], t], axis=-1) * has[..., None, None]
+    return worlds, sp.gt_intrinsics.copy(), has, Rt, pixels
