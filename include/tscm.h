@@ -317,6 +317,46 @@ typedef struct tscm_pose_graph_result {
 int tscm_pose_graph_init(const tscm_pose_graph_problem* problem, int device,
                          tscm_pose_graph_result* result);
 
+/* ---- mono cold start ------------------------------------------------
+ * TripleSphereCamera::calibrate up to the refinement, /root/reference/TS.cpp:36-52, batched over
+ * the frames of one camera:
+ *   estimate_focal      TS.cpp:110-168  per board row a circle fit (cv::SVD::solveZ of the 4-column
+ *                       design matrix), mean of the accepted rows -> fx = fy
+ *   estimate_extrinsic  TS.cpp:170-203  corners lifted to the unit sphere (TS.h:39-57), turned so
+ *                       that a corner near the board centre looks down +z, cv::solvePnPRansac
+ *                       (defaults, identity camera matrix) on the normalised plane, turned back,
+ *                       kept as the 3x3 [r1 r2 t]
+ * One GPU thread per (frame, row) / per frame; every statement in the scalar order without FMA
+ * contraction.  The two OpenCV calls are restated (one-sided Jacobi SVD; homography + LM to
+ * convergence + inlier re-fitting) and pinned against golden vectors of the real OpenCV.
+ *   has_board  F bytes       has_chessboard[k] (a frame without corners: pixels[k].size() == 0)
+ *   pixels     F x K x 2     K = board_width * board_height corners, row-major board order
+ *   worlds     K x 3
+ * has_init_guess = 0: cx, cy = integer halves of the image size - 0.5, xi = lamda = 0, alpha = 0.5
+ * (TS.cpp:43-47) and the focal length is estimated; result->intrinsics[0] == 0 means the estimate
+ * failed (the reference returns false, TS.cpp:50) and no pose is computed.
+ * has_init_guess = 1: result->intrinsics is INPUT (the 7-argument constructor path, TS.cpp:41). */
+typedef struct tscm_mono_init_problem {
+  int32_t num_frames;                 /* F = pixels.size() */
+  int32_t board_width, board_height;  /* chessboard_num */
+  int32_t image_width, image_height;  /* img_size */
+  const double* worlds;
+  const uint8_t* has_board;
+  const double* pixels;
+  int32_t has_init_guess;
+} tscm_mono_init_problem;
+
+typedef struct tscm_mono_init_result {
+  double intrinsics[TSCM_INTRINSIC_SIZE]; /* {fx,fy,cx,cy,xi,lambda,alpha,b,c}: in/out, see above */
+  double* mono_rt;                    /* F x 9: Rt_[k] row-major, zero where frame_ok = 0 */
+  uint8_t* frame_ok;                  /* F: 1 where a pose was found (0: no board, or PnP failed —
+                                         NaN rays under the current guess; OpenCV would raise) */
+  int32_t focal_rows_used;            /* out: total_num of TS.cpp:156 */
+  double kernel_ms;                   /* out: device time of the two kernels (CUDA events) */
+} tscm_mono_init_result;
+
+int tscm_mono_init(const tscm_mono_init_problem* problem, int device, tscm_mono_init_result* result);
+
 const char* tscm_last_error(void);
 const char* tscm_version(void);
 

@@ -21,7 +21,7 @@ _lib = None
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("tscm_oracle.cpp", "tscm_oracle.h", "remap_oracle.c", "pose_graph_oracle.c",
+    src = [os.path.join(_HERE, f) for f in ("tscm_oracle.cpp", "tscm_oracle.h", "remap_oracle.c", "pose_graph_oracle.c", "mono_init_oracle.cpp", "cv_calib3d_port.h",
                                             os.path.join("..", "include", "tscm.h"))]
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in src)):
@@ -70,6 +70,13 @@ def load():
     lib.tscm_oracle_pose_pair_error.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p, u8p,
                                                 c_double_p, c_double_p, c_double_p]
     lib.tscm_oracle_pose_pair_error.restype = C.c_double
+    lib.tscm_oracle_mono_init.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, u8p, c_double_p,
+                                          C.c_int, c_double_p, c_double_p, u8p, i32p]
+    lib.tscm_oracle_mono_init.restype = C.c_int
+    lib.tscm_oracle_solve_z.argtypes = [c_double_p, C.c_int, C.c_int, c_double_p]
+    lib.tscm_oracle_solve_z.restype = None
+    lib.tscm_oracle_solve_pnp.argtypes = [c_double_p, c_double_p, C.c_int, c_double_p, c_double_p]
+    lib.tscm_oracle_solve_pnp.restype = C.c_int
     _lib = lib
     return lib
 
@@ -221,3 +228,53 @@ def pose_pair_error(i, j, worlds, intrinsics, has, mono_rt, pixels, prev_camera_
     pose = np.ascontiguousarray(prev_camera_pose, dtype=np.float64).reshape(12)
     return lib.tscm_oracle_pose_pair_error(int(i), int(j), B, K, _dp(worlds), _dp(intr),
                                            has.ctypes.data_as(C.POINTER(C.c_uint8)), _dp(rt), _dp(px), _dp(pose))
+
+
+class MonoInit:
+    """Result of the mono cold start: intrinsics [9], Rt [F][3][3], frame_ok [F]."""
+
+    def __init__(self, F):
+        self.rc = 0
+        self.intrinsics = np.zeros(9)
+        self.Rt = np.zeros((F, 3, 3))
+        self.frame_ok = np.zeros(F, dtype=np.uint8)
+        self.rows_used = 0
+        self.kernel_ms = 0.0
+
+
+def mono_init(board, image, worlds, has, pixels, guess=None):
+    """CPU restatement of TripleSphereCamera::calibrate up to the refinement (TS.cpp:36-52,
+    110-203), mono_init_oracle.cpp.  board = (W, H), image = (w, h), pixels [F][K][2];
+    guess: 7 or 9 intrinsics of the has_init_guess_ path, None for the cold start."""
+    lib = load()
+    has = np.ascontiguousarray(has, dtype=np.uint8)
+    F = has.shape[0]
+    W, H = int(board[0]), int(board[1])
+    worlds = np.ascontiguousarray(worlds, dtype=np.float64).reshape(W * H, 3)
+    px = np.ascontiguousarray(pixels, dtype=np.float64).reshape(F, W * H, 2)
+    r = MonoInit(F)
+    if guess is not None:
+        r.intrinsics[:len(guess)] = guess
+    rows = C.c_int32(0)
+    u8p = C.POINTER(C.c_uint8)
+    r.rc = lib.tscm_oracle_mono_init(F, W, H, int(image[0]), int(image[1]), _dp(worlds), has.ctypes.data_as(u8p),
+                                     _dp(px), 0 if guess is None else 1, _dp(r.intrinsics), _dp(r.Rt),
+                                     r.frame_ok.ctypes.data_as(u8p), C.byref(rows))
+    r.rows_used = rows.value
+    return r
+
+
+def solve_z(A):
+    lib = load()
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    z = np.zeros(A.shape[1])
+    lib.tscm_oracle_solve_z(_dp(A), A.shape[0], A.shape[1], _dp(z))
+    return z
+
+
+def solve_pnp(obj, img):
+    lib = load()
+    obj, img = np.ascontiguousarray(obj, dtype=np.float64), np.ascontiguousarray(img, dtype=np.float64)
+    r, t = np.zeros(3), np.zeros(3)
+    rc = lib.tscm_oracle_solve_pnp(_dp(obj), _dp(img), obj.shape[0], _dp(r), _dp(t))
+    return rc, r, t

@@ -48,6 +48,10 @@ def hostmath():
 @pytest.fixture(scope="session")
 def hostinit():
     """C wrappers (tests/hostmath/hostinit.cpp) around the C++ TripleSphereCamera adapter."""
+    return build_hostinit()
+
+
+def build_hostinit():
     from tscm_calib_b200 import build as tbuild
     tbuild.build_cuda()
     here = os.path.join(ROOT, "tests", "hostmath")
@@ -57,6 +61,8 @@ def hostinit():
             os.path.join(host, "multi_calib_b200.cpp")]
     deps = srcs + [os.path.join(host, "ts_camera.h"), os.path.join(host, "cv_compat.h"),
                    os.path.join(host, "multi_calib_b200.h"),
+                   os.path.join(ROOT, "oracle", "cv_calib3d_port.h"),
+                   os.path.join(ROOT, "tscm_calib_b200", "libtscm_b200.so"),
                    os.path.join(ROOT, "include", "tscm.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         env = dict(os.environ)

@@ -2,11 +2,13 @@
 // that pytest can drive TripleSphereCamera's cold-start initialisation (TS.cpp:36-52,110-203),
 // the cv shim's solveZ / solvePnPRansac, the full calibrate() and the remap tables through
 // ctypes.  Not part of the product library.
+#include <chrono>
 #include <cstring>
 #include <vector>
 
 #include "../../tscm_calib_b200/host/multi_calib_b200.h"
 #include "../../tscm_calib_b200/host/ts_camera.h"
+#include "../../oracle/cv_calib3d_port.h"   // the restated cv::SVD::solveZ / cv::solvePnPRansac (oracle side)
 
 namespace {
 std::vector<std::vector<cv::Point2d>> unpack(const double* px, const unsigned char* has, int F, int K) {
@@ -222,9 +224,13 @@ int hostinit_pose_graph(int C, int F, int W, int H, double square, const double*
 // mono calibration (TS.cpp:30-108, refinement on the GPU), the pose graph (multi_calib.cpp:6-153),
 // the joint refinement (multi_calib.cpp:155-283, on the GPU).
 // summary5 = {mono calibrations that converged, termination, iterations, final cost, mean error}.
-int hostinit_full_pipeline(int C, int F, int W, int H, double square, int img_w, int img_h, const double* px,
-                           const unsigned char* has, double* intr, double* cam_rt, double* board_rt,
-                           double* summary5) {
+// stage_s (optional) = seconds of {mono calibrations, pose graph, joint refinement}.
+int hostinit_full_pipeline_timed(int C, int F, int W, int H, double square, int img_w, int img_h, const double* px,
+                                 const unsigned char* has, double* intr, double* cam_rt, double* board_rt,
+                                 double* summary5, double* stage_s) {
+  using clk = std::chrono::steady_clock;
+  auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+  const auto t0 = clk::now();
   const int K = W * H;
   const std::vector<cv::Point3d> worlds = board(W, H, square);
   std::vector<TripleSphereCamera> cams;
@@ -239,9 +245,13 @@ int hostinit_full_pipeline(int C, int F, int W, int H, double square, int img_w,
       ++converged;
     cams.push_back(cam);
   }
+  const auto t1 = clk::now();
   MultiCalib calib(cams, worlds);
+  const auto t2 = clk::now();
   calib.device = 0;
   calib.calibrate();
+  const auto t3 = clk::now();
+  if (stage_s) { stage_s[0] = secs(t0, t1); stage_s[1] = secs(t1, t2); stage_s[2] = secs(t2, t3); }
   for (int m = 0; m < C; ++m) {
     std::memcpy(intr + 9 * m, calib.cameras_[m].intrinsic_.data(), 72);
     std::memcpy(cam_rt + 6 * m, calib.cameras_[m].rt_.data(), 48);
@@ -252,6 +262,12 @@ int hostinit_full_pipeline(int C, int F, int W, int H, double square, int img_w,
   summary5[0] = converged; summary5[1] = s.termination_type; summary5[2] = s.num_iterations;
   summary5[3] = s.final_cost; summary5[4] = calib.average_reprojection_error;
   return 0;
+}
+int hostinit_full_pipeline(int C, int F, int W, int H, double square, int img_w, int img_h, const double* px,
+                           const unsigned char* has, double* intr, double* cam_rt, double* board_rt,
+                           double* summary5) {
+  return hostinit_full_pipeline_timed(C, F, W, H, square, img_w, img_h, px, has, intr, cam_rt, board_rt, summary5,
+                                      nullptr);
 }
 
 }  // extern "C"

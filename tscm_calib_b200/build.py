@@ -8,12 +8,14 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libtscm_b200.so")
-SOURCES = ["tscm_b200.cu"]
-HEADERS = ["tscm_kernels.cuh", "tscm_eval5.cuh", "tscm_solve.cuh", "tscm_math.cuh", "tscm_p2p.cuh", "tscm_remap.cuh", "tscm_posegraph.cuh", "tscm_schur_pairs.cuh", "tscm_pair_lists.h", os.path.join("..", "..", "include", "tscm.h")]
+SOURCES = ["tscm_b200.cu", "tscm_monoinit.cu"]
+# per-source flags: the mono cold start mirrors scalar IEEE statements (no FMA contraction)
+SOURCE_FLAGS = {"tscm_monoinit.cu": ["-fmad=false"]}
+HEADERS = ["tscm_kernels.cuh", "tscm_eval5.cuh", "tscm_solve.cuh", "tscm_math.cuh", "tscm_p2p.cuh", "tscm_remap.cuh", "tscm_posegraph.cuh", "tscm_internal.h", "tscm_schur_pairs.cuh", "tscm_pair_lists.h", os.path.join("..", "..", "include", "tscm.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -38,17 +40,39 @@ def build_cuda(force: bool = False, verbose: bool = False, defines=(), out: str 
     lib = out or LIB
     if not force and not defines and not needs_build():
         return lib
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-D" + d for d in defines] + ["-o", lib] + [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     env = dict(os.environ)
     # nvcc must use the distribution g++ (the image's $CXX lacks some specs)
     env.pop("CXX", None)
     env.pop("CC", None)
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    objdir = os.path.join(_HERE, "_obj" + ("_" + os.path.basename(lib) if out else ""))
+    os.makedirs(objdir, exist_ok=True)
+
+    def run(cmd):
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+
+    common = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines]
+    objs, procs = [], []
+    for src in SOURCES:                      # one translation unit each, compiled side by side
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        spath = os.path.join(CSRC, src)
+        if (not force and not defines and os.path.exists(obj)
+                and all(os.path.getmtime(obj) >= os.path.getmtime(d)
+                        for d in [spath] + [os.path.join(CSRC, h) for h in HEADERS])):
+            continue
+        cmd = common + SOURCE_FLAGS.get(src, []) + ["-c", "-o", obj, spath]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)))
+    for cmd, pr in procs:
+        o, e = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + o + e)
+        if verbose:
+            print(e)
+    run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib] + objs + ["-ldl"])
     return lib
 
 

@@ -110,6 +110,24 @@ class TscmPoseGraphResult(C.Structure):
     ]
 
 
+class TscmMonoInitProblem(C.Structure):
+    """tscm_mono_init_problem (include/tscm.h)."""
+    _fields_ = [
+        ("num_frames", C.c_int32), ("board_width", C.c_int32), ("board_height", C.c_int32),
+        ("image_width", C.c_int32), ("image_height", C.c_int32),
+        ("worlds", c_double_p), ("has_board", C.POINTER(C.c_uint8)), ("pixels", c_double_p),
+        ("has_init_guess", C.c_int32),
+    ]
+
+
+class TscmMonoInitResult(C.Structure):
+    """tscm_mono_init_result (include/tscm.h)."""
+    _fields_ = [
+        ("intrinsics", C.c_double * 9), ("mono_rt", c_double_p), ("frame_ok", C.POINTER(C.c_uint8)),
+        ("focal_rows_used", C.c_int32), ("kernel_ms", C.c_double),
+    ]
+
+
 def default_options(**overrides) -> TscmOptions:
     """ceres::Solver::Options defaults in force at TS.cpp:271-274 /
     multi_calib.cpp:209-212 (same values tscm_options_init() writes)."""
@@ -309,6 +327,8 @@ def load_library(path: str | None = None):
     lib.tscm_remap_tables.restype = C.c_int
     lib.tscm_pose_graph_init.argtypes = [P(TscmPoseGraphProblem), C.c_int, P(TscmPoseGraphResult)]
     lib.tscm_pose_graph_init.restype = C.c_int
+    lib.tscm_mono_init.argtypes = [P(TscmMonoInitProblem), C.c_int, P(TscmMonoInitResult)]
+    lib.tscm_mono_init.restype = C.c_int
     lib.tscm_last_error.argtypes = []
     lib.tscm_last_error.restype = C.c_char_p
     lib.tscm_version.argtypes = []
@@ -328,7 +348,7 @@ EXPORTED_SYMBOLS = [
     "tscm_solver_launch_count", "tscm_device_fp64_peak", "tscm_remap_tables",
     "tscm_last_error", "tscm_version", "tscm_cache_configure", "tscm_cache_release",
     "tscm_host_alloc", "tscm_host_free", "tscm_solver_set_exchange_timeout",
-    "tscm_solver_set_schur_form", "tscm_set_debug", "tscm_pose_graph_init",
+    "tscm_solver_set_schur_form", "tscm_set_debug", "tscm_pose_graph_init", "tscm_mono_init",
 ]
 
 SCHUR_FORM = {"auto": 0, "rows": 1, "fused": 2, "pairs": 3}
@@ -529,6 +549,43 @@ def pose_graph_init(worlds, intrinsics, has, mono_rt, pixels, device: int = -1) 
                               _dp(r.board_candidate_error), 0.0, 0)
     check(lib.tscm_pose_graph_init(C.byref(prob), device, C.byref(res)), lib)
     r.kernel_ms, r.projections = res.kernel_ms, res.projections
+    return r
+
+
+class MonoInitResult:
+    """Output of mono_init(): intrinsics [9], Rt [F][3][3], frame_ok [F]."""
+
+    def __init__(self, F):
+        self.intrinsics = np.zeros(9)
+        self.Rt = np.zeros((F, 3, 3))
+        self.frame_ok = np.zeros(F, dtype=np.uint8)
+        self.rows_used = 0
+        self.kernel_ms = 0.0
+
+
+def mono_init(board, image, worlds, has, pixels, guess=None, device: int = -1) -> MonoInitResult:
+    """tscm_mono_init(): TripleSphereCamera::calibrate up to the refinement (TS.cpp:36-52,
+    110-203) on the GPU.  board = (W, H), image = (w, h), pixels [F][K][2]; guess: 7 or 9
+    intrinsics of the has_init_guess_ path, None for the cold start."""
+    lib = load_library()
+    has = np.ascontiguousarray(has, dtype=np.uint8)
+    F = has.shape[0]
+    W, H = int(board[0]), int(board[1])
+    worlds = np.ascontiguousarray(worlds, dtype=np.float64).reshape(W * H, 3)
+    px = np.ascontiguousarray(pixels, dtype=np.float64).reshape(F, W * H, 2)
+    r = MonoInitResult(F)
+    u8p = C.POINTER(C.c_uint8)
+    prob = TscmMonoInitProblem(F, W, H, int(image[0]), int(image[1]), _dp(worlds), has.ctypes.data_as(u8p), _dp(px),
+                               0 if guess is None else 1)
+    res = TscmMonoInitResult()
+    if guess is not None:
+        for k, v in enumerate(guess):
+            res.intrinsics[k] = float(v)
+    res.mono_rt = _dp(r.Rt)
+    res.frame_ok = r.frame_ok.ctypes.data_as(u8p)
+    check(lib.tscm_mono_init(C.byref(prob), device, C.byref(res)), lib)
+    r.intrinsics[:] = list(res.intrinsics)
+    r.rows_used, r.kernel_ms = res.focal_rows_used, res.kernel_ms
     return r
 
 

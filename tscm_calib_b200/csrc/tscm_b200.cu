@@ -38,6 +38,7 @@
 #include "tscm_pair_lists.h"
 #include "tscm_remap.cuh"
 #include "tscm_posegraph.cuh"
+#include "tscm_internal.h"
 
 namespace {
 
@@ -1184,7 +1185,43 @@ int upload_all_observations(tscm_solver* s, const double* obs_xy) {
 
 }  // namespace
 
+// ---- helpers shared with the other translation units (tscm_internal.h) ----
+namespace tscm {
+namespace internal {
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  ::set_error("%s", buf);
+}
+int select_device(int device, const char* what, int* sm_count) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    ::set_error("no CUDA device: %s has no CPU fallback", what);
+    return TSCM_ERR_NO_DEVICE;
+  }
+  if (device >= 0) CUDA_TRY(cudaSetDevice(device));
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  DeviceInfo prop;
+  RC_TRY(device_info(dev, &prop));
+  if (prop.major < 10) {
+    ::set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    return TSCM_ERR_NO_DEVICE;
+  }
+  if (sm_count) *sm_count = prop.sm_count;
+  return TSCM_OK;
+}
+DeviceScope::DeviceScope() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+DeviceScope::~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+}  // namespace internal
+}  // namespace tscm
+
 extern "C" {
+
 
 const char* tscm_last_error(void) { return g_last_error.c_str(); }
 const char* tscm_version(void) { return "tscm-b200 0.2.0 (sm_100a, fp64)"; }

@@ -82,7 +82,9 @@ bool TripleSphereCamera::calibrate(const std::vector<std::vector<cv::Point2d>> p
   return status;
 }
 
-// TS.cpp:36-52: the state calibrate() is in when it reaches the parameter packing.
+// TS.cpp:36-52: the state calibrate() is in when it reaches the parameter packing.  Both
+// estimate_focal (TS.cpp:110-168) and estimate_extrinsic (TS.cpp:170-203) run on the GPU, batched
+// over the frames, through tscm_mono_init(); there is no CPU path.
 bool TripleSphereCamera::initial_guess(const std::vector<std::vector<cv::Point2d>>& pixels,
                                        std::vector<bool> has_chessboard,
                                        const std::vector<cv::Point3d>& worlds, const cv::Size img_size,
@@ -90,120 +92,61 @@ bool TripleSphereCamera::initial_guess(const std::vector<std::vector<cv::Point2d
   pixels_ = pixels;
   has_chessboard_ = has_chessboard;
   const size_t img_num = pixels.size();
-  Rt_.resize(img_num);
+  Rt_.assign(img_num, cv::Mat());
+  const int K = chessboard_num.width * chessboard_num.height;
+  if (img_num == 0 || K <= 0 || (int)worlds.size() != K) {
+    std::cout << "[tscm] initial_guess: " << img_num << " frames, " << worlds.size() << " board points for a "
+              << chessboard_num.width << " x " << chessboard_num.height << " board" << std::endl;
+    return false;
+  }
+  std::vector<double> w(3 * (size_t)K), px(2 * img_num * K, 0.0), rt(9 * img_num, 0.0);
+  std::vector<uint8_t> has(img_num, 0), ok(img_num, 0);
+  for (int j = 0; j < K; ++j) { w[3 * j] = worlds[j].x; w[3 * j + 1] = worlds[j].y; w[3 * j + 2] = worlds[j].z; }
+  for (size_t k = 0; k < img_num; ++k) {
+    // a frame takes part when it has corners (estimate_focal: pixels[k].size() != 0, TS.cpp:129)
+    // and is flagged (estimate_extrinsic: has_chessboard_[k], TS.cpp:174); main.cpp:33-37 sets
+    // the two together
+    if (!has_chessboard_[k] || (int)pixels[k].size() != K) continue;
+    has[k] = 1;
+    std::memcpy(&px[2 * k * K], pixels[k].data(), sizeof(double) * 2 * K);      // cv::Point2d = {x, y}
+  }
+  tscm_mono_init_problem prob;
+  prob.num_frames = (int32_t)img_num;
+  prob.board_width = chessboard_num.width; prob.board_height = chessboard_num.height;
+  prob.image_width = img_size.width; prob.image_height = img_size.height;
+  prob.worlds = w.data(); prob.has_board = has.data(); prob.pixels = px.data();
+  prob.has_init_guess = has_init_guess_ ? 1 : 0;
+  tscm_mono_init_result res;
+  std::memset(&res, 0, sizeof(res));
+  const double guess[TSCM_INTRINSIC_SIZE] = {fx_, fy_, cx_, cy_, xi_, lamda_, alpha_, b_, c_};
+  std::memcpy(res.intrinsics, guess, sizeof(guess));
+  res.mono_rt = rt.data(); res.frame_ok = ok.data();
+  const int rc = tscm_mono_init(&prob, device, &res);
+  if (rc != TSCM_OK) {
+    std::cout << "[tscm] initial guess failed: " << tscm_last_error() << std::endl;
+    return false;
+  }
   if (!has_init_guess_) {
-    cx_ = img_size.width / 2 - 0.5;     // integer halves, as TS.cpp:43-44
-    cy_ = img_size.height / 2 - 0.5;
-    xi_ = 0.0;
-    lamda_ = 0.0;
-    alpha_ = 0.5;
-    estimate_focal(pixels, worlds, img_size, chessboard_num);
+    fx_ = res.intrinsics[0]; fy_ = res.intrinsics[1]; cx_ = res.intrinsics[2]; cy_ = res.intrinsics[3];
+    xi_ = res.intrinsics[4]; lamda_ = res.intrinsics[5]; alpha_ = res.intrinsics[6];
+    if (res.focal_rows_used == 0) std::cout << "焦距估计失败" << std::endl;      // the reference's message (TS.cpp:165)
     std::cout << "[initialize] focal:" << fx_ << ", cx:" << cx_ << ", cy:" << cy_ << ", xi:" << xi_
               << ", lamda:" << lamda_ << ", alpha:" << alpha_ << std::endl;
     if (fx_ == 0) return false;
   }
-  estimate_extrinsic(pixels, worlds, chessboard_num);
-  return true;
-}
-
-namespace {
-
-// Focal length from ONE board row (TS.cpp:127-158).  With xi = lamda = 0, alpha = 0.5 the
-// model is the unified sphere model with unit mirror parameter, under which a 3-D line images
-// as the circle  x^2 + y^2 - 2 f (nx/nz) x - 2 f (ny/nz) y - f^2 = 0  (n = unit normal of the
-// line's plane through the centre).  The row's corners, relative to the principal point, give
-// the design matrix [x  y  1/2  -(x^2 + y^2)/2]; its null vector c fixes f = |c3 / (|..| nz)|.
-// Rows whose plane is too oblique (nx^2 + ny^2 > 0.95) or whose fit is not a real circle are
-// skipped; returns false for those.
-bool focal_from_board_row(const cv::Point2d* row, int count, double cx, double cy, double* focal) {
-  cv::Mat design(count, 4);
-  for (int j = 0; j < count; ++j) {
-    const double x = row[j].x - cx, y = row[j].y - cy;
-    design.at<double>(j, 0) = x;
-    design.at<double>(j, 1) = y;
-    design.at<double>(j, 2) = 0.5;
-    design.at<double>(j, 3) = -0.5 * (x * x + y * y);
-  }
-  cv::Mat nullvec;
-  cv::SVD::solveZ(design, nullvec);
-  const double c[4] = {nullvec.at<double>(0), nullvec.at<double>(1), nullvec.at<double>(2), nullvec.at<double>(3)};
-  const double scale2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[3];
-  if (scale2 < 0) return false;
-  const double inv_norm = std::sqrt(1 / scale2);
-  const double nx = c[0] * inv_norm, ny = c[1] * inv_norm;
-  const double oblique = nx * nx + ny * ny;
-  if (oblique > 0.95) return false;
-  *focal = std::fabs(c[2] * inv_norm / std::sqrt(1 - oblique));
-  return true;
-}
-
-// Rotation that turns the viewing ray p (unit vector) onto +z: first about y by the azimuth,
-// then about x by the elevation (TS.cpp:179-187).
-cv::Mat rotation_facing(const cv::Point3d& p) {
-  const double az = std::atan2(p.x, p.z), el = std::asin(p.y);
-  cv::Mat about_y = (cv::Mat_<double>(3, 3) << std::cos(az), 0, -std::sin(az),
-                                               0, 1, 0,
-                                               std::sin(az), 0, std::cos(az));
-  cv::Mat about_x = (cv::Mat_<double>(3, 3) << 1, 0, 0,
-                                               0, std::cos(el), -std::sin(el),
-                                               0, std::sin(el), std::cos(el));
-  return about_x * about_y;
-}
-
-}  // namespace
-
-// TS.cpp:110-168: mean of the per-row focal estimates over every frame with corners.
-void TripleSphereCamera::estimate_focal(const std::vector<std::vector<cv::Point2d>>& pixels,
-                                        const std::vector<cv::Point3d>& /*worlds*/, cv::Size /*img_size*/,
-                                        const cv::Size chessboard_num) {
-  double sum = 0;
-  int rows_used = 0;
-  for (const std::vector<cv::Point2d>& frame : pixels) {
-    if (frame.empty()) continue;                        // no detection in this image
-    for (int r = 0; r < chessboard_num.height; ++r) {
-      double f;
-      if (!focal_from_board_row(&frame[(size_t)r * chessboard_num.width], chessboard_num.width, cx_, cy_, &f)) continue;
-      sum += f;
-      ++rows_used;
-    }
-  }
-  if (rows_used == 0) std::cout << "焦距估计失败" << std::endl;      // the reference's message (TS.cpp:165)
-  fx_ = fy_ = rows_used > 0 ? sum / rows_used : 0.0;
-}
-
-// TS.cpp:170-203.  Per frame: the corners are lifted to the unit sphere with the current
-// intrinsics, the sphere is turned so that a corner near the board centre looks down +z, the
-// rays are projected to the normalised plane z = 1 and the board pose follows from
-// solvePnPRansac with an identity camera matrix; turned back, it is kept in the [r1 r2 t] form.
-void TripleSphereCamera::estimate_extrinsic(const std::vector<std::vector<cv::Point2d>>& pixels,
-                                            const std::vector<cv::Point3d>& worlds,
-                                            const cv::Size chessboard_num) {
-  const cv::Mat identity = cv::Mat::eye(3, 3, cv::CV_64F);
-  for (size_t k = 0; k < pixels.size(); ++k) {
+  for (size_t k = 0; k < img_num; ++k) {
     if (!has_chessboard_[k]) continue;
-    const std::vector<cv::Point2d>& corners = pixels[k];
-    const size_t centre = corners.size() / 2 - chessboard_num.width / 2 - 1;        // TS.cpp:177
-    const cv::Mat facing = rotation_facing(get_unit_sphere_coordinate(corners[centre], identity));
-    std::vector<cv::Point2d> plane(corners.size());
-    for (size_t i = 0; i < corners.size(); ++i) {
-      const cv::Point3d ray = get_unit_sphere_coordinate(corners[i], facing);
-      plane[i] = cv::Point2d(ray.x / ray.z, ray.y / ray.z);
-    }
-    cv::Mat rvec, tvec, pose;
-    const bool found = cv::solvePnPRansac(worlds, plane, identity, cv::Mat::zeros(4, 0, cv::CV_64F), rvec, tvec);
-    if (!found || rvec.empty() || tvec.empty()) {
+    if (!ok[k]) {
       // no pose (corners outside the model domain under the current guess give NaN rays): the
       // frame does not take part in the refinement — where OpenCV would raise a cv::Exception
       has_chessboard_[k] = false;
       continue;
     }
-    cv::Rodrigues(rvec, pose);
-    const cv::Mat back = facing.t();
-    pose = back * pose;
-    const cv::Mat t = back * tvec;
-    for (int r = 0; r < 3; ++r) pose.at<double>(r, 2) = t.at<double>(r);
+    cv::Mat pose(3, 3);
+    for (int e = 0; e < 9; ++e) pose.at<double>(e / 3, e % 3) = rt[9 * k + e];
     Rt_[k] = pose;
   }
+  return true;
 }
 
 // Replaces TS.cpp:247-282: one residual block per corner of every frame with a board

@@ -5,11 +5,10 @@
 // refinement() (TS.cpp:247-282): instead of building a ceres::Problem and calling
 // ceres::Solve it hands the same arrays to tscm_solve() (include/tscm.h).
 //
-// The cold-start initialisation is host C++ like the reference's:
-// estimate_focal (TS.cpp:110-168, circle fit through cv::SVD::solveZ) and
-// estimate_extrinsic (TS.cpp:170-203, cv::solvePnPRansac on unit-sphere-normalised
-// corners).  With real OpenCV (TSCM_USE_OPENCV) those two calls are OpenCV's; otherwise the
-// shim's restatements in cv_compat.h are used (same minimisers, not bit-identical).
+// The cold-start initialisation — estimate_focal (TS.cpp:110-168, circle fit
+// through cv::SVD::solveZ) and estimate_extrinsic (TS.cpp:170-203, cv::solvePnPRansac on
+// unit-sphere-normalised corners) — runs on the GPU as well, batched over the frames, behind
+// tscm_mono_init() (csrc/tscm_monoinit.cu).
 // The remap tables of undistort / undistort_chessboard (TS.cpp:284-330, §8f #4) are filled
 // by the CUDA kernel behind tscm_remap_tables().
 #pragma once
@@ -77,10 +76,6 @@ class TripleSphereCamera {
   int device = -1;
 
  private:
-  void estimate_focal(const std::vector<std::vector<cv::Point2d>>& pixels, const std::vector<cv::Point3d>& worlds,
-                      cv::Size img_size, const cv::Size chessboard_num);
-  void estimate_extrinsic(const std::vector<std::vector<cv::Point2d>>& pixels,
-                          const std::vector<cv::Point3d>& worlds, const cv::Size chessboard_num);
   bool refinement(const std::vector<std::vector<cv::Point2d>>& pixels, const std::vector<cv::Point3d>& worlds);
 
   bool has_init_guess_;
