@@ -31,6 +31,9 @@
 namespace tscm {
 
 constexpr int kPgThreads = 128;
+#ifndef PG_MIN_CTAS
+#define PG_MIN_CTAS 4      // CTAs per SM the register allocation of k_pg_pair_score aims at
+#endif
 
 // out = a * b for 3x3 row-major doubles: s = 0; s += a(i,k) * b(k,j), k ascending (the cv::Mat
 // product of the reference; the leading 0 + keeps the sign of a zero sum identical)
@@ -128,7 +131,7 @@ __host__ __device__ inline size_t pg_pair_smem_bytes(int K, int tile) {
   return ((((size_t)3 * K + 1) & ~(size_t)1) + (size_t)tile * 2 * (12 + 2 * (size_t)K)) * sizeof(double);
 }
 
-__global__ void __launch_bounds__(kPgThreads)
+__global__ void __launch_bounds__(kPgThreads, PG_MIN_CTAS)
 k_pg_pair_score(PgPairArgs A) {
   extern __shared__ __align__(16) double pg_smem[];
   double* s_w = pg_smem;                          // worlds
