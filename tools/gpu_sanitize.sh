@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 TAG=${TAG:-r02}
 for tool in ${TOOLS:-memcheck racecheck synccheck initcheck}; do
-  for c in ${CASES:-dense pairs mono robust masks}; do
+  for c in ${CASES:-dense pairs mono robust masks init}; do
     log=gpurun_out/${TAG}_sanitizer_${tool}_${c}.log
     timeout ${SAN_TIMEOUT:-420} compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_case.py $c > $log 2>&1
     echo "rc=$?" >> $log

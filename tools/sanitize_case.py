@@ -1,6 +1,6 @@
 """Small solves for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): every kernel of the LM
 iteration graph runs at least twice, on sizes a sanitizer finishes in a minute.
-  python tools/sanitize_case.py dense|pairs|mono|robust|masks|group
+  python tools/sanitize_case.py dense|pairs|mono|robust|masks|group|init
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,6 +8,19 @@ import numpy as np
 from tscm_calib_b200 import capi, synth
 
 case = sys.argv[1] if len(sys.argv) > 1 else "dense"
+if case == "init":       # the callers of the solve: mono cold start, pose graph, remap tables
+    sp = synth.config(2, num_frames=60)
+    worlds, intr, has, Rt, px = synth.mono_results(sp)
+    for m in range(2):
+        r = capi.mono_init((11, 8), (1280, 1080), worlds, has[m], px[m])
+        assert r.frame_ok.sum() == has[m].sum() and r.intrinsics[0] > 0
+    g = capi.pose_graph_init(worlds, intr, has, Rt, px)
+    assert g.board_init.sum() == has.any(axis=0).sum() and np.all(g.camera_choice[1:] >= 0)
+    job = capi.remap_job(intr[0], np.eye(3), (200.0, 200.0, 160.0, 120.0), (320, 240))
+    mx, my, _ = capi.remap_tables([job], (320, 240))
+    assert np.isfinite(mx).all()
+    print(case, "ok", r.kernel_ms, g.kernel_ms)
+    sys.exit(0)
 if case == "dense":      # config 3 shape: k_eval5, k_view_blocks, k_schur_frames, k_schur_update, k_solve, ...
     sp, opt = synth.config(3, num_frames=96), capi.default_options(max_num_iterations=4)
 elif case == "pairs":    # 16-camera ring, sparse visibility: k_pair_frames, k_pair_blocks, k_schur_pairs2, k_reduce_pairs

@@ -32,7 +32,7 @@ namespace tscm {
 
 constexpr int kPgThreads = 128;
 #ifndef PG_MIN_CTAS
-#define PG_MIN_CTAS 4      // CTAs per SM the register allocation of k_pg_pair_score aims at
+#define PG_MIN_CTAS 6      // CTAs per SM the register allocation of k_pg_pair_score aims at (4: 281 ms, 5: 261, 6: 247 at config 3)
 #endif
 
 // out = a * b for 3x3 row-major doubles: s = 0; s += a(i,k) * b(k,j), k ascending (the cv::Mat
