@@ -2122,6 +2122,7 @@ int tscm_pose_graph_init(const tscm_pose_graph_problem* P, int device, tscm_pose
     PG_TRY(cudaMemcpy(d_cam, cam_pose.data(), cam_pose.size() * sizeof(double), cudaMemcpyHostToDevice));
     PG_TRY(cudaMemcpy(d_intr, P->intrinsics, (size_t)C * 9 * sizeof(double), cudaMemcpyHostToDevice));
     PG_TRY(cudaMemcpy(d_has, P->has_board, (size_t)C * B, cudaMemcpyHostToDevice));
+    PG_TRY(cudaMemset(d_E2, 0, E2.size() * sizeof(double)));      // (board, candidate, camera) triples without a view stay 0
     PgBoardArgs A;
     A.pixels = d_px; A.has = d_has; A.cam_pose = d_cam; A.cand = d_bc; A.worlds = d_worlds; A.intr = d_intr;
     A.E = d_E2; A.C = C; A.B = B; A.K = K;

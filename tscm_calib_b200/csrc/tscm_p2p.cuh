@@ -11,7 +11,9 @@
 //            stores); __threadfence_system(); flag [seq & 1][my rank] of the peer = seq
 //   reader:  spin on its OWN (local) flags (>= seq), then read its own mailbox
 // One fence (a round trip) plus a one-way flag store per exchange; a pull design (poll the
-// peer's flag, then load the peer's slot) measured ~10 us more per exchange.
+// peer's flag, then load the peer's slot) measured ~10 us more per exchange.  The Schur
+// exchange (155 CTAs) goes one step further and carries the sequence number inside every
+// 16-byte entry (p2p_put16 / p2p_get16): no fence, no separate flag.
 // Slots are double-buffered by sequence parity: a rank reaches exchange seq + 2 only after
 // every peer has posted seq + 1, which each peer does only after it has finished reading seq.
 //   k_reduce_s_p2p  sum of the local Schur partials (as k_reduce_s) + exchange of [S | rhs];
@@ -43,24 +45,51 @@ struct P2PArgs {
   unsigned long long timeout_ns;   // a wait gives up after this long (tscm_solver_set_exchange_timeout)
 };
 // mailbox layout (8-byte words), W = kP2PMaxRanks source ranks:
-//   A[2][W][nA] | flagA[2][W][nctaA] | B[2][W][nB] | flagB[2][W]
+//   A[2][W][nA] of {value, sequence} pairs (16 bytes) | B[2][W][nB] | flagB[2][W]
 __host__ __device__ inline size_t p2p_mailbox_words(int nA, int nctaA, int nB) {
-  return (size_t)2 * kP2PMaxRanks * ((size_t)nA + nctaA + nB + 1);
+  (void)nctaA;
+  return (size_t)2 * kP2PMaxRanks * ((size_t)2 * nA + nB + 1);
 }
 // slot of source rank `src` in the mailbox of rank `r`
-__device__ __forceinline__ double* p2p_A(const P2PArgs& x, int r, int par, int src) {
-  return x.mb[r] + ((size_t)par * kP2PMaxRanks + src) * x.nA;
-}
-__device__ __forceinline__ unsigned long long* p2p_flagA(const P2PArgs& x, int r, int par, int src) {
-  return reinterpret_cast<unsigned long long*>(x.mb[r] + (size_t)2 * kP2PMaxRanks * x.nA) +
-         ((size_t)par * kP2PMaxRanks + src) * x.nctaA;
+__device__ __forceinline__ double2* p2p_A(const P2PArgs& x, int r, int par, int src) {
+  return reinterpret_cast<double2*>(x.mb[r]) + ((size_t)par * kP2PMaxRanks + src) * x.nA;
 }
 __device__ __forceinline__ double* p2p_B(const P2PArgs& x, int r, int par, int src) {
-  return x.mb[r] + (size_t)2 * kP2PMaxRanks * ((size_t)x.nA + x.nctaA) + ((size_t)par * kP2PMaxRanks + src) * x.nB;
+  return x.mb[r] + (size_t)2 * kP2PMaxRanks * ((size_t)2 * x.nA) + ((size_t)par * kP2PMaxRanks + src) * x.nB;
 }
 __device__ __forceinline__ unsigned long long* p2p_flagB(const P2PArgs& x, int r, int par, int src) {
-  return reinterpret_cast<unsigned long long*>(x.mb[r] + (size_t)2 * kP2PMaxRanks * ((size_t)x.nA + x.nctaA + x.nB)) +
+  return reinterpret_cast<unsigned long long*>(x.mb[r] + (size_t)2 * kP2PMaxRanks * ((size_t)2 * x.nA + x.nB)) +
          (size_t)par * kP2PMaxRanks + src;
+}
+// The Schur exchange carries its flag INSIDE the payload: every entry travels as one aligned
+// 16-byte store {value, sequence number}, which arrives as a unit (the granule NCCL's LL128
+// protocol builds on over NVLink), so the receiver polls the entry itself and no
+// __threadfence_system() — a round trip per CTA and peer, 155 CTAs at once: 14 us per exchange
+// at 2 GPUs — stands between data and flag.  Sequence numbers never repeat (the counter lives
+// as long as the solver, the mailbox starts zeroed), so a stale entry cannot match.
+__device__ __forceinline__ void p2p_put16(double2* dst, double v, unsigned long long s) {
+  asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(dst), "l"(__double_as_longlong(v)), "l"(s) : "memory");
+}
+__device__ __forceinline__ bool p2p_get16(const double2* src, unsigned long long s, const P2PArgs& x, double* v) {
+  unsigned long long t0 = 0;
+  for (unsigned i = 0;; ++i) {
+    long long a;
+    unsigned long long b;
+    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
+    if (b == s) { *v = __longlong_as_double(a); return true; }
+    if (i > 64) {
+      __nanosleep(100);
+      if ((i & 1023u) == 0) {
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > x.timeout_ns) break;
+      }
+    }
+  }
+  *x.err = 1;
+  *v = 0.0;
+  return false;
 }
 __device__ __forceinline__ void p2p_post(unsigned long long* flag, unsigned long long s) {
   *reinterpret_cast<volatile unsigned long long*>(flag) = s;
@@ -134,19 +163,13 @@ k_reduce_s_p2p(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, L
     s_mine[e] = ok ? t : 0.0;
   }
   __syncthreads();
-  // warp p pushes this CTA's 32 sums to rank p and receives rank p's 32 sums
+  // warp p pushes this CTA's 32 sums to rank p and receives rank p's 32 sums: every lane sends
+  // and polls its own {value, sequence} entry
   double v = 0.0;
   if (part < x.world) {
     if (part != x.rank) {
-      p2p_A(x, part, par, x.rank)[blockIdx.x * 32 + e] = s_mine[e];
-      __threadfence_system();
-      __syncwarp();
-      if (e == 0) {
-        p2p_post(p2p_flagA(x, part, par, x.rank) + blockIdx.x, s);
-        p2p_wait(p2p_flagA(x, x.rank, par, part) + blockIdx.x, s, x);
-      }
-      __syncwarp();
-      v = *reinterpret_cast<const volatile double*>(p2p_A(x, x.rank, par, part) + blockIdx.x * 32 + e);
+      p2p_put16(p2p_A(x, part, par, x.rank) + blockIdx.x * 32 + e, s_mine[e], s);
+      p2p_get16(p2p_A(x, x.rank, par, part) + blockIdx.x * 32 + e, s, x, &v);
     } else {
       v = s_mine[e];
     }
