@@ -22,6 +22,7 @@
 // (2K x 9 per frame) lives in a frame-minor global scratch so that the lanes' accesses coalesce.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -204,17 +205,22 @@ __device__ bool chol_solve6(double* A, double* b) {
   return true;
 }
 
-// Per-frame scratch in frame-minor layout: element e of frame f at base[e * F + f].
+// Per-frame scratch in frame-minor layout: element e of frame f at base[e * F + f].  The DLT
+// matrix, which the Jacobi sweeps walk ~10^5 times per frame, lives in SHARED memory when a
+// block's frames fit (16 frames x 12.4 KB at K = 88; lane-minor, so the lanes of an access hit
+// distinct banks) and in the global scratch otherwise.
 struct Scratch {
   double* xy;      // [2K][F] normalised-plane points
-  double* A;       // [2K * 9][F] DLT matrix
+  double* A;       // [2K * 9][F] DLT matrix (global fallback)
   uint8_t* use;    // [K][F] inlier flags
   int F;
+  int a_in_smem;   // 1: the DLT matrix of thread t is at smem[e * blockDim.x + t]
 };
 
 // solvePnP(SOLVEPNP_ITERATIVE) on the flagged points of a planar target with an identity camera
 // matrix: R (row-major), t.  false = fewer than 4 points or a degenerate homography.
-__device__ bool pnp_planar(const Scratch& S, int f, int K, const double* __restrict__ worlds, double* R, double* t) {
+__device__ bool pnp_planar(const Scratch& S, int f, int K, const double* __restrict__ worlds, double* R, double* t,
+                           double* Abase, size_t Astride) {
   const int F = S.F;
   auto X = [&](int i) { return worlds[3 * i]; };
   auto Y = [&](int i) { return worlds[3 * i + 1]; };
@@ -248,14 +254,14 @@ __device__ bool pnp_planar(const Scratch& S, int f, int K, const double* __restr
       const double r0[9] = {a, b, 1, 0, 0, 0, -u * a, -u * b, -u};
       const double r1[9] = {0, 0, 0, a, b, 1, -v * a, -v * b, -v};
       for (int k = 0; k < 9; ++k) {
-        S.A[(size_t)(row * 9 + k) * F + f] = r0[k];
-        S.A[(size_t)((row + 1) * 9 + k) * F + f] = r1[k];
+        Abase[(size_t)(row * 9 + k) * Astride] = r0[k];
+        Abase[(size_t)((row + 1) * 9 + k) * Astride] = r1[k];
       }
       row += 2;
     }
   }
   double Hn[9];
-  solve_z<9>([&](int i, int j) -> double& { return S.A[(size_t)(i * 9 + j) * F + f]; }, 2 * n, Hn);
+  solve_z<9>([&](int i, int j) -> double& { return Abase[(size_t)(i * 9 + j) * Astride]; }, 2 * n, Hn);
   // H = T_img^-1 * Hn * T_obj
   const double Ti[9] = {1 / sx, 0, mx, 0, 1 / sx, my, 0, 0, 1};
   const double To[9] = {sX, 0, -mX * sX, 0, sX, -mY * sX, 0, 0, 1};
@@ -352,9 +358,12 @@ __device__ bool pnp_planar(const Scratch& S, int f, int K, const double* __restr
 __global__ void __launch_bounds__(kThreads)
 k_mi_extrinsic(const double* __restrict__ pixels, const uint8_t* __restrict__ has, const double* __restrict__ worlds,
                int F, int W, int H, Intr I, Scratch S, double* __restrict__ mono_rt, uint8_t* __restrict__ ok) {
+  extern __shared__ __align__(16) double mi_smem[];
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   const int K = W * H;
+  double* Abase = S.a_in_smem ? mi_smem + threadIdx.x : S.A + f;
+  const size_t Astride = S.a_in_smem ? blockDim.x : (size_t)F;
   double* M = mono_rt + 9 * (size_t)f;
   for (int k = 0; k < 9; ++k) M[k] = 0.0;
   ok[f] = 0;
@@ -385,7 +394,7 @@ k_mi_extrinsic(const double* __restrict__ pixels, const uint8_t* __restrict__ ha
   // solvePnPRansac: fit, drop the points beyond the 8.0 threshold, re-fit until the set is stable
   double R[9], t[3], rvec[3];
   for (int round = 0; round < 8; ++round) {
-    if (!pnp_planar(S, f, K, worlds, R, t)) return;
+    if (!pnp_planar(S, f, K, worlds, R, t, Abase, Astride)) return;
     // the pose leaves solvePnP as (rvec, tvec) and is turned back into a matrix for the test
     rodrigues_m2v(R, rvec);
     double Rr[9];
@@ -507,10 +516,22 @@ extern "C" int tscm_mono_init(const tscm_mono_init_problem* P, int device, tscm_
   std::memset(R->frame_ok, 0, (size_t)F);
   if (!P->has_init_guess && I.fx == 0) { cleanup(); return TSCM_OK; }  // the caller returns false (TS.cpp:50)
   MI_TRY(dalloc((void**)&S.xy, (size_t)2 * K * F * sizeof(double)));
-  MI_TRY(dalloc((void**)&S.A, (size_t)2 * K * 9 * F * sizeof(double)));
   MI_TRY(dalloc((void**)&S.use, (size_t)K * F));
+  // frames per block: as many DLT matrices as fit 200 KB of shared memory (16 at K = 88)
+  const size_t a_bytes = (size_t)2 * K * 9 * sizeof(double);
+  int fpb = (int)std::min<size_t>(32, (200 * 1024) / a_bytes);
+  S.A = nullptr;
+  S.a_in_smem = fpb >= 4 ? 1 : 0;
+  size_t smem = 0;
+  if (S.a_in_smem) {
+    smem = a_bytes * fpb;
+    MI_TRY(cudaFuncSetAttribute(mi::k_mi_extrinsic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  } else {
+    fpb = mi::kThreads;
+    MI_TRY(dalloc((void**)&S.A, a_bytes * F));
+  }
   MI_TRY(cudaEventRecord(e0, 0));
-  mi::k_mi_extrinsic<<<(F + mi::kThreads - 1) / mi::kThreads, mi::kThreads>>>(d_px, d_has, d_worlds, F, W, H, I, S, d_rt, d_ok);
+  mi::k_mi_extrinsic<<<(F + fpb - 1) / fpb, fpb, smem>>>(d_px, d_has, d_worlds, F, W, H, I, S, d_rt, d_ok);
   MI_TRY(cudaEventRecord(e1, 0));
   MI_TRY(cudaGetLastError());
   MI_TRY(add_ms());

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <iostream>
+#include <utility>
 
 namespace {
 
@@ -30,8 +31,8 @@ MultiCalib_camera::MultiCalib_camera(double cx, double cy, double fx, double fy,
   rt_ = pack_rt(R, t);
   R_ = R; t_ = t;
   intrinsic_ = {fx, fy, cx, cy, xi, lamda, alpha, b, c};
-  has_chessboard_ = has_chessboard;
-  pixel_coordinates_ = pixel_coordinates;
+  has_chessboard_ = std::move(has_chessboard);
+  pixel_coordinates_ = std::move(pixel_coordinates);
   is_initial_ = true;
   // R_, t_ stay the matrices that were handed in (multi_calib.h:20-21): the pose-graph chain
   // composes them as they are, not their re-orthogonalised Rodrigues round trip
@@ -86,7 +87,7 @@ MultiCalib::MultiCalib(std::vector<TripleSphereCamera> cameras, const std::vecto
     TripleSphereCamera& cam = cameras[m];
     const double in[9] = {cam.fx(), cam.fy(), cam.cx(), cam.cy(), cam.xi(), cam.lamda(), cam.alpha(), cam.b(), cam.c()};
     std::memcpy(intr.data() + 9 * (size_t)m, in, sizeof(in));
-    const auto pixels = cam.pixels();
+    const auto& pixels = cam.pixels_ref();
     for (int i = 0; i < board_num; ++i) {
       const size_t v = (size_t)m * board_num + i;
       if (!cam.has_chessboard(i)) continue;

@@ -66,6 +66,7 @@ class TripleSphereCamera {
   void setRt(std::vector<cv::Mat> Rts) { Rt_ = Rts; }
   void setPixels(std::vector<std::vector<cv::Point2d>> pixels) { pixels_ = pixels; }
   std::vector<std::vector<cv::Point2d>> pixels() { return pixels_; }
+  const std::vector<std::vector<cv::Point2d>>& pixels_ref() const { return pixels_; }   // (no copy; not in the reference)
   std::vector<bool> has_chessboard() { return has_chessboard_; }
   bool has_chessboard(int id) { return has_chessboard_[id]; }
   void setHasChessboard(std::vector<bool> has_chessboard) { has_chessboard_ = has_chessboard; }
