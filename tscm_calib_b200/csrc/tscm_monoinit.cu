@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -206,9 +207,9 @@ __device__ bool chol_solve6(double* A, double* b) {
 }
 
 // Per-frame scratch in frame-minor layout: element e of frame f at base[e * F + f].  The DLT
-// matrix, which the Jacobi sweeps walk ~10^5 times per frame, lives in SHARED memory when a
-// block's frames fit (16 frames x 12.4 KB at K = 88; lane-minor, so the lanes of an access hit
-// distinct banks) and in the global scratch otherwise.
+// matrix, which the Jacobi sweeps walk ~10^5 times per frame, lives in SHARED memory when all
+// frames fit one wave of blocks (16 frames x 12.4 KB per block at K = 88; lane-minor, so the
+// lanes of an access hit distinct banks) and in the global scratch otherwise.
 struct Scratch {
   double* xy;      // [2K][F] normalised-plane points
   double* A;       // [2K * 9][F] DLT matrix (global fallback)
@@ -521,7 +522,12 @@ extern "C" int tscm_mono_init(const tscm_mono_init_problem* P, int device, tscm_
   const size_t a_bytes = (size_t)2 * K * 9 * sizeof(double);
   int fpb = (int)std::min<size_t>(32, (200 * 1024) / a_bytes);
   S.A = nullptr;
-  S.a_in_smem = fpb >= 4 ? 1 : 0;
+  // Shared memory makes a thread 1.45x faster (22 vs 32 ms for its serial chain at K = 88) but caps
+  // an SM at `fpb` frames: it pays while all frames fit one wave (5,000 frames: 46 ms in 2.1 waves
+  // against 32 ms with every frame resident at once on the global scratch).  TSCM_MI_SMEM=0/1 forces.
+  const char* mode = std::getenv("TSCM_MI_SMEM");
+  const bool one_wave = fpb >= 4 && (F + fpb - 1) / fpb <= sm_count;
+  S.a_in_smem = mode ? (mode[0] == '1' && fpb >= 4) : one_wave;
   size_t smem = 0;
   if (S.a_in_smem) {
     smem = a_bytes * fpb;
