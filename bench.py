@@ -358,6 +358,27 @@ def run_b200(args):
                                   "20 timed iterations"}
         del spm
 
+    # ---- BASELINE config 4 (stress: 16-camera ring, visibility masks) on a bounded sample, N = 1 ------
+    # The full 100,000 frames take minutes to synthesise on the host (tools/stress_cfg4.py runs them:
+    # profiles/r0*_stress_cfg4*.json); a 20,000-frame sample of the same generator exercises the
+    # sparse-visibility Schur form (per-camera-pair kernels) inside the driver's run.
+    if world == 1 and args.stress_frames > 0:
+        sps = synth.config_batched(4, args.stress_frames, batch=10000, processes=min(4, os.cpu_count() or 1))
+        ss = capi.Solver(sps.problem, fixed_iteration_options(args.warmup + 10 + 8), device=local_rank)
+        init_s = (sps.init_intrinsics, sps.init_cam_rt, sps.init_board_rt)
+        ss.set_parameters(*init_s)
+        ss.time_stage(4, max(args.warmup, 1))
+        ss.set_parameters(*init_s)
+        ms_s = ss.time_stage(4, 10)
+        ss.close()
+        line["stress_cfg4_sample"] = {
+            "value": sps.num_observations / (ms_s * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_s,
+            "observations_total": int(sps.num_observations), "frames": int(args.stress_frames),
+            "visible_fraction": float(sps.visible.mean()),
+            "what": f"config 4 generator (16-camera ring, masks) at {args.stress_frames} of its 100,000 frames, "
+                    "10 timed LM iterations; the full size on 1/2/4/8 GPUs: profiles/r0*_stress_cfg4*.json"}
+        del sps
+
     # ---- weak scaling beside it (N > 1): 5,000 frames per GPU, one common rig ------------------------
     if world > 1 and not args.no_weak:
         spw = synth.config(3, num_frames=args.frames, frame_seed=rank)
@@ -511,6 +532,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling side figure at N > 1")
     ap.add_argument("--no-masked", action="store_true", help="skip the masked-visibility side figure at N = 1")
+    ap.add_argument("--stress-frames", type=int, default=20000,
+                    help="frames of the config-4 sample timed beside the headline at N = 1 (0 = skip)")
     ap.add_argument("--debug-flags", type=int, default=0, help="tscm_set_debug() flags (4 = no programmatic dependent launch)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -2,9 +2,9 @@
 # Profile visit: parity tests, bench, full ncu captures of the named kernels.
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
+timeout 600 python bench.py --no-cpu-baseline --no-masked --stress-frames 0 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?" >> gpurun_out/bench.err
 for k in $KERNELS; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o gpurun_out/prof_$k python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_$k.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o gpurun_out/prof_$k python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-masked --stress-frames 0 > gpurun_out/ncu_$k.log 2>&1
 done
 tail -8 gpurun_out/pytest_gpu.log; python - <<'PY'
 import json
