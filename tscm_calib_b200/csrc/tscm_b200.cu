@@ -442,7 +442,7 @@ void launch_schur(tscm_solver* s, double radius_override) {
   if (s->schur_form == kSchurRows) {
     SchurSplitArgs b = s->split;
     b.a = a;
-    launch_k(s, k_schur_frames, dim3((s->F + 7) / 8), dim3(256), (size_t)(0), s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
+    launch_k(s, k_schur_frames, dim3((s->F + kSfWarps - 1) / kSfWarps), dim3(32 * kSfWarps), (size_t)(0), s->P, s->ps[0], s->ps[1], s->d_state, s->lm, b);
     if (s->schur_ept == 1)
       launch_k(s, k_schur_update<1>, dim3(s->schur_nblk), dim3(s->schur_nt), (size_t)(s->split_smem), s->P, s->d_state, b);
     else

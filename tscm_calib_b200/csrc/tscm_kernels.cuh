@@ -539,17 +539,21 @@ __host__ __device__ __forceinline__ int pair_pos(int c) { return c + (c >= 7 ? 1
 #ifndef TSCM_SF_MINB
 #define TSCM_SF_MINB 2
 #endif
-__global__ void __launch_bounds__(256, TSCM_SF_MINB)
+#ifndef TSCM_SF_WARPS
+#define TSCM_SF_WARPS 8      // frames (warps) per CTA
+#endif
+constexpr int kSfWarps = TSCM_SF_WARPS;
+__global__ void __launch_bounds__(32 * kSfWarps, TSCM_SF_MINB)
 k_schur_frames(DeviceProblem P, ParamSet ps0, ParamSet ps1, const LmState* st, LmOptions opt,
                SchurSplitArgs B) {
   pdl_entry();
   if (st->done) return;
-  __shared__ double s_scr[8][64];
+  __shared__ double s_scr[kSfWarps][64];
   const SchurArgs& A = B.a;
   const ParamSet& ps = st->cur ? ps1 : ps0;
   const double radius = A.radius_override > 0.0 ? A.radius_override : st->radius;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int f = blockIdx.x * 8 + warp;
+  const int f = blockIdx.x * kSfWarps + warp;
   if (f >= P.F) return;
   const int NLp = A.NLp;
   double* my = s_scr[warp];
