@@ -326,7 +326,7 @@ int tscm_pose_graph_init(const tscm_pose_graph_problem* problem, int device,
  *                       that a corner near the board centre looks down +z, cv::solvePnPRansac
  *                       (defaults, identity camera matrix) on the normalised plane, turned back,
  *                       kept as the 3x3 [r1 r2 t]
- * One GPU thread per (frame, row) / per frame; every statement in the scalar order without FMA
+ * One GPU thread per (frame, row) for the focal fits, one warp per frame for the pose; no FMA
  * contraction.  The two OpenCV calls are restated (one-sided Jacobi SVD; homography + LM to
  * convergence + inlier re-fitting) and pinned against golden vectors of the real OpenCV.
  *   has_board  F bytes       has_chessboard[k] (a frame without corners: pixels[k].size() == 0)

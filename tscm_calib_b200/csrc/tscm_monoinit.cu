@@ -14,12 +14,16 @@
 // threshold in normalised units only removes corners whose back-projection is NaN or blew up) —
 // and pinned, like the CPU oracle, against golden vectors of the real OpenCV 4.13.
 //
-// Mapping: one THREAD per (frame, row) / per frame, every sum in the scalar statement order.  This
-// translation unit is compiled with -fmad=false, so each double operation is one IEEE instruction
-// as in the oracle (oracle/mono_init_oracle.cpp, -ffp-contract=off); what remains is the rounding
-// of sin/cos/atan2/asin in CUDA's libm against glibc's.  The work is tiny against the refinement
-// (config 3: 40,000 PnP problems of 88 points) but minutes of scalar host code; the DLT matrix
-// (2K x 9 per frame) lives in a frame-minor global scratch so that the lanes' accesses coalesce.
+// Mapping: one thread per (frame, board row) for the focal fits; one WARP per frame for the pose
+// (k_mi_extrinsic_warp: the lanes split the rows of the Jacobi sweeps and the points of the
+// Gauss-Newton sums, the frame's DLT matrix lives in the warp's shared memory; 2.7 ms for 5,000
+// frames).  A thread-per-frame form (k_mi_extrinsic) keeps every sum in the oracle's statement
+// order — it is the fallback for boards too large for shared memory and the A/B reference
+// (TSCM_MI_FORM=thread; 32 ms: a single dependent chain per frame).  This translation unit is
+// compiled with -fmad=false, so each double operation is one IEEE instruction as in the oracle
+// (oracle/mono_init_oracle.cpp, -ffp-contract=off); what remains is the rounding of
+// sin/cos/atan2/asin in CUDA's libm against glibc's and, in the warp form, the association of
+// the lane-parallel sums.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -428,6 +432,323 @@ k_mi_extrinsic(const double* __restrict__ pixels, const uint8_t* __restrict__ ha
   ok[f] = 1;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative form of k_mi_extrinsic: ONE WARP per frame.  The thread-per-frame kernel above
+// keeps every sum in the scalar statement order but is a single dependent chain per frame (32 ms
+// for 5,000 frames, each thread walking its DLT matrix ~10^5 times).  Here the lanes split the
+// rows of the Jacobi sweeps and the points of the Gauss-Newton sums; partial sums meet in a
+// butterfly (every lane ends with the same bits, so control flow stays uniform), the DLT matrix,
+// the points and the flags live in the warp's shared memory.  Same algorithm, same stopping
+// rules; what changes is the association of the sums (1e-16 per sum, far inside the 1e-8 flat
+// bottom of the least-squares minimum both forms stop in).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMiWarps = 4;          // frames per CTA
+
+__device__ __forceinline__ double wsum(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+struct WarpScratch {
+  double* A;         // [9][ld] DLT matrix, column-major
+  double* V;         // [9][9] accumulated rotations
+  double* xy;        // [2][K] normalised-plane points (x row, y row)
+  uint8_t* use;      // [K]
+  int ld;
+};
+__host__ __device__ inline size_t mi_warp_smem_bytes(int K) {
+  const size_t ld = 2 * (size_t)K;
+  return (9 * ld + 81 + 2 * (size_t)K) * sizeof(double) + (((size_t)K + 15) & ~(size_t)15);
+}
+
+// solveZ of the m x 9 matrix in S.A: one-sided Jacobi, rows split over the lanes
+__device__ void solve_z9_warp(const WarpScratch& S, int m, int lane, double* z) {
+  const int ld = S.ld;
+  for (int k = lane; k < 81; k += 32) S.V[k] = (k % 10 == 0) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < 8; ++p)
+      for (int q = p + 1; q < 9; ++q) {
+        double* Ap = S.A + p * ld;
+        double* Aq = S.A + q * ld;
+        double a = 0, b = 0, g = 0;
+        for (int i = lane; i < m; i += 32) {
+          const double wp = Ap[i], wq = Aq[i];
+          a += wp * wp; b += wq * wq; g += wp * wq;
+        }
+        a = wsum(a); b = wsum(b); g = wsum(g);
+        if (fabs(g) <= 1e-300 || fabs(g) <= 2.220446049250313e-16 * sqrt(a * b)) continue;
+        rotated = true;
+        const double zeta = (b - a) / (2.0 * g);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+        for (int i = lane; i < m; i += 32) {
+          const double x = Ap[i], y = Aq[i];
+          Ap[i] = c * x - sn * y; Aq[i] = sn * x + c * y;
+        }
+        if (lane < 9) {
+          const double x = S.V[lane * 9 + p], y = S.V[lane * 9 + q];
+          S.V[lane * 9 + p] = c * x - sn * y; S.V[lane * 9 + q] = sn * x + c * y;
+        }
+        __syncwarp();
+      }
+    if (!rotated) break;
+  }
+  int best = 0;
+  double best_norm = -1.0;
+  for (int j = 0; j < 9; ++j) {
+    double sacc = 0;
+    for (int i = lane; i < m; i += 32) sacc += S.A[j * ld + i] * S.A[j * ld + i];
+    sacc = wsum(sacc);
+    if (best_norm < 0 || sacc < best_norm) { best_norm = sacc; best = j; }
+  }
+  double nz = 0;
+  for (int i = 0; i < 9; ++i) nz += S.V[i * 9 + best] * S.V[i * 9 + best];
+  nz = sqrt(nz);
+  for (int i = 0; i < 9; ++i) z[i] = S.V[i * 9 + best] / nz;
+  __syncwarp();
+}
+
+__device__ bool pnp_planar_warp(const WarpScratch& S, int K, const double* __restrict__ worlds, int lane, double* R,
+                                double* t) {
+  const double* xs = S.xy;
+  const double* ys = S.xy + K;
+  // number of flagged points, the first of them, the four means
+  int n = 0, first = K;
+  double mx = 0, my = 0, mX = 0, mY = 0;
+  for (int i = lane; i < K; i += 32) {
+    if (!S.use[i]) continue;
+    ++n; first = min(first, i);
+    mx += xs[i]; my += ys[i]; mX += worlds[3 * i]; mY += worlds[3 * i + 1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    n += __shfl_xor_sync(0xffffffffu, n, o);
+    first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+  }
+  if (n < 4) return false;
+  mx = wsum(mx) / n; my = wsum(my) / n; mX = wsum(mX) / n; mY = wsum(mY) / n;
+  double sx = 0, sX = 0;
+  for (int i = lane; i < K; i += 32) {
+    if (!S.use[i]) continue;
+    sx += sqrt((xs[i] - mx) * (xs[i] - mx) + (ys[i] - my) * (ys[i] - my));
+    sX += sqrt((worlds[3 * i] - mX) * (worlds[3 * i] - mX) + (worlds[3 * i + 1] - mY) * (worlds[3 * i + 1] - mY));
+  }
+  sx = wsum(sx); sX = wsum(sX);
+  if (!(sx > 0) || !(sX > 0)) return false;
+  sx = sqrt(2.0) * n / sx; sX = sqrt(2.0) * n / sX;      // Hartley normalisation
+  // DLT rows of the flagged points, in point order: rows 2 r, 2 r + 1 for the r-th flagged point
+  {
+    int base = 0;
+    for (int i0 = 0; i0 < K; i0 += 32) {
+      const int i = i0 + lane;
+      const bool u_ = i < K && S.use[i];
+      const unsigned mask = __ballot_sync(0xffffffffu, u_);
+      if (u_) {
+        const int row = 2 * (base + __popc(mask & ((1u << lane) - 1u)));
+        const double u = (xs[i] - mx) * sx, v = (ys[i] - my) * sx;
+        const double a = (worlds[3 * i] - mX) * sX, b = (worlds[3 * i + 1] - mY) * sX;
+        const double r0[9] = {a, b, 1, 0, 0, 0, -u * a, -u * b, -u};
+        const double r1[9] = {0, 0, 0, a, b, 1, -v * a, -v * b, -v};
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { S.A[k * S.ld + row] = r0[k]; S.A[k * S.ld + row + 1] = r1[k]; }
+      }
+      base += __popc(mask);
+    }
+  }
+  __syncwarp();
+  double Hn[9];
+  solve_z9_warp(S, 2 * n, lane, Hn);
+  // from here to the Gauss-Newton loop every lane computes the same few hundred flops
+  const double Ti[9] = {1 / sx, 0, mx, 0, 1 / sx, my, 0, 0, 1};
+  const double To[9] = {sX, 0, -mX * sX, 0, sX, -mY * sX, 0, 0, 1};
+  double T1[9], H[9];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double s = 0; for (int k = 0; k < 3; ++k) s += Ti[3 * r + k] * Hn[3 * k + c]; T1[3 * r + c] = s; }
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double s = 0; for (int k = 0; k < 3; ++k) s += T1[3 * r + k] * To[3 * k + c]; H[3 * r + c] = s; }
+  const double n1 = sqrt(H[0] * H[0] + H[3] * H[3] + H[6] * H[6]);
+  const double n2 = sqrt(H[1] * H[1] + H[4] * H[4] + H[7] * H[7]);
+  if (!(n1 > 0) || !(n2 > 0)) return false;
+  double sc = 2.0 / (n1 + n2);
+  const double z0 = worlds[3 * first + 2];
+  if ((H[6] * mX + H[7] * mY + H[8]) * sc < 0) sc = -sc;
+  double r1[3] = {H[0] * sc, H[3] * sc, H[6] * sc}, r2[3] = {H[1] * sc, H[4] * sc, H[7] * sc};
+  t[0] = H[2] * sc; t[1] = H[5] * sc; t[2] = H[8] * sc;
+  {
+    const double a1 = sqrt(r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2]);
+    const double a2 = sqrt(r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2]);
+    for (int k = 0; k < 3; ++k) { r1[k] /= a1; r2[k] /= a2; }
+    double s[3], d[3];
+    for (int k = 0; k < 3; ++k) { s[k] = r1[k] + r2[k]; d[k] = r1[k] - r2[k]; }
+    const double ns = sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+    const double dd = (d[0] * s[0] + d[1] * s[1] + d[2] * s[2]) / (ns * ns);
+    for (int k = 0; k < 3; ++k) d[k] -= dd * s[k];
+    const double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const double h = sqrt(0.5);
+    for (int k = 0; k < 3; ++k) { r1[k] = h * (s[k] / ns + d[k] / nd); r2[k] = h * (s[k] / ns - d[k] / nd); }
+  }
+  R[0] = r1[0]; R[1] = r2[0]; R[2] = r1[1] * r2[2] - r1[2] * r2[1];
+  R[3] = r1[1]; R[4] = r2[1]; R[5] = r1[2] * r2[0] - r1[0] * r2[2];
+  R[6] = r1[2]; R[7] = r2[2]; R[8] = r1[0] * r2[1] - r1[1] * r2[0];
+  for (int k = 0; k < 3; ++k) t[k] -= R[3 * k + 2] * z0;
+  auto cost_at = [&](const double* Rm, const double* tm) {
+    double c = 0;
+    for (int i = lane; i < K; i += 32) {
+      if (!S.use[i]) continue;
+      const double p[3] = {worlds[3 * i], worlds[3 * i + 1], worlds[3 * i + 2]};
+      double P[3];
+      for (int r = 0; r < 3; ++r) P[r] = Rm[3 * r] * p[0] + Rm[3 * r + 1] * p[1] + Rm[3 * r + 2] * p[2] + tm[r];
+      const double eu = P[0] / P[2] - xs[i], ev = P[1] / P[2] - ys[i];
+      c += eu * eu + ev * ev;
+    }
+    return wsum(c);
+  };
+  double lambda = 1e-6, cost = cost_at(R, t);
+  for (int it = 0; it < 200; ++it) {
+    double L[21], Jtr[6];                       // lower triangle of J^T J, row-major packed
+#pragma unroll
+    for (int k = 0; k < 21; ++k) L[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Jtr[k] = 0;
+    for (int i = lane; i < K; i += 32) {
+      if (!S.use[i]) continue;
+      const double p[3] = {worlds[3 * i], worlds[3 * i + 1], worlds[3 * i + 2]};
+      double q[3], P[3];
+      for (int r = 0; r < 3; ++r) { q[r] = R[3 * r] * p[0] + R[3 * r + 1] * p[1] + R[3 * r + 2] * p[2]; P[r] = q[r] + t[r]; }
+      const double iz = 1.0 / P[2], u = P[0] * iz, v = P[1] * iz;
+      const double dP[3][6] = {{0, q[2], -q[1], 1, 0, 0}, {-q[2], 0, q[0], 0, 1, 0}, {q[1], -q[0], 0, 0, 0, 1}};
+      double Ju[6], Jv[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { Ju[k] = iz * (dP[0][k] - u * dP[2][k]); Jv[k] = iz * (dP[1][k] - v * dP[2][k]); }
+      const double eu = u - xs[i], ev = v - ys[i];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        Jtr[a] += Ju[a] * eu + Jv[a] * ev;
+#pragma unroll
+        for (int b = 0; b <= a; ++b) L[a * (a + 1) / 2 + b] += Ju[a] * Ju[b] + Jv[a] * Jv[b];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 21; ++k) L[k] = wsum(L[k]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Jtr[k] = wsum(Jtr[k]);
+    double JtJ[36];
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) { JtJ[a * 6 + b] = L[a * (a + 1) / 2 + b]; JtJ[b * 6 + a] = L[a * (a + 1) / 2 + b]; }
+    bool improved = false;
+    double step_norm = 0;
+    for (int tries = 0; tries < 30 && !improved; ++tries) {
+      double Am[36], d[6];
+      for (int k = 0; k < 36; ++k) Am[k] = JtJ[k];
+      for (int k = 0; k < 6; ++k) { Am[k * 6 + k] *= 1.0 + lambda; d[k] = -Jtr[k]; }
+      if (!chol_solve6(Am, d)) { lambda *= 10; continue; }
+      double dR[9], Rn[9], tn[3];
+      rodrigues_v2m(d, dR);
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { double s = 0; for (int k = 0; k < 3; ++k) s += dR[3 * r + k] * R[3 * k + c]; Rn[3 * r + c] = s; }
+      for (int k = 0; k < 3; ++k) tn[k] = t[k] + d[3 + k];
+      const double cn = cost_at(Rn, tn);
+      if (cn <= cost) {
+        step_norm = 0;
+        for (int k = 0; k < 3; ++k) step_norm += d[k] * d[k] + d[3 + k] * d[3 + k] / (1.0 + t[k] * t[k]);
+        for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+        for (int k = 0; k < 3; ++k) t[k] = tn[k];
+        improved = true; cost = cn; lambda = fmax(lambda * 0.1, 1e-12);
+      } else {
+        lambda *= 10;
+      }
+    }
+    if (!improved || step_norm < 1e-28) break;
+  }
+  return true;
+}
+
+// warp = frame: TS.cpp:172-202
+__global__ void __launch_bounds__(32 * kMiWarps)
+k_mi_extrinsic_warp(const double* __restrict__ pixels, const uint8_t* __restrict__ has,
+                    const double* __restrict__ worlds, int F, int W, int H, Intr I, size_t warp_bytes,
+                    double* __restrict__ mono_rt, uint8_t* __restrict__ ok) {
+  extern __shared__ __align__(16) unsigned char mi_wsmem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f = blockIdx.x * kMiWarps + warp;
+  if (f >= F) return;
+  const int K = W * H;
+  WarpScratch S;
+  S.ld = 2 * K;
+  S.A = reinterpret_cast<double*>(mi_wsmem + (size_t)warp * warp_bytes);
+  S.V = S.A + 9 * (size_t)S.ld;
+  S.xy = S.V + 81;
+  S.use = reinterpret_cast<uint8_t*>(S.xy + 2 * (size_t)K);
+  double* M = mono_rt + 9 * (size_t)f;
+  if (lane == 0) {                       // lane 0 owns the frame's outputs
+    for (int k = 0; k < 9; ++k) M[k] = 0.0;
+    ok[f] = 0;
+  }
+  if (!has[f]) return;
+  const double* px = pixels + (size_t)f * K * 2;
+  const double eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  const int centre = K / 2 - W / 2 - 1;                                    // TS.cpp:177
+  double p[3];
+  unit_sphere(I, px[2 * centre], px[2 * centre + 1], eye, p);
+  const double az = atan2(p[0], p[2]), el = asin(p[1]);
+  const double R1[9] = {cos(az), 0, -sin(az), 0, 1, 0, sin(az), 0, cos(az)};
+  const double R2[9] = {1, 0, 0, 0, cos(el), -sin(el), 0, sin(el), cos(el)};
+  double T[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      double s = 0.0;
+      for (int q = 0; q < 3; ++q) s += R2[3 * r + q] * R1[3 * q + c];
+      T[3 * r + c] = s;
+    }
+  for (int i = lane; i < K; i += 32) {
+    double ray[3];
+    unit_sphere(I, px[2 * i], px[2 * i + 1], T, ray);
+    const double u = ray[0] / ray[2], v = ray[1] / ray[2];
+    S.xy[i] = u;
+    S.xy[K + i] = v;
+    S.use[i] = (isfinite(u) && isfinite(v)) ? 1 : 0;
+  }
+  __syncwarp();
+  double R[9], t[3], rvec[3];
+  for (int round = 0; round < 8; ++round) {
+    if (!pnp_planar_warp(S, K, worlds, lane, R, t)) return;
+    rodrigues_m2v(R, rvec);
+    double Rr[9];
+    rodrigues_v2m(rvec, Rr);
+    bool changed = false;
+    for (int i = lane; i < K; i += 32) {
+      if (!S.use[i]) continue;
+      double P[3];
+      for (int r = 0; r < 3; ++r)
+        P[r] = Rr[3 * r] * worlds[3 * i] + Rr[3 * r + 1] * worlds[3 * i + 1] + Rr[3 * r + 2] * worlds[3 * i + 2] + t[r];
+      const double eu = 1.0 * P[0] / P[2] + 0.0 - S.xy[i];
+      const double ev = 1.0 * P[1] / P[2] + 0.0 - S.xy[K + i];
+      if (!(eu * eu + ev * ev <= 8.0 * 8.0)) { S.use[i] = 0; changed = true; }
+    }
+    changed = __any_sync(0xffffffffu, changed);
+    __syncwarp();
+    if (!changed) break;
+  }
+  double pose[9];
+  rodrigues_v2m(rvec, pose);
+  if (lane == 0) {
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 2; ++c) {
+        double s = 0.0;
+        for (int q = 0; q < 3; ++q) s += T[3 * q + r] * pose[3 * q + c];
+        M[3 * r + c] = s;
+      }
+      double s = 0.0;
+      for (int q = 0; q < 3; ++q) s += T[3 * q + r] * t[q];
+      M[3 * r + 2] = s;
+    }
+    ok[f] = 1;
+  }
+}
+
 }  // namespace mi
 }  // namespace tscm
 
@@ -516,6 +837,25 @@ extern "C" int tscm_mono_init(const tscm_mono_init_problem* P, int device, tscm_
   std::memset(R->mono_rt, 0, sizeof(double) * 9 * (size_t)F);
   std::memset(R->frame_ok, 0, (size_t)F);
   if (!P->has_init_guess && I.fx == 0) { cleanup(); return TSCM_OK; }  // the caller returns false (TS.cpp:50)
+  // warp-per-frame form whenever a frame's scratch fits shared memory (K <= ~350); TSCM_MI_FORM=thread
+  // selects the thread-per-frame kernel, which keeps the oracle's statement order (A/B, tests)
+  {
+    const size_t wb = (mi::mi_warp_smem_bytes(K) + 15) & ~(size_t)15;
+    const char* form = std::getenv("TSCM_MI_FORM");
+    if (wb * mi::kMiWarps <= 200 * 1024 && !(form && form[0] == 't')) {
+      MI_TRY(cudaFuncSetAttribute(mi::k_mi_extrinsic_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(wb * mi::kMiWarps)));
+      MI_TRY(cudaEventRecord(e0, 0));
+      mi::k_mi_extrinsic_warp<<<(F + mi::kMiWarps - 1) / mi::kMiWarps, 32 * mi::kMiWarps, wb * mi::kMiWarps>>>(
+          d_px, d_has, d_worlds, F, W, H, I, wb, d_rt, d_ok);
+      MI_TRY(cudaEventRecord(e1, 0));
+      MI_TRY(cudaGetLastError());
+      MI_TRY(add_ms());
+      MI_TRY(cudaMemcpy(R->mono_rt, d_rt, (size_t)F * 9 * sizeof(double), cudaMemcpyDeviceToHost));
+      MI_TRY(cudaMemcpy(R->frame_ok, d_ok, (size_t)F, cudaMemcpyDeviceToHost));
+      cleanup();
+      return TSCM_OK;
+    }
+  }
   MI_TRY(dalloc((void**)&S.xy, (size_t)2 * K * F * sizeof(double)));
   MI_TRY(dalloc((void**)&S.use, (size_t)K * F));
   // frames per block: as many DLT matrices as fit 200 KB of shared memory (16 at K = 88)
