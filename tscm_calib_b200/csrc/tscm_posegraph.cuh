@@ -95,21 +95,28 @@ __device__ __forceinline__ double pg_corner_error(const PgIntr& I, const double*
   return __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
 }
 
-// Sum over the K corners in corner order; two independent chains per trip for latency.
+// Sum over the K corners in corner order; PG_ILP independent chains per trip for latency.
+#ifndef PG_ILP
+#define PG_ILP 2
+#endif
 template <typename PixelLoad>
 __device__ __forceinline__ double pg_reproject_error(const PgIntr& I, const double* pose, const double* worlds,
                                                      int K, PixelLoad pixel) {
   double e = 0.0;
   int j = 0;
-  for (; j + 1 < K; j += 2) {
-    const double2 p0 = pixel(j), p1 = pixel(j + 1);
-    const double e0 = pg_corner_error(I, pose, worlds + 3 * j, p0.x, p0.y);
-    const double e1 = pg_corner_error(I, pose, worlds + 3 * j + 3, p1.x, p1.y);
-    e = __dadd_rn(__dadd_rn(e, e0), e1);
+  for (; j + PG_ILP <= K; j += PG_ILP) {
+    double ej[PG_ILP];
+#pragma unroll
+    for (int u = 0; u < PG_ILP; ++u) {
+      const double2 p = pixel(j + u);
+      ej[u] = pg_corner_error(I, pose, worlds + 3 * (j + u), p.x, p.y);
+    }
+#pragma unroll
+    for (int u = 0; u < PG_ILP; ++u) e = __dadd_rn(e, ej[u]);
   }
-  if (j < K) {
-    const double2 p0 = pixel(j);
-    e = __dadd_rn(e, pg_corner_error(I, pose, worlds + 3 * j, p0.x, p0.y));
+  for (; j < K; ++j) {
+    const double2 p = pixel(j);
+    e = __dadd_rn(e, pg_corner_error(I, pose, worlds + 3 * j, p.x, p.y));
   }
   return e;
 }
