@@ -27,6 +27,9 @@ The JSON line also carries:
   e2e                     the same metric through ONE tscm_solve() call — the call the
                           reference adapters make in place of ceres::Solve — with HOST buffers;
                           at N > 1 rank 0 alone makes the call with options.num_gpus = N
+  masked (N = 1)          config 3 with per-frame all-or-nothing visibility masks
+  stress_cfg4_sample      (N = 1) a 20,000-frame sample of BASELINE config 4's generator
+                          (16-camera ring, sparse visibility: the per-camera-pair Schur form)
 
 `--impl reference` times the CPU restatement of the reference's Ceres path (the
 reference itself cannot be built: Ceres/Eigen/OpenCV are absent) on the host cores.
