@@ -49,6 +49,9 @@ def test_options_init_matches_ceres_defaults(lib):
 def test_struct_sizes():
     # 4 int32 + 4 pointers + int32 (+pad)
     assert C.sizeof(capi.TscmProblem) == 56
+    # the init entry points (sizes of the C structs as gcc lays them out: include/tscm.h)
+    assert C.sizeof(capi.TscmPoseGraphProblem) == 56 and C.sizeof(capi.TscmPoseGraphResult) == 72
+    assert C.sizeof(capi.TscmMonoInitProblem) == 56 and C.sizeof(capi.TscmMonoInitResult) == 104
     assert C.sizeof(capi.TscmSummary) == 16 + 3 * 8 + 8 + 5 * 8
 
 

@@ -233,6 +233,23 @@ def test_gpu_mono_init_matches_oracle_per_camera(oracle, cfg, frames, kw):
 
 
 @pytest.mark.gpu
+def test_gpu_warp_and_thread_forms_agree(oracle, monkeypatch):
+    """The warp-per-frame kernel (default) against the thread-per-frame kernel that keeps the
+    oracle's statement order (TSCM_MI_FORM=thread): same frame decisions, same focal length bit for
+    bit (the focal kernel is shared), poses to the width of the flat bottom."""
+    args = (G["board"], G["image"], G["worlds"], G["has"], G["pixels"])
+    for guess in (None, G["guess7"]):
+        monkeypatch.delenv("TSCM_MI_FORM", raising=False)
+        rw = capi.mono_init(*args, guess=guess)
+        monkeypatch.setenv("TSCM_MI_FORM", "thread")
+        rt = capi.mono_init(*args, guess=guess)
+        monkeypatch.delenv("TSCM_MI_FORM", raising=False)
+        np.testing.assert_array_equal(rw.intrinsics, rt.intrinsics)
+        assert_same_init(rw, rt)
+        assert_same_init(rt, oracle.mono_init(*args, guess=guess))
+
+
+@pytest.mark.gpu
 def test_gpu_focal_failure_and_bad_arguments():
     r = capi.mono_init((9, 6), (1280, 1080), G["worlds"], np.zeros(3, dtype=np.uint8), np.zeros((3, 54, 2)))
     assert r.intrinsics[0] == 0.0 and r.rows_used == 0 and not r.frame_ok.any() and not r.Rt.any()
