@@ -80,7 +80,7 @@ def test_both_ceres_tolerance_gatings_match_the_oracle(oracle, needs_success):
 @pytest.mark.parametrize("form", ["auto", "rows", "pairs"])
 def test_masked_ring_sample_matches_the_oracle(oracle, form):
     """8-camera outward ring with all-or-nothing visibility masks (config 3's named shape) at a
-    size the oracle solves in seconds; the default form here is the fused k_schur2.  The start is
+    size the oracle solves in seconds, under every Schur form.  The start is
     hard enough for rejected steps, which the trace must reproduce too."""
     sp = synth.config(3, num_frames=150, dense=False, rig="ring")
     opt = capi.default_options(max_num_iterations=25)

@@ -624,7 +624,10 @@ double visibility_fill(const tscm_solver* s) {
 int choose_schur_form(const tscm_solver* s) {
   const int NLp = s->schur.NLp, ntiles = s->schur.ntiles;
   const size_t split_smem = (size_t)(2 * (2 * kSchurFB * 6 * NLp + kSchurFB * 6)) * sizeof(double);
-  if (visibility_fill(s) >= 0.4 && split_smem <= s->smem_optin) return kSchurRows;
+  // dense rows whenever they fit shared memory and the reduced system is wide enough to amortise
+  // the second kernel (measured, tools/form_ab.py: 8-camera ring at fill 0.39, 150-5,000 frames: rows
+  // 3-10 % ahead of the fused form; 4-camera rig at fill 0.39: fused 0-5 % ahead)
+  if (split_smem <= s->smem_optin && (visibility_fill(s) >= 0.4 || s->P.NL >= 64)) return kSchurRows;
   const int schur2_nt = kSchurFB * 32 + (ntiles + 31) / 32 * 32;
   const size_t schur2_smem = (size_t)(2 * (2 * kSchurFB * 6 * NLp + kSchurFB * 6) + kSchurFB * 64) * sizeof(double);
   if (schur2_nt <= 640 && schur2_smem <= s->smem_optin) return kSchurFused;
