@@ -2078,6 +2078,10 @@ int tscm_pose_graph_init(const tscm_pose_graph_problem* P, int device, tscm_pose
       const int gx = (nc + kPgThreads - 1) / kPgThreads;
       int t = tile;
       while (t > 1 && (int64_t)gx * ((n + t - 1) / t) < (int64_t)prop.sm_count * 8) --t;
+      if ((n + t - 1) / t > 65535) {
+        set_error("%d shared boards exceed the scoring grid (%d boards per CTA)", n, t);
+        cleanup(); return TSCM_ERR_UNSUPPORTED;
+      }
       PgPairArgs A;
       A.pixels = d_px; A.shared = d_shared; A.base = d_base; A.cand = d_T + (size_t)c0 * 24;
       A.worlds = d_worlds; A.E = d_E;
