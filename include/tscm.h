@@ -155,7 +155,9 @@ int tscm_solve(const tscm_problem* problem, const tscm_options* options,
                tscm_summary* summary, int device);
 void tscm_cache_configure(int32_t max_solvers);   /* default 1; 0 = no caching */
 void tscm_cache_release(void);
-/* Page-locked host memory for observation staging (cudaHostAlloc / cudaFreeHost). */
+/* Page-locked host memory for observation staging (cudaHostAlloc / cudaFreeHost).  The last block
+ * freed is kept for the next request of at most its size (page-locking 56 MB costs more than a warm
+ * solve); tscm_cache_configure(0) disables that, tscm_cache_release() frees it. */
 void* tscm_host_alloc(size_t bytes);
 void tscm_host_free(void* p);
 

@@ -1169,6 +1169,9 @@ std::mutex g_cache_mu;
 std::vector<CacheEntry> g_cache;
 int g_cache_max = 1;
 uint64_t g_cache_clock = 0;
+void* g_host_block = nullptr;       // tscm_host_alloc: the one page-locked block kept for reuse
+size_t g_host_bytes = 0;
+bool g_host_busy = false;
 
 bool same_structure(const tscm_solver* s, const tscm_problem* p) {
   if (s->C != p->num_cameras || s->F != p->num_frames || s->K != p->corners_per_board || s->V != p->num_views ||
@@ -1256,16 +1259,39 @@ void tscm_options_init(tscm_options* o) {
   o->num_gpus = 1;
 }
 
+// Page-locking 56 MB costs 15-30 ms and unlocking it as much again — more than the solve of a warm
+// start.  The last block handed back is therefore kept (one slot, like the solver cache and under the
+// same switch: tscm_cache_configure(0) turns it off, tscm_cache_release() frees it).
 void* tscm_host_alloc(size_t bytes) {
+  bytes = std::max<size_t>(1, bytes);
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    if (g_host_block && !g_host_busy && g_host_bytes >= bytes) { g_host_busy = true; return g_host_block; }
+  }
   void* p = nullptr;
-  if (cudaMallocHost(&p, std::max<size_t>(1, bytes)) != cudaSuccess) {
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
     set_error("cudaMallocHost(%zu) failed", bytes);
     cudaGetLastError();
     return nullptr;
   }
+  std::lock_guard<std::mutex> lock(g_cache_mu);
+  if (g_cache_max > 0 && !g_host_busy) {           // this block becomes the cached one
+    if (g_host_block) cudaFreeHost(g_host_block);
+    g_host_block = p; g_host_bytes = bytes; g_host_busy = true;
+  }
   return p;
 }
-void tscm_host_free(void* p) { if (p) cudaFreeHost(p); }
+void tscm_host_free(void* p) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    if (p == g_host_block) {
+      if (g_cache_max > 0) { g_host_busy = false; return; }
+      g_host_block = nullptr; g_host_bytes = 0; g_host_busy = false;
+    }
+  }
+  cudaFreeHost(p);
+}
 
 int tscm_solver_set_options(tscm_solver* s, const tscm_options* o) {
   if (!s || !o) { set_error("NULL argument"); return TSCM_ERR_INVALID_ARGUMENT; }
@@ -1455,12 +1481,14 @@ void tscm_cache_configure(int32_t max_solvers) {
   std::lock_guard<std::mutex> lock(g_cache_mu);
   g_cache_max = std::max(0, (int)max_solvers);
   while ((int)g_cache.size() > g_cache_max) cache_evict_oldest_locked();
+  if (g_cache_max == 0 && g_host_block && !g_host_busy) { cudaFreeHost(g_host_block); g_host_block = nullptr; g_host_bytes = 0; }
 }
 void tscm_cache_release(void) {
   DeviceGuard device_guard_;
   std::lock_guard<std::mutex> lock(g_cache_mu);
   for (CacheEntry& e : g_cache) destroy_solver(e.solver);
   g_cache.clear();
+  if (g_host_block && !g_host_busy) { cudaFreeHost(g_host_block); g_host_block = nullptr; g_host_bytes = 0; }
 }
 
 int tscm_solve(const tscm_problem* problem, const tscm_options* options, double* intrinsics,
